@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the GTCRN-Micro inference hot path (BASELINE.json: audio-seconds per second per B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the whole hot path (STFT -> model -> iSTFT) over one batch of 1024 synthetic
+10 s / 16 kHz noisy utterances per GPU (BASELINE.json configs[1]); utterances are independent, so N GPUs
+process N such batches with no collective (weak scaling).  One JSON line is printed by rank 0.
+
+  value         device-timed (CUDA events on the launching stream), inputs resident in HBM
+  e2e           same metric through `GTCRNMicro.enhance_host` (C ABI gtcrnb_enhance_host): pinned HOST
+                buffers in, pinned HOST buffers out, H2D / D2H inside the timed region
+  roofline      dominant kernel (decoder GTConv 3x3), timed live with CUDA events inside the library
+  cpu_baseline  the oracle (torch-CPU port of the reference, same ATen ops) on this box's host cores
+  streaming     frame-by-frame path: per-hop latency for N concurrent streams vs the 16 ms deadline
+
+`--impl reference` times the reference's CPU implementation of the same path.  The reference is pure
+Python/PyTorch and is not present on the GPU box, so this arm runs the oracle port (oracle/gtcrn_oracle.py,
+pinned against the reference by oracle/check_against_reference.py) with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "audio_seconds_per_second"
+UNIT = "audio-s/s"
+SR = 16000
+SECONDS = 10
+L_UTT = SR * SECONDS                      # 160,000 samples -> T = 626 frames
+FRAMES_PER_UTT = 1 + L_UTT // 256
+MAC_PER_FRAME = 614_530                   # conv/linear MACs of the reference's own ops
+DEC_GT_MAC_PER_FRAME = 84_582             # one decoder GTConvBlock
+FP32_PEAK_TFLOPS = 73.4                   # measured on this pool's B200: tools/microbench/ffma_feed.cu -> profiles/ffma_feed_r1.txt
+WEIGHTS = os.path.join(ROOT, "tests", "golden", "weights_dns3.npz")
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def synth_on_device(B: int, L: int, device, seed: int) -> torch.Tensor:
+    """Same recipe as oracle.synth_batch generated on the device in fp32: 5 harmonics of
+    f0~U(90,250) Hz, 4 Hz syllable envelope, RMS 0.05, white noise at SNR~U(0,15) dB, clipped."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty(B, L, device=device, dtype=torch.float32)
+    t = torch.arange(L, device=device, dtype=torch.float32) / SR
+    for b0 in range(0, B, 128):
+        nb = min(128, B - b0)
+        f0 = 90 + 160 * torch.rand(nb, 1, generator=g, device=device)
+        clean = torch.zeros(nb, L, device=device)
+        for h in range(5):
+            ph = 6.2831853 * torch.rand(nb, 1, generator=g, device=device)
+            clean += torch.sin(6.2831853 * f0 * (h + 1) * t + ph) / (h + 1)
+        env = 0.5 * (1 + torch.sin(6.2831853 * 4.0 * t + 6.2831853 * torch.rand(nb, 1, generator=g, device=device)))
+        clean *= env
+        clean *= 0.05 / clean.pow(2).mean(dim=1, keepdim=True).sqrt()
+        snr = 15 * torch.rand(nb, 1, generator=g, device=device)
+        noise = torch.randn(nb, L, generator=g, device=device) * (0.05 / 10 ** (snr / 20))
+        out[b0:b0 + nb] = (clean + noise).clamp_(-1, 1)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, f"/tmp/gtcrn_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_throughput(batches, reps: int, budget_s: float):
+    """Best audio-s/s over batch sizes (SURVEY 8d protocol: 1 warm-up + best of `reps` per B)."""
+    import gtcrn_oracle as O
+    W = O.load_weights_npz(WEIGHTS)
+    torch.set_num_threads(os.cpu_count() or 1)
+    best, detail, t_start = 0.0, {}, time.perf_counter()
+    for B in batches:
+        x = O.synth_batch(B, L_UTT, seed=4321)
+        O.enhance(W, x[:1])
+        times = []
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            O.enhance(W, x)
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start > budget_s:
+                break
+        t = min(times[1:]) if len(times) > 1 else times[0]
+        detail[str(B)] = round(B * SECONDS / t, 1)
+        best = max(best, B * SECONDS / t)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    return best, detail
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import gtcrn_oracle as O
+    W = O.load_weights_npz(WEIGHTS)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # pick the batch size that suits this host (bounded sample of the 1024-utterance workload)
+    best_B, best_v = 16, 0.0
+    for B in (4, 16, 64):
+        x = O.synth_batch(B, L_UTT, seed=4321)
+        O.enhance(W, x[:1])
+        t0 = time.perf_counter(); O.enhance(W, x); dt = time.perf_counter() - t0
+        if B * SECONDS / dt > best_v:
+            best_B, best_v = B, B * SECONDS / dt
+    x = O.synth_batch(best_B, L_UTT, seed=4321)
+    for _ in range(args.warmup):
+        O.enhance(W, x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.enhance(W, x)
+    dt = time.perf_counter() - t0
+    value = best_B * SECONDS * args.steps / dt
+    sample = f"{best_B} x {SECONDS} s utterances per step (bounded sample of the 1024-utterance batch), torch {torch.__version__} CPU, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"GTCRN-Micro offline batched inference, 1024 x {SECONDS} s synthetic 16 kHz utterances per GPU (configs[1]); CPU arm times a bounded sample"},
+        "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def bench_streaming(G, model, device, n_list=(4096, 16384), hops=60, warm=10):
+    """Per-hop latency of the frame-by-frame path (spectral frames in, spectral frames out)."""
+    res = {}
+    smodel = G.StreamGTCRNMicro()
+    G.convert_to_stream(smodel, model)
+    g = torch.Generator(device=device).manual_seed(99)
+    for N in n_list:
+        st = smodel.new_state(N, device)
+        frames = [torch.randn(N, 257, 2, device=device, generator=g) for _ in range(4)]
+        out = torch.empty(N, 257, 2, device=device)
+        for i in range(warm):
+            smodel.step(frames[i % 4], st, out)
+        torch.cuda.synchronize(device)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(hops)]
+        for i in range(hops):
+            evs[i][0].record()
+            smodel.step(frames[i % 4], st, out)
+            evs[i][1].record()
+        torch.cuda.synchronize(device)
+        ms = sorted(a.elapsed_time(b) for a, b in evs)
+        res[str(N)] = {"hop_ms_p50": round(ms[len(ms) // 2], 4), "hop_ms_p99": round(ms[min(len(ms) - 1, int(0.99 * len(ms)))], 4),
+                       "hop_ms_max": round(ms[-1], 4), "realtime": ms[-1] < 16.0,
+                       "streams_at_deadline_est": int(N * 16.0 / ms[-1])}
+        del st
+    return res
+
+
+def run_b200(args):
+    import gtcrn_micro_b200 as G
+    import gtcrn_oracle as O
+    from gtcrn_micro_b200 import build
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    W = O.load_weights_npz(WEIGHTS)                      # weights only; the oracle's compute is not used on this arm
+    model = G.GTCRNMicro()
+    model.load_state_dict(W)
+
+    B = args.batch
+    x = synth_on_device(B, L_UTT, device, seed=1234 + rank * B)      # 655 MB per rank, > L2 (126 MB)
+    # warm-up (also sizes the workspace) ----------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        y = model.enhance(x)
+    torch.cuda.synchronize(device)
+    model.profile(True); model.profile_read(reset=True)
+    clocks = ClockSampler(local)
+    launches0 = model.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    clocks.start()
+    e0.record()
+    for _ in range(args.steps):
+        y = model.enhance(x)
+    e1.record()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = model.launch_count() - launches0
+    prof = model.profile_read(reset=True)
+    model.profile(False)
+    assert bool(torch.isfinite(y).all())
+
+    # e2e: pinned host buffers through the C-ABI host entry point ----------------------------------
+    xh = torch.empty((B, L_UTT), dtype=torch.float32, pin_memory=True)
+    xh.copy_(x)
+    yh = torch.empty((B, 256 * (L_UTT // 256)), dtype=torch.float32, pin_memory=True)
+    del x, y
+    for _ in range(2):
+        model.enhance_host(xh, yh, device=device)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.enhance_host(xh, yh, device=device)          # synchronous: returns when the last D2H landed
+    torch.cuda.synchronize(device)
+    e2e_s = time.perf_counter() - t0
+
+    times = torch.tensor([ms_total, e2e_s * 1e3], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)        # plumbing only: max over ranks of the device time
+    ms_total, e2e_ms = float(times[0]), float(times[1])
+    if rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    audio_s = world * B * SECONDS * args.steps
+    value = audio_s / (ms_total * 1e-3)
+    e2e_value = audio_s / (e2e_ms * 1e-3)
+    peaks = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # roofline of the dominant kernel (decoder GTConvBlock: full 16->16 3x3 conv + 1x1s + TRALite), live CUDA-event timing
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    dk = prof["dec_gtconv"]
+    dec_tflops = (2.0 * DEC_GT_MAC_PER_FRAME * dk["frames"]) / (dk["ms"] * 1e-3) / 1e12 if dk["ms"] > 0 else 0.0
+    step_kernel_ms = sum(v["ms"] for v in prof.values())
+    roofline = {
+        "kernel": "k_gtconv<DEC> (decoder GTConvBlock, 3 launches per chunk)", "bound": "fp32_fma",
+        "achieved": round(dec_tflops, 2), "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": round(dec_tflops / FP32_PEAK_TFLOPS, 4),
+        "peak_source": "measured FFMA micro-benchmark on this pool's B200 (tools/microbench/ffma_feed.cu, profiles/ffma_feed_r1.txt); "
+                       "MEASURED_PEAKS.json carries HBM and bf16-tensor peaks only and this path is FP32-FMA bound (SURVEY 8d)",
+        "traffic": None,
+        "ms_per_launch": round(dk["ms"] / max(1, dk["launches"]), 4), "launches": dk["launches"],
+        "share_of_step": round(dk["ms"] / step_kernel_ms, 4) if step_kernel_ms else None,
+        "dominant_class_by_time": dom,
+        "whole_path": {"achieved_tflops": round(2.0 * MAC_PER_FRAME * FRAMES_PER_UTT * world * B * args.steps / (ms_total * 1e-3) / 1e12 / world, 2),
+                       "frac_fp32": round(2.0 * MAC_PER_FRAME * FRAMES_PER_UTT * B * args.steps / (ms_total * 1e-3) / 1e12 / FP32_PEAK_TFLOPS, 4),
+                       "achieved_hbm_gbs_algorithmic": round(8.0 * L_UTT * B * args.steps / (ms_total * 1e-3) / 1e9, 1),
+                       "frac_hbm": round(8.0 * L_UTT * B * args.steps / (ms_total * 1e-3) / 1e9 / hbm_peak, 4),
+                       "hbm_peak_gbs": hbm_peak, "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
+        "per_class_ms": {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]},
+    }
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"GTCRN-Micro offline batched inference, {B} x {SECONDS} s synthetic 16 kHz utterances per GPU (BASELINE configs[1]), "
+                               f"STFT+model+iSTFT, shipped DNS3 checkpoint weights",
+                   "batch_per_gpu": B, "samples_per_utt": L_UTT, "frames_per_utt": FRAMES_PER_UTT,
+                   "cache": f"inputs {B * L_UTT * 4 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+                   "parallelism": f"{world} independent shard(s), no collective"},
+        "clocks": clk,
+        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": B * L_UTT * 4, "d2h_bytes_per_step": B * 256 * (L_UTT // 256) * 4,
+                "ms_per_step": round(e2e_ms / args.steps, 3), "api": "GTCRNMicro.enhance_host -> gtcrnb_enhance_host (pinned host in/out)"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    if not args.no_stream:
+        try:
+            line["streaming"] = bench_streaming(G, model, device)
+        except Exception as e:  # streaming is reported, never allowed to sink the offline number
+            line["streaming"] = {"error": f"{type(e).__name__}: {e}"}
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, detail = cpu_throughput((1, 4, 16, 64), reps=2, budget_s=45.0)
+        line["cpu_baseline"] = {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"oracle port (torch {torch.__version__} CPU, same ATen ops as the reference), {SECONDS} s utterances, "
+                                          f"best of B in {detail} (1 warm-up + best of 2 each); 1024-utterance batch extrapolated from this sample"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="utterances per GPU per step (BASELINE configs[1]: 1024)")
+    ap.add_argument("--no-stream", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

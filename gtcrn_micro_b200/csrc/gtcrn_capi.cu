@@ -1,0 +1,482 @@
+// C-ABI of libgtcrn_b200.so (declared in include/gtcrn_b200.h): handle, activation workspace,
+// kernel launch plumbing.  No torch types, no CPU fallback: every entry point either launches the
+// sm_100a kernels of gtcrn_kernels.cuh / gtcrn_stream.cuh or returns an error code.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gtcrn_b200.h"
+#include "gtcrn_kernels.cuh"
+#include "gtcrn_stream.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(GTCRNB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kAbiVersion = 1;
+constexpr int64_t kMaxChunkFrames = 160 * 1024;   // activation workspace capacity (frames)
+constexpr int kNumAct33 = 9;                      // en1..en4, gtcn1, gtcn2, de0..de2
+const char* const kActNames[kNumAct33] = {"en1", "en2", "en3", "en4", "gtcn1", "gtcn2", "de0", "de1", "de2"};
+
+enum KernelClass { KC_STFT = 0, KC_FRONT, KC_ENC_GT, KC_GTCN, KC_DEC_GT, KC_BACK, KC_ISTFT, KC_STREAM, kNumKernelClasses };
+struct ProfEvent { int cls; int64_t frames; cudaEvent_t e0, e1; };
+
+}  // namespace
+
+struct gtcrnb_handle {
+    int device = 0;
+    int sm_count = 148;
+    float* blob = nullptr;
+    // activation workspace for one chunk of utterances
+    int64_t cap_frames = 0;
+    float* en0 = nullptr;
+    float* act[kNumAct33] = {};
+    float* spec_in = nullptr;
+    float* spec_out = nullptr;
+    // host pipeline staging
+    float* stage_in[2] = {nullptr, nullptr};
+    float* stage_out[2] = {nullptr, nullptr};
+    size_t stage_in_floats = 0, stage_out_floats = 0;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
+    // occupancy (resident CTAs per SM) of the walking kernels, for segment selection
+    int occ_gt_enc = 1, occ_gt_dec = 1, occ_tcn = 1;
+    int64_t launches = 0;
+    int64_t last_B = 0, last_T = 0;
+    // optional per-kernel-class timing with CUDA events on the launching stream (gtcrnb_profile_*)
+    bool profiling = false;
+    std::vector<ProfEvent> prof_events;
+    double prof_ms[kNumKernelClasses] = {};
+    int64_t prof_launches[kNumKernelClasses] = {};
+    int64_t prof_frames[kNumKernelClasses] = {};
+};
+
+namespace {
+
+int ensure_workspace(gtcrnb_handle* h, int64_t frames) {
+    if (frames <= h->cap_frames) return GTCRNB_OK;
+    auto freep = [](float*& p) { if (p) cudaFree(p); p = nullptr; };
+    freep(h->en0); freep(h->spec_in); freep(h->spec_out);
+    for (auto& p : h->act) freep(p);
+    h->cap_frames = 0;
+    auto alloc = [&](float*& p, size_t floats_per_frame) -> bool {
+        return cudaMalloc(&p, sizeof(float) * floats_per_frame * (size_t)frames) == cudaSuccess;
+    };
+    bool ok = alloc(h->en0, gk::kF1 * 16) && alloc(h->spec_in, gk::kSpecFrame) && alloc(h->spec_out, gk::kSpecFrame);
+    for (auto& p : h->act) ok = ok && alloc(p, gk::kF2 * 16);
+    if (!ok) {
+        cudaGetLastError();
+        return fail(GTCRNB_E_NOMEM, "workspace allocation for %lld frames failed", (long long)frames);
+    }
+    h->cap_frames = frames;
+    return GTCRNB_OK;
+}
+
+// RAII: brackets a kernel launch with two events when profiling is on
+struct ProfScope {
+    gtcrnb_handle* h; cudaStream_t st; ProfEvent ev; bool on;
+    ProfScope(gtcrnb_handle* h_, int cls, int64_t frames, cudaStream_t st_) : h(h_), st(st_), on(h_->profiling) {
+        if (!on) return;
+        ev.cls = cls; ev.frames = frames;
+        cudaEventCreate(&ev.e0); cudaEventCreate(&ev.e1);
+        cudaEventRecord(ev.e0, st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(ev.e1, st);
+        h->prof_events.push_back(ev);
+    }
+};
+
+// Split T frames into segments for a walking kernel: minimise waves * (segment length + warm-up).
+int pick_seg_len(int64_t ctas_per_seg_row, int T, int NT, int warm, int slots) {
+    const int max_tiles = (T + NT - 1) / NT;
+    double best = 1e300;
+    int best_len = max_tiles * NT;
+    for (int tiles = max_tiles; tiles >= 1; --tiles) {
+        const int seg_len = tiles * NT;
+        const int nseg = (T + seg_len - 1) / seg_len;
+        const int64_t ctas = ctas_per_seg_row * nseg;
+        const double waves = (double)((ctas + slots - 1) / slots);
+        const double cost = waves * (seg_len + (nseg > 1 ? warm : 0) + 0.25 * NT);   // + fixed per-CTA prologue
+        if (cost < best - 1e-9) { best = cost; best_len = seg_len; }
+    }
+    return best_len;
+}
+
+// The model proper on an internal chunk: spec (strided) -> enhanced spec (strided).
+int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t B, int64_t T, float* out,
+              const int64_t os[4], cudaStream_t st) {
+    using namespace gk;
+    const int Ti = (int)T;
+    const int64_t nframes = B * T;
+    const dim3 gfr((unsigned)((nframes + FR_NF - 1) / FR_NF));
+    {
+        ProfScope ps(h, KC_FRONT, nframes, st);
+        k_front<<<gfr, FR_THREADS, FR_SMEM_FLOATS * sizeof(float), st>>>(spec, is[0], is[1], is[2], is[3], Ti, nframes, h->blob, h->en0, h->act[0]);
+    }
+    h->launches++;
+    {
+        const int seg = pick_seg_len(B, Ti, GT_NT, GT_WARMUP, h->sm_count * h->occ_gt_enc);
+        const dim3 g((unsigned)((Ti + seg - 1) / seg), (unsigned)B);
+        for (int i = 0; i < 3; ++i) {
+            ProfScope ps(h, KC_ENC_GT, nframes, st);
+            k_gtconv<false><<<g, GT_THREADS, gt_smem_floats<false>() * sizeof(float), st>>>(
+                h->act[i], nullptr, h->act[i + 1], h->blob + blob::ENCGT_OFF + i * blob::ENCGT_SIZE, Ti, seg);
+            h->launches++;
+        }
+    }
+    {
+        const int seg = pick_seg_len(B * 3, Ti, TC_NT, TC_WARMUP, h->sm_count * h->occ_tcn);
+        const dim3 g((unsigned)(((Ti + seg - 1) / seg) * 3), (unsigned)B);
+        for (int i = 0; i < 2; ++i) {
+            ProfScope ps(h, KC_GTCN, nframes, st);
+            k_gtcn<<<g, TC_THREADS, TC_SMEM_FLOATS * sizeof(float), st>>>(
+                h->act[3 + i], h->act[4 + i], h->blob + blob::TCN_OFF + i * 4 * blob::TCN_SIZE, Ti, seg);
+            h->launches++;
+        }
+    }
+    {
+        const int seg = pick_seg_len(B, Ti, GT_NT, GT_WARMUP, h->sm_count * h->occ_gt_dec);
+        const dim3 g((unsigned)((Ti + seg - 1) / seg), (unsigned)B);
+        for (int i = 0; i < 3; ++i) {
+            // de_i consumes (previous + en_outs[4 - i]) : skips en4, en3, en2 = act[3], act[2], act[1]
+            ProfScope ps(h, KC_DEC_GT, nframes, st);
+            k_gtconv<true><<<g, GT_THREADS, gt_smem_floats<true>() * sizeof(float), st>>>(
+                h->act[5 + i], h->act[3 - i], h->act[6 + i], h->blob + blob::DECGT_OFF + i * blob::DECGT_SIZE, Ti, seg);
+            h->launches++;
+        }
+    }
+    {
+        ProfScope ps(h, KC_BACK, nframes, st);
+        k_back<<<gfr, BK_THREADS, BK_SMEM_FLOATS * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, spec, is[0], is[1], is[2], is[3],
+                                                                         out, os[0], os[1], os[2], os[3], Ti, nframes, h->blob);
+    }
+    h->launches++;
+    CU(cudaGetLastError());
+    return GTCRNB_OK;
+}
+
+gs::Ws stream_ws(gtcrnb_handle* h) {
+    gs::Ws ws;
+    ws.en0 = h->en0;
+    for (int i = 0; i < kNumAct33; ++i) ws.act[i] = h->act[i];
+    ws.spec_in = h->spec_in;
+    ws.spec_out = h->spec_out;
+    return ws;
+}
+
+int64_t chunk_utts(int64_t B, int64_t T) { return std::max<int64_t>(1, std::min<int64_t>({B, kMaxChunkFrames / T, (int64_t)65535})); }
+
+}  // namespace
+
+extern "C" {
+
+int gtcrnb_abi_version(void) { return kAbiVersion; }
+size_t gtcrnb_blob_floats(void) { return (size_t)blob::kBlobFloats; }
+const char* gtcrnb_last_error(void) { return g_err.c_str(); }
+int64_t gtcrnb_launch_count(const gtcrnb_handle* h) { return h ? h->launches : 0; }
+
+void* gtcrnb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void gtcrnb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) {
+    if (!blob_host || !out) return fail(GTCRNB_E_INVALID, "gtcrnb_create: NULL argument");
+    if (n_floats != (size_t)blob::kBlobFloats) return fail(GTCRNB_E_BLOB, "weight blob has %zu floats, expected %d", n_floats, blob::kBlobFloats);
+    if (blob_host[0] != blob::kVersion || blob_host[1] != (float)blob::kBlobFloats)
+        return fail(GTCRNB_E_BLOB, "weight blob version %.1f / size %.0f does not match library (%.1f / %d)", blob_host[0], blob_host[1], blob::kVersion, blob::kBlobFloats);
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail(GTCRNB_E_ARCH, "device %s is sm_%d%d; this library contains sm_100a code only", prop.name, prop.major, prop.minor);
+    gtcrnb_handle* h = new gtcrnb_handle();
+    h->device = dev;
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaMalloc(&h->blob, sizeof(float) * n_floats) != cudaSuccess) { delete h; return fail(GTCRNB_E_NOMEM, "cudaMalloc(blob) failed"); }
+    if (cudaMemcpy(h->blob, blob_host, sizeof(float) * n_floats, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(h->blob); delete h; return fail(GTCRNB_E_CUDA, "cudaMemcpy(blob) failed");
+    }
+    using namespace gk;
+    struct { const void* fn; int floats; } attrs[] = {
+        {(const void*)k_front, FR_SMEM_FLOATS},
+        {(const void*)k_gtconv<false>, gt_smem_floats<false>()},
+        {(const void*)k_gtconv<true>, gt_smem_floats<true>()},
+        {(const void*)k_gtcn, TC_SMEM_FLOATS},
+        {(const void*)k_back, BK_SMEM_FLOATS},
+    };
+    for (auto& a : attrs) {
+        cudaError_t e = cudaFuncSetAttribute(a.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, a.floats * (int)sizeof(float));
+        if (e != cudaSuccess) { gtcrnb_destroy(h); return fail(GTCRNB_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); }
+    }
+    int e2 = gs::stream_init_attributes();
+    if (e2 != 0) { gtcrnb_destroy(h); return fail(GTCRNB_E_CUDA, "stream kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e2)); }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_gt_enc, k_gtconv<false>, GT_THREADS, gt_smem_floats<false>() * sizeof(float));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_gt_dec, k_gtconv<true>, GT_THREADS, gt_smem_floats<true>() * sizeof(float));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn, TC_THREADS, TC_SMEM_FLOATS * sizeof(float));
+    h->occ_gt_enc = std::max(1, h->occ_gt_enc); h->occ_gt_dec = std::max(1, h->occ_gt_dec); h->occ_tcn = std::max(1, h->occ_tcn);
+    *out = h;
+    return GTCRNB_OK;
+}
+
+void gtcrnb_destroy(gtcrnb_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    auto freep = [](float* p) { if (p) cudaFree(p); };
+    freep(h->blob); freep(h->en0); freep(h->spec_in); freep(h->spec_out);
+    for (auto p : h->act) freep(p);
+    for (int i = 0; i < 2; ++i) {
+        freep(h->stage_in[i]); freep(h->stage_out[i]);
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+        if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+    }
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    delete h;
+}
+
+int gtcrnb_forward_spec(gtcrnb_handle* h, const float* spec_dev, const int64_t in_strides[4], int64_t B, int64_t T,
+                        float* out_dev, const int64_t out_strides[4], void* stream) {
+    if (B < 0 || T < 0 || T > (1 << 24)) return fail(GTCRNB_E_INVALID, "gtcrnb_forward_spec: bad shape B=%lld T=%lld", (long long)B, (long long)T);
+    if (h && (B == 0 || T == 0)) return GTCRNB_OK;           // empty batch: nothing to do (pointers may be NULL)
+    if (!h || !spec_dev || !out_dev || !in_strides || !out_strides) return fail(GTCRNB_E_INVALID, "gtcrnb_forward_spec: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t Bc = chunk_utts(B, T);
+    int rc = ensure_workspace(h, Bc * T);
+    if (rc) return rc;
+    h->last_B = Bc; h->last_T = T;
+    for (int64_t b0 = B - (B % Bc ? B % Bc : Bc); b0 >= 0; b0 -= Bc) {   // last chunk first so chunk 0 stays in the workspace for debug taps
+        const int64_t nb = std::min(Bc, B - b0);
+        rc = run_model(h, spec_dev + b0 * in_strides[0], in_strides, nb, T, out_dev + b0 * out_strides[0], out_strides, st);
+        if (rc) return rc;
+    }
+    return GTCRNB_OK;
+}
+
+int gtcrnb_stft(gtcrnb_handle* h, const float* wav_dev, int64_t B, int64_t L, int64_t in_stride, float* spec_dev, void* stream) {
+    if (!h || !wav_dev || !spec_dev) return fail(GTCRNB_E_INVALID, "gtcrnb_stft: NULL argument");
+    if (L <= 256 || L > (int64_t)1 << 30 || B < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stft: need 256 < L < 2^30 (reflect padding), got L=%lld", (long long)L);
+    if (B == 0) return GTCRNB_OK;
+    const int T = (int)(1 + L / gk::kHop);
+    for (int64_t b0 = 0; b0 < B; b0 += 65535) {
+        const int64_t nb = std::min<int64_t>(65535, B - b0);
+        ProfScope ps(h, KC_STFT, nb * T, (cudaStream_t)stream);
+        gk::k_stft<<<dim3((T + gk::STFT_FPB - 1) / gk::STFT_FPB, (unsigned)nb), 256, 0, (cudaStream_t)stream>>>(
+            wav_dev + b0 * in_stride, in_stride, (int)L, T, h->blob, spec_dev + b0 * (int64_t)T * gk::kSpecFrame);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
+    return GTCRNB_OK;
+}
+
+int gtcrnb_istft(gtcrnb_handle* h, const float* spec_dev, int64_t B, int64_t T, float* wav_dev, int64_t out_stride, void* stream) {
+    if (!h || !spec_dev || !wav_dev) return fail(GTCRNB_E_INVALID, "gtcrnb_istft: NULL argument");
+    if (T < 1 || B < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_istft: bad shape");
+    if (B == 0 || T == 1) return GTCRNB_OK;
+    for (int64_t b0 = 0; b0 < B; b0 += 65535) {
+        const int64_t nb = std::min<int64_t>(65535, B - b0);
+        ProfScope ps(h, KC_ISTFT, nb * T, (cudaStream_t)stream);
+        gk::k_istft<<<dim3((unsigned)((T - 1 + gk::ISTFT_HOPS - 1) / gk::ISTFT_HOPS), (unsigned)nb), 256, 0, (cudaStream_t)stream>>>(
+            spec_dev + b0 * T * gk::kSpecFrame, T * gk::kSpecFrame, 2, gk::kSpecFrame, 1, (int)T, h->blob, wav_dev + b0 * out_stride, out_stride);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
+    return GTCRNB_OK;
+}
+
+int gtcrnb_enhance(gtcrnb_handle* h, const float* wav_dev, int64_t B, int64_t L, int64_t in_stride, float* out_dev,
+                   int64_t out_stride, void* stream) {
+    if (L <= 256 || L > (int64_t)1 << 30 || B < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_enhance: need 256 < L < 2^30 (reflect padding), got L=%lld", (long long)L);
+    if (h && B == 0) return GTCRNB_OK;
+    if (!h || !wav_dev || !out_dev) return fail(GTCRNB_E_INVALID, "gtcrnb_enhance: NULL argument");
+    const int64_t T = 1 + L / gk::kHop;
+    const int64_t Bc = chunk_utts(B, T);
+    int rc = ensure_workspace(h, Bc * T);
+    if (rc) return rc;
+    h->last_B = Bc; h->last_T = T;
+    const int64_t is[4] = {T * gk::kSpecFrame, 2, gk::kSpecFrame, 1};
+    for (int64_t b0 = B - (B % Bc ? B % Bc : Bc); b0 >= 0; b0 -= Bc) {
+        const int64_t nb = std::min(Bc, B - b0);
+        rc = gtcrnb_stft(h, wav_dev + b0 * in_stride, nb, L, in_stride, h->spec_in, stream);
+        if (rc) return rc;
+        rc = run_model(h, h->spec_in, is, nb, T, h->spec_out, is, (cudaStream_t)stream);
+        if (rc) return rc;
+        rc = gtcrnb_istft(h, h->spec_out, nb, T, out_dev + b0 * out_stride, out_stride, stream);
+        if (rc) return rc;
+    }
+    return GTCRNB_OK;
+}
+
+int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int64_t L, float* out_host) {
+    if (!h || !wav_host || !out_host) return fail(GTCRNB_E_INVALID, "gtcrnb_enhance_host: NULL argument");
+    if (L <= 256 || B < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_enhance_host: need L > 256");
+    if (B == 0) return GTCRNB_OK;
+    const int64_t T = 1 + L / gk::kHop, Lout = gk::kHop * (T - 1);
+    if (!h->s_h2d) {
+        CU(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    // chunks of ~64 utterance-equivalents of 10 s keep the three engines (H2D, SMs, D2H) overlapped
+    const int64_t Bc = std::max<int64_t>(1, std::min<int64_t>(B, (64 * 160000) / L));
+    const size_t need_in = (size_t)Bc * L, need_out = (size_t)Bc * Lout;
+    if (need_in > h->stage_in_floats || need_out > h->stage_out_floats) {
+        for (int i = 0; i < 2; ++i) {
+            if (h->stage_in[i]) cudaFree(h->stage_in[i]);
+            if (h->stage_out[i]) cudaFree(h->stage_out[i]);
+            h->stage_in[i] = h->stage_out[i] = nullptr;
+        }
+        h->stage_in_floats = h->stage_out_floats = 0;
+        for (int i = 0; i < 2; ++i) {
+            if (cudaMalloc(&h->stage_in[i], need_in * sizeof(float)) != cudaSuccess ||
+                cudaMalloc(&h->stage_out[i], need_out * sizeof(float)) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(GTCRNB_E_NOMEM, "staging allocation failed");
+            }
+        }
+        h->stage_in_floats = need_in; h->stage_out_floats = need_out;
+    }
+    int64_t c = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += Bc, ++c) {
+        const int i = (int)(c & 1);
+        const int64_t nb = std::min(Bc, B - b0);
+        if (c >= 2) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[i], 0));      // input buffer i consumed
+        CU(cudaMemcpyAsync(h->stage_in[i], wav_host + b0 * L, sizeof(float) * nb * L, cudaMemcpyHostToDevice, h->s_h2d));
+        CU(cudaEventRecord(h->ev_h2d[i], h->s_h2d));
+        CU(cudaStreamWaitEvent(h->s_comp, h->ev_h2d[i], 0));
+        if (c >= 2) CU(cudaStreamWaitEvent(h->s_comp, h->ev_d2h[i], 0));      // output buffer i drained
+        int rc = gtcrnb_enhance(h, h->stage_in[i], nb, L, L, h->stage_out[i], Lout, h->s_comp);
+        if (rc) return rc;
+        CU(cudaEventRecord(h->ev_comp[i], h->s_comp));
+        CU(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[i], 0));
+        CU(cudaMemcpyAsync(out_host + b0 * Lout, h->stage_out[i], sizeof(float) * nb * Lout, cudaMemcpyDeviceToHost, h->s_d2h));
+        CU(cudaEventRecord(h->ev_d2h[i], h->s_d2h));
+    }
+    CU(cudaStreamSynchronize(h->s_d2h));
+    CU(cudaStreamSynchronize(h->s_comp));
+    return GTCRNB_OK;
+}
+
+int gtcrnb_debug_activation(gtcrnb_handle* h, const char* name, float* out_dev, size_t n_floats, void* stream) {
+    if (!h || !name || !out_dev) return fail(GTCRNB_E_INVALID, "gtcrnb_debug_activation: NULL argument");
+    const float* src = nullptr;
+    size_t per_frame = gk::kF2 * 16;
+    if (!strcmp(name, "en0")) { src = h->en0; per_frame = gk::kF1 * 16; }
+    for (int i = 0; i < kNumAct33 && !src; ++i)
+        if (!strcmp(name, kActNames[i])) src = h->act[i];
+    if (!src) return fail(GTCRNB_E_INVALID, "unknown activation '%s'", name);
+    const size_t have = per_frame * (size_t)(h->last_B * h->last_T);
+    if (n_floats > have) return fail(GTCRNB_E_INVALID, "activation '%s' holds %zu floats, %zu requested", name, have, n_floats);
+    CU(cudaMemcpyAsync(out_dev, src, n_floats * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return GTCRNB_OK;
+}
+
+// ---------------------------------------------------------------- per-kernel profiling
+int gtcrnb_profile_enable(gtcrnb_handle* h, int on) {
+    if (!h) return fail(GTCRNB_E_INVALID, "gtcrnb_profile_enable: NULL handle");
+    h->profiling = on != 0;
+    return GTCRNB_OK;
+}
+
+int gtcrnb_profile_read(gtcrnb_handle* h, int reset, double* ms_out, int64_t* launches_out, int64_t* frames_out) {
+    if (!h || !ms_out || !launches_out || !frames_out) return fail(GTCRNB_E_INVALID, "gtcrnb_profile_read: NULL argument");
+    for (auto& ev : h->prof_events) {
+        CU(cudaEventSynchronize(ev.e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
+        h->prof_ms[ev.cls] += ms; h->prof_launches[ev.cls] += 1; h->prof_frames[ev.cls] += ev.frames;
+        cudaEventDestroy(ev.e0); cudaEventDestroy(ev.e1);
+    }
+    h->prof_events.clear();
+    for (int i = 0; i < kNumKernelClasses; ++i) {
+        ms_out[i] = h->prof_ms[i]; launches_out[i] = h->prof_launches[i]; frames_out[i] = h->prof_frames[i];
+        if (reset) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; h->prof_frames[i] = 0; }
+    }
+    return GTCRNB_OK;
+}
+
+int gtcrnb_profile_num_classes(void) { return kNumKernelClasses; }
+const char* gtcrnb_profile_class_name(int i) {
+    static const char* const names[kNumKernelClasses] = {"stft", "front", "enc_gtconv", "gtcn", "dec_gtconv", "back", "istft", "stream"};
+    return (i >= 0 && i < kNumKernelClasses) ? names[i] : "";
+}
+
+// ---------------------------------------------------------------- streaming
+size_t gtcrnb_stream_state_bytes(int64_t N) { return N < 0 ? 0 : gs::state_bytes(N); }
+
+int gtcrnb_stream_reset(gtcrnb_handle* h, void* state_dev, int64_t N, void* stream) {
+    if (!h || !state_dev || N < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_reset: bad argument");
+    CU(cudaMemsetAsync(state_dev, 0, gs::state_bytes(N), (cudaStream_t)stream));
+    return GTCRNB_OK;
+}
+
+int gtcrnb_stream_step_spec(gtcrnb_handle* h, void* state_dev, const float* spec_dev, float* out_dev, int64_t N, void* stream) {
+    if (!h || !state_dev || !spec_dev || !out_dev || N < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_step_spec: bad argument");
+    if (N == 0) return GTCRNB_OK;
+    int rc = ensure_workspace(h, N);
+    if (rc) return rc;
+    h->launches += gs::step_spec(h->blob, state_dev, stream_ws(h), spec_dev, out_dev, N, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return GTCRNB_OK;
+}
+
+int gtcrnb_stream_step_wav(gtcrnb_handle* h, void* state_dev, const float* hop_in_dev, float* hop_out_dev, int64_t N, void* stream) {
+    if (!h || !state_dev || !hop_in_dev || !hop_out_dev || N < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_step_wav: bad argument");
+    if (N == 0) return GTCRNB_OK;
+    int rc = ensure_workspace(h, N);
+    if (rc) return rc;
+    h->launches += gs::step_wav(h->blob, state_dev, stream_ws(h), hop_in_dev, hop_out_dev, N, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return GTCRNB_OK;
+}
+
+int gtcrnb_stream_import_caches(gtcrnb_handle* h, void* state_dev, int64_t N, const float* conv_cache_dev, const float* tra_cache_dev,
+                                const float* const tcn_cache_dev[8], void* stream) {
+    if (!h || !state_dev || !conv_cache_dev || !tra_cache_dev || !tcn_cache_dev || N < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_import_caches: bad argument");
+    if (N == 0) return GTCRNB_OK;
+    h->launches += gs::convert_caches(true, state_dev, N, const_cast<float*>(conv_cache_dev), const_cast<float*>(tra_cache_dev),
+                                      const_cast<float* const*>(tcn_cache_dev), (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return GTCRNB_OK;
+}
+
+int gtcrnb_stream_export_caches(gtcrnb_handle* h, const void* state_dev, int64_t N, float* conv_cache_dev, float* tra_cache_dev,
+                                float* const tcn_cache_dev[8], void* stream) {
+    if (!h || !state_dev || !conv_cache_dev || !tra_cache_dev || !tcn_cache_dev || N < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_export_caches: bad argument");
+    if (N == 0) return GTCRNB_OK;
+    h->launches += gs::convert_caches(false, const_cast<void*>(state_dev), N, conv_cache_dev, tra_cache_dev, tcn_cache_dev, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return GTCRNB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,847 @@
+// GTCRN-Micro inference kernels for sm_100a (B200).  Hand-written CUDA, fp32 throughout.
+//
+// Data layout in HBM
+//   wav        [B][L]                 fp32
+//   spec       [B][T][257][2]         fp32 (internal; user tensors are addressed with element strides)
+//   activation [B][T][F][16]          fp32, channel-last: one position's 16 channels = 64 contiguous bytes
+//                                     (F = 65 after en0, 33 everywhere else)
+//   weights    one packed blob (blob_layout.h): BN folded, every contraction stored [k][ci][co]
+//
+// Kernel design: the layers are tiny channel contractions (K = 8..144, N = 16) applied to
+// B*T*F independent positions, so the path is FP32-FMA bound, not HBM or tensor-core bound.  Every
+// contraction uses the same register tile: one thread owns TWO frame slots x 16 (or 8) output channels at
+// one frequency bin, activations come from shared memory as LDS.128 in a [row][ci/4][col][4] layout
+// (conflict-free for consecutive bins) and the warp-uniform weight vectors as broadcast LDS.128.  That
+// feed was measured at 47 TFLOP/s (64 % of the 73.4 TFLOP/s FFMA peak) in tools/microbench/ffma_feed.cu.
+//
+// Temporal layers (GTConv 3x3 + TRALite, dilated TCNs) are computed by CTAs that WALK along time over one
+// utterance segment, carrying their causal history (2 frames of point-conv output, 2 TRA energies, 2d
+// frames per TCN) in shared memory between tiles -- the same role the reference's streaming caches play
+// (gtcrn_micro_stream.py:416-429, :490-500) -- so no halo is recomputed except a short warm-up when an
+// utterance is split into several segments for occupancy.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "blob_layout.h"
+
+namespace gk {
+
+constexpr int kBins = 257;   // n_fft/2 + 1
+constexpr int kErb = 129;    // 65 low bins + 64 ERB bands
+constexpr int kF1 = 65;      // after en0
+constexpr int kF2 = 33;      // after en1
+constexpr int kSpecFrame = kBins * 2;
+constexpr int kHop = 256;
+constexpr int kNfft = 512;
+
+__device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : a * v; }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float f4get(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+
+__device__ __forceinline__ void copy_f4(float* dst, const float* __restrict__ src, int n_floats, int tid, int nthr) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int i = tid; i < (n_floats >> 2); i += nthr) d4[i] = s4[i];
+}
+__device__ __forceinline__ void zero_f4(float* dst, int n_floats, int tid, int nthr) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = tid; i < (n_floats >> 2); i += nthr) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// acc[0..N) += x * w[0..N)  with w read as broadcast LDS.128 (N multiple of 4)
+template <int N>
+__device__ __forceinline__ void axpy2(float (&a0)[N], float (&a1)[N], float x0, float x1, const float* __restrict__ w) {
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+#pragma unroll
+    for (int v = 0; v < N / 4; ++v) {
+        const float4 ww = w4[v];
+        a0[4 * v + 0] = fmaf(x0, ww.x, a0[4 * v + 0]); a1[4 * v + 0] = fmaf(x1, ww.x, a1[4 * v + 0]);
+        a0[4 * v + 1] = fmaf(x0, ww.y, a0[4 * v + 1]); a1[4 * v + 1] = fmaf(x1, ww.y, a1[4 * v + 1]);
+        a0[4 * v + 2] = fmaf(x0, ww.z, a0[4 * v + 2]); a1[4 * v + 2] = fmaf(x1, ww.z, a1[4 * v + 2]);
+        a0[4 * v + 3] = fmaf(x0, ww.w, a0[4 * v + 3]); a1[4 * v + 3] = fmaf(x1, ww.w, a1[4 * v + 3]);
+    }
+}
+
+// ================================================================================================
+// 256-point complex FFT, radix-4 Stockham autosort, 64 threads per transform, 4 stages.
+// (the 512-point real transforms of torch.stft / torch.istft are done as one 256-point complex FFT
+//  plus an O(N) split step; reference call sites infer.py:60-67, :73-76)
+// ================================================================================================
+__device__ __forceinline__ void fft256_stage(const float2* __restrict__ in, float2* __restrict__ out,
+                                             const float2* __restrict__ tw, int j, int Ns) {
+    const int k = j & (Ns - 1);
+    float2 v0 = in[j], v1 = in[j + 64], v2 = in[j + 128], v3 = in[j + 192];
+    if (Ns > 1) {
+        const int m = k * (64 / Ns);
+        v1 = cmul(v1, tw[m]);
+        v2 = cmul(v2, tw[2 * m]);
+        v3 = cmul(v3, tw[3 * m]);
+    }
+    const float2 s0 = make_float2(v0.x + v2.x, v0.y + v2.y), s1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+    const float2 s2 = make_float2(v1.x + v3.x, v1.y + v3.y), d = make_float2(v1.x - v3.x, v1.y - v3.y);
+    const float2 s3 = make_float2(d.y, -d.x);   // d * (-i)
+    const int j0 = ((j - k) << 2) + k;
+    out[j0] = make_float2(s0.x + s2.x, s0.y + s2.y);
+    out[j0 + Ns] = make_float2(s1.x + s3.x, s1.y + s3.y);
+    out[j0 + 2 * Ns] = make_float2(s0.x - s2.x, s0.y - s2.y);
+    out[j0 + 3 * Ns] = make_float2(s1.x - s3.x, s1.y - s3.y);
+}
+// all threads of the block must call this (it contains __syncthreads); result ends in `a`
+__device__ __forceinline__ void fft256(float2* a, float2* b, const float2* tw, int j) {
+    fft256_stage(a, b, tw, j, 1);  __syncthreads();
+    fft256_stage(b, a, tw, j, 4);  __syncthreads();
+    fft256_stage(a, b, tw, j, 16); __syncthreads();
+    fft256_stage(b, a, tw, j, 64); __syncthreads();
+}
+
+__device__ __forceinline__ int reflect_idx(int i, int L) {
+    if (i < 0) i = -i;
+    if (i >= L) i = 2 * (L - 1) - i;
+    return i;
+}
+
+struct FftTables {
+    float2 tw256[256];
+    float2 tw512[258];
+    float win[512];
+};
+__device__ __forceinline__ void load_fft_tables(FftTables& t, const float* __restrict__ blobp, int tid, int nthr) {
+    const float* f = blobp + blob::FFT_OFF;
+    copy_f4(reinterpret_cast<float*>(t.tw256), f + blob::FFT_TW256, 512, tid, nthr);
+    copy_f4(reinterpret_cast<float*>(t.tw512), f + blob::FFT_TW512, 516, tid, nthr);
+    copy_f4(t.win, f + blob::FFT_WIN, 512, tid, nthr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// STFT: wav [B][L] -> spec [B][T][257][2], T = 1 + L/256.  centre=True, reflect padding, sqrt-Hann.
+// grid (ceil(T/4), B), 256 threads = 4 frames x 64 threads.
+// ------------------------------------------------------------------------------------------------
+constexpr int STFT_FPB = 4;
+__global__ void __launch_bounds__(256) k_stft(const float* __restrict__ wav, int64_t in_stride, int L, int T,
+                                              const float* __restrict__ blobp, float* __restrict__ spec) {
+    __shared__ FftTables tb;
+    __shared__ float2 buf[STFT_FPB][2][256];
+    const int tid = threadIdx.x, fr = tid >> 6, j = tid & 63;
+    const int t = blockIdx.x * STFT_FPB + fr, b = blockIdx.y;
+    const bool valid = t < T;
+    load_fft_tables(tb, blobp, tid, 256);
+    __syncthreads();
+    float2* A = buf[fr][0];
+    float2* Bf = buf[fr][1];
+    if (valid) {
+        const float* x = wav + (int64_t)b * in_stride;
+        const int base = kHop * t - kHop;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int n = j + 64 * r;
+            const int i0 = reflect_idx(base + 2 * n, L), i1 = reflect_idx(base + 2 * n + 1, L);
+            A[n] = make_float2(tb.win[2 * n] * x[i0], tb.win[2 * n + 1] * x[i1]);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) A[j + 64 * r] = make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    fft256(A, Bf, tb.tw256, j);
+    if (valid) {
+        float2* o = reinterpret_cast<float2*>(spec + ((int64_t)b * T + t) * kSpecFrame);
+        for (int k = j; k <= 256; k += 64) {
+            const float2 zk = A[k & 255];
+            float2 zc = A[(256 - k) & 255];
+            zc.y = -zc.y;
+            const float2 w = tb.tw512[k];
+            const float dx = zk.x - zc.x, dy = zk.y - zc.y;
+            o[k] = make_float2(0.5f * (zk.x + zc.x) + 0.5f * (w.x * dy + w.y * dx),
+                               0.5f * (zk.y + zc.y) - 0.5f * (w.x * dx - w.y * dy));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// iSTFT + overlap-add: spec [B][T][257][2] (element strides sb, sf, st, sc) -> wav [B][256 (T-1)].
+// grid (ceil((T-1)/ISTFT_HOPS), B), 256 threads.  A block inverts ISTFT_HOPS+1 frames (4 at a time).
+// ------------------------------------------------------------------------------------------------
+constexpr int ISTFT_HOPS = 7;
+__global__ void __launch_bounds__(256) k_istft(const float* __restrict__ spec, int64_t sb, int64_t sf, int64_t st, int64_t sc,
+                                               int T, const float* __restrict__ blobp, float* __restrict__ wav, int64_t out_stride) {
+    __shared__ FftTables tb;
+    __shared__ float2 buf[4][2][256];
+    __shared__ float frames[ISTFT_HOPS + 1][512];
+    __shared__ float inv_env[256];
+    const int tid = threadIdx.x, fr = tid >> 6, j = tid & 63;
+    const int b = blockIdx.y, k0 = blockIdx.x * ISTFT_HOPS;
+    const int nhop = min(ISTFT_HOPS, (T - 1) - k0);
+    load_fft_tables(tb, blobp, tid, 256);
+    inv_env[tid] = blobp[blob::FFT_OFF + blob::FFT_INV_ENV + tid];
+    __syncthreads();
+    const float* sp = spec + (int64_t)b * sb;
+    for (int r0 = 0; r0 < nhop + 1; r0 += 4) {
+        const int fi = r0 + fr;
+        const bool valid = fi < nhop + 1;
+        const int t = k0 + fi;
+        float2* A = buf[fr][0];
+        float2* Bf = buf[fr][1];
+        if (valid) {
+            const float* xt = sp + (int64_t)t * st;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int k = j + 64 * r;                       // 0..255
+                float2 xk = make_float2(xt[(int64_t)k * sf], xt[(int64_t)k * sf + sc]);
+                float2 xc = make_float2(xt[(int64_t)(256 - k) * sf], -xt[(int64_t)(256 - k) * sf + sc]);
+                if (k == 0) { xk.y = 0.f; xc.y = 0.f; }         // imag of DC / Nyquist ignored (C2R semantics)
+                const float2 w = tb.tw512[k];
+                const float dx = xk.x - xc.x, dy = xk.y - xc.y;
+                const float a = w.x * dx + w.y * dy, bq = w.x * dy - w.y * dx;   // conj(w) * D
+                const float zx = 0.5f * (xk.x + xc.x) - 0.5f * bq, zy = 0.5f * (xk.y + xc.y) + 0.5f * a;
+                A[k] = make_float2(zx, -zy);                    // conj(Z): inverse FFT through the forward kernel
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) A[j + 64 * r] = make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+        fft256(A, Bf, tb.tw256, j);
+        if (valid) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int m = j + 64 * r;
+                const float2 z = A[m];
+                frames[fi][2 * m] = tb.win[2 * m] * (z.x * (1.0f / 256.0f));
+                frames[fi][2 * m + 1] = tb.win[2 * m + 1] * (-z.y * (1.0f / 256.0f));
+            }
+        }
+        __syncthreads();
+    }
+    float* o = wav + (int64_t)b * out_stride;
+    for (int h = 0; h < nhop; ++h)
+        o[(int64_t)(k0 + h) * kHop + tid] = (frames[h][256 + tid] + frames[h + 1][tid]) * inv_env[tid];
+}
+
+// ================================================================================================
+// FRONT: spec -> |.|,re,im -> ERB compress -> SFE-Lite -> en0 (3->16, k5 s2) -> en1 (16->16, k5 s2)
+// reference: gtcrn_micro.py:512-518 (features, erb.bm, sfe), :344-364 (en_convs[0..1])
+// Frames are independent here, so (b,t) is flattened: grid ceil(B*T/8), 288 threads, 8 frames per CTA
+// (the streaming path calls the same kernel with T = 1).  Writes en0 [B][T][65][16], en1 [B][T][33][16].
+// ================================================================================================
+constexpr int FR_NF = 8;
+constexpr int FR_THREADS = 288;
+constexpr int FR_FEAT = 3 * 260;           // per slot
+constexpr int FR_ERB = 3 * 132;            // [c][1 + j], zero at 0 and 130
+constexpr int FR_SFE = 133 * 4;            // [f + 2][4]
+constexpr int FR_A0 = 4 * 69 * 4;          // [q][f' + 2][4]
+constexpr int FR_SMEM_FLOATS = blob::FRONT_SIZE + FR_NF * (FR_FEAT + FR_ERB + FR_SFE + FR_A0);
+
+__global__ void __launch_bounds__(FR_THREADS) k_front(const float* __restrict__ spec, int64_t sb, int64_t sf, int64_t st, int64_t sc,
+                                                      int T, int64_t nframes, const float* __restrict__ blobp,
+                                                      float* __restrict__ en0, float* __restrict__ en1) {
+    extern __shared__ float4 smem4[];
+    float* W = reinterpret_cast<float*>(smem4);
+    float* feat = W + blob::FRONT_SIZE;
+    float* erb = feat + FR_NF * FR_FEAT;
+    float* sfe = erb + FR_NF * FR_ERB;
+    float* a0 = sfe + FR_NF * FR_SFE;
+    const int tid = threadIdx.x;
+    const int64_t fi0 = (int64_t)blockIdx.x * FR_NF;              // first flattened frame (b * T + t) of this CTA
+
+    copy_f4(W, blobp + blob::FRONT_OFF, blob::FRONT_SIZE, tid, FR_THREADS);
+    zero_f4(erb, FR_NF * (FR_ERB + FR_SFE + FR_A0), tid, FR_THREADS);     // zero pads (erb, sfe, a0 are contiguous)
+    // ---- a: features
+    for (int idx = tid; idx < FR_NF * kBins; idx += FR_THREADS) {
+        const int slot = idx / kBins, k = idx - slot * kBins;
+        const int64_t fi = fi0 + slot;
+        float re = 0.f, im = 0.f;
+        if (fi < nframes) {
+            const int64_t b = fi / T, t = fi - b * T;
+            const float* p = spec + b * sb + t * st + (int64_t)k * sf;
+            re = p[0];
+            im = p[sc];
+        }
+        float* fs = feat + slot * FR_FEAT;
+        fs[k] = sqrtf(re * re + im * im + 1e-12f);
+        fs[260 + k] = re;
+        fs[520 + k] = im;
+    }
+    __syncthreads();
+    // ---- b: ERB compress (sparse triangular bank)
+    {
+        const int* estart = reinterpret_cast<const int*>(W + blob::FRONT_ERB_START);
+        const int* ecnt = reinterpret_cast<const int*>(W + blob::FRONT_ERB_CNT);
+        const float* ew = W + blob::FRONT_ERB_W;
+        for (int idx = tid; idx < FR_NF * 3 * kErb; idx += FR_THREADS) {
+            const int slot = idx / (3 * kErb), r = idx - slot * 3 * kErb, c = r / kErb, jb = r - c * kErb;
+            const float* fs = feat + slot * FR_FEAT + c * 260;
+            float v;
+            if (jb < 65) {
+                v = fs[jb];
+            } else {
+                const int bnd = jb - 65, s = estart[bnd], n = ecnt[bnd];
+                v = 0.f;
+                for (int i = 0; i < n; ++i) v = fmaf(ew[bnd * blob::kErbMaxTap + i], fs[65 + s + i], v);
+            }
+            erb[slot * FR_ERB + c * 132 + 1 + jb] = v;
+        }
+    }
+    __syncthreads();
+    // ---- c: SFE-Lite (depthwise 3-tap along F, no bias)
+    {
+        const float* sw = W + blob::FRONT_SFE_W;
+        for (int idx = tid; idx < FR_NF * kErb; idx += FR_THREADS) {
+            const int slot = idx / kErb, f = idx - slot * kErb;
+            const float* e = erb + slot * FR_ERB + f;
+            float4 v;
+            v.x = sw[0] * e[0] + sw[1] * e[1] + sw[2] * e[2];
+            v.y = sw[3] * e[132] + sw[4] * e[133] + sw[5] * e[134];
+            v.z = sw[6] * e[264] + sw[7] * e[265] + sw[8] * e[266];
+            v.w = 0.f;
+            reinterpret_cast<float4*>(sfe + slot * FR_SFE)[f + 2] = v;
+        }
+    }
+    __syncthreads();
+    // ---- d: en0  (thread = 2 slots x 16 co at one f')
+    if (tid < (FR_NF / 2) * kF1) {
+        const int sp2 = tid / kF1, f = tid - sp2 * kF1, s0 = 2 * sp2, s1 = s0 + 1;
+        float acc0[16], acc1[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = W[blob::FRONT_EN0_B + c];
+        const float4* i0p = reinterpret_cast<const float4*>(sfe + s0 * FR_SFE) + 2 * f;
+        const float4* i1p = reinterpret_cast<const float4*>(sfe + s1 * FR_SFE) + 2 * f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const float4 x0 = i0p[k], x1 = i1p[k];
+            const float* w = W + blob::FRONT_EN0_W + k * 48;
+            axpy2<16>(acc0, acc1, x0.x, x1.x, w);
+            axpy2<16>(acc0, acc1, x0.y, x1.y, w + 16);
+            axpy2<16>(acc0, acc1, x0.z, x1.z, w + 32);
+        }
+        const float a = W[blob::FRONT_SLOPE + 0];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { acc0[c] = prelu(acc0[c], a); acc1[c] = prelu(acc1[c], a); }
+        float4* o0 = reinterpret_cast<float4*>(a0 + s0 * FR_A0);
+        float4* o1 = reinterpret_cast<float4*>(a0 + s1 * FR_A0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            o0[q * 69 + f + 2] = make_float4(acc0[4 * q], acc0[4 * q + 1], acc0[4 * q + 2], acc0[4 * q + 3]);
+            o1[q * 69 + f + 2] = make_float4(acc1[4 * q], acc1[4 * q + 1], acc1[4 * q + 2], acc1[4 * q + 3]);
+        }
+        if (fi0 + s0 < nframes) {
+            float4* g = reinterpret_cast<float4*>(en0 + ((fi0 + s0) * kF1 + f) * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) g[q] = make_float4(acc0[4 * q], acc0[4 * q + 1], acc0[4 * q + 2], acc0[4 * q + 3]);
+        }
+        if (fi0 + s1 < nframes) {
+            float4* g = reinterpret_cast<float4*>(en0 + ((fi0 + s1) * kF1 + f) * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) g[q] = make_float4(acc1[4 * q], acc1[4 * q + 1], acc1[4 * q + 2], acc1[4 * q + 3]);
+        }
+    }
+    __syncthreads();
+    // ---- e: en1  (thread = 2 slots x 8 co at one f'')
+    if (tid < 2 * (FR_NF / 2) * kF2) {
+        const int h = tid / ((FR_NF / 2) * kF2), r = tid - h * (FR_NF / 2) * kF2;
+        const int sp2 = r / kF2, f = r - sp2 * kF2, s0 = 2 * sp2, s1 = s0 + 1;
+        float acc0[8], acc1[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc0[c] = acc1[c] = W[blob::FRONT_EN1_B + 8 * h + c];
+        const float4* i0p = reinterpret_cast<const float4*>(a0 + s0 * FR_A0) + 2 * f;
+        const float4* i1p = reinterpret_cast<const float4*>(a0 + s1 * FR_A0) + 2 * f;
+#pragma unroll 1
+        for (int k = 0; k < 5; ++k) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 x0 = i0p[q * 69 + k], x1 = i1p[q * 69 + k];
+                const float* w = W + blob::FRONT_EN1_W + (k * 16 + 4 * q) * 16 + 8 * h;
+                axpy2<8>(acc0, acc1, x0.x, x1.x, w);
+                axpy2<8>(acc0, acc1, x0.y, x1.y, w + 16);
+                axpy2<8>(acc0, acc1, x0.z, x1.z, w + 32);
+                axpy2<8>(acc0, acc1, x0.w, x1.w, w + 48);
+            }
+        }
+        const float a = W[blob::FRONT_SLOPE + 1];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { acc0[c] = prelu(acc0[c], a); acc1[c] = prelu(acc1[c], a); }
+        if (fi0 + s0 < nframes) {
+            float4* g = reinterpret_cast<float4*>(en1 + ((fi0 + s0) * kF2 + f) * 16 + 8 * h);
+            g[0] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+            g[1] = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
+        }
+        if (fi0 + s1 < nframes) {
+            float4* g = reinterpret_cast<float4*>(en1 + ((fi0 + s1) * kF2 + f) * 16 + 8 * h);
+            g[0] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+            g[1] = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
+        }
+    }
+}
+
+// ================================================================================================
+// GTConvBlock (+TRALite +channel shuffle), encoder (depthwise 3x3) and decoder (full 16->16 3x3) variants.
+// reference: gtcrn_micro.py:167-253, TRALite :122-139, shuffle :222-227, decoder skip-add :464-469
+// One CTA walks one utterance segment [s0, s1) in tiles of GT_NT frames.  Shared-memory state carried
+// from tile to tile: the last 2 frames of point-conv-1 output (rows 0,1 of Pb) and the last 2 TRA
+// energies (rows 0,1 of Ev).  Segments that do not start at t = 0 warm up on the 4 preceding frames.
+// grid (nseg, B), 288 threads (264 active = 8 slot pairs x 33 bins).
+// ================================================================================================
+constexpr int GT_NT = 16;
+constexpr int GT_THREADS = 288;
+constexpr int GT_ACTIVE = (GT_NT / 2) * kF2;
+constexpr int GT_ROW4 = 4 * 35;                 // float4 per Pb row: [q][col = f + 1]
+constexpr int GT_WARMUP = 4;
+template <bool DEC> __host__ __device__ constexpr int gt_chunk() { return DEC ? blob::DECGT_SIZE : blob::ENCGT_SIZE; }
+template <bool DEC> __host__ __device__ constexpr int gt_smem_floats() {
+    return gt_chunk<DEC>() + (GT_NT + 2) * GT_ROW4 * 4 + GT_NT * kF2 * 8 + (GT_NT + 2) * 8 + GT_NT * 8;
+}
+
+template <bool DEC>
+__global__ void __launch_bounds__(GT_THREADS) k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip,
+                                                       float* __restrict__ out, const float* __restrict__ wblk,
+                                                       int T, int seg_len) {
+    constexpr int PC1_W = DEC ? blob::DECGT_PC1_W : blob::ENCGT_PC1_W;
+    constexpr int PC1_B = DEC ? blob::DECGT_PC1_B : blob::ENCGT_PC1_B;
+    constexpr int MID_W = DEC ? blob::DECGT_FULL_W : blob::ENCGT_DW_W;
+    constexpr int MID_B = DEC ? blob::DECGT_FULL_B : blob::ENCGT_DW_B;
+    constexpr int PC2_W = DEC ? blob::DECGT_PC2_W : blob::ENCGT_PC2_W;
+    constexpr int PC2_B = DEC ? blob::DECGT_PC2_B : blob::ENCGT_PC2_B;
+    constexpr int TDW_W = DEC ? blob::DECGT_TRA_DW_W : blob::ENCGT_TRA_DW_W;
+    constexpr int TDW_B = DEC ? blob::DECGT_TRA_DW_B : blob::ENCGT_TRA_DW_B;
+    constexpr int TPW_W = DEC ? blob::DECGT_TRA_PW_W : blob::ENCGT_TRA_PW_W;
+    constexpr int TPW_B = DEC ? blob::DECGT_TRA_PW_B : blob::ENCGT_TRA_PW_B;
+    constexpr int SLOPE = DEC ? blob::DECGT_SLOPE : blob::ENCGT_SLOPE;
+
+    extern __shared__ float4 smem4[];
+    float* W = reinterpret_cast<float*>(smem4);
+    float4* Pb = reinterpret_cast<float4*>(W + gt_chunk<DEC>());
+    float* E2 = reinterpret_cast<float*>(Pb + (GT_NT + 2) * GT_ROW4);
+    float* Ev = E2 + GT_NT * kF2 * 8;
+    float* G = Ev + (GT_NT + 2) * 8;
+
+    const int tid = threadIdx.x, b = blockIdx.y;
+    const int s0 = blockIdx.x * seg_len, s1 = min(T, s0 + seg_len);
+    if (s0 >= s1) return;
+    const int tw0 = max(0, s0 - GT_WARMUP);
+    copy_f4(W, wblk, gt_chunk<DEC>(), tid, GT_THREADS);
+    zero_f4(reinterpret_cast<float*>(Pb), (GT_NT + 2) * GT_ROW4 * 4, tid, GT_THREADS);
+    if (tid < 16) Ev[tid] = 0.f;
+    __syncthreads();
+
+    const bool act = tid < GT_ACTIVE;
+    const int sp2 = tid / kF2, f = tid - sp2 * kF2;
+    const int64_t ubase = (int64_t)b * T * kF2 * 16;
+    const float a1 = W[SLOPE + 0], a2 = W[SLOPE + 1];
+
+    for (int t0 = tw0; t0 < s1; t0 += GT_NT) {
+        float x2[2][8], q[2][8];
+        // ---- phase 1: point conv 1 (8 -> 16) + PReLU into Pb rows 2..NT+1
+        if (act) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int slot = 2 * sp2 + s, t = t0 + slot;
+                float p[16];
+                if (t < s1) {
+                    const float4* px = reinterpret_cast<const float4*>(xin + ubase + ((int64_t)t * kF2 + f) * 16);
+                    float4 v0 = px[0], v1 = px[1], v2 = px[2], v3 = px[3];
+                    if (DEC) {
+                        const float4* ps = reinterpret_cast<const float4*>(skip + ubase + ((int64_t)t * kF2 + f) * 16);
+                        const float4 u0 = ps[0], u1 = ps[1], u2 = ps[2], u3 = ps[3];
+                        v0.x += u0.x; v0.y += u0.y; v0.z += u0.z; v0.w += u0.w;
+                        v1.x += u1.x; v1.y += u1.y; v1.z += u1.z; v1.w += u1.w;
+                        v2.x += u2.x; v2.y += u2.y; v2.z += u2.z; v2.w += u2.w;
+                        v3.x += u3.x; v3.y += u3.y; v3.z += u3.z; v3.w += u3.w;
+                    }
+                    const float x1[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    x2[s][0] = v2.x; x2[s][1] = v2.y; x2[s][2] = v2.z; x2[s][3] = v2.w;
+                    x2[s][4] = v3.x; x2[s][5] = v3.y; x2[s][6] = v3.z; x2[s][7] = v3.w;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) p[c] = W[PC1_B + c];
+#pragma unroll
+                    for (int ci = 0; ci < 8; ++ci) {
+                        const float4* w4 = reinterpret_cast<const float4*>(W + PC1_W + ci * 16);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float4 ww = w4[v];
+                            p[4 * v + 0] = fmaf(x1[ci], ww.x, p[4 * v + 0]);
+                            p[4 * v + 1] = fmaf(x1[ci], ww.y, p[4 * v + 1]);
+                            p[4 * v + 2] = fmaf(x1[ci], ww.z, p[4 * v + 2]);
+                            p[4 * v + 3] = fmaf(x1[ci], ww.w, p[4 * v + 3]);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) p[c] = prelu(p[c], a1);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) p[c] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) x2[s][c] = 0.f;
+                }
+                float4* row = Pb + (slot + 2) * GT_ROW4 + f + 1;
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) row[qd * 35] = make_float4(p[4 * qd], p[4 * qd + 1], p[4 * qd + 2], p[4 * qd + 3]);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: 3x3 conv over (t-2..t, f-1..f+1) + PReLU, point conv 2 (16 -> 8), energies
+        if (act) {
+            float d0[16], d1[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) d0[c] = d1[c] = W[MID_B + c];
+            const float4* r0 = Pb + (2 * sp2) * GT_ROW4 + f;          // tap (kt,kf) of slot s: row slot+kt, col f+kf
+            if (DEC) {
+#pragma unroll 1
+                for (int kt = 0; kt < 3; ++kt) {
+#pragma unroll 1
+                    for (int kf = 0; kf < 3; ++kf) {
+                        const float* wk = W + MID_W + (kt * 3 + kf) * 256;
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) {
+                            const float4 i0 = r0[kt * GT_ROW4 + qd * 35 + kf];
+                            const float4 i1 = r0[(kt + 1) * GT_ROW4 + qd * 35 + kf];
+                            axpy2<16>(d0, d1, i0.x, i1.x, wk + (4 * qd + 0) * 16);
+                            axpy2<16>(d0, d1, i0.y, i1.y, wk + (4 * qd + 1) * 16);
+                            axpy2<16>(d0, d1, i0.z, i1.z, wk + (4 * qd + 2) * 16);
+                            axpy2<16>(d0, d1, i0.w, i1.w, wk + (4 * qd + 3) * 16);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int kt = 0; kt < 3; ++kt) {
+#pragma unroll
+                    for (int kf = 0; kf < 3; ++kf) {
+                        const float4* w4 = reinterpret_cast<const float4*>(W + MID_W + (kt * 3 + kf) * 16);
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) {
+                            const float4 ww = w4[qd];
+                            const float4 i0 = r0[kt * GT_ROW4 + qd * 35 + kf];
+                            const float4 i1 = r0[(kt + 1) * GT_ROW4 + qd * 35 + kf];
+                            d0[4 * qd + 0] = fmaf(i0.x, ww.x, d0[4 * qd + 0]); d1[4 * qd + 0] = fmaf(i1.x, ww.x, d1[4 * qd + 0]);
+                            d0[4 * qd + 1] = fmaf(i0.y, ww.y, d0[4 * qd + 1]); d1[4 * qd + 1] = fmaf(i1.y, ww.y, d1[4 * qd + 1]);
+                            d0[4 * qd + 2] = fmaf(i0.z, ww.z, d0[4 * qd + 2]); d1[4 * qd + 2] = fmaf(i1.z, ww.z, d1[4 * qd + 2]);
+                            d0[4 * qd + 3] = fmaf(i0.w, ww.w, d0[4 * qd + 3]); d1[4 * qd + 3] = fmaf(i1.w, ww.w, d1[4 * qd + 3]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { d0[c] = prelu(d0[c], a2); d1[c] = prelu(d1[c], a2); }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) q[0][c] = q[1][c] = W[PC2_B + c];
+#pragma unroll
+            for (int ci = 0; ci < 16; ++ci) axpy2<8>(q[0], q[1], d0[ci], d1[ci], W + PC2_W + ci * 8);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                float4* e4 = reinterpret_cast<float4*>(E2 + ((2 * sp2 + s) * kF2 + f) * 8);
+                e4[0] = make_float4(q[s][0] * q[s][0], q[s][1] * q[s][1], q[s][2] * q[s][2], q[s][3] * q[s][3]);
+                e4[1] = make_float4(q[s][4] * q[s][4], q[s][5] * q[s][5], q[s][6] * q[s][6], q[s][7] * q[s][7]);
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: TRALite energies (fixed summation order -> bitwise deterministic / causal)
+        if (tid < GT_NT * 8) {
+            const int slot = tid >> 3, c = tid & 7;
+            const float* e = E2 + slot * kF2 * 8 + c;
+            float s = 0.f;
+#pragma unroll
+            for (int ff = 0; ff < kF2; ++ff) s += e[ff * 8];
+            Ev[(slot + 2) * 8 + c] = s / 33.0f;
+        }
+        __syncthreads();
+        if (tid < GT_NT * 8) {
+            const int slot = tid >> 3, c = tid & 7;
+            float v = W[TPW_B + c];
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+                float y = W[TDW_B + ci];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) y = fmaf(W[TDW_W + k * 8 + ci], Ev[(slot + k) * 8 + ci], y);
+                v = fmaf(W[TPW_W + ci * 8 + c], y, v);
+            }
+            G[slot * 8 + c] = 1.0f / (1.0f + expf(-v));
+        }
+        __syncthreads();
+        // ---- phase 4: gate, channel shuffle [q0,x2_0,q1,x2_1,...], store; carry history to rows 0,1
+        if (act) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int slot = 2 * sp2 + s, t = t0 + slot;
+                if (t >= s0 && t < s1) {
+                    const float* g = G + slot * 8;
+                    float4* po = reinterpret_cast<float4*>(out + ubase + ((int64_t)t * kF2 + f) * 16);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        po[v] = make_float4(q[s][2 * v] * g[2 * v], x2[s][2 * v], q[s][2 * v + 1] * g[2 * v + 1], x2[s][2 * v + 1]);
+                }
+            }
+        }
+        for (int i = tid; i < 2 * GT_ROW4; i += GT_THREADS) Pb[i] = Pb[GT_NT * GT_ROW4 + i];
+        if (tid < 16) Ev[tid] = Ev[GT_NT * 8 + tid];
+        __syncthreads();
+    }
+}
+
+// ================================================================================================
+// GTCN: 4 TCN blocks (dilation 1,2,4,8) fused.  reference: gtcrn_micro.py:256-336
+// TCNs never mix frequency bins, so a CTA owns 11 of the 33 bins of one utterance segment and walks
+// along time in tiles of TC_NT frames; the block input x stays in registers through all four TCNs.
+// Y holds [16 history rows | TC_NT new rows] of conv1 output for the TCN being evaluated; `carry`
+// keeps the last 2d rows of every TCN between tiles (the streaming tcn_cache, gtcrn_micro_stream.py:620-623).
+// grid (nseg * 3, B), 288 threads (264 active = 24 slot pairs x 11 bins).
+// ================================================================================================
+constexpr int TC_NT = 48;
+constexpr int TC_FC = 11;
+constexpr int TC_THREADS = 288;
+constexpr int TC_ACTIVE = (TC_NT / 2) * TC_FC;
+constexpr int TC_HIST = 16;
+constexpr int TC_ROW4 = 4 * 12;                 // float4 per row: [q][col (11, padded to 12)]
+constexpr int TC_WARMUP = 30;
+constexpr int TC_SMEM_FLOATS = 4 * blob::TCN_SIZE + (TC_HIST + TC_NT) * TC_ROW4 * 4 + 30 * TC_ROW4 * 4;
+
+__global__ void __launch_bounds__(TC_THREADS) k_gtcn(const float* __restrict__ xin, float* __restrict__ out,
+                                                     const float* __restrict__ wblk, int T, int seg_len) {
+    extern __shared__ float4 smem4[];
+    float* W = reinterpret_cast<float*>(smem4);
+    float4* Y = reinterpret_cast<float4*>(W + 4 * blob::TCN_SIZE);
+    float4* carry = Y + (TC_HIST + TC_NT) * TC_ROW4;
+
+    const int tid = threadIdx.x, b = blockIdx.y;
+    const int seg = blockIdx.x / 3, col0 = (blockIdx.x - seg * 3) * TC_FC;
+    const int s0 = seg * seg_len, s1 = min(T, s0 + seg_len);
+    if (s0 >= s1) return;
+    const int tw0 = max(0, s0 - TC_WARMUP);
+    copy_f4(W, wblk, 4 * blob::TCN_SIZE, tid, TC_THREADS);
+    zero_f4(reinterpret_cast<float*>(Y), ((TC_HIST + TC_NT) + 30) * TC_ROW4 * 4, tid, TC_THREADS);
+    __syncthreads();
+
+    const bool act = tid < TC_ACTIVE;
+    const int sp2 = tid / TC_FC, col = tid - sp2 * TC_FC;
+    const int64_t ubase = (int64_t)b * T * kF2 * 16;
+
+    for (int t0 = tw0; t0 < s1; t0 += TC_NT) {
+        float x[2][16];
+        if (act) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int t = t0 + 2 * sp2 + s;
+                if (t < s1) {
+                    const float4* px = reinterpret_cast<const float4*>(xin + ubase + ((int64_t)t * kF2 + col0 + col) * 16);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float4 u = px[v];
+                        x[s][4 * v] = u.x; x[s][4 * v + 1] = u.y; x[s][4 * v + 2] = u.z; x[s][4 * v + 3] = u.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) x[s][c] = 0.f;
+                }
+            }
+        }
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const int d = 1 << k, coff = (2 << k) - 2;            // carry rows of TCN k start at 2^(k+1) - 2
+            const float* Wk = W + k * blob::TCN_SIZE;
+            // history rows [16-2d, 16) <- carry
+            for (int i = tid; i < 2 * d * TC_ROW4; i += TC_THREADS) Y[(TC_HIST - 2 * d) * TC_ROW4 + i] = carry[coff * TC_ROW4 + i];
+            float y1[2][16];
+            if (act) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) y1[0][c] = y1[1][c] = Wk[blob::TCN_B1 + c];
+#pragma unroll
+                for (int ci = 0; ci < 16; ++ci) axpy2<16>(y1[0], y1[1], x[0][ci], x[1][ci], Wk + blob::TCN_W1 + ci * 16);
+                const float a1 = Wk[blob::TCN_SLOPE + 0];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    float4* row = Y + (TC_HIST + 2 * sp2 + s) * TC_ROW4 + col;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) y1[s][c] = prelu(y1[s][c], a1);
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd)
+                        row[qd * 12] = make_float4(y1[s][4 * qd], y1[s][4 * qd + 1], y1[s][4 * qd + 2], y1[s][4 * qd + 3]);
+                }
+            }
+            __syncthreads();
+            if (act) {
+                const float a2 = Wk[blob::TCN_SLOPE + 1], a3 = Wk[blob::TCN_SLOPE + 2];
+                float y2[2][16];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const float4* rA = Y + (TC_HIST + 2 * sp2 + s - 2 * d) * TC_ROW4 + col;
+                    const float4* rB = Y + (TC_HIST + 2 * sp2 + s - d) * TC_ROW4 + col;
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        const float4 ta = rA[qd * 12], tb = rB[qd * 12];
+                        const float4 w0 = reinterpret_cast<const float4*>(Wk + blob::TCN_W2)[qd];
+                        const float4 w1 = reinterpret_cast<const float4*>(Wk + blob::TCN_W2 + 16)[qd];
+                        const float4 w2 = reinterpret_cast<const float4*>(Wk + blob::TCN_W2 + 32)[qd];
+                        const float4 bb = reinterpret_cast<const float4*>(Wk + blob::TCN_B2)[qd];
+                        y2[s][4 * qd + 0] = prelu(fmaf(w2.x, y1[s][4 * qd + 0], fmaf(w1.x, tb.x, fmaf(w0.x, ta.x, bb.x))), a2);
+                        y2[s][4 * qd + 1] = prelu(fmaf(w2.y, y1[s][4 * qd + 1], fmaf(w1.y, tb.y, fmaf(w0.y, ta.y, bb.y))), a2);
+                        y2[s][4 * qd + 2] = prelu(fmaf(w2.z, y1[s][4 * qd + 2], fmaf(w1.z, tb.z, fmaf(w0.z, ta.z, bb.z))), a2);
+                        y2[s][4 * qd + 3] = prelu(fmaf(w2.w, y1[s][4 * qd + 3], fmaf(w1.w, tb.w, fmaf(w0.w, ta.w, bb.w))), a2);
+                    }
+                }
+                float o[2][16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) { o[0][c] = Wk[blob::TCN_B3 + c] + x[0][c]; o[1][c] = Wk[blob::TCN_B3 + c] + x[1][c]; }
+#pragma unroll
+                for (int ci = 0; ci < 16; ++ci) axpy2<16>(o[0], o[1], y2[0][ci], y2[1][ci], Wk + blob::TCN_W3 + ci * 16);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) { x[0][c] = prelu(o[0][c], a3); x[1][c] = prelu(o[1][c], a3); }
+            }
+            // carry <- last 2d rows of [history | new]
+            for (int i = tid; i < 2 * d * TC_ROW4; i += TC_THREADS) carry[coff * TC_ROW4 + i] = Y[(TC_HIST + TC_NT - 2 * d) * TC_ROW4 + i];
+            __syncthreads();
+        }
+        if (act) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int t = t0 + 2 * sp2 + s;
+                if (t >= s0 && t < s1) {
+                    float4* po = reinterpret_cast<float4*>(out + ubase + ((int64_t)t * kF2 + col0 + col) * 16);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) po[v] = make_float4(x[s][4 * v], x[s][4 * v + 1], x[s][4 * v + 2], x[s][4 * v + 3]);
+                }
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// BACK: (de2 + en1) -> de3 ConvT(16->16,k5,s2) +PReLU -> (+en0) -> de4 ConvT(16->2,k5,s2) + tanh
+//       -> ERB expand -> complex mask * spec -> enhanced spec.
+// reference: gtcrn_micro.py:441-460 (de_convs[3..4]), :69-73 (erb.bs), :478-482 (Mask), :529-530
+// transposed convs in gather form: out[g] = sum_{k : g+2-k even} w[k] . x[(g+2-k)/2]
+// Frames are independent: (b,t) flattened, grid ceil(B*T/8), 288 threads, 8 frames per CTA.
+// ================================================================================================
+constexpr int BK_NF = 8;
+constexpr int BK_THREADS = 288;
+constexpr int BK_X4 = 4 * 35;                    // float4 per slot: [q][f + 1]
+constexpr int BK_Y4 = 4 * 67;                    // float4 per slot: [q][g + 1]
+constexpr int BK_M = 130 * 2;                    // floats per slot: [h][2]
+constexpr int BK_SMEM_FLOATS = blob::BACK_SIZE + BK_NF * (BK_X4 * 4 + BK_Y4 * 4 + BK_M);
+
+__global__ void __launch_bounds__(BK_THREADS) k_back(const float* __restrict__ de2, const float* __restrict__ en1,
+                                                     const float* __restrict__ en0, const float* __restrict__ spec,
+                                                     int64_t sb, int64_t sf, int64_t st, int64_t sc,
+                                                     float* __restrict__ outp, int64_t ob, int64_t of, int64_t ot, int64_t oc,
+                                                     int T, int64_t nframes, const float* __restrict__ blobp) {
+    extern __shared__ float4 smem4[];
+    float* W = reinterpret_cast<float*>(smem4);
+    float4* X = reinterpret_cast<float4*>(W + blob::BACK_SIZE);
+    float4* Y3 = X + BK_NF * BK_X4;
+    float* M = reinterpret_cast<float*>(Y3 + BK_NF * BK_Y4);
+    const int tid = threadIdx.x;
+    const int64_t fi0 = (int64_t)blockIdx.x * BK_NF;
+
+    copy_f4(W, blobp + blob::BACK_OFF, blob::BACK_SIZE, tid, BK_THREADS);
+    zero_f4(reinterpret_cast<float*>(X), BK_NF * (BK_X4 + BK_Y4) * 4, tid, BK_THREADS);
+    __syncthreads();
+    // ---- a: x = de2 + en1 into X
+    if (tid < (BK_NF / 2) * kF2) {
+        const int sp2 = tid / kF2, f = tid - sp2 * kF2;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int slot = 2 * sp2 + s;
+            if (fi0 + slot < nframes) {
+                const int64_t off = ((fi0 + slot) * kF2 + f) * 16;
+                const float4* pa = reinterpret_cast<const float4*>(de2 + off);
+                const float4* pb = reinterpret_cast<const float4*>(en1 + off);
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    const float4 u = pa[qd], v = pb[qd];
+                    X[slot * BK_X4 + qd * 35 + f + 1] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- b: de3 (thread = 2 slots x 16 co at one output bin g; even bins first so warps are parity-uniform)
+    if (tid < (BK_NF / 2) * kF1) {
+        const int sp2 = tid / kF1, pg = tid - sp2 * kF1;
+        const int g = pg < 33 ? 2 * pg : 2 * (pg - 33) + 1;
+        const int m = g >> 1, odd = g & 1, ntap = 3 - odd;
+        float acc0[16], acc1[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = W[blob::BACK_DE3_B + c];
+        const float4* x0 = X + (2 * sp2) * BK_X4;
+        const float4* x1 = x0 + BK_X4;
+#pragma unroll 1
+        for (int j = 0; j < ntap; ++j) {
+            const int k = 2 * j + odd, colx = m + 2 - j;       // input bin f = m + 1 - j, stored at col f + 1
+            const float* wk = W + blob::BACK_DE3_W + k * 256;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                const float4 i0 = x0[qd * 35 + colx], i1 = x1[qd * 35 + colx];
+                axpy2<16>(acc0, acc1, i0.x, i1.x, wk + (4 * qd + 0) * 16);
+                axpy2<16>(acc0, acc1, i0.y, i1.y, wk + (4 * qd + 1) * 16);
+                axpy2<16>(acc0, acc1, i0.z, i1.z, wk + (4 * qd + 2) * 16);
+                axpy2<16>(acc0, acc1, i0.w, i1.w, wk + (4 * qd + 3) * 16);
+            }
+        }
+        const float a = W[blob::BACK_SLOPE + 0];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int slot = 2 * sp2 + s;
+            float* acc = s ? acc1 : acc0;
+            if (fi0 + slot < nframes) {
+                const float4* pe = reinterpret_cast<const float4*>(en0 + ((fi0 + slot) * kF1 + g) * 16);
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    const float4 e = pe[qd];
+                    Y3[slot * BK_Y4 + qd * 67 + g + 1] = make_float4(prelu(acc[4 * qd], a) + e.x, prelu(acc[4 * qd + 1], a) + e.y,
+                                                                     prelu(acc[4 * qd + 2], a) + e.z, prelu(acc[4 * qd + 3], a) + e.w);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- c: de4 (16 -> 2) + tanh -> mask on the 129 ERB bins
+    for (int idx = tid; idx < BK_NF * kErb; idx += BK_THREADS) {
+        const int slot = idx / kErb, h = idx - slot * kErb;
+        const int m = h >> 1, odd = h & 1, ntap = 3 - odd;
+        float m0 = W[blob::BACK_DE4_B + 0], m1 = W[blob::BACK_DE4_B + 1];
+        const float4* y = Y3 + slot * BK_Y4;
+        for (int j = 0; j < ntap; ++j) {
+            const int k = 2 * j + odd, colx = m + 2 - j;
+            const float4* w4 = reinterpret_cast<const float4*>(W + blob::BACK_DE4_W + k * 32);
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                const float4 i = y[qd * 67 + colx];
+                const float4 wa = w4[2 * qd], wb = w4[2 * qd + 1];   // (ci,co): (4q,0) (4q,1) (4q+1,0) (4q+1,1) | (4q+2,..) (4q+3,..)
+                m0 = fmaf(i.x, wa.x, m0); m1 = fmaf(i.x, wa.y, m1);
+                m0 = fmaf(i.y, wa.z, m0); m1 = fmaf(i.y, wa.w, m1);
+                m0 = fmaf(i.z, wb.x, m0); m1 = fmaf(i.z, wb.y, m1);
+                m0 = fmaf(i.w, wb.z, m0); m1 = fmaf(i.w, wb.w, m1);
+            }
+        }
+        M[slot * BK_M + 2 * h] = tanhf(m0);
+        M[slot * BK_M + 2 * h + 1] = tanhf(m1);
+    }
+    __syncthreads();
+    // ---- d: ERB expand + complex ratio mask
+    {
+        const int* ib0 = reinterpret_cast<const int*>(W + blob::BACK_IERB_B0);
+        const float* iw = W + blob::BACK_IERB_W;
+        for (int idx = tid; idx < BK_NF * kBins; idx += BK_THREADS) {
+            const int slot = idx / kBins, i = idx - slot * kBins;
+            const int64_t fi = fi0 + slot;
+            if (fi >= nframes) continue;
+            const int64_t b = fi / T, t = fi - b * T;
+            const float* ms = M + slot * BK_M;
+            float m0, m1;
+            if (i < 65) {
+                m0 = ms[2 * i];
+                m1 = ms[2 * i + 1];
+            } else {
+                const int j = i - 65, bb = 65 + ib0[j];
+                const float w0 = iw[2 * j], w1 = iw[2 * j + 1];
+                m0 = w0 * ms[2 * bb] + w1 * ms[2 * bb + 2];
+                m1 = w0 * ms[2 * bb + 1] + w1 * ms[2 * bb + 3];
+            }
+            const float* p = spec + b * sb + t * st + (int64_t)i * sf;
+            const float re = p[0], im = p[sc];
+            float* o = outp + b * ob + t * ot + (int64_t)i * of;
+            o[0] = re * m0 - im * m1;
+            o[oc] = im * m0 + re * m1;
+        }
+    }
+}
+
+}  // namespace gk

@@ -1,0 +1,603 @@
+// Frame-by-frame (streaming) kernels: one 16 ms hop for N concurrent streams per call.
+// reference: StreamGTCRNMicro.forward gtcrn_micro_stream.py:541-574, StreamGTConvBlock :182-262,
+//            StreamTCN :265-319, StreamConv2d / StreamConvTranspose2d convolution.py:62-253.
+//
+// The reference threads shift-register caches through every call (cat([cache, x]) ... cache' = input[:, :, 1:],
+// convolution.py:116-119) -- 305 KB of cache traffic per stream and hop.  Here the caches of all N streams live in
+// ONE device buffer as RING buffers indexed by the frame counter, so a hop only reads the taps it needs and
+// writes the one new frame per cache (~93 KB per stream-hop):
+//
+//   header (256 B): int64 frame_step, int64 wav_calls, int32 skip
+//   per stream (38,880 floats, contiguous):
+//     GT_P   [6 blocks][2 slots][33][16]   point-conv-1 outputs of frames t-2, t-1   (blocks 0-2 en2..en4, 3-5 de0..de2)
+//     TRA_E  [6 blocks][2 slots][8]        TRALite energies of frames t-2, t-1
+//     TCN_Y  [2 gtcn][30 rows][33][16]     conv1 outputs, TCN k owns 2d_k rows starting at row 2^(k+1)-2
+//     WAV_IN [2 slots][256]                last two input hops       (wav entry point only)
+//     OLA    [256]                         overlap-add tail          (wav entry point only)
+//   ring slot of frame t in a cache of depth R: t mod R.
+//
+// Work mapping: the per-frame kernels of the offline path (k_front, k_back) are reused with T = 1; the temporal
+// kernels get tiles ACROSS streams (8 streams x 33 bins per CTA for GTConv, 512 (stream,bin) columns per CTA for
+// the two GTCNs, which are purely per-column recurrences and need no shared-memory exchange at all).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "blob_layout.h"
+#include "gtcrn_kernels.cuh"
+
+namespace gs {
+
+using gk::kF1;
+using gk::kF2;
+
+constexpr int kHdrFloats = 64;
+constexpr int kGtP = 0;
+constexpr int kTraE = kGtP + 6 * 2 * kF2 * 16;            // 6336
+constexpr int kTcnY = kTraE + 6 * 2 * 8;                  // 6432
+constexpr int kModelFloats = kTcnY + 2 * 30 * kF2 * 16;   // 38112
+constexpr int kWavIn = kModelFloats;
+constexpr int kOla = kWavIn + 2 * 256;
+constexpr int kPerStream = kOla + 256;                    // 38880
+
+struct Header {
+    long long frame_step;
+    long long wav_calls;
+    int skip;
+};
+
+struct Ws {          // per-hop activation workspace (owned by the handle), all [N][F][16]
+    float* en0;
+    float* act[9];
+    float* spec_in;
+    float* spec_out;
+};
+
+inline size_t state_bytes(int64_t N) { return sizeof(float) * ((size_t)kHdrFloats + (size_t)N * kPerStream); }
+
+__device__ __forceinline__ float* stream_base(void* state, int64_t n) {
+    return reinterpret_cast<float*>(state) + kHdrFloats + n * (int64_t)kPerStream;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GTConvBlock, one frame for SG_NS streams per CTA.  Same arithmetic as gk::k_gtconv; the two history rows
+// of every stream come from the GT_P ring instead of the previous tile.
+// grid ceil(N/8), 160 threads (132 active = 4 stream pairs x 33 bins).
+// ------------------------------------------------------------------------------------------------
+constexpr int SG_NS = 8;
+constexpr int SG_THREADS = 160;
+constexpr int SG_ACTIVE = (SG_NS / 2) * kF2;
+constexpr int SG_ROW4 = gk::GT_ROW4;
+template <bool DEC> __host__ __device__ constexpr int sg_smem_floats() {
+    return gk::gt_chunk<DEC>() + SG_NS * 3 * SG_ROW4 * 4 + SG_NS * kF2 * 8 + SG_NS * 3 * 8 + SG_NS * 8;
+}
+
+template <bool DEC>
+__global__ void __launch_bounds__(SG_THREADS) ks_gtconv(const float* __restrict__ xin, const float* __restrict__ skip,
+                                                        float* __restrict__ out, const float* __restrict__ wblk,
+                                                        void* state, int blk, int64_t N) {
+    using namespace gk;
+    constexpr int PC1_W = DEC ? blob::DECGT_PC1_W : blob::ENCGT_PC1_W;
+    constexpr int PC1_B = DEC ? blob::DECGT_PC1_B : blob::ENCGT_PC1_B;
+    constexpr int MID_W = DEC ? blob::DECGT_FULL_W : blob::ENCGT_DW_W;
+    constexpr int MID_B = DEC ? blob::DECGT_FULL_B : blob::ENCGT_DW_B;
+    constexpr int PC2_W = DEC ? blob::DECGT_PC2_W : blob::ENCGT_PC2_W;
+    constexpr int PC2_B = DEC ? blob::DECGT_PC2_B : blob::ENCGT_PC2_B;
+    constexpr int TDW_W = DEC ? blob::DECGT_TRA_DW_W : blob::ENCGT_TRA_DW_W;
+    constexpr int TDW_B = DEC ? blob::DECGT_TRA_DW_B : blob::ENCGT_TRA_DW_B;
+    constexpr int TPW_W = DEC ? blob::DECGT_TRA_PW_W : blob::ENCGT_TRA_PW_W;
+    constexpr int TPW_B = DEC ? blob::DECGT_TRA_PW_B : blob::ENCGT_TRA_PW_B;
+    constexpr int SLOPE = DEC ? blob::DECGT_SLOPE : blob::ENCGT_SLOPE;
+
+    const Header* hdr = reinterpret_cast<const Header*>(state);
+    if (hdr->skip) return;
+    const int slot_old = (int)(hdr->frame_step & 1);          // holds frame t-2; overwritten with frame t
+    const int slot_mid = slot_old ^ 1;                        // holds frame t-1
+
+    extern __shared__ float4 smem4[];
+    float* W = reinterpret_cast<float*>(smem4);
+    float4* Pb = reinterpret_cast<float4*>(W + gt_chunk<DEC>());      // [stream][3 rows: t-2, t-1, t][q][col]
+    float* E2 = reinterpret_cast<float*>(Pb + SG_NS * 3 * SG_ROW4);
+    float* Ev = E2 + SG_NS * kF2 * 8;                                 // [stream][3][8]
+    float* G = Ev + SG_NS * 3 * 8;
+
+    const int tid = threadIdx.x;
+    const int64_t n0 = (int64_t)blockIdx.x * SG_NS;
+    copy_f4(W, wblk, gt_chunk<DEC>(), tid, SG_THREADS);
+    zero_f4(reinterpret_cast<float*>(Pb), SG_NS * 3 * SG_ROW4 * 4, tid, SG_THREADS);
+    __syncthreads();
+
+    const bool act = tid < SG_ACTIVE;
+    const int sp2 = tid / kF2, f = tid - sp2 * kF2;
+    const float a1 = W[SLOPE + 0], a2 = W[SLOPE + 1];
+    float x2[2][8], q[2][8];
+
+    // ---- phase 1: history rows from the ring, point conv 1 of the new frame (also written to the ring)
+    if (act) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int ls = 2 * sp2 + s;
+            const int64_t n = n0 + ls;
+            float p[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) p[c] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) x2[s][c] = 0.f;
+            if (n < N) {
+                float* ring = stream_base(state, n) + kGtP + blk * (2 * kF2 * 16) + f * 16;
+                const float4* h2 = reinterpret_cast<const float4*>(ring + slot_old * (kF2 * 16));
+                const float4* h1 = reinterpret_cast<const float4*>(ring + slot_mid * (kF2 * 16));
+                float4* row = Pb + (ls * 3) * SG_ROW4 + f + 1;
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) { row[qd * 35] = h2[qd]; row[SG_ROW4 + qd * 35] = h1[qd]; }
+                const float4* px = reinterpret_cast<const float4*>(xin + (n * kF2 + f) * 16);
+                float4 v0 = px[0], v1 = px[1], v2 = px[2], v3 = px[3];
+                if (DEC) {
+                    const float4* ps = reinterpret_cast<const float4*>(skip + (n * kF2 + f) * 16);
+                    const float4 u0 = ps[0], u1 = ps[1], u2 = ps[2], u3 = ps[3];
+                    v0.x += u0.x; v0.y += u0.y; v0.z += u0.z; v0.w += u0.w;
+                    v1.x += u1.x; v1.y += u1.y; v1.z += u1.z; v1.w += u1.w;
+                    v2.x += u2.x; v2.y += u2.y; v2.z += u2.z; v2.w += u2.w;
+                    v3.x += u3.x; v3.y += u3.y; v3.z += u3.z; v3.w += u3.w;
+                }
+                const float x1[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                x2[s][0] = v2.x; x2[s][1] = v2.y; x2[s][2] = v2.z; x2[s][3] = v2.w;
+                x2[s][4] = v3.x; x2[s][5] = v3.y; x2[s][6] = v3.z; x2[s][7] = v3.w;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) p[c] = W[PC1_B + c];
+#pragma unroll
+                for (int ci = 0; ci < 8; ++ci) {
+                    const float4* w4 = reinterpret_cast<const float4*>(W + PC1_W + ci * 16);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float4 ww = w4[v];
+                        p[4 * v + 0] = fmaf(x1[ci], ww.x, p[4 * v + 0]);
+                        p[4 * v + 1] = fmaf(x1[ci], ww.y, p[4 * v + 1]);
+                        p[4 * v + 2] = fmaf(x1[ci], ww.z, p[4 * v + 2]);
+                        p[4 * v + 3] = fmaf(x1[ci], ww.w, p[4 * v + 3]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) p[c] = prelu(p[c], a1);
+                float4* newest = reinterpret_cast<float4*>(ring + slot_old * (kF2 * 16));
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) newest[qd] = make_float4(p[4 * qd], p[4 * qd + 1], p[4 * qd + 2], p[4 * qd + 3]);
+            }
+            float4* row = Pb + (ls * 3 + 2) * SG_ROW4 + f + 1;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) row[qd * 35] = make_float4(p[4 * qd], p[4 * qd + 1], p[4 * qd + 2], p[4 * qd + 3]);
+        }
+    }
+    if (tid < SG_NS * 16) {                                           // TRA energy history -> Ev rows 0,1
+        const int ls = tid >> 4, r = (tid >> 3) & 1, c = tid & 7;
+        const int64_t n = n0 + ls;
+        float v = 0.f;
+        if (n < N) v = stream_base(state, n)[kTraE + blk * 16 + (r == 0 ? slot_old : slot_mid) * 8 + c];
+        Ev[(ls * 3 + r) * 8 + c] = v;
+    }
+    __syncthreads();
+    // ---- phase 2: 3x3 conv + PReLU, point conv 2, energies
+    if (act) {
+        float d0[16], d1[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) d0[c] = d1[c] = W[MID_B + c];
+        const float4* r0 = Pb + (2 * sp2 * 3) * SG_ROW4 + f;           // stream s, tap kt: row (2 sp2 + s) * 3 + kt
+        if (DEC) {
+#pragma unroll 1
+            for (int kt = 0; kt < 3; ++kt) {
+#pragma unroll 1
+                for (int kf = 0; kf < 3; ++kf) {
+                    const float* wk = W + MID_W + (kt * 3 + kf) * 256;
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        const float4 i0 = r0[kt * SG_ROW4 + qd * 35 + kf];
+                        const float4 i1 = r0[(kt + 3) * SG_ROW4 + qd * 35 + kf];
+                        axpy2<16>(d0, d1, i0.x, i1.x, wk + (4 * qd + 0) * 16);
+                        axpy2<16>(d0, d1, i0.y, i1.y, wk + (4 * qd + 1) * 16);
+                        axpy2<16>(d0, d1, i0.z, i1.z, wk + (4 * qd + 2) * 16);
+                        axpy2<16>(d0, d1, i0.w, i1.w, wk + (4 * qd + 3) * 16);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int kt = 0; kt < 3; ++kt) {
+#pragma unroll
+                for (int kf = 0; kf < 3; ++kf) {
+                    const float4* w4 = reinterpret_cast<const float4*>(W + MID_W + (kt * 3 + kf) * 16);
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        const float4 ww = w4[qd];
+                        const float4 i0 = r0[kt * SG_ROW4 + qd * 35 + kf];
+                        const float4 i1 = r0[(kt + 3) * SG_ROW4 + qd * 35 + kf];
+                        d0[4 * qd + 0] = fmaf(i0.x, ww.x, d0[4 * qd + 0]); d1[4 * qd + 0] = fmaf(i1.x, ww.x, d1[4 * qd + 0]);
+                        d0[4 * qd + 1] = fmaf(i0.y, ww.y, d0[4 * qd + 1]); d1[4 * qd + 1] = fmaf(i1.y, ww.y, d1[4 * qd + 1]);
+                        d0[4 * qd + 2] = fmaf(i0.z, ww.z, d0[4 * qd + 2]); d1[4 * qd + 2] = fmaf(i1.z, ww.z, d1[4 * qd + 2]);
+                        d0[4 * qd + 3] = fmaf(i0.w, ww.w, d0[4 * qd + 3]); d1[4 * qd + 3] = fmaf(i1.w, ww.w, d1[4 * qd + 3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { d0[c] = prelu(d0[c], a2); d1[c] = prelu(d1[c], a2); }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) q[0][c] = q[1][c] = W[PC2_B + c];
+#pragma unroll
+        for (int ci = 0; ci < 16; ++ci) axpy2<8>(q[0], q[1], d0[ci], d1[ci], W + PC2_W + ci * 8);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            float4* e4 = reinterpret_cast<float4*>(E2 + ((2 * sp2 + s) * kF2 + f) * 8);
+            e4[0] = make_float4(q[s][0] * q[s][0], q[s][1] * q[s][1], q[s][2] * q[s][2], q[s][3] * q[s][3]);
+            e4[1] = make_float4(q[s][4] * q[s][4], q[s][5] * q[s][5], q[s][6] * q[s][6], q[s][7] * q[s][7]);
+        }
+    }
+    __syncthreads();
+    // ---- phase 3: TRALite energy of the new frame (same summation order as the offline kernel) -> ring, gate
+    if (tid < SG_NS * 8) {
+        const int ls = tid >> 3, c = tid & 7;
+        const float* e = E2 + ls * kF2 * 8 + c;
+        float s = 0.f;
+#pragma unroll
+        for (int ff = 0; ff < kF2; ++ff) s += e[ff * 8];
+        s = s / 33.0f;
+        Ev[(ls * 3 + 2) * 8 + c] = s;
+        const int64_t n = n0 + ls;
+        if (n < N) stream_base(state, n)[kTraE + blk * 16 + slot_old * 8 + c] = s;
+    }
+    __syncthreads();
+    if (tid < SG_NS * 8) {
+        const int ls = tid >> 3, c = tid & 7;
+        float v = W[TPW_B + c];
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+            float y = W[TDW_B + ci];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) y = fmaf(W[TDW_W + k * 8 + ci], Ev[(ls * 3 + k) * 8 + ci], y);
+            v = fmaf(W[TPW_W + ci * 8 + c], y, v);
+        }
+        G[ls * 8 + c] = 1.0f / (1.0f + expf(-v));
+    }
+    __syncthreads();
+    // ---- phase 4: gate, shuffle, store
+    if (act) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int ls = 2 * sp2 + s;
+            const int64_t n = n0 + ls;
+            if (n < N) {
+                const float* g = G + ls * 8;
+                float4* po = reinterpret_cast<float4*>(out + (n * kF2 + f) * 16);
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    po[v] = make_float4(q[s][2 * v] * g[2 * v], x2[s][2 * v], q[s][2 * v + 1] * g[2 * v + 1], x2[s][2 * v + 1]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Both GTCNs (8 TCN blocks) for one frame: a pure per-(stream, bin) recurrence.  A thread owns two columns,
+// keeps x in registers through all eight TCNs and touches exactly 2 taps + 1 new row per TCN in the ring.
+// grid ceil(N*33 / 512), 256 threads.
+// ------------------------------------------------------------------------------------------------
+constexpr int ST_THREADS = 256;
+constexpr int ST_SMEM_FLOATS = 8 * blob::TCN_SIZE;
+
+__global__ void __launch_bounds__(ST_THREADS) ks_gtcn(const float* __restrict__ xin, float* __restrict__ out,
+                                                      const float* __restrict__ wblk, void* state, int64_t N) {
+    using namespace gk;
+    const Header* hdr = reinterpret_cast<const Header*>(state);
+    if (hdr->skip) return;
+    const long long step = hdr->frame_step;
+    extern __shared__ float4 smem4[];
+    float* W = reinterpret_cast<float*>(smem4);
+    const int tid = threadIdx.x;
+    copy_f4(W, wblk, ST_SMEM_FLOATS, tid, ST_THREADS);
+    __syncthreads();
+
+    const int64_t npos = N * kF2;
+    int64_t pos[2] = {(int64_t)blockIdx.x * (2 * ST_THREADS) + tid, (int64_t)blockIdx.x * (2 * ST_THREADS) + tid + ST_THREADS};
+    bool ok[2] = {pos[0] < npos, pos[1] < npos};
+    if (!ok[0]) return;                                      // pos[1] > pos[0]: nothing to do for this thread
+    float* ybase[2];
+    float x[2][16];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int64_t p = ok[s] ? pos[s] : pos[0];           // inactive second column mirrors the first (no store)
+        const int64_t n = p / kF2;
+        const int f = (int)(p - n * kF2);
+        ybase[s] = stream_base(state, n) + kTcnY + f * 16;
+        const float4* px = reinterpret_cast<const float4*>(xin + p * 16);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const float4 u = px[v];
+            x[s][4 * v] = u.x; x[s][4 * v + 1] = u.y; x[s][4 * v + 2] = u.z; x[s][4 * v + 3] = u.w;
+        }
+    }
+#pragma unroll 1
+    for (int gk_ = 0; gk_ < 8; ++gk_) {
+        const int g = gk_ >> 2, k = gk_ & 3, d = 1 << k, row0 = g * 30 + (2 << k) - 2;
+        const int slotA = (int)(step & (2 * d - 1));          // frame t-2d, overwritten with frame t
+        const int slotB = (int)((step + d) & (2 * d - 1));    // frame t-d
+        const float* Wk = W + gk_ * blob::TCN_SIZE;
+        float y1[2][16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) y1[0][c] = y1[1][c] = Wk[blob::TCN_B1 + c];
+#pragma unroll
+        for (int ci = 0; ci < 16; ++ci) axpy2<16>(y1[0], y1[1], x[0][ci], x[1][ci], Wk + blob::TCN_W1 + ci * 16);
+        const float a1 = Wk[blob::TCN_SLOPE + 0], a2 = Wk[blob::TCN_SLOPE + 1], a3 = Wk[blob::TCN_SLOPE + 2];
+        float y2[2][16];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            float4* rA = reinterpret_cast<float4*>(ybase[s] + (row0 + slotA) * (kF2 * 16));
+            const float4* rB = reinterpret_cast<const float4*>(ybase[s] + (row0 + slotB) * (kF2 * 16));
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                const float4 ta = rA[qd], tb = rB[qd];
+                y1[s][4 * qd + 0] = prelu(y1[s][4 * qd + 0], a1); y1[s][4 * qd + 1] = prelu(y1[s][4 * qd + 1], a1);
+                y1[s][4 * qd + 2] = prelu(y1[s][4 * qd + 2], a1); y1[s][4 * qd + 3] = prelu(y1[s][4 * qd + 3], a1);
+                if (s == 0 || ok[1]) rA[qd] = make_float4(y1[s][4 * qd], y1[s][4 * qd + 1], y1[s][4 * qd + 2], y1[s][4 * qd + 3]);
+                const float4 w0 = reinterpret_cast<const float4*>(Wk + blob::TCN_W2)[qd];
+                const float4 w1 = reinterpret_cast<const float4*>(Wk + blob::TCN_W2 + 16)[qd];
+                const float4 w2 = reinterpret_cast<const float4*>(Wk + blob::TCN_W2 + 32)[qd];
+                const float4 bb = reinterpret_cast<const float4*>(Wk + blob::TCN_B2)[qd];
+                y2[s][4 * qd + 0] = prelu(fmaf(w2.x, y1[s][4 * qd + 0], fmaf(w1.x, tb.x, fmaf(w0.x, ta.x, bb.x))), a2);
+                y2[s][4 * qd + 1] = prelu(fmaf(w2.y, y1[s][4 * qd + 1], fmaf(w1.y, tb.y, fmaf(w0.y, ta.y, bb.y))), a2);
+                y2[s][4 * qd + 2] = prelu(fmaf(w2.z, y1[s][4 * qd + 2], fmaf(w1.z, tb.z, fmaf(w0.z, ta.z, bb.z))), a2);
+                y2[s][4 * qd + 3] = prelu(fmaf(w2.w, y1[s][4 * qd + 3], fmaf(w1.w, tb.w, fmaf(w0.w, ta.w, bb.w))), a2);
+            }
+        }
+        float o[2][16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { o[0][c] = Wk[blob::TCN_B3 + c] + x[0][c]; o[1][c] = Wk[blob::TCN_B3 + c] + x[1][c]; }
+#pragma unroll
+        for (int ci = 0; ci < 16; ++ci) axpy2<16>(o[0], o[1], y2[0][ci], y2[1][ci], Wk + blob::TCN_W3 + ci * 16);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { x[0][c] = prelu(o[0][c], a3); x[1][c] = prelu(o[1][c], a3); }
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        if (!ok[s]) continue;
+        float4* po = reinterpret_cast<float4*>(out + pos[s] * 16);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) po[v] = make_float4(x[s][4 * v], x[s][4 * v + 1], x[s][4 * v + 2], x[s][4 * v + 3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming STFT / iSTFT for the wav entry point.  Call k (0-based) receives input hop k.
+//   k = 0 : nothing can be framed yet (frame 0 needs sample 256): hop stored, model skipped, zeros out
+//   k >= 1: frame k-1 = [hop k-2 | hop k-1]  (frame 0 = [reflect(hop 0, x[256]) | hop 0]) -> model -> iSTFT;
+//           output hop k-2 = OLA tail of frame k-2 + first half of frame k-1 (zeros for k = 1: trimmed pre-roll)
+// so the enhanced stream lags the input by two hops (512 samples); every emitted hop equals the offline output.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ks_stft_step(void* state, const float* __restrict__ hop_in, const float* __restrict__ blobp,
+                                                    float* __restrict__ spec, int64_t N) {
+    using namespace gk;
+    __shared__ FftTables tb;
+    __shared__ float2 buf[4][2][256];
+    Header* hdr = reinterpret_cast<Header*>(state);
+    const long long k = hdr->wav_calls;
+    const int tid = threadIdx.x, fr = tid >> 6, j = tid & 63;
+    const int64_t n = (int64_t)blockIdx.x * 4 + fr;
+    const bool valid = n < N;
+    load_fft_tables(tb, blobp, tid, 256);
+    __syncthreads();
+    float2* A = buf[fr][0];
+    float2* Bf = buf[fr][1];
+    float* ring = valid ? stream_base(state, n) + kWavIn : nullptr;
+    const float* nh = valid ? hop_in + n * 256 : nullptr;
+    if (valid && k >= 1) {
+        const float* h_prev = ring + ((k - 1) & 1) * 256;      // hop k-1
+        const float* h_prev2 = ring + (k & 1) * 256;           // hop k-2 (garbage for k = 1, unused then)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int m = j + 64 * r;
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = 2 * m + e;                       // position in the 512-sample frame
+                if (i >= 256) v[e] = h_prev[i - 256];
+                else if (k >= 2) v[e] = h_prev2[i];
+                else v[e] = (256 - i == 256) ? nh[0] : h_prev[256 - i];     // reflect: x[256 - i], x[256] is the new hop's first sample
+            }
+            A[m] = make_float2(tb.win[2 * m] * v[0], tb.win[2 * m + 1] * v[1]);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) A[j + 64 * r] = make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    if (valid) {                                              // store hop k over hop k-2 (all reads of it are done)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) ring[(k & 1) * 256 + j + 64 * r] = nh[j + 64 * r];
+    }
+    fft256(A, Bf, tb.tw256, j);
+    if (valid && k >= 1) {
+        float2* o = reinterpret_cast<float2*>(spec + n * kSpecFrame);
+        for (int kk = j; kk <= 256; kk += 64) {
+            const float2 zk = A[kk & 255];
+            float2 zc = A[(256 - kk) & 255];
+            zc.y = -zc.y;
+            const float2 w = tb.tw512[kk];
+            const float dx = zk.x - zc.x, dy = zk.y - zc.y;
+            o[kk] = make_float2(0.5f * (zk.x + zc.x) + 0.5f * (w.x * dy + w.y * dx),
+                                0.5f * (zk.y + zc.y) - 0.5f * (w.x * dx - w.y * dy));
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) hdr->skip = (k == 0) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) ks_istft_step(void* state, const float* __restrict__ spec, const float* __restrict__ blobp,
+                                                     float* __restrict__ hop_out, int64_t N) {
+    using namespace gk;
+    __shared__ FftTables tb;
+    __shared__ float2 buf[4][2][256];
+    __shared__ float inv_env[256];
+    const Header* hdr = reinterpret_cast<const Header*>(state);
+    const long long k = hdr->wav_calls;
+    const int tid = threadIdx.x, fr = tid >> 6, j = tid & 63;
+    const int64_t n = (int64_t)blockIdx.x * 4 + fr;
+    const bool valid = n < N;
+    load_fft_tables(tb, blobp, tid, 256);
+    inv_env[tid] = blobp[blob::FFT_OFF + blob::FFT_INV_ENV + tid];
+    __syncthreads();
+    float2* A = buf[fr][0];
+    float2* Bf = buf[fr][1];
+    if (valid && k >= 1) {
+        const float* xt = spec + n * kSpecFrame;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int kk = j + 64 * r;
+            float2 xk = make_float2(xt[2 * kk], xt[2 * kk + 1]);
+            float2 xc = make_float2(xt[2 * (256 - kk)], -xt[2 * (256 - kk) + 1]);
+            if (kk == 0) { xk.y = 0.f; xc.y = 0.f; }
+            const float2 w = tb.tw512[kk];
+            const float dx = xk.x - xc.x, dy = xk.y - xc.y;
+            const float a = w.x * dx + w.y * dy, bq = w.x * dy - w.y * dx;
+            A[kk] = make_float2(0.5f * (xk.x + xc.x) - 0.5f * bq, -(0.5f * (xk.y + xc.y) + 0.5f * a));
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) A[j + 64 * r] = make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    fft256(A, Bf, tb.tw256, j);
+    if (!valid) return;
+    float* o = hop_out + n * 256;
+    if (k == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) o[j + 64 * r] = 0.f;
+        return;
+    }
+    float* tail = stream_base(state, n) + kOla;
+    // time-domain samples 2m, 2m+1 of the frame = (Re z[m], -Im z[m]) / 256, windowed.  m = j + 64 r: the thread that
+    // consumes tail[2m] (r = 0,1) is the same thread that rewrites it from sample m + 128 (r = 2,3) -> no barrier needed.
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int m = j + 64 * r;
+        const float2 z = A[m];
+        const float v0 = tb.win[2 * m] * (z.x * (1.0f / 256.0f)), v1 = tb.win[2 * m + 1] * (-z.y * (1.0f / 256.0f));
+        if (m < 128) {                                        // first half: completes output hop k-2
+            const float2 t2 = *reinterpret_cast<const float2*>(tail + 2 * m);
+            const float2 res = (k >= 2) ? make_float2((t2.x + v0) * inv_env[2 * m], (t2.y + v1) * inv_env[2 * m + 1]) : make_float2(0.f, 0.f);
+            *reinterpret_cast<float2*>(o + 2 * m) = res;
+        } else {                                              // second half: new overlap-add tail
+            *reinterpret_cast<float2*>(tail + 2 * (m - 128)) = make_float2(v0, v1);
+        }
+    }
+}
+
+__global__ void ks_advance(void* state, int wav_mode) {
+    Header* hdr = reinterpret_cast<Header*>(state);
+    if (!hdr->skip) hdr->frame_step += 1;
+    if (wav_mode) hdr->wav_calls += 1;
+    hdr->skip = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// import / export of the model caches in the reference's tensor layout (gtcrn_micro_stream.py:618-623)
+//   conv_cache [2][N][16][6][33], tra_cache [2][3][N][8][2], tcn_cache[g][k] [N][16][2d][33]
+// export: j-th oldest entry of a depth-R cache = ring slot (step + j) mod R.  import: step := 0, slot j := entry j.
+// ------------------------------------------------------------------------------------------------
+struct TcnPtrs { float* p[8]; };
+
+__global__ void __launch_bounds__(256) ks_convert(int import, void* state, int64_t N, float* conv_cache, float* tra_cache, TcnPtrs tcn) {
+    Header* hdr = reinterpret_cast<Header*>(state);
+    const long long step = import ? 0 : hdr->frame_step;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * kModelFloats) return;
+    const int64_t n = idx / kModelFloats;
+    const int e = (int)(idx - n * kModelFloats);
+    float* mine = stream_base(state, n) + e;
+    float* theirs;
+    if (e < kTraE) {                                          // GT_P [blk][slot][f][c]
+        const int blk = e / (2 * kF2 * 16), r = e - blk * (2 * kF2 * 16);
+        const int slot = r / (kF2 * 16), f = (r / 16) % kF2, c = r & 15;
+        const int j = (int)((slot - step) & 1);               // age index (0 = oldest) of this ring slot
+        const int half = blk / 3, i = blk % 3;
+        const int fr = (half == 0 ? 2 * i : 4 - 2 * i) + j;   // decoder blocks use the slices in reverse (de0 -> [4:6])
+        theirs = conv_cache + ((((int64_t)half * N + n) * 16 + c) * 6 + fr) * kF2 + f;
+    } else if (e < kTcnY) {                                   // TRA_E [blk][slot][c]
+        const int r = e - kTraE, blk = r / 16, slot = (r >> 3) & 1, c = r & 7;
+        const int j = (int)((slot - step) & 1);
+        const int half = blk / 3, i = blk % 3;
+        theirs = tra_cache + ((((int64_t)half * 3 + i) * N + n) * 8 + c) * 2 + j;
+    } else {                                                  // TCN_Y [g][30 rows][f][c]
+        const int r = e - kTcnY, g = r / (30 * kF2 * 16), rr = r - g * (30 * kF2 * 16);
+        const int row = rr / (kF2 * 16), f = (rr / 16) % kF2, c = rr & 15;
+        const int k = row < 2 ? 0 : row < 6 ? 1 : row < 14 ? 2 : 3;
+        const int d = 1 << k, slot = row - ((2 << k) - 2);
+        const int j = (int)((slot - step) & (2 * d - 1));
+        theirs = tcn.p[g * 4 + k] + (((int64_t)n * 16 + c) * (2 * d) + j) * kF2 + f;
+    }
+    if (import) *mine = *theirs; else *theirs = *mine;
+    if (import && idx == 0) { hdr->frame_step = 0; hdr->skip = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------
+inline int stream_init_attributes() {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(ks_gtconv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg_smem_floats<false>() * (int)sizeof(float));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(ks_gtconv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg_smem_floats<true>() * (int)sizeof(float));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(ks_gtcn, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_FLOATS * (int)sizeof(float));
+    return (int)e;
+}
+
+// model step on spectra already in `spec` ([N][257][2] contiguous); returns the number of launches
+inline int model_step(const float* blobp, void* state, const Ws& ws, const float* spec, float* out, int64_t N, cudaStream_t st) {
+    using namespace gk;
+    int launches = 0;
+    const unsigned gfr = (unsigned)((N + FR_NF - 1) / FR_NF);
+    // T = 1: strides {b: 514, f: 2, t: 0, c: 1}.  k_front / k_back do not know about `skip`; on the skipped call
+    // (first wav hop) they run on a zero spectrum and their outputs are simply never consumed.
+    k_front<<<gfr, FR_THREADS, FR_SMEM_FLOATS * sizeof(float), st>>>(spec, kSpecFrame, 2, 0, 1, 1, N, blobp, ws.en0, ws.act[0]);
+    ++launches;
+    const unsigned gsg = (unsigned)((N + SG_NS - 1) / SG_NS);
+    for (int i = 0; i < 3; ++i) {
+        ks_gtconv<false><<<gsg, SG_THREADS, sg_smem_floats<false>() * sizeof(float), st>>>(
+            ws.act[i], nullptr, ws.act[i + 1], blobp + blob::ENCGT_OFF + i * blob::ENCGT_SIZE, state, i, N);
+        ++launches;
+    }
+    ks_gtcn<<<(unsigned)((N * kF2 + 2 * ST_THREADS - 1) / (2 * ST_THREADS)), ST_THREADS, ST_SMEM_FLOATS * sizeof(float), st>>>(
+        ws.act[3], ws.act[5], blobp + blob::TCN_OFF, state, N);
+    ++launches;
+    for (int i = 0; i < 3; ++i) {
+        ks_gtconv<true><<<gsg, SG_THREADS, sg_smem_floats<true>() * sizeof(float), st>>>(
+            ws.act[5 + i], ws.act[3 - i], ws.act[6 + i], blobp + blob::DECGT_OFF + i * blob::DECGT_SIZE, state, 3 + i, N);
+        ++launches;
+    }
+    k_back<<<gfr, BK_THREADS, BK_SMEM_FLOATS * sizeof(float), st>>>(ws.act[8], ws.act[0], ws.en0, spec, kSpecFrame, 2, 0, 1,
+                                                                    out, kSpecFrame, 2, 0, 1, 1, N, blobp);
+    ++launches;
+    return launches;
+}
+
+inline int step_spec(const float* blobp, void* state, const Ws& ws, const float* spec, float* out, int64_t N, cudaStream_t st) {
+    int launches = model_step(blobp, state, ws, spec, out, N, st);
+    ks_advance<<<1, 1, 0, st>>>(state, 0);
+    return launches + 1;
+}
+
+inline int step_wav(const float* blobp, void* state, const Ws& ws, const float* hop_in, float* hop_out, int64_t N, cudaStream_t st) {
+    const unsigned g4 = (unsigned)((N + 3) / 4);
+    ks_stft_step<<<g4, 256, 0, st>>>(state, hop_in, blobp, ws.spec_in, N);
+    int launches = 1 + model_step(blobp, state, ws, ws.spec_in, ws.spec_out, N, st);
+    ks_istft_step<<<g4, 256, 0, st>>>(state, ws.spec_out, blobp, hop_out, N);
+    ks_advance<<<1, 1, 0, st>>>(state, 1);
+    return launches + 2;
+}
+
+inline int convert_caches(bool import, void* state, int64_t N, float* conv_cache, float* tra_cache, float* const* tcn, cudaStream_t st) {
+    TcnPtrs tp;
+    for (int i = 0; i < 8; ++i) tp.p[i] = tcn[i];
+    const int64_t total = N * kModelFloats;
+    ks_convert<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(import ? 1 : 0, state, N, conv_cache, tra_cache, tp);
+    return 1;
+}
+
+}  // namespace gs

@@ -1,0 +1,415 @@
+"""nn.Module surface of the B200 path: same constructors, `forward` contracts and `state_dict` keys as
+the reference, every computation delegated to libgtcrn_b200.so (hand-written sm_100a kernels).
+
+  GTCRNMicro              gtcrn_micro/models/gtcrn_micro.py:485-532
+  StreamGTCRNMicro        gtcrn_micro/streaming/gtcrn_micro_stream.py:521-574
+  convert_to_stream       gtcrn_micro/streaming/conversion/convert.py:7-56
+  enhance / enhance_host  the STFT -> model -> iSTFT core of gtcrn_micro/infer.py:60-76 (batched)
+
+The modules hold parameters/buffers only (no nn.Conv2d etc.): a checkpoint is loaded with the usual
+`model.load_state_dict(torch.load(path)["model"])`, packed on the host (pack.py) and handed to the
+library.  Inference only (no autograd).  No CPU or PyTorch fallback exists: tensors must live on a
+CUDA device of compute capability 10.x and the shared library must have been built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import lib as _lib
+from . import pack as _pack
+from .erb import erb_filter_bank
+
+_BN = ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")
+TCN_DILATIONS = (1, 2, 4, 8)
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter tree: (key, shape, kind)   kind: "w" conv-like weight, "b" bias, "bn_*", "prelu", "erb", "erbT"
+# ------------------------------------------------------------------------------------------------
+def _bn(prefix: str, n: int):
+    return [(f"{prefix}.weight", (n,), "bn_w"), (f"{prefix}.bias", (n,), "bn_b"), (f"{prefix}.running_mean", (n,), "bn_m"),
+            (f"{prefix}.running_var", (n,), "bn_v"), (f"{prefix}.num_batches_tracked", (), "bn_n")]
+
+
+def _conv_block(p: str, cin: int, cout: int, deconv: bool, last: bool):
+    wshape = (cin, cout, 1, 5) if deconv else (cout, cin, 1, 5)
+    out = [(f"{p}.conv.weight", wshape, "w"), (f"{p}.conv.bias", (cout,), "b")] + _bn(f"{p}.bn", cout)
+    if not last:
+        out.append((f"{p}.act.weight", (1,), "prelu"))
+    return out
+
+
+def _gt_block(p: str, deconv: bool, stream: bool):
+    infix = (".ConvTranspose2d" if deconv else ".Conv2d") if stream else ""
+    # the streaming twin stores the decoder 3x3 as a flipped Conv2d weight [out,in,kt,kf]; same shape (16,16,3,3)
+    out = [(f"{p}.point_conv1.weight", (8, 16, 1, 1) if deconv else (16, 8, 1, 1), "w"), (f"{p}.point_conv1.bias", (16,), "b")]
+    out += _bn(f"{p}.point_bn1", 16) + [(f"{p}.point_act.weight", (1,), "prelu")]
+    out += [(f"{p}.depth_conv{infix}.weight", (16, 16, 3, 3) if deconv else (16, 1, 3, 3), "w"), (f"{p}.depth_conv{infix}.bias", (16,), "b")]
+    out += _bn(f"{p}.depth_bn", 16) + [(f"{p}.depth_act.weight", (1,), "prelu")]
+    out += [(f"{p}.point_conv2.weight", (16, 8, 1, 1) if deconv else (8, 16, 1, 1), "w"), (f"{p}.point_conv2.bias", (8,), "b")]
+    out += _bn(f"{p}.point_bn2", 8)
+    out += [(f"{p}.tra.depth_conv.weight", (8, 1, 3), "w"), (f"{p}.tra.depth_conv.bias", (8,), "b"),
+            (f"{p}.tra.point_conv.weight", (8, 8, 1), "w"), (f"{p}.tra.point_conv.bias", (8,), "b")]
+    return out
+
+
+def _tcn(p: str, stream: bool):
+    infix = ".Conv2d" if stream else ""
+    out = [(f"{p}.conv1.weight", (16, 16, 1, 1), "w"), (f"{p}.conv1.bias", (16,), "b")] + _bn(f"{p}.bn1", 16) + [(f"{p}.act1.weight", (1,), "prelu")]
+    out += [(f"{p}.conv2{infix}.weight", (16, 1, 3, 1), "w"), (f"{p}.conv2{infix}.bias", (16,), "b")] + _bn(f"{p}.bn2", 16) + [(f"{p}.act2.weight", (1,), "prelu")]
+    out += [(f"{p}.conv3.weight", (16, 16, 1, 1), "w"), (f"{p}.conv3.bias", (16,), "b")] + _bn(f"{p}.bn3", 16) + [(f"{p}.act3.weight", (1,), "prelu")]
+    return out
+
+
+def param_spec(stream: bool):
+    spec = [("erb.erb_fc.weight", (64, 192), "erb"), ("erb.ierb_fc.weight", (192, 64), "erbT"),
+            ("sfe.depth_conv.weight", (3, 1, 1, 3), "w")]
+    spec += _conv_block("encoder.en_convs.0", 3, 16, False, False) + _conv_block("encoder.en_convs.1", 16, 16, False, False)
+    for i in (2, 3, 4):
+        spec += _gt_block(f"encoder.en_convs.{i}", False, stream)
+    for g in (1, 2):
+        for k in range(4):
+            spec += _tcn(f"gtcn{g}.blocks.{k}", stream)
+    for i in (0, 1, 2):
+        spec += _gt_block(f"decoder.de_convs.{i}", True, stream)
+    spec += _conv_block("decoder.de_convs.3", 16, 16, True, False) + _conv_block("decoder.de_convs.4", 16, 2, True, True)
+    return spec
+
+
+class _Node(nn.Module):
+    """Pure container: gives parameters their dotted reference names."""
+
+
+def _attach(root: nn.Module, key: str, tensor: torch.Tensor, kind: str) -> None:
+    parts = key.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, _Node())
+        mod = mod._modules[p]
+    if kind.startswith("bn_m") or kind.startswith("bn_v") or kind == "bn_n":
+        mod.register_buffer(parts[-1], tensor)
+    else:
+        mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+def _init_tensor(shape, kind: str, gen: torch.Generator) -> torch.Tensor:
+    if kind == "erb":
+        return torch.from_numpy(erb_filter_bank())
+    if kind == "erbT":
+        return torch.from_numpy(np.ascontiguousarray(erb_filter_bank().T))
+    if kind == "bn_w" or kind == "bn_v":
+        return torch.ones(shape)
+    if kind == "bn_b" or kind == "bn_m":
+        return torch.zeros(shape)
+    if kind == "bn_n":
+        return torch.zeros((), dtype=torch.long)
+    if kind == "prelu":
+        return torch.full(shape, 0.25)
+    fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else int(shape[0])
+    bound = 1.0 / np.sqrt(max(1, fan_in))
+    return (torch.rand(shape, generator=gen) * 2 - 1) * bound
+
+
+# ------------------------------------------------------------------------------------------------
+class _B200Module(nn.Module):
+    _stream = False
+
+    def __init__(self, n_fft: int = 512, hop_len: int = 256, win_len: int = 512):
+        # like the reference constructor (gtcrn_micro.py:486-504) the three arguments are accepted for
+        # config compatibility; the architecture is fixed at n_fft 512 / hop 256.
+        super().__init__()
+        gen = torch.Generator().manual_seed(torch.initial_seed() % (2 ** 31))
+        for key, shape, kind in param_spec(self._stream):
+            _attach(self, key, _init_tensor(shape, kind, gen), kind)
+        self._handle = C.c_void_p(None)
+        self._handle_key = None
+        self.eval()
+
+    # -- native handle management --------------------------------------------------------------
+    def _weights_key(self):
+        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+
+    def _ensure_handle(self, device: torch.device) -> C.c_void_p:
+        if device.type != "cuda":
+            raise _lib.GtcrnB200Error("gtcrn_micro_b200 has no CPU path: tensors must be on a CUDA (sm_100a) device")
+        key = (device.index if device.index is not None else torch.cuda.current_device(), self._weights_key())
+        if self._handle.value is not None and key == self._handle_key:
+            return self._handle
+        L = _lib.load()
+        self._release()
+        blob = _pack.pack_state_dict(self.state_dict())
+        with torch.cuda.device(device):
+            h = C.c_void_p(None)
+            _lib.check(L.gtcrnb_create(blob.ctypes.data_as(C.c_void_p), blob.size, C.byref(h)), "gtcrnb_create")
+        self._handle, self._handle_key = h, key
+        return h
+
+    def _release(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value is not None:
+            try:
+                _lib.load().gtcrnb_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = C.c_void_p(None)
+            self._handle_key = None
+
+    def __del__(self):
+        self._release()
+
+    def profile(self, on: bool) -> None:
+        """Bracket every kernel launch of this model with CUDA events (see `profile_read`)."""
+        if self._handle.value is None:
+            raise _lib.GtcrnB200Error("run the model once before enabling profiling")
+        _lib.check(_lib.load().gtcrnb_profile_enable(self._handle, int(on)), "gtcrnb_profile_enable")
+
+    def profile_read(self, reset: bool = True) -> dict:
+        """{kernel class: {"ms": total device ms, "launches": n, "frames": frames processed}}"""
+        L = _lib.load()
+        n = L.gtcrnb_profile_num_classes()
+        ms, ln, fr = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_int64 * n)()
+        _lib.check(L.gtcrnb_profile_read(self._handle, int(reset), ms, ln, fr), "gtcrnb_profile_read")
+        return {L.gtcrnb_profile_class_name(i).decode(): {"ms": ms[i], "launches": ln[i], "frames": fr[i]} for i in range(n)}
+
+    def launch_count(self) -> int:
+        return int(_lib.load().gtcrnb_launch_count(self._handle)) if self._handle.value is not None else 0
+
+    @staticmethod
+    def _check_spec(spec: torch.Tensor, T: Optional[int] = None):
+        if spec.dim() != 4 or spec.shape[1] != 257 or spec.shape[3] != 2:
+            raise ValueError(f"spec must be [B,257,T,2], got {tuple(spec.shape)}")
+        if spec.dtype != torch.float32:
+            raise TypeError("spec must be float32")
+        if T is not None and spec.shape[2] != T:
+            raise ValueError(f"streaming forward takes T = {T} frame per call, got {spec.shape[2]}")
+
+
+class GTCRNMicro(_B200Module):
+    """Drop-in for the reference `GTCRNMicro` (offline, whole utterance)."""
+
+    @torch.no_grad()
+    def forward(self, spec: torch.Tensor) -> torch.Tensor:
+        """spec [B,257,T,2] float32 CUDA (any strides, e.g. torch.stft output) -> enhanced spec [B,257,T,2]
+        (a permuted view of a [B,T,257,2] buffer, like the reference returns a permuted view)."""
+        self._check_spec(spec)
+        h = self._ensure_handle(spec.device)
+        B, _, T, _ = spec.shape
+        out = torch.empty((B, T, 257, 2), dtype=torch.float32, device=spec.device).permute(0, 2, 1, 3)
+        L = _lib.load()
+        with torch.cuda.device(spec.device):
+            _lib.check(L.gtcrnb_forward_spec(h, spec.data_ptr(), _lib.strides4(spec.stride()), B, T, out.data_ptr(),
+                                             _lib.strides4(out.stride()), torch.cuda.current_stream().cuda_stream),
+                       "gtcrnb_forward_spec")
+        return out
+
+    @torch.no_grad()
+    def enhance(self, wav: torch.Tensor) -> torch.Tensor:
+        """wav [B,L] (or [L]) float32 CUDA -> enhanced wav [B, 256*(L//256)]: fused STFT -> model -> iSTFT."""
+        squeeze = wav.dim() == 1
+        if squeeze:
+            wav = wav[None]
+        if wav.dim() != 2 or wav.dtype != torch.float32:
+            raise ValueError("wav must be float32 [B,L]")
+        if wav.stride(1) != 1:
+            wav = wav.contiguous()
+        h = self._ensure_handle(wav.device)
+        B, Ls = wav.shape
+        out = torch.empty((B, 256 * (Ls // 256)), dtype=torch.float32, device=wav.device)
+        L = _lib.load()
+        with torch.cuda.device(wav.device):
+            _lib.check(L.gtcrnb_enhance(h, wav.data_ptr(), B, Ls, wav.stride(0), out.data_ptr(), out.stride(0),
+                                        torch.cuda.current_stream().cuda_stream), "gtcrnb_enhance")
+        return out[0] if squeeze else out
+
+    @torch.no_grad()
+    def enhance_host(self, wav: torch.Tensor, out: Optional[torch.Tensor] = None, device: Optional[torch.device] = None) -> torch.Tensor:
+        """Same as `enhance` for HOST tensors (ideally pinned): chunked H2D / compute / D2H pipeline inside the library."""
+        if wav.is_cuda or wav.dim() != 2 or wav.dtype != torch.float32 or not wav.is_contiguous():
+            raise ValueError("wav must be a contiguous float32 CPU tensor [B,L]")
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        h = self._ensure_handle(dev)
+        B, Ls = wav.shape
+        if out is None:
+            out = torch.empty((B, 256 * (Ls // 256)), dtype=torch.float32, pin_memory=True)
+        L = _lib.load()
+        with torch.cuda.device(dev):
+            _lib.check(L.gtcrnb_enhance_host(h, wav.data_ptr(), B, Ls, out.data_ptr()), "gtcrnb_enhance_host")
+        return out
+
+    @torch.no_grad()
+    def stft(self, wav: torch.Tensor) -> torch.Tensor:
+        """torch.stft(wav,512,256,512,sqrt-hann,return_complex=False) replacement: [B,L] -> [B,257,T,2] (view)."""
+        h = self._ensure_handle(wav.device)
+        wav = wav if wav.stride(1) == 1 else wav.contiguous()
+        B, Ls = wav.shape
+        T = 1 + Ls // 256
+        spec = torch.empty((B, T, 257, 2), dtype=torch.float32, device=wav.device)
+        with torch.cuda.device(wav.device):
+            _lib.check(_lib.load().gtcrnb_stft(h, wav.data_ptr(), B, Ls, wav.stride(0), spec.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream), "gtcrnb_stft")
+        return spec.permute(0, 2, 1, 3)
+
+    @torch.no_grad()
+    def istft(self, spec: torch.Tensor) -> torch.Tensor:
+        """torch.istft replacement: spec [B,257,T,2] -> wav [B, 256*(T-1)]."""
+        self._check_spec(spec)
+        h = self._ensure_handle(spec.device)
+        s = spec.permute(0, 2, 1, 3).contiguous()      # [B,T,257,2]
+        B, T = s.shape[0], s.shape[1]
+        wav = torch.empty((B, 256 * (T - 1)), dtype=torch.float32, device=spec.device)
+        with torch.cuda.device(spec.device):
+            _lib.check(_lib.load().gtcrnb_istft(h, s.data_ptr(), B, T, wav.data_ptr(), wav.stride(0),
+                                                torch.cuda.current_stream().cuda_stream), "gtcrnb_istft")
+        return wav
+
+    @torch.no_grad()
+    def debug_activation(self, name: str, B: int, T: int) -> torch.Tensor:
+        """Intermediate activation of the last forward/enhance call, [B,T,F,16] channel-last (tests only)."""
+        Fq = 65 if name == "en0" else 33
+        dev = torch.device("cuda", self._handle_key[0])
+        out = torch.empty((B, T, Fq, 16), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().gtcrnb_debug_activation(self._handle, name.encode(), out.data_ptr(), out.numel(),
+                                                           torch.cuda.current_stream().cuda_stream), "gtcrnb_debug_activation")
+        return out
+
+
+class StreamState:
+    """Opaque per-batch streaming state living in one device buffer (conv / TRA / TCN ring buffers of N
+    streams plus the STFT / overlap-add tails used by `step_wav`)."""
+
+    def __init__(self, n_streams: int, device: torch.device):
+        self.n = int(n_streams)
+        nbytes = int(_lib.load().gtcrnb_stream_state_bytes(self.n))
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr()
+
+
+class StreamGTCRNMicro(_B200Module):
+    """Drop-in for the reference `StreamGTCRNMicro` plus a native state API for many concurrent streams."""
+    _stream = True
+
+    # ---- reference-compatible call (cache tensors in the reference's own layout) -------------------
+    @torch.no_grad()
+    def forward(self, spec: torch.Tensor, conv_cache: torch.Tensor, tra_cache: torch.Tensor, tcn_cache: List[List[torch.Tensor]]):
+        """spec [B,257,1,2]; conv_cache [2,B,16,6,33]; tra_cache [2,3,B,8,2]; tcn_cache[2][4] of [B,16,2d,33].
+        Returns (spec_enh [B,257,1,2], conv_cache, tra_cache, tcn_cache) with the caches advanced by one frame."""
+        self._check_spec(spec, T=1)
+        B = spec.shape[0]
+        assert tuple(conv_cache.shape) == (2, B, 16, 6, 33), conv_cache.shape
+        assert tuple(tra_cache.shape) == (2, 3, B, 8, 2), tra_cache.shape
+        for g in range(2):
+            for k, d in enumerate(TCN_DILATIONS):
+                assert tuple(tcn_cache[g][k].shape) == (B, 16, 2 * d, 33), tcn_cache[g][k].shape
+        h = self._ensure_handle(spec.device)
+        L = _lib.load()
+        st = StreamState(B, spec.device)
+        cc, tc = conv_cache.contiguous(), tra_cache.contiguous()
+        nc = [[tcn_cache[g][k].contiguous() for k in range(4)] for g in range(2)]
+        ptrs = (C.c_void_p * 8)(*[nc[g][k].data_ptr() for g in range(2) for k in range(4)])
+        frame = spec[:, :, 0, :].contiguous()
+        out = torch.empty_like(frame)
+        with torch.cuda.device(spec.device):
+            s = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.gtcrnb_stream_import_caches(h, st.ptr, B, cc.data_ptr(), tc.data_ptr(), ptrs, s), "gtcrnb_stream_import_caches")
+            _lib.check(L.gtcrnb_stream_step_spec(h, st.ptr, frame.data_ptr(), out.data_ptr(), B, s), "gtcrnb_stream_step_spec")
+            _lib.check(L.gtcrnb_stream_export_caches(h, st.ptr, B, cc.data_ptr(), tc.data_ptr(), ptrs, s), "gtcrnb_stream_export_caches")
+        if cc.data_ptr() != conv_cache.data_ptr():
+            conv_cache.copy_(cc)
+        if tc.data_ptr() != tra_cache.data_ptr():
+            tra_cache.copy_(tc)
+        new_tcn = [[nc[g][k] for k in range(4)] for g in range(2)]
+        return out[:, :, None, :], conv_cache, tra_cache, new_tcn
+
+    # ---- native API: state stays on the device as ring buffers ------------------------------------
+    def new_state(self, n_streams: int, device=None) -> StreamState:
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._ensure_handle(dev)
+        return StreamState(n_streams, dev)
+
+    @torch.no_grad()
+    def reset(self, state: StreamState) -> None:
+        h = self._ensure_handle(state.buf.device)
+        with torch.cuda.device(state.buf.device):
+            _lib.check(_lib.load().gtcrnb_stream_reset(h, state.ptr, state.n, torch.cuda.current_stream().cuda_stream), "gtcrnb_stream_reset")
+
+    @torch.no_grad()
+    def step(self, frame: torch.Tensor, state: StreamState, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One 16 ms hop on spectra: frame [N,257,2] contiguous -> enhanced [N,257,2]."""
+        if tuple(frame.shape) != (state.n, 257, 2) or frame.dtype != torch.float32 or not frame.is_contiguous():
+            raise ValueError(f"frame must be contiguous float32 [{state.n},257,2]")
+        h = self._ensure_handle(frame.device)
+        if out is None:
+            out = torch.empty_like(frame)
+        with torch.cuda.device(frame.device):
+            _lib.check(_lib.load().gtcrnb_stream_step_spec(h, state.ptr, frame.data_ptr(), out.data_ptr(), state.n,
+                                                           torch.cuda.current_stream().cuda_stream), "gtcrnb_stream_step_spec")
+        return out
+
+    @torch.no_grad()
+    def step_wav(self, hop: torch.Tensor, state: StreamState, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One hop on waveforms: hop [N,256] new samples -> [N,256] enhanced samples delayed by 2 hops (512 samples)."""
+        if tuple(hop.shape) != (state.n, 256) or hop.dtype != torch.float32 or not hop.is_contiguous():
+            raise ValueError(f"hop must be contiguous float32 [{state.n},256]")
+        h = self._ensure_handle(hop.device)
+        if out is None:
+            out = torch.empty_like(hop)
+        with torch.cuda.device(hop.device):
+            _lib.check(_lib.load().gtcrnb_stream_step_wav(h, state.ptr, hop.data_ptr(), out.data_ptr(), state.n,
+                                                          torch.cuda.current_stream().cuda_stream), "gtcrnb_stream_step_wav")
+        return out
+
+
+def convert_to_stream(stream_model: nn.Module, model: nn.Module) -> None:
+    """Copy offline weights into the streaming twin (same contract as convert.py:7-56, including the
+    ConvTranspose2d weight re-layout and `ValueError("Key error!")` for unknown keys)."""
+    src = model.state_dict()
+    dst = stream_model.state_dict()
+    for key in list(dst.keys()):
+        if key in src:
+            dst[key] = src[key]
+            continue
+        for infix in ("Conv1d.", "Conv2d.", ".deconv"):
+            k2 = key.replace(infix, "")
+            if k2 != key and k2 in src:
+                dst[key] = src[k2]
+                break
+        else:
+            k2 = key.replace("ConvTranspose2d.", "")
+            if k2 == key or k2 not in src:
+                raise ValueError("Key error!")
+            if key.endswith("weight"):
+                w = torch.flip(src[k2].permute(1, 0, 2, 3).contiguous(), dims=[-2, -1])
+                assert w.shape == dst[key].shape, (w.shape, dst[key].shape)
+                dst[key] = w
+            else:
+                dst[key] = src[k2]
+    stream_model.load_state_dict(dst)
+
+
+def load_checkpoint(path: str, stream: bool = False, map_location="cpu") -> nn.Module:
+    """Build a model from a reference training checkpoint `{"epoch","optimizer","scheduler","model"}`
+    (train.py:206-211); also tolerates a bare state_dict, `state_dict`/`model_state_dict` keys and a DDP
+    `module.` prefix like the reference's export scripts (stream_onnx.py:38-47)."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    sd = ckpt
+    for k in ("model", "state_dict", "model_state_dict"):
+        if isinstance(ckpt, dict) and k in ckpt and isinstance(ckpt[k], dict):
+            sd = ckpt[k]
+            break
+    sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in sd.items()}
+    model = GTCRNMicro()
+    model.load_state_dict(sd)
+    if not stream:
+        return model
+    smodel = StreamGTCRNMicro()
+    convert_to_stream(smodel, model)
+    return smodel

@@ -1,0 +1,124 @@
+"""Parity of the CUDA streaming path (frame by frame, ring-buffer state) through the C ABI.
+
+Anchors: the reference's whole-model stream-vs-offline comparison (gtcrn_micro_stream.py:577-657, printed there,
+asserted here), its cache layout (:618-623) and the golden reference streaming outputs in tests/golden.
+"""
+import numpy as np
+import pytest
+import torch
+
+import gtcrn_micro_b200 as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+REL_TOL = 1e-4
+WAV_TOL = 1e-4
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu(); b = b.detach().double().cpu()
+    return float((a - b).abs().max() / max(1.0, float(b.abs().max())))
+
+
+def models(W):
+    m = G.GTCRNMicro(); m.load_state_dict(W)
+    s = G.StreamGTCRNMicro(); G.convert_to_stream(s, m)
+    return m, s
+
+
+def run_stream(smodel, spec):
+    """spec [B,257,T,2] on DEV -> [B,257,T,2] via the native state API"""
+    B, _, T, _ = spec.shape
+    st = smodel.new_state(B, DEV)
+    frames = spec.permute(2, 0, 1, 3).contiguous()
+    outs = [smodel.step(frames[t], st) for t in range(T)]
+    return torch.stack(outs, dim=2)
+
+
+def test_stream_equals_offline_and_reference(oracle, weights, ref_outputs, b200_lib):
+    tag, W = weights
+    m, s = models(W)
+    spec = torch.from_numpy(ref_outputs["spec"]).to(DEV)                    # [2,257,41,2]
+    ys = run_stream(s, spec)
+    y_off = m(spec)
+    bitwise = bool(torch.equal(ys, y_off.contiguous()))
+    e_off = rel_err(ys, y_off)
+    e_ref = rel_err(ys, torch.from_numpy(ref_outputs[f"{tag}.stream_spec_out"]))
+    with torch.inference_mode():
+        e_or = rel_err(ys, oracle.forward_spec(W, spec.cpu()))
+    print(f"[{tag}] stream vs own offline {e_off:.2e} (bitwise {bitwise}); vs reference stream {e_ref:.2e}; vs oracle offline {e_or:.2e}")
+    assert e_off <= 1e-5 and e_ref <= REL_TOL and e_or <= REL_TOL
+    assert s.launch_count() == 41 * 10
+
+
+def test_reference_cache_api(oracle, weights, ref_outputs, b200_lib):
+    # drive StreamGTCRNMicro.forward exactly like the reference loop (gtcrn_micro_stream.py:618-636)
+    tag, W = weights
+    _, s = models(W)
+    spec = torch.from_numpy(ref_outputs["spec"]).to(DEV)
+    B = spec.shape[0]
+    conv_cache = torch.zeros(2, B, 16, 6, 33, device=DEV)
+    tra_cache = torch.zeros(2, 3, B, 8, 2, device=DEV)
+    tcn_cache = [[torch.zeros(B, 16, 2 * d, 33, device=DEV) for d in (1, 2, 4, 8)] for _ in range(2)]
+    ys = []
+    for t in range(25):
+        yi, conv_cache, tra_cache, tcn_cache = s(spec[:, :, t:t + 1], conv_cache, tra_cache, tcn_cache)
+        assert yi.shape == (B, 257, 1, 2)
+        ys.append(yi)
+        if t == 20:
+            assert rel_err(conv_cache, torch.from_numpy(ref_outputs[f"{tag}.conv_cache20"])) <= REL_TOL
+            assert rel_err(tra_cache, torch.from_numpy(ref_outputs[f"{tag}.tra_cache20"])) <= REL_TOL
+            for g in range(2):
+                for k in range(4):
+                    assert rel_err(tcn_cache[g][k], torch.from_numpy(ref_outputs[f"{tag}.tcn_cache20.{g}.{k}"])) <= REL_TOL, (g, k)
+    ys = torch.cat(ys, dim=2)
+    assert rel_err(ys, torch.from_numpy(ref_outputs[f"{tag}.stream_spec_out"][:, :, :25])) <= REL_TOL
+    with pytest.raises(ValueError):
+        s(spec[:, :, :2], conv_cache, tra_cache, tcn_cache)                 # T = 1 per call, like the reference
+    with pytest.raises(AssertionError):
+        s(spec[:, :, :1], conv_cache[:, :, :, :4], tra_cache, tcn_cache)    # cache shape asserts (gtcrn_micro_stream.py:131-138)
+
+
+def test_stream_wav_equals_offline(oracle, weights_dns3, b200_lib):
+    m, s = models(weights_dns3)
+    N, hops = 5, 40
+    x = oracle.synth_batch(N, 256 * hops, seed=31).to(DEV)
+    off = m.enhance(x)                                                        # [N, 256*40]
+    st = s.new_state(N, DEV)
+    outs = [s.step_wav(x[:, 256 * k:256 * (k + 1)].contiguous(), st) for k in range(hops)]
+    y = torch.cat(outs, dim=1)
+    assert float(y[:, :512].abs().max()) == 0.0                               # two hops of latency
+    # call k emits hop k-2; the last offline hop depends on the end-of-file reflection and is never streamed
+    got, want = y[:, 512:], off[:, :256 * (hops - 2)]
+    err = float((got - want).abs().max())
+    print(f"stream wav vs offline: max-abs {err:.2e}")
+    assert err <= 1e-6
+    ref = oracle.enhance(weights_dns3, x.cpu())
+    assert float((got.cpu() - ref[:, :256 * (hops - 2)]).abs().max()) <= WAV_TOL
+    # reset -> identical replay
+    s.reset(st)
+    y2 = torch.cat([s.step_wav(x[:, 256 * k:256 * (k + 1)].contiguous(), st) for k in range(hops)], dim=1)
+    assert torch.equal(y, y2)
+
+
+def test_many_streams_independent(oracle, weights_dns3, b200_lib):
+    _, s = models(weights_dns3)
+    N, T = 1003, 20                                                           # not a multiple of any tile size
+    g = torch.Generator(device=DEV).manual_seed(5)
+    spec = torch.randn(N, 257, T, 2, device=DEV, generator=g)
+    ys = run_stream(s, spec)
+    assert bool(torch.isfinite(ys).all())
+    for i in (0, 7, 500, 1002):
+        alone = run_stream(s, spec[i:i + 1])
+        assert torch.equal(alone, ys[i:i + 1]), i
+    with torch.inference_mode():
+        ref = oracle.forward_spec(weights_dns3, spec[1000:1003].cpu())
+    assert rel_err(ys[1000:1003], ref) <= REL_TOL
+
+
+def test_long_stream_ring_wraparound(oracle, weights_dns3, b200_lib):
+    # 200 frames: every ring (depth 2..16) wraps many times
+    m, s = models(weights_dns3)
+    spec = m.stft(oracle.synth_batch(2, 256 * 199 + 3, seed=8).to(DEV))
+    ys = run_stream(s, spec)
+    assert rel_err(ys, m(spec)) <= 1e-5
