@@ -227,9 +227,13 @@ int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) 
         {(const void*)k_gtconv<true>, gt_smem_floats<true>()},
         {(const void*)k_gtcn, TC_SMEM_FLOATS},
         {(const void*)k_back, BK_SMEM_FLOATS},
+        {(const void*)k_stft, 0},
+        {(const void*)k_istft, 0},
     };
     for (auto& a : attrs) {
         cudaError_t e = cudaFuncSetAttribute(a.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, a.floats * (int)sizeof(float));
+        // without this the driver picks the smallest carveout that fits ONE CTA and occupancy collapses (ncu: occ_smem = 1)
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(a.fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { gtcrnb_destroy(h); return fail(GTCRNB_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); }
     }
     int e2 = gs::stream_init_attributes();

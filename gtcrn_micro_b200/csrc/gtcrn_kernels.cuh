@@ -392,7 +392,7 @@ template <bool DEC> __host__ __device__ constexpr int gt_smem_floats() {
 }
 
 template <bool DEC>
-__global__ void __launch_bounds__(GT_THREADS) k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip,
+__global__ void __launch_bounds__(GT_THREADS, 3) k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip,
                                                        float* __restrict__ out, const float* __restrict__ wblk,
                                                        int T, int seg_len) {
     constexpr int PC1_W = DEC ? blob::DECGT_PC1_W : blob::ENCGT_PC1_W;
@@ -594,7 +594,7 @@ constexpr int TC_ROW4 = 4 * 12;                 // float4 per row: [q][col (11, 
 constexpr int TC_WARMUP = 30;
 constexpr int TC_SMEM_FLOATS = 4 * blob::TCN_SIZE + (TC_HIST + TC_NT) * TC_ROW4 * 4 + 30 * TC_ROW4 * 4;
 
-__global__ void __launch_bounds__(TC_THREADS) k_gtcn(const float* __restrict__ xin, float* __restrict__ out,
+__global__ void __launch_bounds__(TC_THREADS, 2) k_gtcn(const float* __restrict__ xin, float* __restrict__ out,
                                                      const float* __restrict__ wblk, int T, int seg_len) {
     extern __shared__ float4 smem4[];
     float* W = reinterpret_cast<float*>(smem4);

@@ -540,6 +540,12 @@ __global__ void __launch_bounds__(256) ks_convert(int import, void* state, int64
 // ------------------------------------------------------------------------------------------------
 inline int stream_init_attributes() {
     cudaError_t e;
+    const void* fns[] = {(const void*)ks_gtconv<false>, (const void*)ks_gtconv<true>, (const void*)ks_gtcn,
+                         (const void*)ks_stft_step, (const void*)ks_istft_step};
+    for (const void* f : fns) {
+        e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+    }
     e = cudaFuncSetAttribute(ks_gtconv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg_smem_floats<false>() * (int)sizeof(float));
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(ks_gtconv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg_smem_floats<true>() * (int)sizeof(float));
