@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -33,7 +34,7 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr int kAbiVersion = 1;
-constexpr int64_t kMaxChunkFrames = 160 * 1024;   // activation workspace capacity (frames)
+constexpr int64_t kMaxChunkFrames = 1024 * 1024;  // activation workspace capacity (frames): 1024 x 10 s utterances fit one chunk (17.5 GB)
 constexpr int kNumAct33 = 9;                      // en1..en4, gtcn1, gtcn2, de0..de2
 const char* const kActNames[kNumAct33] = {"en1", "en2", "en3", "en4", "gtcn1", "gtcn2", "de0", "de1", "de2"};
 
@@ -46,6 +47,8 @@ struct gtcrnb_handle {
     int device = 0;
     int sm_count = 148;
     float* blob = nullptr;
+    gs::HostParams* hp = nullptr;                 // host copies of the weight chunks passed as kernel parameters
+    int gt_enc = 0, gt_dec = 0;                   // index into kGtVariants for the encoder / decoder GTConv kernels
     // activation workspace for one chunk of utterances
     int64_t cap_frames = 0;
     float* en0 = nullptr;
@@ -89,6 +92,24 @@ int ensure_workspace(gtcrnb_handle* h, int64_t frames) {
     }
     h->cap_frames = frames;
     return GTCRNB_OK;
+}
+
+// GTConv walking-kernel variants (frame slots per thread PS, slot groups per CTA G)
+struct GtVariant { int ps, g, threads, smem_bytes; const void* enc; const void* dec; };
+template <int PS, int G> GtVariant make_gt_variant() {
+    return {PS, G, gk::gt_threads(G), gk::gt_smem_floats(PS, G) * (int)sizeof(float),
+            (const void*)gk::k_gtconv<false, PS, G>, (const void*)gk::k_gtconv<true, PS, G>};
+}
+const GtVariant kGtVariants[] = {make_gt_variant<2, 8>(), make_gt_variant<3, 8>(), make_gt_variant<4, 7>()};
+constexpr int kNumGtVariants = 3;
+
+template <bool DEC>
+void launch_gtconv(const GtVariant& v, dim3 grid, cudaStream_t st, const float* x, const float* skip, float* out,
+                   const gk::ParamBlock<gk::gt_chunk<DEC>()>& prm, int T, int seg) {
+    using namespace gk;
+    if (v.ps == 2) k_gtconv<DEC, 2, 8><<<grid, v.threads, v.smem_bytes, st>>>(x, skip, out, prm, T, seg);
+    else if (v.ps == 3) k_gtconv<DEC, 3, 8><<<grid, v.threads, v.smem_bytes, st>>>(x, skip, out, prm, T, seg);
+    else k_gtconv<DEC, 4, 7><<<grid, v.threads, v.smem_bytes, st>>>(x, skip, out, prm, T, seg);
 }
 
 // RAII: brackets a kernel launch with two events when profiling is on
@@ -136,12 +157,12 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
     }
     h->launches++;
     {
-        const int seg = pick_seg_len(B, Ti, GT_NT, GT_WARMUP, h->sm_count * h->occ_gt_enc);
+        const GtVariant& v = kGtVariants[h->gt_enc];
+        const int seg = pick_seg_len(B, Ti, v.ps * v.g, GT_WARMUP, h->sm_count * h->occ_gt_enc);
         const dim3 g((unsigned)((Ti + seg - 1) / seg), (unsigned)B);
         for (int i = 0; i < 3; ++i) {
             ProfScope ps(h, KC_ENC_GT, nframes, st);
-            k_gtconv<false><<<g, GT_THREADS, gt_smem_floats<false>() * sizeof(float), st>>>(
-                h->act[i], nullptr, h->act[i + 1], h->blob + blob::ENCGT_OFF + i * blob::ENCGT_SIZE, Ti, seg);
+            launch_gtconv<false>(v, g, st, h->act[i], nullptr, h->act[i + 1], h->hp->enc[i], Ti, seg);
             h->launches++;
         }
     }
@@ -150,19 +171,18 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
         const dim3 g((unsigned)(((Ti + seg - 1) / seg) * 3), (unsigned)B);
         for (int i = 0; i < 2; ++i) {
             ProfScope ps(h, KC_GTCN, nframes, st);
-            k_gtcn<<<g, TC_THREADS, TC_SMEM_FLOATS * sizeof(float), st>>>(
-                h->act[3 + i], h->act[4 + i], h->blob + blob::TCN_OFF + i * 4 * blob::TCN_SIZE, Ti, seg);
+            k_gtcn<<<g, TC_THREADS, TC_SMEM_FLOATS * sizeof(float), st>>>(h->act[3 + i], h->act[4 + i], h->hp->gtcn[i], Ti, seg);
             h->launches++;
         }
     }
     {
-        const int seg = pick_seg_len(B, Ti, GT_NT, GT_WARMUP, h->sm_count * h->occ_gt_dec);
+        const GtVariant& v = kGtVariants[h->gt_dec];
+        const int seg = pick_seg_len(B, Ti, v.ps * v.g, GT_WARMUP, h->sm_count * h->occ_gt_dec);
         const dim3 g((unsigned)((Ti + seg - 1) / seg), (unsigned)B);
         for (int i = 0; i < 3; ++i) {
             // de_i consumes (previous + en_outs[4 - i]) : skips en4, en3, en2 = act[3], act[2], act[1]
             ProfScope ps(h, KC_DEC_GT, nframes, st);
-            k_gtconv<true><<<g, GT_THREADS, gt_smem_floats<true>() * sizeof(float), st>>>(
-                h->act[5 + i], h->act[3 - i], h->act[6 + i], h->blob + blob::DECGT_OFF + i * blob::DECGT_SIZE, Ti, seg);
+            launch_gtconv<true>(v, g, st, h->act[5 + i], h->act[3 - i], h->act[6 + i], h->hp->dec[i], Ti, seg);
             h->launches++;
         }
     }
@@ -223,8 +243,9 @@ int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) 
     using namespace gk;
     struct { const void* fn; int floats; } attrs[] = {
         {(const void*)k_front, FR_SMEM_FLOATS},
-        {(const void*)k_gtconv<false>, gt_smem_floats<false>()},
-        {(const void*)k_gtconv<true>, gt_smem_floats<true>()},
+        {kGtVariants[0].enc, kGtVariants[0].smem_bytes / 4}, {kGtVariants[0].dec, kGtVariants[0].smem_bytes / 4},
+        {kGtVariants[1].enc, kGtVariants[1].smem_bytes / 4}, {kGtVariants[1].dec, kGtVariants[1].smem_bytes / 4},
+        {kGtVariants[2].enc, kGtVariants[2].smem_bytes / 4}, {kGtVariants[2].dec, kGtVariants[2].smem_bytes / 4},
         {(const void*)k_gtcn, TC_SMEM_FLOATS},
         {(const void*)k_back, BK_SMEM_FLOATS},
         {(const void*)k_stft, 0},
@@ -238,8 +259,18 @@ int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) 
     }
     int e2 = gs::stream_init_attributes();
     if (e2 != 0) { gtcrnb_destroy(h); return fail(GTCRNB_E_CUDA, "stream kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e2)); }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_gt_enc, k_gtconv<false>, GT_THREADS, gt_smem_floats<false>() * sizeof(float));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_gt_dec, k_gtconv<true>, GT_THREADS, gt_smem_floats<true>() * sizeof(float));
+    h->hp = new gs::HostParams();
+    h->hp->load(blob_host);
+    auto pick = [](const char* env, int dflt) {
+        const char* e = getenv(env);
+        if (!e) return dflt;
+        for (int i = 0; i < kNumGtVariants; ++i) if (kGtVariants[i].ps == atoi(e)) return i;
+        return dflt;
+    };
+    h->gt_enc = pick("GTCRNB_GT_PS_ENC", 0);
+    h->gt_dec = pick("GTCRNB_GT_PS_DEC", 2);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_gt_enc, kGtVariants[h->gt_enc].enc, kGtVariants[h->gt_enc].threads, kGtVariants[h->gt_enc].smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_gt_dec, kGtVariants[h->gt_dec].dec, kGtVariants[h->gt_dec].threads, kGtVariants[h->gt_dec].smem_bytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn, TC_THREADS, TC_SMEM_FLOATS * sizeof(float));
     h->occ_gt_enc = std::max(1, h->occ_gt_enc); h->occ_gt_dec = std::max(1, h->occ_gt_dec); h->occ_tcn = std::max(1, h->occ_tcn);
     *out = h;
@@ -251,6 +282,7 @@ void gtcrnb_destroy(gtcrnb_handle* h) {
     cudaSetDevice(h->device);
     auto freep = [](float* p) { if (p) cudaFree(p); };
     freep(h->blob); freep(h->en0); freep(h->spec_in); freep(h->spec_out);
+    delete h->hp;
     for (auto p : h->act) freep(p);
     for (int i = 0; i < 2; ++i) {
         freep(h->stage_in[i]); freep(h->stage_out[i]);
@@ -449,7 +481,7 @@ int gtcrnb_stream_step_spec(gtcrnb_handle* h, void* state_dev, const float* spec
     if (N == 0) return GTCRNB_OK;
     int rc = ensure_workspace(h, N);
     if (rc) return rc;
-    h->launches += gs::step_spec(h->blob, state_dev, stream_ws(h), spec_dev, out_dev, N, (cudaStream_t)stream);
+    h->launches += gs::step_spec(h->blob, *h->hp, state_dev, stream_ws(h), spec_dev, out_dev, N, (cudaStream_t)stream);
     CU(cudaGetLastError());
     return GTCRNB_OK;
 }
@@ -459,7 +491,7 @@ int gtcrnb_stream_step_wav(gtcrnb_handle* h, void* state_dev, const float* hop_i
     if (N == 0) return GTCRNB_OK;
     int rc = ensure_workspace(h, N);
     if (rc) return rc;
-    h->launches += gs::step_wav(h->blob, state_dev, stream_ws(h), hop_in_dev, hop_out_dev, N, (cudaStream_t)stream);
+    h->launches += gs::step_wav(h->blob, *h->hp, state_dev, stream_ws(h), hop_in_dev, hop_out_dev, N, (cudaStream_t)stream);
     CU(cudaGetLastError());
     return GTCRNB_OK;
 }

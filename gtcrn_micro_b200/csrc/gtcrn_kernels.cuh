@@ -35,7 +35,9 @@ constexpr int kSpecFrame = kBins * 2;
 constexpr int kHop = 256;
 constexpr int kNfft = 512;
 
-__device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : a * v; }
+// PReLU(v) = v > 0 ? v : a v.  For a <= 1 this is max(v, a v), for a > 1 min(v, a v): FMUL + FMNMX (the predicate is
+// warp-uniform and hoisted), one instruction less than compare + select.  Bit-identical to the select form.
+__device__ __forceinline__ float prelu(float v, float a) { const float m = a * v; return a <= 1.f ? fmaxf(v, m) : fminf(v, m); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float f4get(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
@@ -62,6 +64,20 @@ __device__ __forceinline__ void axpy2(float (&a0)[N], float (&a1)[N], float x0, 
         a0[4 * v + 3] = fmaf(x0, ww.w, a0[4 * v + 3]); a1[4 * v + 3] = fmaf(x1, ww.w, a1[4 * v + 3]);
     }
 }
+
+// same with the weights coming from a kernel parameter struct (constant bank, warp-uniform index): no LDS, no
+// staging registers -- ptxas turns the reads into LDCU + FFMA-with-uniform-register
+template <int N>
+__device__ __forceinline__ void axpy2c(float (&a0)[N], float (&a1)[N], float x0, float x1, const float* w) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        const float ww = w[c];
+        a0[c] = fmaf(x0, ww, a0[c]);
+        a1[c] = fmaf(x1, ww, a1[c]);
+    }
+}
+
+template <int NF> struct alignas(16) ParamBlock { float w[NF]; };
 
 // ================================================================================================
 // 256-point complex FFT, radix-4 Stockham autosort, 64 threads per transform, 4 stages.
@@ -229,38 +245,58 @@ constexpr int FR_THREADS = 288;
 constexpr int FR_FEAT = 3 * 260;           // per slot
 constexpr int FR_ERB = 3 * 132;            // [c][1 + j], zero at 0 and 130
 constexpr int FR_SFE = 133 * 4;            // [f + 2][4]
-constexpr int FR_A0 = 4 * 69 * 4;          // [q][f' + 2][4]
-constexpr int FR_SMEM_FLOATS = blob::FRONT_SIZE + FR_NF * (FR_FEAT + FR_ERB + FR_SFE + FR_A0);
+constexpr int FR_A0 = 4 * 69 * 4;          // [q][f' + 2][4]  -- aliases feat|erb (dead once SFE is done)
+constexpr int FR_SLOT = FR_FEAT + FR_ERB + FR_SFE;
+static_assert(FR_A0 <= FR_FEAT + FR_ERB, "a0 must fit in the dead feat|erb region");
+constexpr int FR_SMEM_FLOATS = blob::FRONT_SIZE + FR_NF * FR_SLOT;
 
-__global__ void __launch_bounds__(FR_THREADS) k_front(const float* __restrict__ spec, int64_t sb, int64_t sf, int64_t st, int64_t sc,
-                                                      int T, int64_t nframes, const float* __restrict__ blobp,
-                                                      float* __restrict__ en0, float* __restrict__ en1) {
+__global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict__ spec, int64_t sb, int64_t sf, int64_t st, int64_t sc,
+                                                         int T, int64_t nframes, const float* __restrict__ blobp,
+                                                         float* __restrict__ en0, float* __restrict__ en1) {
     extern __shared__ float4 smem4[];
     float* W = reinterpret_cast<float*>(smem4);
-    float* feat = W + blob::FRONT_SIZE;
-    float* erb = feat + FR_NF * FR_FEAT;
-    float* sfe = erb + FR_NF * FR_ERB;
-    float* a0 = sfe + FR_NF * FR_SFE;
+    float* slots = W + blob::FRONT_SIZE;       // per slot: [feat | erb | sfe]; a0 overlays feat|erb
     const int tid = threadIdx.x;
     const int64_t fi0 = (int64_t)blockIdx.x * FR_NF;              // first flattened frame (b * T + t) of this CTA
 
-    copy_f4(W, blobp + blob::FRONT_OFF, blob::FRONT_SIZE, tid, FR_THREADS);
-    zero_f4(erb, FR_NF * (FR_ERB + FR_SFE + FR_A0), tid, FR_THREADS);     // zero pads (erb, sfe, a0 are contiguous)
-    // ---- a: features
-    for (int idx = tid; idx < FR_NF * kBins; idx += FR_THREADS) {
-        const int slot = idx / kBins, k = idx - slot * kBins;
-        const int64_t fi = fi0 + slot;
-        float re = 0.f, im = 0.f;
-        if (fi < nframes) {
-            const int64_t b = fi / T, t = fi - b * T;
-            const float* p = spec + b * sb + t * st + (int64_t)k * sf;
-            re = p[0];
-            im = p[sc];
+    // ---- a: features.  All global loads of the tile are issued first (8 independent loads per thread in flight).
+    {
+        const bool vec2 = sc == 1 && (((sb | st | sf) & 1) == 0) && ((reinterpret_cast<uintptr_t>(spec) & 7) == 0);
+        float re[8], im[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + i * FR_THREADS;
+            const int slot = idx / kBins, k = idx - slot * kBins;
+            const int64_t fi = fi0 + slot;
+            re[i] = 0.f; im[i] = 0.f;
+            if (idx < FR_NF * kBins && fi < nframes) {
+                const int64_t b = fi / T, t = fi - b * T;
+                const float* p = spec + b * sb + t * st + (int64_t)k * sf;
+                if (vec2) { const float2 v = *reinterpret_cast<const float2*>(p); re[i] = v.x; im[i] = v.y; }
+                else { re[i] = p[0]; im[i] = p[sc]; }
+            }
         }
-        float* fs = feat + slot * FR_FEAT;
-        fs[k] = sqrtf(re * re + im * im + 1e-12f);
-        fs[260 + k] = re;
-        fs[520 + k] = im;
+        copy_f4(W, blobp + blob::FRONT_OFF, blob::FRONT_SIZE, tid, FR_THREADS);
+        for (int i = tid; i < FR_NF * 3; i += FR_THREADS) {       // zero pads of erb (idx 0, 130, 131 per channel) and sfe (4 columns)
+            float* e = slots + (i / 3) * FR_SLOT + FR_FEAT + (i % 3) * 132;
+            e[0] = 0.f; e[130] = 0.f; e[131] = 0.f;
+        }
+        for (int i = tid; i < FR_NF * 4; i += FR_THREADS) {
+            float4* sfe4 = reinterpret_cast<float4*>(slots + (i >> 2) * FR_SLOT + FR_FEAT + FR_ERB);
+            const int c = i & 3;
+            sfe4[c < 2 ? c : 129 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + i * FR_THREADS;
+            if (idx < FR_NF * kBins) {
+                const int slot = idx / kBins, k = idx - slot * kBins;
+                float* fs = slots + slot * FR_SLOT;
+                fs[k] = sqrtf(re[i] * re[i] + im[i] * im[i] + 1e-12f);
+                fs[260 + k] = re[i];
+                fs[520 + k] = im[i];
+            }
+        }
     }
     __syncthreads();
     // ---- b: ERB compress (sparse triangular bank)
@@ -270,7 +306,7 @@ __global__ void __launch_bounds__(FR_THREADS) k_front(const float* __restrict__ 
         const float* ew = W + blob::FRONT_ERB_W;
         for (int idx = tid; idx < FR_NF * 3 * kErb; idx += FR_THREADS) {
             const int slot = idx / (3 * kErb), r = idx - slot * 3 * kErb, c = r / kErb, jb = r - c * kErb;
-            const float* fs = feat + slot * FR_FEAT + c * 260;
+            const float* fs = slots + slot * FR_SLOT + c * 260;
             float v;
             if (jb < 65) {
                 v = fs[jb];
@@ -279,7 +315,7 @@ __global__ void __launch_bounds__(FR_THREADS) k_front(const float* __restrict__ 
                 v = 0.f;
                 for (int i = 0; i < n; ++i) v = fmaf(ew[bnd * blob::kErbMaxTap + i], fs[65 + s + i], v);
             }
-            erb[slot * FR_ERB + c * 132 + 1 + jb] = v;
+            slots[slot * FR_SLOT + FR_FEAT + c * 132 + 1 + jb] = v;
         }
     }
     __syncthreads();
@@ -288,24 +324,28 @@ __global__ void __launch_bounds__(FR_THREADS) k_front(const float* __restrict__ 
         const float* sw = W + blob::FRONT_SFE_W;
         for (int idx = tid; idx < FR_NF * kErb; idx += FR_THREADS) {
             const int slot = idx / kErb, f = idx - slot * kErb;
-            const float* e = erb + slot * FR_ERB + f;
+            const float* e = slots + slot * FR_SLOT + FR_FEAT + f;
             float4 v;
             v.x = sw[0] * e[0] + sw[1] * e[1] + sw[2] * e[2];
             v.y = sw[3] * e[132] + sw[4] * e[133] + sw[5] * e[134];
             v.z = sw[6] * e[264] + sw[7] * e[265] + sw[8] * e[266];
             v.w = 0.f;
-            reinterpret_cast<float4*>(sfe + slot * FR_SFE)[f + 2] = v;
+            reinterpret_cast<float4*>(slots + slot * FR_SLOT + FR_FEAT + FR_ERB)[f + 2] = v;
         }
     }
     __syncthreads();
-    // ---- d: en0  (thread = 2 slots x 16 co at one f')
+    // ---- d: en0  (thread = 2 slots x 16 co at one f').  Output a0 overlays the dead feat|erb region; its pad columns are zeroed here.
+    if (tid >= 160 && tid < 160 + FR_NF * 16) {
+        const int i = tid - 160, slot = i >> 4, q = (i >> 2) & 3, c = i & 3;
+        reinterpret_cast<float4*>(slots + slot * FR_SLOT)[q * 69 + (c < 2 ? c : 65 + c)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (tid < (FR_NF / 2) * kF1) {
         const int sp2 = tid / kF1, f = tid - sp2 * kF1, s0 = 2 * sp2, s1 = s0 + 1;
         float acc0[16], acc1[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = W[blob::FRONT_EN0_B + c];
-        const float4* i0p = reinterpret_cast<const float4*>(sfe + s0 * FR_SFE) + 2 * f;
-        const float4* i1p = reinterpret_cast<const float4*>(sfe + s1 * FR_SFE) + 2 * f;
+        const float4* i0p = reinterpret_cast<const float4*>(slots + s0 * FR_SLOT + FR_FEAT + FR_ERB) + 2 * f;
+        const float4* i1p = reinterpret_cast<const float4*>(slots + s1 * FR_SLOT + FR_FEAT + FR_ERB) + 2 * f;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
             const float4 x0 = i0p[k], x1 = i1p[k];
@@ -317,8 +357,8 @@ __global__ void __launch_bounds__(FR_THREADS) k_front(const float* __restrict__ 
         const float a = W[blob::FRONT_SLOPE + 0];
 #pragma unroll
         for (int c = 0; c < 16; ++c) { acc0[c] = prelu(acc0[c], a); acc1[c] = prelu(acc1[c], a); }
-        float4* o0 = reinterpret_cast<float4*>(a0 + s0 * FR_A0);
-        float4* o1 = reinterpret_cast<float4*>(a0 + s1 * FR_A0);
+        float4* o0 = reinterpret_cast<float4*>(slots + s0 * FR_SLOT);
+        float4* o1 = reinterpret_cast<float4*>(slots + s1 * FR_SLOT);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             o0[q * 69 + f + 2] = make_float4(acc0[4 * q], acc0[4 * q + 1], acc0[4 * q + 2], acc0[4 * q + 3]);
@@ -343,8 +383,8 @@ __global__ void __launch_bounds__(FR_THREADS) k_front(const float* __restrict__ 
         float acc0[8], acc1[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc0[c] = acc1[c] = W[blob::FRONT_EN1_B + 8 * h + c];
-        const float4* i0p = reinterpret_cast<const float4*>(a0 + s0 * FR_A0) + 2 * f;
-        const float4* i1p = reinterpret_cast<const float4*>(a0 + s1 * FR_A0) + 2 * f;
+        const float4* i0p = reinterpret_cast<const float4*>(slots + s0 * FR_SLOT) + 2 * f;
+        const float4* i1p = reinterpret_cast<const float4*>(slots + s1 * FR_SLOT) + 2 * f;
 #pragma unroll 1
         for (int k = 0; k < 5; ++k) {
 #pragma unroll
@@ -376,245 +416,354 @@ __global__ void __launch_bounds__(FR_THREADS) k_front(const float* __restrict__ 
 // ================================================================================================
 // GTConvBlock (+TRALite +channel shuffle), encoder (depthwise 3x3) and decoder (full 16->16 3x3) variants.
 // reference: gtcrn_micro.py:167-253, TRALite :122-139, shuffle :222-227, decoder skip-add :464-469
-// One CTA walks one utterance segment [s0, s1) in tiles of GT_NT frames.  Shared-memory state carried
-// from tile to tile: the last 2 frames of point-conv-1 output (rows 0,1 of Pb) and the last 2 TRA
-// energies (rows 0,1 of Ev).  Segments that do not start at t = 0 warm up on the 4 preceding frames.
-// grid (nseg, B), 288 threads (264 active = 8 slot pairs x 33 bins).
+//
+// One CTA walks one utterance segment [s0, s1) in tiles of NT = 8*PS frames.  A thread owns PS consecutive frame
+// slots x 16 channels at one bin, so the PS+2 tap rows it reads per (kf, ci-quad) are shared by its PS outputs.
+// Weights are a kernel parameter (constant bank): every weight is one LDCU feeding PS FFMAs, no LDS, no staging
+// registers (the v1 kernel spent half its shared-memory wavefronts on broadcast weight loads, ncu r1_v1).
+// The point-conv-1 rows live in a RING of NT+2 rows, so the 2-frame causal history is simply the previous rows of
+// the ring (no carry copy), and the TRALite gate is evaluated per thread: 3 barriers per tile.
+// Segments that do not start at t = 0 warm up on the 4 preceding frames (exactly the dependency cone).
+// grid (nseg, B), G*33 active threads (G slot groups x 33 bins), rounded up to whole warps.
 // ================================================================================================
-constexpr int GT_NT = 16;
-constexpr int GT_THREADS = 288;
-constexpr int GT_ACTIVE = (GT_NT / 2) * kF2;
-constexpr int GT_ROW4 = 4 * 35;                 // float4 per Pb row: [q][col = f + 1]
+constexpr int GT_ROW4 = 4 * 35;                 // float4 per ring row: [ci quad][col = f + 1], cols 0 and 34 stay zero
 constexpr int GT_WARMUP = 4;
 template <bool DEC> __host__ __device__ constexpr int gt_chunk() { return DEC ? blob::DECGT_SIZE : blob::ENCGT_SIZE; }
-template <bool DEC> __host__ __device__ constexpr int gt_smem_floats() {
-    return gt_chunk<DEC>() + (GT_NT + 2) * GT_ROW4 * 4 + GT_NT * kF2 * 8 + (GT_NT + 2) * 8 + GT_NT * 8;
+// PS frame slots per thread, G slot groups per CTA: NT = G*PS frames per tile, G*33 active threads
+__host__ __device__ constexpr int gt_threads(int G) { return (G * kF2 + 31) / 32 * 32; }
+__host__ __device__ constexpr int gt_smem_floats(int PS, int G) {
+    return (G * PS + 2) * GT_ROW4 * 4 + G * PS * kF2 * 8 + (G * PS + 2) * 8;
+}
+__host__ __device__ constexpr int gt_min_blocks(int PS) { return PS >= 4 ? 2 : (PS == 3 ? 2 : 3); }
+
+template <bool DEC> struct GtOff {
+    static constexpr int PC1_W = DEC ? blob::DECGT_PC1_W : blob::ENCGT_PC1_W;
+    static constexpr int PC1_B = DEC ? blob::DECGT_PC1_B : blob::ENCGT_PC1_B;
+    static constexpr int MID_W = DEC ? blob::DECGT_FULL_W : blob::ENCGT_DW_W;
+    static constexpr int MID_B = DEC ? blob::DECGT_FULL_B : blob::ENCGT_DW_B;
+    static constexpr int PC2_W = DEC ? blob::DECGT_PC2_W : blob::ENCGT_PC2_W;
+    static constexpr int PC2_B = DEC ? blob::DECGT_PC2_B : blob::ENCGT_PC2_B;
+    static constexpr int TDW_W = DEC ? blob::DECGT_TRA_DW_W : blob::ENCGT_TRA_DW_W;
+    static constexpr int TDW_B = DEC ? blob::DECGT_TRA_DW_B : blob::ENCGT_TRA_DW_B;
+    static constexpr int TPW_W = DEC ? blob::DECGT_TRA_PW_W : blob::ENCGT_TRA_PW_W;
+    static constexpr int TPW_B = DEC ? blob::DECGT_TRA_PW_B : blob::ENCGT_TRA_PW_B;
+    static constexpr int SLOPE = DEC ? blob::DECGT_SLOPE : blob::ENCGT_SLOPE;
+};
+
+// ---- pieces shared with the streaming kernel (same operation order => bit-identical results) ----
+// point conv 1: p[16] = PReLU(b + W1^T x1), x1 = channels 0..7 of (x [+ skip])
+template <bool DEC, class PB>
+__device__ __forceinline__ void gt_pc1(const PB& prm, const float (&x1)[8], float (&p)[16]) {
+    using O = GtOff<DEC>;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) p[c] = prm.w[O::PC1_B + c];
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) p[c] = fmaf(x1[ci], prm.w[O::PC1_W + ci * 16 + c], p[c]);
+    const float a1 = prm.w[O::SLOPE + 0];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) p[c] = prelu(p[c], a1);
+}
+// one (kf, ci-quad) step of the 3x3 conv for PS slots: in[j] = tap row j (slot s uses rows s, s+1, s+2 for kt = 0,1,2)
+template <bool DEC, int PS, class PB>
+__device__ __forceinline__ void gt_mid_step(const PB& prm, int kf, int qd, const float4 (&in)[PS + 2], float (&acc)[PS][16]) {
+    using O = GtOff<DEC>;
+    if (DEC) {
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int wb = O::MID_W + ((kt * 3 + kf) * 16 + 4 * qd + i) * 16;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float ww = prm.w[wb + c];
+#pragma unroll
+                    for (int s = 0; s < PS; ++s) acc[s][c] = fmaf(f4get(in[s + kt], i), ww, acc[s][c]);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float ww = prm.w[O::MID_W + (kt * 3 + kf) * 16 + 4 * qd + i];
+#pragma unroll
+                for (int s = 0; s < PS; ++s) acc[s][4 * qd + i] = fmaf(f4get(in[s + kt], i), ww, acc[s][4 * qd + i]);
+            }
+        }
+    }
+}
+// PReLU, point conv 2 (16 -> 8, BN folded): q[8]
+template <bool DEC, class PB>
+__device__ __forceinline__ void gt_pc2(const PB& prm, float (&d)[16], float (&q)[8]) {
+    using O = GtOff<DEC>;
+    const float a2 = prm.w[O::SLOPE + 1];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) d[c] = prelu(d[c], a2);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) q[c] = prm.w[O::PC2_B + c];
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) q[c] = fmaf(d[ci], prm.w[O::PC2_W + ci * 8 + c], q[c]);
+}
+// TRALite gate from the energies of frames t-2, t-1, t (e0, e1, e2 point at 8 floats each)
+template <bool DEC, class PB>
+__device__ __forceinline__ void gt_gate(const PB& prm, const float* e0, const float* e1, const float* e2, float (&g)[8]) {
+    using O = GtOff<DEC>;
+    float y[8];
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci) {
+        float v = prm.w[O::TDW_B + ci];
+        v = fmaf(prm.w[O::TDW_W + 0 * 8 + ci], e0[ci], v);
+        v = fmaf(prm.w[O::TDW_W + 1 * 8 + ci], e1[ci], v);
+        v = fmaf(prm.w[O::TDW_W + 2 * 8 + ci], e2[ci], v);
+        y[ci] = v;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float v = prm.w[O::TPW_B + c];
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) v = fmaf(prm.w[O::TPW_W + ci * 8 + c], y[ci], v);
+        g[c] = 1.0f / (1.0f + expf(-v));
+    }
+}
+// fixed-order energy sum over the 33 bins of one frame slot: E2 [33][8] -> mean
+__device__ __forceinline__ float gt_energy(const float* e2_slot_c) {
+    float s = 0.f;
+#pragma unroll
+    for (int ff = 0; ff < kF2; ++ff) s += e2_slot_c[ff * 8];
+    return s / 33.0f;
 }
 
-template <bool DEC>
-__global__ void __launch_bounds__(GT_THREADS, 3) k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip,
-                                                       float* __restrict__ out, const float* __restrict__ wblk,
-                                                       int T, int seg_len) {
-    constexpr int PC1_W = DEC ? blob::DECGT_PC1_W : blob::ENCGT_PC1_W;
-    constexpr int PC1_B = DEC ? blob::DECGT_PC1_B : blob::ENCGT_PC1_B;
-    constexpr int MID_W = DEC ? blob::DECGT_FULL_W : blob::ENCGT_DW_W;
-    constexpr int MID_B = DEC ? blob::DECGT_FULL_B : blob::ENCGT_DW_B;
-    constexpr int PC2_W = DEC ? blob::DECGT_PC2_W : blob::ENCGT_PC2_W;
-    constexpr int PC2_B = DEC ? blob::DECGT_PC2_B : blob::ENCGT_PC2_B;
-    constexpr int TDW_W = DEC ? blob::DECGT_TRA_DW_W : blob::ENCGT_TRA_DW_W;
-    constexpr int TDW_B = DEC ? blob::DECGT_TRA_DW_B : blob::ENCGT_TRA_DW_B;
-    constexpr int TPW_W = DEC ? blob::DECGT_TRA_PW_W : blob::ENCGT_TRA_PW_W;
-    constexpr int TPW_B = DEC ? blob::DECGT_TRA_PW_B : blob::ENCGT_TRA_PW_B;
-    constexpr int SLOPE = DEC ? blob::DECGT_SLOPE : blob::ENCGT_SLOPE;
-
+template <bool DEC, int PS, int G>
+__global__ void __launch_bounds__(gt_threads(G), gt_min_blocks(PS))
+k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* __restrict__ out,
+         const __grid_constant__ ParamBlock<gt_chunk<DEC>()> prm, int T, int seg_len) {
+    constexpr int NT = G * PS, R = NT + 2, GT_THREADS = gt_threads(G), GT_ACTIVE = G * kF2;
+    static_assert(NT * 8 <= GT_THREADS, "phase 3 needs one thread per (slot, channel)");
     extern __shared__ float4 smem4[];
-    float* W = reinterpret_cast<float*>(smem4);
-    float4* Pb = reinterpret_cast<float4*>(W + gt_chunk<DEC>());
-    float* E2 = reinterpret_cast<float*>(Pb + (GT_NT + 2) * GT_ROW4);
-    float* Ev = E2 + GT_NT * kF2 * 8;
-    float* G = Ev + (GT_NT + 2) * 8;
+    float4* Pb = smem4;                                               // ring: R rows x GT_ROW4
+    float* E2 = reinterpret_cast<float*>(Pb + R * GT_ROW4);           // [NT][33][8] q^2 of the current tile
+    float* Ev = E2 + NT * kF2 * 8;                                    // ring: R rows x 8 TRA energies
 
     const int tid = threadIdx.x, b = blockIdx.y;
     const int s0 = blockIdx.x * seg_len, s1 = min(T, s0 + seg_len);
     if (s0 >= s1) return;
     const int tw0 = max(0, s0 - GT_WARMUP);
-    copy_f4(W, wblk, gt_chunk<DEC>(), tid, GT_THREADS);
-    zero_f4(reinterpret_cast<float*>(Pb), (GT_NT + 2) * GT_ROW4 * 4, tid, GT_THREADS);
-    if (tid < 16) Ev[tid] = 0.f;
+    zero_f4(reinterpret_cast<float*>(Pb), gt_smem_floats(PS, G), tid, GT_THREADS);
     __syncthreads();
 
     const bool act = tid < GT_ACTIVE;
-    const int sp2 = tid / kF2, f = tid - sp2 * kF2;
+    const int g = tid / kF2, f = tid - g * kF2;
     const int64_t ubase = (int64_t)b * T * kF2 * 16;
-    const float a1 = W[SLOPE + 0], a2 = W[SLOPE + 1];
+    int rb = 2;                                                       // ring row of slot 0 (rows 0,1: zero history)
 
-    for (int t0 = tw0; t0 < s1; t0 += GT_NT) {
-        float x2[2][8], q[2][8];
-        // ---- phase 1: point conv 1 (8 -> 16) + PReLU into Pb rows 2..NT+1
+    for (int t0 = tw0; t0 < s1; t0 += NT) {
+        int rrow[PS + 2];                                             // ring rows of frames (slot0 - 2 .. slot0 + PS - 1) of this thread
+#pragma unroll
+        for (int j = 0; j < PS + 2; ++j) {
+            int v = rb + g * PS + j + (R - 2);
+            v -= (v >= R) ? R : 0;
+            v -= (v >= R) ? R : 0;
+            rrow[j] = v;
+        }
+        // ---- phase 1: point conv 1 of the new frames into the ring
         if (act) {
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int slot = 2 * sp2 + s, t = t0 + slot;
+            for (int s = 0; s < PS; ++s) {
+                const int t = t0 + g * PS + s;
                 float p[16];
                 if (t < s1) {
                     const float4* px = reinterpret_cast<const float4*>(xin + ubase + ((int64_t)t * kF2 + f) * 16);
-                    float4 v0 = px[0], v1 = px[1], v2 = px[2], v3 = px[3];
+                    float4 v0 = px[0], v1 = px[1];
                     if (DEC) {
                         const float4* ps = reinterpret_cast<const float4*>(skip + ubase + ((int64_t)t * kF2 + f) * 16);
-                        const float4 u0 = ps[0], u1 = ps[1], u2 = ps[2], u3 = ps[3];
+                        const float4 u0 = ps[0], u1 = ps[1];
                         v0.x += u0.x; v0.y += u0.y; v0.z += u0.z; v0.w += u0.w;
                         v1.x += u1.x; v1.y += u1.y; v1.z += u1.z; v1.w += u1.w;
-                        v2.x += u2.x; v2.y += u2.y; v2.z += u2.z; v2.w += u2.w;
-                        v3.x += u3.x; v3.y += u3.y; v3.z += u3.z; v3.w += u3.w;
                     }
                     const float x1[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    x2[s][0] = v2.x; x2[s][1] = v2.y; x2[s][2] = v2.z; x2[s][3] = v2.w;
-                    x2[s][4] = v3.x; x2[s][5] = v3.y; x2[s][6] = v3.z; x2[s][7] = v3.w;
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) p[c] = W[PC1_B + c];
-#pragma unroll
-                    for (int ci = 0; ci < 8; ++ci) {
-                        const float4* w4 = reinterpret_cast<const float4*>(W + PC1_W + ci * 16);
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            const float4 ww = w4[v];
-                            p[4 * v + 0] = fmaf(x1[ci], ww.x, p[4 * v + 0]);
-                            p[4 * v + 1] = fmaf(x1[ci], ww.y, p[4 * v + 1]);
-                            p[4 * v + 2] = fmaf(x1[ci], ww.z, p[4 * v + 2]);
-                            p[4 * v + 3] = fmaf(x1[ci], ww.w, p[4 * v + 3]);
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) p[c] = prelu(p[c], a1);
+                    gt_pc1<DEC>(prm, x1, p);
                 } else {
 #pragma unroll
                     for (int c = 0; c < 16; ++c) p[c] = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) x2[s][c] = 0.f;
                 }
-                float4* row = Pb + (slot + 2) * GT_ROW4 + f + 1;
+                float4* row = Pb + rrow[s + 2] * GT_ROW4 + f + 1;
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) row[qd * 35] = make_float4(p[4 * qd], p[4 * qd + 1], p[4 * qd + 2], p[4 * qd + 3]);
             }
         }
         __syncthreads();
-        // ---- phase 2: 3x3 conv over (t-2..t, f-1..f+1) + PReLU, point conv 2 (16 -> 8), energies
+        // ---- phase 2: 3x3 conv over (t-2..t, f-1..f+1), PReLU, point conv 2, q^2
+        float q[PS][8];
         if (act) {
-            float d0[16], d1[16];
+            float acc[PS][16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) d0[c] = d1[c] = W[MID_B + c];
-            const float4* r0 = Pb + (2 * sp2) * GT_ROW4 + f;          // tap (kt,kf) of slot s: row slot+kt, col f+kf
+            for (int s = 0; s < PS; ++s)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[s][c] = prm.w[GtOff<DEC>::MID_B + c];
+            // (kf, ci-quad) loop kept rolled: the body (3 kt x 4 ci x 16 co x PS FFMAs) is ~8 KB of code; fully unrolled
+            // it was 32 KB per kf and the kernel stalled 23 % of the time on instruction fetch (ncu r1_v2: no_inst)
             if (DEC) {
 #pragma unroll 1
-                for (int kt = 0; kt < 3; ++kt) {
-#pragma unroll 1
-                    for (int kf = 0; kf < 3; ++kf) {
-                        const float* wk = W + MID_W + (kt * 3 + kf) * 256;
+                for (int kq = 0; kq < 12; ++kq) {
+                    const int kf = kq >> 2, qd = kq & 3;
+                    float4 in[PS + 2];
 #pragma unroll
-                        for (int qd = 0; qd < 4; ++qd) {
-                            const float4 i0 = r0[kt * GT_ROW4 + qd * 35 + kf];
-                            const float4 i1 = r0[(kt + 1) * GT_ROW4 + qd * 35 + kf];
-                            axpy2<16>(d0, d1, i0.x, i1.x, wk + (4 * qd + 0) * 16);
-                            axpy2<16>(d0, d1, i0.y, i1.y, wk + (4 * qd + 1) * 16);
-                            axpy2<16>(d0, d1, i0.z, i1.z, wk + (4 * qd + 2) * 16);
-                            axpy2<16>(d0, d1, i0.w, i1.w, wk + (4 * qd + 3) * 16);
-                        }
-                    }
+                    for (int j = 0; j < PS + 2; ++j) in[j] = Pb[rrow[j] * GT_ROW4 + qd * 35 + f + kf];
+                    gt_mid_step<DEC, PS>(prm, kf, qd, in, acc);
                 }
             } else {
+#pragma unroll 1
+                for (int kf = 0; kf < 3; ++kf) {
 #pragma unroll
-                for (int kt = 0; kt < 3; ++kt) {
+                    for (int qd = 0; qd < 4; ++qd) {
+                        float4 in[PS + 2];
 #pragma unroll
-                    for (int kf = 0; kf < 3; ++kf) {
-                        const float4* w4 = reinterpret_cast<const float4*>(W + MID_W + (kt * 3 + kf) * 16);
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd) {
-                            const float4 ww = w4[qd];
-                            const float4 i0 = r0[kt * GT_ROW4 + qd * 35 + kf];
-                            const float4 i1 = r0[(kt + 1) * GT_ROW4 + qd * 35 + kf];
-                            d0[4 * qd + 0] = fmaf(i0.x, ww.x, d0[4 * qd + 0]); d1[4 * qd + 0] = fmaf(i1.x, ww.x, d1[4 * qd + 0]);
-                            d0[4 * qd + 1] = fmaf(i0.y, ww.y, d0[4 * qd + 1]); d1[4 * qd + 1] = fmaf(i1.y, ww.y, d1[4 * qd + 1]);
-                            d0[4 * qd + 2] = fmaf(i0.z, ww.z, d0[4 * qd + 2]); d1[4 * qd + 2] = fmaf(i1.z, ww.z, d1[4 * qd + 2]);
-                            d0[4 * qd + 3] = fmaf(i0.w, ww.w, d0[4 * qd + 3]); d1[4 * qd + 3] = fmaf(i1.w, ww.w, d1[4 * qd + 3]);
-                        }
+                        for (int j = 0; j < PS + 2; ++j) in[j] = Pb[rrow[j] * GT_ROW4 + qd * 35 + f + kf];
+                        gt_mid_step<DEC, PS>(prm, kf, qd, in, acc);
                     }
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 16; ++c) { d0[c] = prelu(d0[c], a2); d1[c] = prelu(d1[c], a2); }
-#pragma unroll
-            for (int c = 0; c < 8; ++c) q[0][c] = q[1][c] = W[PC2_B + c];
-#pragma unroll
-            for (int ci = 0; ci < 16; ++ci) axpy2<8>(q[0], q[1], d0[ci], d1[ci], W + PC2_W + ci * 8);
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                float4* e4 = reinterpret_cast<float4*>(E2 + ((2 * sp2 + s) * kF2 + f) * 8);
+            for (int s = 0; s < PS; ++s) {
+                gt_pc2<DEC>(prm, acc[s], q[s]);
+                float4* e4 = reinterpret_cast<float4*>(E2 + ((g * PS + s) * kF2 + f) * 8);
                 e4[0] = make_float4(q[s][0] * q[s][0], q[s][1] * q[s][1], q[s][2] * q[s][2], q[s][3] * q[s][3]);
                 e4[1] = make_float4(q[s][4] * q[s][4], q[s][5] * q[s][5], q[s][6] * q[s][6], q[s][7] * q[s][7]);
             }
         }
         __syncthreads();
-        // ---- phase 3: TRALite energies (fixed summation order -> bitwise deterministic / causal)
-        if (tid < GT_NT * 8) {
+        // ---- phase 3: TRALite energies, fixed summation order (bitwise deterministic / causal)
+        if (tid < NT * 8) {
             const int slot = tid >> 3, c = tid & 7;
-            const float* e = E2 + slot * kF2 * 8 + c;
-            float s = 0.f;
-#pragma unroll
-            for (int ff = 0; ff < kF2; ++ff) s += e[ff * 8];
-            Ev[(slot + 2) * 8 + c] = s / 33.0f;
+            int v = rb + slot;
+            v -= (v >= R) ? R : 0;
+            Ev[v * 8 + c] = gt_energy(E2 + slot * kF2 * 8 + c);
         }
         __syncthreads();
-        if (tid < GT_NT * 8) {
-            const int slot = tid >> 3, c = tid & 7;
-            float v = W[TPW_B + c];
-#pragma unroll
-            for (int ci = 0; ci < 8; ++ci) {
-                float y = W[TDW_B + ci];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) y = fmaf(W[TDW_W + k * 8 + ci], Ev[(slot + k) * 8 + ci], y);
-                v = fmaf(W[TPW_W + ci * 8 + c], y, v);
-            }
-            G[slot * 8 + c] = 1.0f / (1.0f + expf(-v));
-        }
-        __syncthreads();
-        // ---- phase 4: gate, channel shuffle [q0,x2_0,q1,x2_1,...], store; carry history to rows 0,1
+        // ---- phase 4: gate (per thread), channel shuffle [q0,x2_0,q1,x2_1,...], store
         if (act) {
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int slot = 2 * sp2 + s, t = t0 + slot;
+            for (int s = 0; s < PS; ++s) {
+                const int t = t0 + g * PS + s;
                 if (t >= s0 && t < s1) {
-                    const float* g = G + slot * 8;
+                    const float4* px = reinterpret_cast<const float4*>(xin + ubase + ((int64_t)t * kF2 + f) * 16);
+                    float4 v2 = px[2], v3 = px[3];                    // untouched half (re-read: L2 hit, saves 8*PS registers)
+                    if (DEC) {
+                        const float4* ps = reinterpret_cast<const float4*>(skip + ubase + ((int64_t)t * kF2 + f) * 16);
+                        const float4 u2 = ps[2], u3 = ps[3];
+                        v2.x += u2.x; v2.y += u2.y; v2.z += u2.z; v2.w += u2.w;
+                        v3.x += u3.x; v3.y += u3.y; v3.z += u3.z; v3.w += u3.w;
+                    }
+                    float gate[8];
+                    gt_gate<DEC>(prm, Ev + rrow[s] * 8, Ev + rrow[s + 1] * 8, Ev + rrow[s + 2] * 8, gate);
                     float4* po = reinterpret_cast<float4*>(out + ubase + ((int64_t)t * kF2 + f) * 16);
-#pragma unroll
-                    for (int v = 0; v < 4; ++v)
-                        po[v] = make_float4(q[s][2 * v] * g[2 * v], x2[s][2 * v], q[s][2 * v + 1] * g[2 * v + 1], x2[s][2 * v + 1]);
+                    po[0] = make_float4(q[s][0] * gate[0], v2.x, q[s][1] * gate[1], v2.y);
+                    po[1] = make_float4(q[s][2] * gate[2], v2.z, q[s][3] * gate[3], v2.w);
+                    po[2] = make_float4(q[s][4] * gate[4], v3.x, q[s][5] * gate[5], v3.y);
+                    po[3] = make_float4(q[s][6] * gate[6], v3.z, q[s][7] * gate[7], v3.w);
                 }
             }
         }
-        for (int i = tid; i < 2 * GT_ROW4; i += GT_THREADS) Pb[i] = Pb[GT_NT * GT_ROW4 + i];
-        if (tid < 16) Ev[tid] = Ev[GT_NT * 8 + tid];
-        __syncthreads();
+        rb += NT;
+        rb -= (rb >= R) ? R : 0;
+        // no barrier needed here: the next phase 1 only writes ring rows whose readers finished before the
+        // barrier after phase 2, and every later writer of E2 / Ev is separated from this tile's readers by >= 1 barrier
     }
 }
 
 // ================================================================================================
 // GTCN: 4 TCN blocks (dilation 1,2,4,8) fused.  reference: gtcrn_micro.py:256-336
-// TCNs never mix frequency bins, so a CTA owns 11 of the 33 bins of one utterance segment and walks
-// along time in tiles of TC_NT frames; the block input x stays in registers through all four TCNs.
-// Y holds [16 history rows | TC_NT new rows] of conv1 output for the TCN being evaluated; `carry`
-// keeps the last 2d rows of every TCN between tiles (the streaming tcn_cache, gtcrn_micro_stream.py:620-623).
+// TCNs never mix frequency bins, so a CTA owns 11 of the 33 bins of one utterance segment and walks along time in
+// tiles of TC_NT frames; the block input x stays in registers through all four TCNs.  Weights: kernel parameter
+// (constant bank).  Y holds the conv1 output of the tile for the TCN being evaluated; H[parity] keeps the last 2d
+// rows of every TCN from the previous tile (the streaming tcn_cache, gtcrn_micro_stream.py:620-623), ping-ponged so
+// that saving the new history overlaps the tap reads: 2 barriers per TCN, half the copies of v1.
 // grid (nseg * 3, B), 288 threads (264 active = 24 slot pairs x 11 bins).
 // ================================================================================================
 constexpr int TC_NT = 48;
 constexpr int TC_FC = 11;
 constexpr int TC_THREADS = 288;
 constexpr int TC_ACTIVE = (TC_NT / 2) * TC_FC;
-constexpr int TC_HIST = 16;
 constexpr int TC_ROW4 = 4 * 12;                 // float4 per row: [q][col (11, padded to 12)]
 constexpr int TC_WARMUP = 30;
-constexpr int TC_SMEM_FLOATS = 4 * blob::TCN_SIZE + (TC_HIST + TC_NT) * TC_ROW4 * 4 + 30 * TC_ROW4 * 4;
+constexpr int TC_SMEM_FLOATS = (TC_NT + 2 * 30) * TC_ROW4 * 4;
 
-__global__ void __launch_bounds__(TC_THREADS, 2) k_gtcn(const float* __restrict__ xin, float* __restrict__ out,
-                                                     const float* __restrict__ wblk, int T, int seg_len) {
+// one TCN for two positions: y1 (conv1 output, already PReLU'd) given, taps ta (t-2d) / tb (t-d); x updated in place
+template <class PB>
+__device__ __forceinline__ void tcn_conv1(const PB& prm, int wo, const float (&x)[2][16], float (&y1)[2][16]) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) y1[0][c] = y1[1][c] = prm.w[wo + blob::TCN_B1 + c];
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float ww = prm.w[wo + blob::TCN_W1 + ci * 16 + c];
+            y1[0][c] = fmaf(x[0][ci], ww, y1[0][c]);
+            y1[1][c] = fmaf(x[1][ci], ww, y1[1][c]);
+        }
+    const float a1 = prm.w[wo + blob::TCN_SLOPE + 0];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { y1[0][c] = prelu(y1[0][c], a1); y1[1][c] = prelu(y1[1][c], a1); }
+}
+template <class PB>
+__device__ __forceinline__ void tcn_dw(const PB& prm, int wo, const float4 (&ta)[4], const float4 (&tb)[4], const float (&y1)[16], float (&y2)[16]) {
+    const float a2 = prm.w[wo + blob::TCN_SLOPE + 1];
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = 4 * qd + i;
+            float v = prm.w[wo + blob::TCN_B2 + c];
+            v = fmaf(prm.w[wo + blob::TCN_W2 + c], f4get(ta[qd], i), v);
+            v = fmaf(prm.w[wo + blob::TCN_W2 + 16 + c], f4get(tb[qd], i), v);
+            v = fmaf(prm.w[wo + blob::TCN_W2 + 32 + c], y1[c], v);
+            y2[c] = prelu(v, a2);
+        }
+    }
+}
+template <class PB>
+__device__ __forceinline__ void tcn_conv3(const PB& prm, int wo, const float (&y2)[2][16], float (&x)[2][16]) {
+    float o[2][16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { const float bb = prm.w[wo + blob::TCN_B3 + c]; o[0][c] = bb + x[0][c]; o[1][c] = bb + x[1][c]; }
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float ww = prm.w[wo + blob::TCN_W3 + ci * 16 + c];
+            o[0][c] = fmaf(y2[0][ci], ww, o[0][c]);
+            o[1][c] = fmaf(y2[1][ci], ww, o[1][c]);
+        }
+    const float a3 = prm.w[wo + blob::TCN_SLOPE + 2];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { x[0][c] = prelu(o[0][c], a3); x[1][c] = prelu(o[1][c], a3); }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_constant__ ParamBlock<4 * blob::TCN_SIZE> prm, int T, int seg_len) {
     extern __shared__ float4 smem4[];
-    float* W = reinterpret_cast<float*>(smem4);
-    float4* Y = reinterpret_cast<float4*>(W + 4 * blob::TCN_SIZE);
-    float4* carry = Y + (TC_HIST + TC_NT) * TC_ROW4;
+    float4* Y = smem4;                               // [TC_NT rows]
+    float4* H = Y + TC_NT * TC_ROW4;                 // [2 parities][30 rows]
 
     const int tid = threadIdx.x, b = blockIdx.y;
     const int seg = blockIdx.x / 3, col0 = (blockIdx.x - seg * 3) * TC_FC;
     const int s0 = seg * seg_len, s1 = min(T, s0 + seg_len);
     if (s0 >= s1) return;
     const int tw0 = max(0, s0 - TC_WARMUP);
-    copy_f4(W, wblk, 4 * blob::TCN_SIZE, tid, TC_THREADS);
-    zero_f4(reinterpret_cast<float*>(Y), ((TC_HIST + TC_NT) + 30) * TC_ROW4 * 4, tid, TC_THREADS);
+    zero_f4(reinterpret_cast<float*>(Y), TC_SMEM_FLOATS, tid, TC_THREADS);
     __syncthreads();
 
     const bool act = tid < TC_ACTIVE;
     const int sp2 = tid / TC_FC, col = tid - sp2 * TC_FC;
     const int64_t ubase = (int64_t)b * T * kF2 * 16;
+    int par = 0;
 
-    for (int t0 = tw0; t0 < s1; t0 += TC_NT) {
+    for (int t0 = tw0; t0 < s1; t0 += TC_NT, par ^= 1) {
         float x[2][16];
         if (act) {
 #pragma unroll
@@ -635,22 +784,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_gtcn(const float* __restrict_
         }
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
-            const int d = 1 << k, coff = (2 << k) - 2;            // carry rows of TCN k start at 2^(k+1) - 2
-            const float* Wk = W + k * blob::TCN_SIZE;
-            // history rows [16-2d, 16) <- carry
-            for (int i = tid; i < 2 * d * TC_ROW4; i += TC_THREADS) Y[(TC_HIST - 2 * d) * TC_ROW4 + i] = carry[coff * TC_ROW4 + i];
+            const int d = 1 << k, coff = (2 << k) - 2, wo = k * blob::TCN_SIZE;   // history rows of TCN k start at 2^(k+1) - 2
+            const float4* Hc = H + (par * 30 + coff) * TC_ROW4;                    // frames t0-2d .. t0-1 (from the previous tile)
+            float4* Hn = H + ((par ^ 1) * 30 + coff) * TC_ROW4;
             float y1[2][16];
             if (act) {
-#pragma unroll
-                for (int c = 0; c < 16; ++c) y1[0][c] = y1[1][c] = Wk[blob::TCN_B1 + c];
-#pragma unroll
-                for (int ci = 0; ci < 16; ++ci) axpy2<16>(y1[0], y1[1], x[0][ci], x[1][ci], Wk + blob::TCN_W1 + ci * 16);
-                const float a1 = Wk[blob::TCN_SLOPE + 0];
+                tcn_conv1(prm, wo, x, y1);
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
-                    float4* row = Y + (TC_HIST + 2 * sp2 + s) * TC_ROW4 + col;
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) y1[s][c] = prelu(y1[s][c], a1);
+                    float4* row = Y + (2 * sp2 + s) * TC_ROW4 + col;
 #pragma unroll
                     for (int qd = 0; qd < 4; ++qd)
                         row[qd * 12] = make_float4(y1[s][4 * qd], y1[s][4 * qd + 1], y1[s][4 * qd + 2], y1[s][4 * qd + 3]);
@@ -658,35 +800,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_gtcn(const float* __restrict_
             }
             __syncthreads();
             if (act) {
-                const float a2 = Wk[blob::TCN_SLOPE + 1], a3 = Wk[blob::TCN_SLOPE + 2];
                 float y2[2][16];
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
-                    const float4* rA = Y + (TC_HIST + 2 * sp2 + s - 2 * d) * TC_ROW4 + col;
-                    const float4* rB = Y + (TC_HIST + 2 * sp2 + s - d) * TC_ROW4 + col;
+                    const int sl = 2 * sp2 + s;
+                    const float4* rA = (sl >= 2 * d ? Y + (sl - 2 * d) * TC_ROW4 : Hc + sl * TC_ROW4) + col;
+                    const float4* rB = (sl >= d ? Y + (sl - d) * TC_ROW4 : Hc + (sl + d) * TC_ROW4) + col;
+                    float4 ta[4], tb[4];
 #pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        const float4 ta = rA[qd * 12], tb = rB[qd * 12];
-                        const float4 w0 = reinterpret_cast<const float4*>(Wk + blob::TCN_W2)[qd];
-                        const float4 w1 = reinterpret_cast<const float4*>(Wk + blob::TCN_W2 + 16)[qd];
-                        const float4 w2 = reinterpret_cast<const float4*>(Wk + blob::TCN_W2 + 32)[qd];
-                        const float4 bb = reinterpret_cast<const float4*>(Wk + blob::TCN_B2)[qd];
-                        y2[s][4 * qd + 0] = prelu(fmaf(w2.x, y1[s][4 * qd + 0], fmaf(w1.x, tb.x, fmaf(w0.x, ta.x, bb.x))), a2);
-                        y2[s][4 * qd + 1] = prelu(fmaf(w2.y, y1[s][4 * qd + 1], fmaf(w1.y, tb.y, fmaf(w0.y, ta.y, bb.y))), a2);
-                        y2[s][4 * qd + 2] = prelu(fmaf(w2.z, y1[s][4 * qd + 2], fmaf(w1.z, tb.z, fmaf(w0.z, ta.z, bb.z))), a2);
-                        y2[s][4 * qd + 3] = prelu(fmaf(w2.w, y1[s][4 * qd + 3], fmaf(w1.w, tb.w, fmaf(w0.w, ta.w, bb.w))), a2);
-                    }
+                    for (int qd = 0; qd < 4; ++qd) { ta[qd] = rA[qd * 12]; tb[qd] = rB[qd * 12]; }
+                    tcn_dw(prm, wo, ta, tb, y1[s], y2[s]);
                 }
-                float o[2][16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) { o[0][c] = Wk[blob::TCN_B3 + c] + x[0][c]; o[1][c] = Wk[blob::TCN_B3 + c] + x[1][c]; }
-#pragma unroll
-                for (int ci = 0; ci < 16; ++ci) axpy2<16>(o[0], o[1], y2[0][ci], y2[1][ci], Wk + blob::TCN_W3 + ci * 16);
-#pragma unroll
-                for (int c = 0; c < 16; ++c) { x[0][c] = prelu(o[0][c], a3); x[1][c] = prelu(o[1][c], a3); }
+                tcn_conv3(prm, wo, y2, x);
             }
-            // carry <- last 2d rows of [history | new]
-            for (int i = tid; i < 2 * d * TC_ROW4; i += TC_THREADS) carry[coff * TC_ROW4 + i] = Y[(TC_HIST + TC_NT - 2 * d) * TC_ROW4 + i];
+            // history for the next tile <- last 2d rows of this tile (other parity: tap readers of Hc are not disturbed)
+            for (int i = tid; i < 2 * d * TC_ROW4; i += TC_THREADS) Hn[i] = Y[(TC_NT - 2 * d) * TC_ROW4 + i];
             __syncthreads();
         }
         if (act) {
@@ -714,42 +842,51 @@ constexpr int BK_NF = 8;
 constexpr int BK_THREADS = 288;
 constexpr int BK_X4 = 4 * 35;                    // float4 per slot: [q][f + 1]
 constexpr int BK_Y4 = 4 * 67;                    // float4 per slot: [q][g + 1]
-constexpr int BK_M = 130 * 2;                    // floats per slot: [h][2]
-constexpr int BK_SMEM_FLOATS = blob::BACK_SIZE + BK_NF * (BK_X4 * 4 + BK_Y4 * 4 + BK_M);
+constexpr int BK_M = 130 * 2;                    // floats per slot: [h][2] -- overlays X (dead after de3)
+static_assert(BK_M <= BK_X4 * 4, "mask buffer must fit in the dead input tile");
+constexpr int BK_SMEM_FLOATS = blob::BACK_SIZE + BK_NF * (BK_X4 * 4 + BK_Y4 * 4);
 
-__global__ void __launch_bounds__(BK_THREADS) k_back(const float* __restrict__ de2, const float* __restrict__ en1,
-                                                     const float* __restrict__ en0, const float* __restrict__ spec,
-                                                     int64_t sb, int64_t sf, int64_t st, int64_t sc,
-                                                     float* __restrict__ outp, int64_t ob, int64_t of, int64_t ot, int64_t oc,
-                                                     int T, int64_t nframes, const float* __restrict__ blobp) {
+__global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict__ de2, const float* __restrict__ en1,
+                                                        const float* __restrict__ en0, const float* __restrict__ spec,
+                                                        int64_t sb, int64_t sf, int64_t st, int64_t sc,
+                                                        float* __restrict__ outp, int64_t ob, int64_t of, int64_t ot, int64_t oc,
+                                                        int T, int64_t nframes, const float* __restrict__ blobp) {
     extern __shared__ float4 smem4[];
     float* W = reinterpret_cast<float*>(smem4);
     float4* X = reinterpret_cast<float4*>(W + blob::BACK_SIZE);
     float4* Y3 = X + BK_NF * BK_X4;
-    float* M = reinterpret_cast<float*>(Y3 + BK_NF * BK_Y4);
+    float* M = reinterpret_cast<float*>(X);          // stride BK_X4 * 4 floats per slot
+    constexpr int M_STRIDE = BK_X4 * 4;
     const int tid = threadIdx.x;
     const int64_t fi0 = (int64_t)blockIdx.x * BK_NF;
 
-    copy_f4(W, blobp + blob::BACK_OFF, blob::BACK_SIZE, tid, BK_THREADS);
-    zero_f4(reinterpret_cast<float*>(X), BK_NF * (BK_X4 + BK_Y4) * 4, tid, BK_THREADS);
-    __syncthreads();
-    // ---- a: x = de2 + en1 into X
+    // ---- a: x = de2 + en1 into X (loads issued before the weight copy so their latency overlaps it)
     if (tid < (BK_NF / 2) * kF2) {
         const int sp2 = tid / kF2, f = tid - sp2 * kF2;
+        float4 u[2][4], v[2][4];
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const int slot = 2 * sp2 + s;
-            if (fi0 + slot < nframes) {
-                const int64_t off = ((fi0 + slot) * kF2 + f) * 16;
-                const float4* pa = reinterpret_cast<const float4*>(de2 + off);
-                const float4* pb = reinterpret_cast<const float4*>(en1 + off);
+            const bool ok = fi0 + slot < nframes;
+            const int64_t off = ((fi0 + (ok ? slot : 0)) * kF2 + f) * 16;
+            const float4* pa = reinterpret_cast<const float4*>(de2 + off);
+            const float4* pb = reinterpret_cast<const float4*>(en1 + off);
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    const float4 u = pa[qd], v = pb[qd];
-                    X[slot * BK_X4 + qd * 35 + f + 1] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
-                }
-            }
+            for (int qd = 0; qd < 4; ++qd) { u[s][qd] = pa[qd]; v[s][qd] = pb[qd]; }
         }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int slot = 2 * sp2 + s;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd)
+                X[slot * BK_X4 + qd * 35 + f + 1] = make_float4(u[s][qd].x + v[s][qd].x, u[s][qd].y + v[s][qd].y, u[s][qd].z + v[s][qd].z, u[s][qd].w + v[s][qd].w);
+        }
+    }
+    copy_f4(W, blobp + blob::BACK_OFF, blob::BACK_SIZE, tid, BK_THREADS);
+    for (int i = tid; i < BK_NF * 8; i += BK_THREADS) {            // zero pad columns of X (0, 34) and Y3 (0, 66)
+        const int slot = i >> 3, q = (i >> 1) & 3, side = i & 1;
+        X[slot * BK_X4 + q * 35 + (side ? 34 : 0)] = make_float4(0.f, 0.f, 0.f, 0.f);
+        Y3[slot * BK_Y4 + q * 67 + (side ? 66 : 0)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
     // ---- b: de3 (thread = 2 slots x 16 co at one output bin g; even bins first so warps are parity-uniform)
@@ -780,8 +917,9 @@ __global__ void __launch_bounds__(BK_THREADS) k_back(const float* __restrict__ d
         for (int s = 0; s < 2; ++s) {
             const int slot = 2 * sp2 + s;
             float* acc = s ? acc1 : acc0;
-            if (fi0 + slot < nframes) {
-                const float4* pe = reinterpret_cast<const float4*>(en0 + ((fi0 + slot) * kF1 + g) * 16);
+            {
+                const bool ok = fi0 + slot < nframes;
+                const float4* pe = reinterpret_cast<const float4*>(en0 + ((fi0 + (ok ? slot : 0)) * kF1 + g) * 16);
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
                     const float4 e = pe[qd];
@@ -811,8 +949,8 @@ __global__ void __launch_bounds__(BK_THREADS) k_back(const float* __restrict__ d
                 m0 = fmaf(i.w, wb.z, m0); m1 = fmaf(i.w, wb.w, m1);
             }
         }
-        M[slot * BK_M + 2 * h] = tanhf(m0);
-        M[slot * BK_M + 2 * h + 1] = tanhf(m1);
+        M[slot * M_STRIDE + 2 * h] = tanhf(m0);
+        M[slot * M_STRIDE + 2 * h + 1] = tanhf(m1);
     }
     __syncthreads();
     // ---- d: ERB expand + complex ratio mask
@@ -824,7 +962,7 @@ __global__ void __launch_bounds__(BK_THREADS) k_back(const float* __restrict__ d
             const int64_t fi = fi0 + slot;
             if (fi >= nframes) continue;
             const int64_t b = fi / T, t = fi - b * T;
-            const float* ms = M + slot * BK_M;
+            const float* ms = M + slot * M_STRIDE;
             float m0, m1;
             if (i < 65) {
                 m0 = ms[2 * i];

@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "blob_layout.h"
 #include "gtcrn_kernels.cuh"
@@ -60,241 +61,153 @@ __device__ __forceinline__ float* stream_base(void* state, int64_t n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// GTConvBlock, one frame for SG_NS streams per CTA.  Same arithmetic as gk::k_gtconv; the two history rows
-// of every stream come from the GT_P ring instead of the previous tile.
-// grid ceil(N/8), 160 threads (132 active = 4 stream pairs x 33 bins).
+// GTConvBlock, one frame for SG_NS streams per CTA.  Same device functions and operation order as gk::k_gtconv
+// (bit-identical results); the two history rows of every stream come from the GT_P ring instead of the previous tile.
+// grid ceil(N/8), 288 threads (264 active = 8 streams x 33 bins), one stream per thread.
 // ------------------------------------------------------------------------------------------------
 constexpr int SG_NS = 8;
-constexpr int SG_THREADS = 160;
-constexpr int SG_ACTIVE = (SG_NS / 2) * kF2;
+constexpr int SG_THREADS = 288;
+constexpr int SG_ACTIVE = SG_NS * kF2;
 constexpr int SG_ROW4 = gk::GT_ROW4;
-template <bool DEC> __host__ __device__ constexpr int sg_smem_floats() {
-    return gk::gt_chunk<DEC>() + SG_NS * 3 * SG_ROW4 * 4 + SG_NS * kF2 * 8 + SG_NS * 3 * 8 + SG_NS * 8;
-}
+constexpr int SG_SMEM_FLOATS = SG_NS * 3 * SG_ROW4 * 4 + SG_NS * kF2 * 8 + SG_NS * 3 * 8;
 
 template <bool DEC>
-__global__ void __launch_bounds__(SG_THREADS) ks_gtconv(const float* __restrict__ xin, const float* __restrict__ skip,
-                                                        float* __restrict__ out, const float* __restrict__ wblk,
-                                                        void* state, int blk, int64_t N) {
+__global__ void __launch_bounds__(SG_THREADS, 2)
+ks_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* __restrict__ out,
+          const __grid_constant__ gk::ParamBlock<gk::gt_chunk<DEC>()> prm, void* state, int blk, int64_t N) {
     using namespace gk;
-    constexpr int PC1_W = DEC ? blob::DECGT_PC1_W : blob::ENCGT_PC1_W;
-    constexpr int PC1_B = DEC ? blob::DECGT_PC1_B : blob::ENCGT_PC1_B;
-    constexpr int MID_W = DEC ? blob::DECGT_FULL_W : blob::ENCGT_DW_W;
-    constexpr int MID_B = DEC ? blob::DECGT_FULL_B : blob::ENCGT_DW_B;
-    constexpr int PC2_W = DEC ? blob::DECGT_PC2_W : blob::ENCGT_PC2_W;
-    constexpr int PC2_B = DEC ? blob::DECGT_PC2_B : blob::ENCGT_PC2_B;
-    constexpr int TDW_W = DEC ? blob::DECGT_TRA_DW_W : blob::ENCGT_TRA_DW_W;
-    constexpr int TDW_B = DEC ? blob::DECGT_TRA_DW_B : blob::ENCGT_TRA_DW_B;
-    constexpr int TPW_W = DEC ? blob::DECGT_TRA_PW_W : blob::ENCGT_TRA_PW_W;
-    constexpr int TPW_B = DEC ? blob::DECGT_TRA_PW_B : blob::ENCGT_TRA_PW_B;
-    constexpr int SLOPE = DEC ? blob::DECGT_SLOPE : blob::ENCGT_SLOPE;
-
     const Header* hdr = reinterpret_cast<const Header*>(state);
     if (hdr->skip) return;
     const int slot_old = (int)(hdr->frame_step & 1);          // holds frame t-2; overwritten with frame t
     const int slot_mid = slot_old ^ 1;                        // holds frame t-1
 
     extern __shared__ float4 smem4[];
-    float* W = reinterpret_cast<float*>(smem4);
-    float4* Pb = reinterpret_cast<float4*>(W + gt_chunk<DEC>());      // [stream][3 rows: t-2, t-1, t][q][col]
-    float* E2 = reinterpret_cast<float*>(Pb + SG_NS * 3 * SG_ROW4);
+    float4* Pb = smem4;                                               // [stream][3 rows: t-2, t-1, t][q][col]
+    float* E2 = reinterpret_cast<float*>(Pb + SG_NS * 3 * SG_ROW4);   // [stream][33][8]
     float* Ev = E2 + SG_NS * kF2 * 8;                                 // [stream][3][8]
-    float* G = Ev + SG_NS * 3 * 8;
 
     const int tid = threadIdx.x;
     const int64_t n0 = (int64_t)blockIdx.x * SG_NS;
-    copy_f4(W, wblk, gt_chunk<DEC>(), tid, SG_THREADS);
-    zero_f4(reinterpret_cast<float*>(Pb), SG_NS * 3 * SG_ROW4 * 4, tid, SG_THREADS);
+    zero_f4(reinterpret_cast<float*>(Pb), SG_SMEM_FLOATS, tid, SG_THREADS);
     __syncthreads();
 
-    const bool act = tid < SG_ACTIVE;
-    const int sp2 = tid / kF2, f = tid - sp2 * kF2;
-    const float a1 = W[SLOPE + 0], a2 = W[SLOPE + 1];
-    float x2[2][8], q[2][8];
-
+    const int ls = tid / kF2, f = tid - ls * kF2;
+    const int64_t n = n0 + ls;
+    const bool act = tid < SG_ACTIVE && n < N;
+    float* ring = nullptr;
     // ---- phase 1: history rows from the ring, point conv 1 of the new frame (also written to the ring)
     if (act) {
+        ring = stream_base(state, n) + kGtP + blk * (2 * kF2 * 16) + f * 16;
+        const float4* h2 = reinterpret_cast<const float4*>(ring + slot_old * (kF2 * 16));
+        const float4* h1 = reinterpret_cast<const float4*>(ring + slot_mid * (kF2 * 16));
+        float4* row = Pb + (ls * 3) * SG_ROW4 + f + 1;
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const int ls = 2 * sp2 + s;
-            const int64_t n = n0 + ls;
-            float p[16];
+        for (int qd = 0; qd < 4; ++qd) { row[qd * 35] = h2[qd]; row[SG_ROW4 + qd * 35] = h1[qd]; }
+        const float4* px = reinterpret_cast<const float4*>(xin + (n * kF2 + f) * 16);
+        float4 v0 = px[0], v1 = px[1];
+        if (DEC) {
+            const float4* ps = reinterpret_cast<const float4*>(skip + (n * kF2 + f) * 16);
+            const float4 u0 = ps[0], u1 = ps[1];
+            v0.x += u0.x; v0.y += u0.y; v0.z += u0.z; v0.w += u0.w;
+            v1.x += u1.x; v1.y += u1.y; v1.z += u1.z; v1.w += u1.w;
+        }
+        const float x1[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float p[16];
+        gt_pc1<DEC>(prm, x1, p);
+        float4* newest = reinterpret_cast<float4*>(ring + slot_old * (kF2 * 16));
 #pragma unroll
-            for (int c = 0; c < 16; ++c) p[c] = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) x2[s][c] = 0.f;
-            if (n < N) {
-                float* ring = stream_base(state, n) + kGtP + blk * (2 * kF2 * 16) + f * 16;
-                const float4* h2 = reinterpret_cast<const float4*>(ring + slot_old * (kF2 * 16));
-                const float4* h1 = reinterpret_cast<const float4*>(ring + slot_mid * (kF2 * 16));
-                float4* row = Pb + (ls * 3) * SG_ROW4 + f + 1;
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) { row[qd * 35] = h2[qd]; row[SG_ROW4 + qd * 35] = h1[qd]; }
-                const float4* px = reinterpret_cast<const float4*>(xin + (n * kF2 + f) * 16);
-                float4 v0 = px[0], v1 = px[1], v2 = px[2], v3 = px[3];
-                if (DEC) {
-                    const float4* ps = reinterpret_cast<const float4*>(skip + (n * kF2 + f) * 16);
-                    const float4 u0 = ps[0], u1 = ps[1], u2 = ps[2], u3 = ps[3];
-                    v0.x += u0.x; v0.y += u0.y; v0.z += u0.z; v0.w += u0.w;
-                    v1.x += u1.x; v1.y += u1.y; v1.z += u1.z; v1.w += u1.w;
-                    v2.x += u2.x; v2.y += u2.y; v2.z += u2.z; v2.w += u2.w;
-                    v3.x += u3.x; v3.y += u3.y; v3.z += u3.z; v3.w += u3.w;
-                }
-                const float x1[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                x2[s][0] = v2.x; x2[s][1] = v2.y; x2[s][2] = v2.z; x2[s][3] = v2.w;
-                x2[s][4] = v3.x; x2[s][5] = v3.y; x2[s][6] = v3.z; x2[s][7] = v3.w;
-#pragma unroll
-                for (int c = 0; c < 16; ++c) p[c] = W[PC1_B + c];
-#pragma unroll
-                for (int ci = 0; ci < 8; ++ci) {
-                    const float4* w4 = reinterpret_cast<const float4*>(W + PC1_W + ci * 16);
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const float4 ww = w4[v];
-                        p[4 * v + 0] = fmaf(x1[ci], ww.x, p[4 * v + 0]);
-                        p[4 * v + 1] = fmaf(x1[ci], ww.y, p[4 * v + 1]);
-                        p[4 * v + 2] = fmaf(x1[ci], ww.z, p[4 * v + 2]);
-                        p[4 * v + 3] = fmaf(x1[ci], ww.w, p[4 * v + 3]);
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < 16; ++c) p[c] = prelu(p[c], a1);
-                float4* newest = reinterpret_cast<float4*>(ring + slot_old * (kF2 * 16));
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) newest[qd] = make_float4(p[4 * qd], p[4 * qd + 1], p[4 * qd + 2], p[4 * qd + 3]);
-            }
-            float4* row = Pb + (ls * 3 + 2) * SG_ROW4 + f + 1;
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) row[qd * 35] = make_float4(p[4 * qd], p[4 * qd + 1], p[4 * qd + 2], p[4 * qd + 3]);
+        for (int qd = 0; qd < 4; ++qd) {
+            const float4 v = make_float4(p[4 * qd], p[4 * qd + 1], p[4 * qd + 2], p[4 * qd + 3]);
+            newest[qd] = v;
+            row[2 * SG_ROW4 + qd * 35] = v;
         }
     }
     if (tid < SG_NS * 16) {                                           // TRA energy history -> Ev rows 0,1
-        const int ls = tid >> 4, r = (tid >> 3) & 1, c = tid & 7;
-        const int64_t n = n0 + ls;
+        const int l2 = tid >> 4, r = (tid >> 3) & 1, c = tid & 7;
+        const int64_t n2 = n0 + l2;
         float v = 0.f;
-        if (n < N) v = stream_base(state, n)[kTraE + blk * 16 + (r == 0 ? slot_old : slot_mid) * 8 + c];
-        Ev[(ls * 3 + r) * 8 + c] = v;
+        if (n2 < N) v = stream_base(state, n2)[kTraE + blk * 16 + (r == 0 ? slot_old : slot_mid) * 8 + c];
+        Ev[(l2 * 3 + r) * 8 + c] = v;
     }
     __syncthreads();
     // ---- phase 2: 3x3 conv + PReLU, point conv 2, energies
+    float q[8];
     if (act) {
-        float d0[16], d1[16];
+        float acc[1][16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) d0[c] = d1[c] = W[MID_B + c];
-        const float4* r0 = Pb + (2 * sp2 * 3) * SG_ROW4 + f;           // stream s, tap kt: row (2 sp2 + s) * 3 + kt
+        for (int c = 0; c < 16; ++c) acc[0][c] = prm.w[GtOff<DEC>::MID_B + c];
+        const float4* r0 = Pb + (ls * 3) * SG_ROW4 + f;
         if (DEC) {
 #pragma unroll 1
-            for (int kt = 0; kt < 3; ++kt) {
-#pragma unroll 1
-                for (int kf = 0; kf < 3; ++kf) {
-                    const float* wk = W + MID_W + (kt * 3 + kf) * 256;
+            for (int kq = 0; kq < 12; ++kq) {
+                const int kf = kq >> 2, qd = kq & 3;
+                float4 in[3];
 #pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        const float4 i0 = r0[kt * SG_ROW4 + qd * 35 + kf];
-                        const float4 i1 = r0[(kt + 3) * SG_ROW4 + qd * 35 + kf];
-                        axpy2<16>(d0, d1, i0.x, i1.x, wk + (4 * qd + 0) * 16);
-                        axpy2<16>(d0, d1, i0.y, i1.y, wk + (4 * qd + 1) * 16);
-                        axpy2<16>(d0, d1, i0.z, i1.z, wk + (4 * qd + 2) * 16);
-                        axpy2<16>(d0, d1, i0.w, i1.w, wk + (4 * qd + 3) * 16);
-                    }
-                }
+                for (int j = 0; j < 3; ++j) in[j] = r0[j * SG_ROW4 + qd * 35 + kf];
+                gt_mid_step<DEC, 1>(prm, kf, qd, in, acc);
             }
         } else {
+#pragma unroll 1
+            for (int kf = 0; kf < 3; ++kf) {
 #pragma unroll
-            for (int kt = 0; kt < 3; ++kt) {
+                for (int qd = 0; qd < 4; ++qd) {
+                    float4 in[3];
 #pragma unroll
-                for (int kf = 0; kf < 3; ++kf) {
-                    const float4* w4 = reinterpret_cast<const float4*>(W + MID_W + (kt * 3 + kf) * 16);
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        const float4 ww = w4[qd];
-                        const float4 i0 = r0[kt * SG_ROW4 + qd * 35 + kf];
-                        const float4 i1 = r0[(kt + 3) * SG_ROW4 + qd * 35 + kf];
-                        d0[4 * qd + 0] = fmaf(i0.x, ww.x, d0[4 * qd + 0]); d1[4 * qd + 0] = fmaf(i1.x, ww.x, d1[4 * qd + 0]);
-                        d0[4 * qd + 1] = fmaf(i0.y, ww.y, d0[4 * qd + 1]); d1[4 * qd + 1] = fmaf(i1.y, ww.y, d1[4 * qd + 1]);
-                        d0[4 * qd + 2] = fmaf(i0.z, ww.z, d0[4 * qd + 2]); d1[4 * qd + 2] = fmaf(i1.z, ww.z, d1[4 * qd + 2]);
-                        d0[4 * qd + 3] = fmaf(i0.w, ww.w, d0[4 * qd + 3]); d1[4 * qd + 3] = fmaf(i1.w, ww.w, d1[4 * qd + 3]);
-                    }
+                    for (int j = 0; j < 3; ++j) in[j] = r0[j * SG_ROW4 + qd * 35 + kf];
+                    gt_mid_step<DEC, 1>(prm, kf, qd, in, acc);
                 }
             }
         }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) { d0[c] = prelu(d0[c], a2); d1[c] = prelu(d1[c], a2); }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) q[0][c] = q[1][c] = W[PC2_B + c];
-#pragma unroll
-        for (int ci = 0; ci < 16; ++ci) axpy2<8>(q[0], q[1], d0[ci], d1[ci], W + PC2_W + ci * 8);
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            float4* e4 = reinterpret_cast<float4*>(E2 + ((2 * sp2 + s) * kF2 + f) * 8);
-            e4[0] = make_float4(q[s][0] * q[s][0], q[s][1] * q[s][1], q[s][2] * q[s][2], q[s][3] * q[s][3]);
-            e4[1] = make_float4(q[s][4] * q[s][4], q[s][5] * q[s][5], q[s][6] * q[s][6], q[s][7] * q[s][7]);
-        }
+        gt_pc2<DEC>(prm, acc[0], q);
+        float4* e4 = reinterpret_cast<float4*>(E2 + (ls * kF2 + f) * 8);
+        e4[0] = make_float4(q[0] * q[0], q[1] * q[1], q[2] * q[2], q[3] * q[3]);
+        e4[1] = make_float4(q[4] * q[4], q[5] * q[5], q[6] * q[6], q[7] * q[7]);
     }
     __syncthreads();
-    // ---- phase 3: TRALite energy of the new frame (same summation order as the offline kernel) -> ring, gate
+    // ---- phase 3: TRALite energy of the new frame (same summation order as the offline kernel) -> ring
     if (tid < SG_NS * 8) {
-        const int ls = tid >> 3, c = tid & 7;
-        const float* e = E2 + ls * kF2 * 8 + c;
-        float s = 0.f;
-#pragma unroll
-        for (int ff = 0; ff < kF2; ++ff) s += e[ff * 8];
-        s = s / 33.0f;
-        Ev[(ls * 3 + 2) * 8 + c] = s;
-        const int64_t n = n0 + ls;
-        if (n < N) stream_base(state, n)[kTraE + blk * 16 + slot_old * 8 + c] = s;
-    }
-    __syncthreads();
-    if (tid < SG_NS * 8) {
-        const int ls = tid >> 3, c = tid & 7;
-        float v = W[TPW_B + c];
-#pragma unroll
-        for (int ci = 0; ci < 8; ++ci) {
-            float y = W[TDW_B + ci];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) y = fmaf(W[TDW_W + k * 8 + ci], Ev[(ls * 3 + k) * 8 + ci], y);
-            v = fmaf(W[TPW_W + ci * 8 + c], y, v);
-        }
-        G[ls * 8 + c] = 1.0f / (1.0f + expf(-v));
+        const int l2 = tid >> 3, c = tid & 7;
+        const float e = gt_energy(E2 + l2 * kF2 * 8 + c);
+        Ev[(l2 * 3 + 2) * 8 + c] = e;
+        const int64_t n2 = n0 + l2;
+        if (n2 < N) stream_base(state, n2)[kTraE + blk * 16 + slot_old * 8 + c] = e;
     }
     __syncthreads();
     // ---- phase 4: gate, shuffle, store
     if (act) {
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const int ls = 2 * sp2 + s;
-            const int64_t n = n0 + ls;
-            if (n < N) {
-                const float* g = G + ls * 8;
-                float4* po = reinterpret_cast<float4*>(out + (n * kF2 + f) * 16);
-#pragma unroll
-                for (int v = 0; v < 4; ++v)
-                    po[v] = make_float4(q[s][2 * v] * g[2 * v], x2[s][2 * v], q[s][2 * v + 1] * g[2 * v + 1], x2[s][2 * v + 1]);
-            }
+        const float4* px = reinterpret_cast<const float4*>(xin + (n * kF2 + f) * 16);
+        float4 v2 = px[2], v3 = px[3];
+        if (DEC) {
+            const float4* ps = reinterpret_cast<const float4*>(skip + (n * kF2 + f) * 16);
+            const float4 u2 = ps[2], u3 = ps[3];
+            v2.x += u2.x; v2.y += u2.y; v2.z += u2.z; v2.w += u2.w;
+            v3.x += u3.x; v3.y += u3.y; v3.z += u3.z; v3.w += u3.w;
         }
+        float gate[8];
+        gt_gate<DEC>(prm, Ev + (ls * 3) * 8, Ev + (ls * 3 + 1) * 8, Ev + (ls * 3 + 2) * 8, gate);
+        float4* po = reinterpret_cast<float4*>(out + (n * kF2 + f) * 16);
+        po[0] = make_float4(q[0] * gate[0], v2.x, q[1] * gate[1], v2.y);
+        po[1] = make_float4(q[2] * gate[2], v2.z, q[3] * gate[3], v2.w);
+        po[2] = make_float4(q[4] * gate[4], v3.x, q[5] * gate[5], v3.y);
+        po[3] = make_float4(q[6] * gate[6], v3.z, q[7] * gate[7], v3.w);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Both GTCNs (8 TCN blocks) for one frame: a pure per-(stream, bin) recurrence.  A thread owns two columns,
 // keeps x in registers through all eight TCNs and touches exactly 2 taps + 1 new row per TCN in the ring.
-// grid ceil(N*33 / 512), 256 threads.
+// No shared memory at all (weights: kernel parameter / constant bank).  grid ceil(N*33 / 512), 256 threads.
 // ------------------------------------------------------------------------------------------------
 constexpr int ST_THREADS = 256;
-constexpr int ST_SMEM_FLOATS = 8 * blob::TCN_SIZE;
 
-__global__ void __launch_bounds__(ST_THREADS) ks_gtcn(const float* __restrict__ xin, float* __restrict__ out,
-                                                      const float* __restrict__ wblk, void* state, int64_t N) {
+__global__ void __launch_bounds__(ST_THREADS, 2)
+ks_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_constant__ gk::ParamBlock<8 * blob::TCN_SIZE> prm,
+        void* state, int64_t N) {
     using namespace gk;
     const Header* hdr = reinterpret_cast<const Header*>(state);
     if (hdr->skip) return;
     const long long step = hdr->frame_step;
-    extern __shared__ float4 smem4[];
-    float* W = reinterpret_cast<float*>(smem4);
     const int tid = threadIdx.x;
-    copy_f4(W, wblk, ST_SMEM_FLOATS, tid, ST_THREADS);
-    __syncthreads();
-
     const int64_t npos = N * kF2;
     int64_t pos[2] = {(int64_t)blockIdx.x * (2 * ST_THREADS) + tid, (int64_t)blockIdx.x * (2 * ST_THREADS) + tid + ST_THREADS};
     bool ok[2] = {pos[0] < npos, pos[1] < npos};
@@ -303,7 +216,7 @@ __global__ void __launch_bounds__(ST_THREADS) ks_gtcn(const float* __restrict__ 
     float x[2][16];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-        const int64_t p = ok[s] ? pos[s] : pos[0];           // inactive second column mirrors the first (no store)
+        const int64_t p = ok[s] ? pos[s] : pos[0];           // an inactive second column mirrors the first (never stored)
         const int64_t n = p / kF2;
         const int f = (int)(p - n * kF2);
         ybase[s] = stream_base(state, n) + kTcnY + f * 16;
@@ -316,44 +229,25 @@ __global__ void __launch_bounds__(ST_THREADS) ks_gtcn(const float* __restrict__ 
     }
 #pragma unroll 1
     for (int gk_ = 0; gk_ < 8; ++gk_) {
-        const int g = gk_ >> 2, k = gk_ & 3, d = 1 << k, row0 = g * 30 + (2 << k) - 2;
+        const int g = gk_ >> 2, k = gk_ & 3, d = 1 << k, row0 = g * 30 + (2 << k) - 2, wo = gk_ * blob::TCN_SIZE;
         const int slotA = (int)(step & (2 * d - 1));          // frame t-2d, overwritten with frame t
         const int slotB = (int)((step + d) & (2 * d - 1));    // frame t-d
-        const float* Wk = W + gk_ * blob::TCN_SIZE;
-        float y1[2][16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) y1[0][c] = y1[1][c] = Wk[blob::TCN_B1 + c];
-#pragma unroll
-        for (int ci = 0; ci < 16; ++ci) axpy2<16>(y1[0], y1[1], x[0][ci], x[1][ci], Wk + blob::TCN_W1 + ci * 16);
-        const float a1 = Wk[blob::TCN_SLOPE + 0], a2 = Wk[blob::TCN_SLOPE + 1], a3 = Wk[blob::TCN_SLOPE + 2];
-        float y2[2][16];
+        float y1[2][16], y2[2][16];
+        tcn_conv1(prm, wo, x, y1);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             float4* rA = reinterpret_cast<float4*>(ybase[s] + (row0 + slotA) * (kF2 * 16));
             const float4* rB = reinterpret_cast<const float4*>(ybase[s] + (row0 + slotB) * (kF2 * 16));
+            float4 ta[4], tb[4];
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
-                const float4 ta = rA[qd], tb = rB[qd];
-                y1[s][4 * qd + 0] = prelu(y1[s][4 * qd + 0], a1); y1[s][4 * qd + 1] = prelu(y1[s][4 * qd + 1], a1);
-                y1[s][4 * qd + 2] = prelu(y1[s][4 * qd + 2], a1); y1[s][4 * qd + 3] = prelu(y1[s][4 * qd + 3], a1);
-                if (s == 0 || ok[1]) rA[qd] = make_float4(y1[s][4 * qd], y1[s][4 * qd + 1], y1[s][4 * qd + 2], y1[s][4 * qd + 3]);
-                const float4 w0 = reinterpret_cast<const float4*>(Wk + blob::TCN_W2)[qd];
-                const float4 w1 = reinterpret_cast<const float4*>(Wk + blob::TCN_W2 + 16)[qd];
-                const float4 w2 = reinterpret_cast<const float4*>(Wk + blob::TCN_W2 + 32)[qd];
-                const float4 bb = reinterpret_cast<const float4*>(Wk + blob::TCN_B2)[qd];
-                y2[s][4 * qd + 0] = prelu(fmaf(w2.x, y1[s][4 * qd + 0], fmaf(w1.x, tb.x, fmaf(w0.x, ta.x, bb.x))), a2);
-                y2[s][4 * qd + 1] = prelu(fmaf(w2.y, y1[s][4 * qd + 1], fmaf(w1.y, tb.y, fmaf(w0.y, ta.y, bb.y))), a2);
-                y2[s][4 * qd + 2] = prelu(fmaf(w2.z, y1[s][4 * qd + 2], fmaf(w1.z, tb.z, fmaf(w0.z, ta.z, bb.z))), a2);
-                y2[s][4 * qd + 3] = prelu(fmaf(w2.w, y1[s][4 * qd + 3], fmaf(w1.w, tb.w, fmaf(w0.w, ta.w, bb.w))), a2);
+            for (int qd = 0; qd < 4; ++qd) { ta[qd] = rA[qd]; tb[qd] = rB[qd]; }
+            if (s == 0 || ok[1]) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) rA[qd] = make_float4(y1[s][4 * qd], y1[s][4 * qd + 1], y1[s][4 * qd + 2], y1[s][4 * qd + 3]);
             }
+            tcn_dw(prm, wo, ta, tb, y1[s], y2[s]);
         }
-        float o[2][16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) { o[0][c] = Wk[blob::TCN_B3 + c] + x[0][c]; o[1][c] = Wk[blob::TCN_B3 + c] + x[1][c]; }
-#pragma unroll
-        for (int ci = 0; ci < 16; ++ci) axpy2<16>(o[0], o[1], y2[0][ci], y2[1][ci], Wk + blob::TCN_W3 + ci * 16);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) { x[0][c] = prelu(o[0][c], a3); x[1][c] = prelu(o[1][c], a3); }
+        tcn_conv3(prm, wo, y2, x);
     }
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
@@ -540,22 +434,35 @@ __global__ void __launch_bounds__(256) ks_convert(int import, void* state, int64
 // ------------------------------------------------------------------------------------------------
 inline int stream_init_attributes() {
     cudaError_t e;
-    const void* fns[] = {(const void*)ks_gtconv<false>, (const void*)ks_gtconv<true>, (const void*)ks_gtcn,
-                         (const void*)ks_stft_step, (const void*)ks_istft_step};
+    const void* fns[] = {(const void*)ks_gtconv<false>, (const void*)ks_gtconv<true>, (const void*)ks_stft_step, (const void*)ks_istft_step};
     for (const void* f : fns) {
         e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
     }
-    e = cudaFuncSetAttribute(ks_gtconv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg_smem_floats<false>() * (int)sizeof(float));
+    e = cudaFuncSetAttribute(ks_gtconv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM_FLOATS * (int)sizeof(float));
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(ks_gtconv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg_smem_floats<true>() * (int)sizeof(float));
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(ks_gtcn, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_FLOATS * (int)sizeof(float));
+    e = cudaFuncSetAttribute(ks_gtconv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM_FLOATS * (int)sizeof(float));
     return (int)e;
 }
 
+// host copies of the per-kernel weight chunks, passed by value as kernel parameters (constant bank)
+struct HostParams {
+    gk::ParamBlock<blob::ENCGT_SIZE> enc[3];
+    gk::ParamBlock<blob::DECGT_SIZE> dec[3];
+    gk::ParamBlock<4 * blob::TCN_SIZE> gtcn[2];
+    gk::ParamBlock<8 * blob::TCN_SIZE> tcn8;
+    void load(const float* blob_host) {
+        for (int i = 0; i < 3; ++i) {
+            memcpy(enc[i].w, blob_host + blob::ENCGT_OFF + i * blob::ENCGT_SIZE, sizeof(enc[i].w));
+            memcpy(dec[i].w, blob_host + blob::DECGT_OFF + i * blob::DECGT_SIZE, sizeof(dec[i].w));
+        }
+        for (int i = 0; i < 2; ++i) memcpy(gtcn[i].w, blob_host + blob::TCN_OFF + i * 4 * blob::TCN_SIZE, sizeof(gtcn[i].w));
+        memcpy(tcn8.w, blob_host + blob::TCN_OFF, sizeof(tcn8.w));
+    }
+};
+
 // model step on spectra already in `spec` ([N][257][2] contiguous); returns the number of launches
-inline int model_step(const float* blobp, void* state, const Ws& ws, const float* spec, float* out, int64_t N, cudaStream_t st) {
+inline int model_step(const float* blobp, const HostParams& hp, void* state, const Ws& ws, const float* spec, float* out, int64_t N, cudaStream_t st) {
     using namespace gk;
     int launches = 0;
     const unsigned gfr = (unsigned)((N + FR_NF - 1) / FR_NF);
@@ -565,16 +472,13 @@ inline int model_step(const float* blobp, void* state, const Ws& ws, const float
     ++launches;
     const unsigned gsg = (unsigned)((N + SG_NS - 1) / SG_NS);
     for (int i = 0; i < 3; ++i) {
-        ks_gtconv<false><<<gsg, SG_THREADS, sg_smem_floats<false>() * sizeof(float), st>>>(
-            ws.act[i], nullptr, ws.act[i + 1], blobp + blob::ENCGT_OFF + i * blob::ENCGT_SIZE, state, i, N);
+        ks_gtconv<false><<<gsg, SG_THREADS, SG_SMEM_FLOATS * sizeof(float), st>>>(ws.act[i], nullptr, ws.act[i + 1], hp.enc[i], state, i, N);
         ++launches;
     }
-    ks_gtcn<<<(unsigned)((N * kF2 + 2 * ST_THREADS - 1) / (2 * ST_THREADS)), ST_THREADS, ST_SMEM_FLOATS * sizeof(float), st>>>(
-        ws.act[3], ws.act[5], blobp + blob::TCN_OFF, state, N);
+    ks_gtcn<<<(unsigned)((N * kF2 + 2 * ST_THREADS - 1) / (2 * ST_THREADS)), ST_THREADS, 0, st>>>(ws.act[3], ws.act[5], hp.tcn8, state, N);
     ++launches;
     for (int i = 0; i < 3; ++i) {
-        ks_gtconv<true><<<gsg, SG_THREADS, sg_smem_floats<true>() * sizeof(float), st>>>(
-            ws.act[5 + i], ws.act[3 - i], ws.act[6 + i], blobp + blob::DECGT_OFF + i * blob::DECGT_SIZE, state, 3 + i, N);
+        ks_gtconv<true><<<gsg, SG_THREADS, SG_SMEM_FLOATS * sizeof(float), st>>>(ws.act[5 + i], ws.act[3 - i], ws.act[6 + i], hp.dec[i], state, 3 + i, N);
         ++launches;
     }
     k_back<<<gfr, BK_THREADS, BK_SMEM_FLOATS * sizeof(float), st>>>(ws.act[8], ws.act[0], ws.en0, spec, kSpecFrame, 2, 0, 1,
@@ -583,16 +487,16 @@ inline int model_step(const float* blobp, void* state, const Ws& ws, const float
     return launches;
 }
 
-inline int step_spec(const float* blobp, void* state, const Ws& ws, const float* spec, float* out, int64_t N, cudaStream_t st) {
-    int launches = model_step(blobp, state, ws, spec, out, N, st);
+inline int step_spec(const float* blobp, const HostParams& hp, void* state, const Ws& ws, const float* spec, float* out, int64_t N, cudaStream_t st) {
+    int launches = model_step(blobp, hp, state, ws, spec, out, N, st);
     ks_advance<<<1, 1, 0, st>>>(state, 0);
     return launches + 1;
 }
 
-inline int step_wav(const float* blobp, void* state, const Ws& ws, const float* hop_in, float* hop_out, int64_t N, cudaStream_t st) {
+inline int step_wav(const float* blobp, const HostParams& hp, void* state, const Ws& ws, const float* hop_in, float* hop_out, int64_t N, cudaStream_t st) {
     const unsigned g4 = (unsigned)((N + 3) / 4);
     ks_stft_step<<<g4, 256, 0, st>>>(state, hop_in, blobp, ws.spec_in, N);
-    int launches = 1 + model_step(blobp, state, ws, ws.spec_in, ws.spec_out, N, st);
+    int launches = 1 + model_step(blobp, hp, state, ws, ws.spec_in, ws.spec_out, N, st);
     ks_istft_step<<<g4, 256, 0, st>>>(state, ws.spec_out, blobp, hop_out, N);
     ks_advance<<<1, 1, 0, st>>>(state, 1);
     return launches + 2;
