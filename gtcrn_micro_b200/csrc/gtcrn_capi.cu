@@ -48,6 +48,8 @@ struct gtcrnb_handle {
     int sm_count = 148;
     float* blob = nullptr;
     gs::HostParams* hp = nullptr;                 // host copies of the weight chunks passed as kernel parameters
+    bool fuse_fft = true;                         // fuse STFT / iSTFT into the front / back kernels in gtcrnb_enhance
+    int tcn_p = 2;                                // frame slots per lane of the GTCN kernel (2..4)
     int gt_enc = 0, gt_dec = 0;                   // index into kGtVariants for the encoder / decoder GTConv kernels
     // activation workspace for one chunk of utterances
     int64_t cap_frames = 0;
@@ -128,37 +130,47 @@ struct ProfScope {
     }
 };
 
-// Split T frames into segments for a walking kernel: minimise waves * (segment length + warm-up).
-int pick_seg_len(int64_t ctas_per_seg_row, int T, int NT, int warm, int slots) {
-    const int max_tiles = (T + NT - 1) / NT;
+// Split T frames into `nseg` equal segments for a walking kernel: minimise waves * (segment work + warm-up + per-CTA overhead).
+// Segments need not be tile aligned (tiles start at the segment's own warm-up frame and slot groups past the end are skipped);
+// `gran` is the granularity at which trailing work is skipped (frames).
+int pick_seg_len(int64_t ctas_per_seg_row, int T, int gran, int warm, int slots) {
     double best = 1e300;
-    int best_len = max_tiles * NT;
-    for (int tiles = max_tiles; tiles >= 1; --tiles) {
-        const int seg_len = tiles * NT;
-        const int nseg = (T + seg_len - 1) / seg_len;
+    int best_len = T;
+    const int max_seg = std::max(1, std::min(64, T / (4 * warm + 1) + 1));
+    for (int nseg = 1; nseg <= max_seg; ++nseg) {
+        const int seg_len = (T + nseg - 1) / nseg;
         const int64_t ctas = ctas_per_seg_row * nseg;
         const double waves = (double)((ctas + slots - 1) / slots);
-        const double cost = waves * (seg_len + (nseg > 1 ? warm : 0) + 0.25 * NT);   // + fixed per-CTA prologue
+        const double work = (double)((seg_len + (nseg > 1 ? warm : 0) + gran - 1) / gran * gran) + 8.0;   // + fixed per-CTA prologue
+        const double cost = waves * work;
         if (cost < best - 1e-9) { best = cost; best_len = seg_len; }
     }
     return best_len;
 }
 
-// The model proper on an internal chunk: spec (strided) -> enhanced spec (strided).
+// Fused wav -> wav mode (wav != nullptr): the STFT runs inside k_front (spectrum parked in h->spec_in for the mask stage)
+// and the iSTFT + overlap-add inside k_back (wav_out must be zeroed by the caller).
 int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t B, int64_t T, float* out,
-              const int64_t os[4], cudaStream_t st) {
+              const int64_t os[4], cudaStream_t st, const float* wav = nullptr, int64_t wav_stride = 0, int L = 0,
+              float* wav_out = nullptr, int64_t wav_out_stride = 0) {
     using namespace gk;
     const int Ti = (int)T;
     const int64_t nframes = B * T;
     const dim3 gfr((unsigned)((nframes + FR_NF - 1) / FR_NF));
+    const bool fused = wav != nullptr;
     {
         ProfScope ps(h, KC_FRONT, nframes, st);
-        k_front<<<gfr, FR_THREADS, FR_SMEM_FLOATS * sizeof(float), st>>>(spec, is[0], is[1], is[2], is[3], Ti, nframes, h->blob, h->en0, h->act[0]);
+        if (fused)
+            k_front<true><<<gfr, FR_THREADS, fr_smem_floats(true) * sizeof(float), st>>>(nullptr, 0, 0, 0, 0, wav, wav_stride, L, h->spec_in,
+                                                                                         Ti, nframes, h->blob, h->en0, h->act[0]);
+        else
+            k_front<false><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, is[0], is[1], is[2], is[3], nullptr, 0, 0, nullptr,
+                                                                                           Ti, nframes, h->blob, h->en0, h->act[0]);
     }
     h->launches++;
     {
         const GtVariant& v = kGtVariants[h->gt_enc];
-        const int seg = pick_seg_len(B, Ti, v.ps * v.g, GT_WARMUP, h->sm_count * h->occ_gt_enc);
+        const int seg = pick_seg_len(B, Ti, v.ps, GT_WARMUP, h->sm_count * h->occ_gt_enc);
         const dim3 g((unsigned)((Ti + seg - 1) / seg), (unsigned)B);
         for (int i = 0; i < 3; ++i) {
             ProfScope ps(h, KC_ENC_GT, nframes, st);
@@ -167,17 +179,22 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
         }
     }
     {
-        const int seg = pick_seg_len(B * 3, Ti, TC_NT, TC_WARMUP, h->sm_count * h->occ_tcn);
-        const dim3 g((unsigned)(((Ti + seg - 1) / seg) * 3), (unsigned)B);
+        const int64_t ncols = B * kF2;
+        const int64_t ctas = (ncols + WC_WARPS - 1) / WC_WARPS;
+        const int P = h->tcn_p;
+        const int seg = pick_seg_len(ctas, Ti, 32, TC_WARMUP, h->sm_count * h->occ_tcn);
+        const dim3 g((unsigned)ctas, (unsigned)((Ti + seg - 1) / seg));
         for (int i = 0; i < 2; ++i) {
             ProfScope ps(h, KC_GTCN, nframes, st);
-            k_gtcn<<<g, TC_THREADS, TC_SMEM_FLOATS * sizeof(float), st>>>(h->act[3 + i], h->act[4 + i], h->hp->gtcn[i], Ti, seg);
+            if (P == 4) k_gtcn<4><<<g, WC_WARPS * 32, wc_smem_floats(4) * sizeof(float), st>>>(h->act[3 + i], h->act[4 + i], h->hp->gtcn[i], Ti, seg, ncols);
+            else if (P == 3) k_gtcn<3><<<g, WC_WARPS * 32, wc_smem_floats(3) * sizeof(float), st>>>(h->act[3 + i], h->act[4 + i], h->hp->gtcn[i], Ti, seg, ncols);
+            else k_gtcn<2><<<g, WC_WARPS * 32, wc_smem_floats(2) * sizeof(float), st>>>(h->act[3 + i], h->act[4 + i], h->hp->gtcn[i], Ti, seg, ncols);
             h->launches++;
         }
     }
     {
         const GtVariant& v = kGtVariants[h->gt_dec];
-        const int seg = pick_seg_len(B, Ti, v.ps * v.g, GT_WARMUP, h->sm_count * h->occ_gt_dec);
+        const int seg = pick_seg_len(B, Ti, v.ps, GT_WARMUP, h->sm_count * h->occ_gt_dec);
         const dim3 g((unsigned)((Ti + seg - 1) / seg), (unsigned)B);
         for (int i = 0; i < 3; ++i) {
             // de_i consumes (previous + en_outs[4 - i]) : skips en4, en3, en2 = act[3], act[2], act[1]
@@ -188,8 +205,14 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
     }
     {
         ProfScope ps(h, KC_BACK, nframes, st);
-        k_back<<<gfr, BK_THREADS, BK_SMEM_FLOATS * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, spec, is[0], is[1], is[2], is[3],
-                                                                         out, os[0], os[1], os[2], os[3], Ti, nframes, h->blob);
+        if (fused) {
+            const int64_t ss[4] = {T * kSpecFrame, 2, kSpecFrame, 1};
+            k_back<true><<<gfr, BK_THREADS, bk_smem_floats(true) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, h->spec_in, ss[0], ss[1], ss[2], ss[3],
+                                                                                        nullptr, 0, 0, 0, 0, wav_out, wav_out_stride, Ti, nframes, h->blob);
+        } else {
+            k_back<false><<<gfr, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, spec, is[0], is[1], is[2], is[3],
+                                                                                          out, os[0], os[1], os[2], os[3], nullptr, 0, Ti, nframes, h->blob);
+        }
     }
     h->launches++;
     CU(cudaGetLastError());
@@ -242,12 +265,12 @@ int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) 
     }
     using namespace gk;
     struct { const void* fn; int floats; } attrs[] = {
-        {(const void*)k_front, FR_SMEM_FLOATS},
+        {(const void*)k_front<false>, fr_smem_floats(false)}, {(const void*)k_front<true>, fr_smem_floats(true)},
         {kGtVariants[0].enc, kGtVariants[0].smem_bytes / 4}, {kGtVariants[0].dec, kGtVariants[0].smem_bytes / 4},
         {kGtVariants[1].enc, kGtVariants[1].smem_bytes / 4}, {kGtVariants[1].dec, kGtVariants[1].smem_bytes / 4},
         {kGtVariants[2].enc, kGtVariants[2].smem_bytes / 4}, {kGtVariants[2].dec, kGtVariants[2].smem_bytes / 4},
-        {(const void*)k_gtcn, TC_SMEM_FLOATS},
-        {(const void*)k_back, BK_SMEM_FLOATS},
+        {(const void*)k_gtcn<2>, wc_smem_floats(2)}, {(const void*)k_gtcn<3>, wc_smem_floats(3)}, {(const void*)k_gtcn<4>, wc_smem_floats(4)},
+        {(const void*)k_back<false>, bk_smem_floats(false)}, {(const void*)k_back<true>, bk_smem_floats(true)},
         {(const void*)k_stft, 0},
         {(const void*)k_istft, 0},
     };
@@ -271,7 +294,11 @@ int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) 
     h->gt_dec = pick("GTCRNB_GT_PS_DEC", 2);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_gt_enc, kGtVariants[h->gt_enc].enc, kGtVariants[h->gt_enc].threads, kGtVariants[h->gt_enc].smem_bytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_gt_dec, kGtVariants[h->gt_dec].dec, kGtVariants[h->gt_dec].threads, kGtVariants[h->gt_dec].smem_bytes);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn, TC_THREADS, TC_SMEM_FLOATS * sizeof(float));
+    if (const char* e = getenv("GTCRNB_FUSE_FFT")) h->fuse_fft = atoi(e) != 0;
+    if (const char* e = getenv("GTCRNB_TCN_P")) h->tcn_p = std::min(4, std::max(2, atoi(e)));
+    if (h->tcn_p == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn<4>, WC_WARPS * 32, wc_smem_floats(4) * sizeof(float));
+    else if (h->tcn_p == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn<3>, WC_WARPS * 32, wc_smem_floats(3) * sizeof(float));
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn<2>, WC_WARPS * 32, wc_smem_floats(2) * sizeof(float));
     h->occ_gt_enc = std::max(1, h->occ_gt_enc); h->occ_gt_dec = std::max(1, h->occ_gt_dec); h->occ_tcn = std::max(1, h->occ_tcn);
     *out = h;
     return GTCRNB_OK;
@@ -356,8 +383,19 @@ int gtcrnb_enhance(gtcrnb_handle* h, const float* wav_dev, int64_t B, int64_t L,
     if (rc) return rc;
     h->last_B = Bc; h->last_T = T;
     const int64_t is[4] = {T * gk::kSpecFrame, 2, gk::kSpecFrame, 1};
+    const int64_t Lout = gk::kHop * (T - 1);
+    // fused STFT / iSTFT path needs 8-byte aligned output rows (vector RED.ADD); otherwise use the separate kernels
+    const bool fuse = h->fuse_fft && (out_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(out_dev) & 7) == 0);
     for (int64_t b0 = B - (B % Bc ? B % Bc : Bc); b0 >= 0; b0 -= Bc) {
         const int64_t nb = std::min(Bc, B - b0);
+        if (fuse) {
+            float* o = out_dev + b0 * out_stride;
+            if (out_stride == Lout) CU(cudaMemsetAsync(o, 0, sizeof(float) * nb * Lout, (cudaStream_t)stream));
+            else CU(cudaMemset2DAsync(o, sizeof(float) * out_stride, 0, sizeof(float) * Lout, nb, (cudaStream_t)stream));
+            rc = run_model(h, nullptr, is, nb, T, nullptr, is, (cudaStream_t)stream, wav_dev + b0 * in_stride, in_stride, (int)L, o, out_stride);
+            if (rc) return rc;
+            continue;
+        }
         rc = gtcrnb_stft(h, wav_dev + b0 * in_stride, nb, L, in_stride, h->spec_in, stream);
         if (rc) return rc;
         rc = run_model(h, h->spec_in, is, nb, T, h->spec_out, is, (cudaStream_t)stream);
@@ -384,7 +422,10 @@ int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int6
         }
     }
     // chunks of ~64 utterance-equivalents of 10 s keep the three engines (H2D, SMs, D2H) overlapped
-    const int64_t Bc = std::max<int64_t>(1, std::min<int64_t>(B, (64 * 160000) / L));
+    // chunk size trades pipeline fill/drain (first H2D and last D2H are exposed) against per-chunk kernel efficiency
+    int64_t chunk_units = 128;                                     // in 10-second-utterance equivalents
+    if (const char* e = getenv("GTCRNB_HOST_CHUNK")) chunk_units = std::max(1, atoi(e));
+    const int64_t Bc = std::max<int64_t>(1, std::min<int64_t>(B, (chunk_units * 160000) / L));
     const size_t need_in = (size_t)Bc * L, need_out = (size_t)Bc * Lout;
     if (need_in > h->stage_in_floats || need_out > h->stage_out_floats) {
         for (int i = 0; i < 2; ++i) {

@@ -111,6 +111,18 @@ __device__ __forceinline__ void fft256(float2* a, float2* b, const float2* tw, i
     fft256_stage(b, a, tw, j, 64); __syncthreads();
 }
 
+// same, for blocks with more than 4 x 64 threads: threads with active == false only take part in the barriers
+__device__ __forceinline__ void fft256_masked(float2* a, float2* b, const float2* tw, int j, bool active) {
+    if (active) fft256_stage(a, b, tw, j, 1);
+    __syncthreads();
+    if (active) fft256_stage(b, a, tw, j, 4);
+    __syncthreads();
+    if (active) fft256_stage(a, b, tw, j, 16);
+    __syncthreads();
+    if (active) fft256_stage(b, a, tw, j, 64);
+    __syncthreads();
+}
+
 __device__ __forceinline__ int reflect_idx(int i, int L) {
     if (i < 0) i = -i;
     if (i >= L) i = 2 * (L - 1) - i;
@@ -248,9 +260,17 @@ constexpr int FR_SFE = 133 * 4;            // [f + 2][4]
 constexpr int FR_A0 = 4 * 69 * 4;          // [q][f' + 2][4]  -- aliases feat|erb (dead once SFE is done)
 constexpr int FR_SLOT = FR_FEAT + FR_ERB + FR_SFE;
 static_assert(FR_A0 <= FR_FEAT + FR_ERB, "a0 must fit in the dead feat|erb region");
-constexpr int FR_SMEM_FLOATS = blob::FRONT_SIZE + FR_NF * FR_SLOT;
+constexpr int FR_FFT_FLOATS = 1540;         // FftTables: tw256 (512) + tw512 (516) + win (512)
+static_assert(sizeof(FftTables) == FR_FFT_FLOATS * 4, "FftTables layout");
+__host__ __device__ constexpr int fr_smem_floats(bool from_wav) { return blob::FRONT_SIZE + FR_NF * FR_SLOT + (from_wav ? FR_FFT_FLOATS : 0); }
 
+// FROM_WAV = false: `spec` is the input spectrum (element strides sb, sf, st, sc), `wav`/`spec_out` unused.
+// FROM_WAV = true : the STFT is fused in: frames are cut from `wav` [B][L] (reflect padding, sqrt-Hann), transformed in
+//                   shared memory (the FFT ping-pong buffers overlay the slot's own feat / sfe regions) and the spectrum is
+//                   written once to `spec_out` [B][T][257][2] for the mask stage; it is never read back here.
+template <bool FROM_WAV>
 __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict__ spec, int64_t sb, int64_t sf, int64_t st, int64_t sc,
+                                                         const float* __restrict__ wav, int64_t wav_stride, int L, float* __restrict__ spec_out,
                                                          int T, int64_t nframes, const float* __restrict__ blobp,
                                                          float* __restrict__ en0, float* __restrict__ en1) {
     extern __shared__ float4 smem4[];
@@ -259,6 +279,70 @@ __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict
     const int tid = threadIdx.x;
     const int64_t fi0 = (int64_t)blockIdx.x * FR_NF;              // first flattened frame (b * T + t) of this CTA
 
+    if (FROM_WAV) {
+        // ---- a (fused STFT): 4 frames per round, 64 threads per 256-point FFT.  A = slot's sfe region, B = slot's feat region.
+        FftTables& tb = *reinterpret_cast<FftTables*>(slots + FR_NF * FR_SLOT);
+        load_fft_tables(tb, blobp, tid, FR_THREADS);
+        copy_f4(W, blobp + blob::FRONT_OFF, blob::FRONT_SIZE, tid, FR_THREADS);
+        for (int i = tid; i < FR_NF * 3; i += FR_THREADS) {       // zero pads of erb (idx 0, 130, 131 per channel)
+            float* e = slots + (i / 3) * FR_SLOT + FR_FEAT + (i % 3) * 132;
+            e[0] = 0.f; e[130] = 0.f; e[131] = 0.f;
+        }
+        __syncthreads();
+        const int fr = tid >> 6, j = tid & 63;
+        const bool fft_thread = tid < 256;
+#pragma unroll 1
+        for (int r = 0; r < FR_NF / 4; ++r) {
+            const int slot = r * 4 + (fft_thread ? fr : 0);
+            const int64_t fi = fi0 + slot;
+            const bool valid = fft_thread && fi < nframes;
+            float2* A = reinterpret_cast<float2*>(slots + slot * FR_SLOT + FR_FEAT + FR_ERB);
+            float2* Bf = reinterpret_cast<float2*>(slots + slot * FR_SLOT);
+            int64_t b = 0; int t = 0;
+            if (valid) { b = fi / T; t = (int)(fi - b * T); }
+            if (fft_thread) {
+                if (valid) {
+                    const float* x = wav + b * wav_stride;
+                    const int base = kHop * t - kHop;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int n = j + 64 * q;
+                        const int i0 = reflect_idx(base + 2 * n, L), i1 = reflect_idx(base + 2 * n + 1, L);
+                        A[n] = make_float2(tb.win[2 * n] * x[i0], tb.win[2 * n + 1] * x[i1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) A[j + 64 * q] = make_float2(0.f, 0.f);
+                }
+            }
+            __syncthreads();
+            fft256_masked(A, Bf, tb.tw256, j, fft_thread);
+            if (fft_thread) {
+                float* fs = slots + slot * FR_SLOT;                // feat region (B is dead now)
+                float2* o = valid ? reinterpret_cast<float2*>(spec_out + fi * kSpecFrame) : nullptr;
+                for (int k = j; k <= 256; k += 64) {
+                    const float2 zk = A[k & 255];
+                    float2 zc = A[(256 - k) & 255];
+                    zc.y = -zc.y;
+                    const float2 w = tb.tw512[k];
+                    const float dx = zk.x - zc.x, dy = zk.y - zc.y;
+                    const float re = 0.5f * (zk.x + zc.x) + 0.5f * (w.x * dy + w.y * dx);
+                    const float im = 0.5f * (zk.y + zc.y) - 0.5f * (w.x * dx - w.y * dy);
+                    if (valid) o[k] = make_float2(re, im);
+                    fs[k] = sqrtf(re * re + im * im + 1e-12f);
+                    fs[260 + k] = re;
+                    fs[520 + k] = im;
+                }
+            }
+            // no barrier needed between rounds: round r+1 touches other slots; the barrier below orders everything
+        }
+        __syncthreads();
+        for (int i = tid; i < FR_NF * 4; i += FR_THREADS) {       // sfe pad columns (its region held FFT buffer A until now)
+            float4* sfe4 = reinterpret_cast<float4*>(slots + (i >> 2) * FR_SLOT + FR_FEAT + FR_ERB);
+            const int c = i & 3;
+            sfe4[c < 2 ? c : 129 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else
     // ---- a: features.  All global loads of the tile are issued first (8 independent loads per thread in flight).
     {
         const bool vec2 = sc == 1 && (((sb | st | sf) & 1) == 0) && ((reinterpret_cast<uintptr_t>(spec) & 7) == 0);
@@ -598,8 +682,20 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
         }
         __syncthreads();
         // ---- phase 2: 3x3 conv over (t-2..t, f-1..f+1), PReLU, point conv 2, q^2
+        // (slot groups lying wholly past the segment end skip the arithmetic: the last tile of an utterance is mostly empty)
         float q[PS][8];
-        if (act) {
+        const bool live = act && (t0 + g * PS < s1);
+        if (!live && act) {
+#pragma unroll
+            for (int s = 0; s < PS; ++s) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) q[s][c] = 0.f;
+                float4* e4 = reinterpret_cast<float4*>(E2 + ((g * PS + s) * kF2 + f) * 8);
+                e4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                e4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (live) {
             float acc[PS][16];
 #pragma unroll
             for (int s = 0; s < PS; ++s)
@@ -678,40 +774,41 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
 
 // ================================================================================================
 // GTCN: 4 TCN blocks (dilation 1,2,4,8) fused.  reference: gtcrn_micro.py:256-336
-// TCNs never mix frequency bins, so a CTA owns 11 of the 33 bins of one utterance segment and walks along time in
-// tiles of TC_NT frames; the block input x stays in registers through all four TCNs.  Weights: kernel parameter
-// (constant bank).  Y holds the conv1 output of the tile for the TCN being evaluated; H[parity] keeps the last 2d
-// rows of every TCN from the previous tile (the streaming tcn_cache, gtcrn_micro_stream.py:620-623), ping-ponged so
-// that saving the new history overlaps the tap reads: 2 barriers per TCN, half the copies of v1.
-// grid (nseg * 3, B), 288 threads (264 active = 24 slot pairs x 11 bins).
+// TCNs never mix frequency bins: every (utterance, bin) column is an independent causal recurrence along time.  The
+// block input x stays in registers through all four TCNs; weights are a kernel parameter (constant bank).  Y holds the
+// conv1 output of the tile for the TCN being evaluated; H[parity] keeps the last 2d rows of every TCN from the previous
+// tile (the streaming tcn_cache, gtcrn_micro_stream.py:620-623), ping-ponged so saving the new history never disturbs the
+// tap readers of the current one.  Segments that do not start at t = 0 warm up on the 30 preceding frames.
 // ================================================================================================
-constexpr int TC_NT = 48;
-constexpr int TC_FC = 11;
-constexpr int TC_THREADS = 288;
-constexpr int TC_ACTIVE = (TC_NT / 2) * TC_FC;
-constexpr int TC_ROW4 = 4 * 12;                 // float4 per row: [q][col (11, padded to 12)]
 constexpr int TC_WARMUP = 30;
-constexpr int TC_SMEM_FLOATS = (TC_NT + 2 * 30) * TC_ROW4 * 4;
 
-// one TCN for two positions: y1 (conv1 output, already PReLU'd) given, taps ta (t-2d) / tb (t-d); x updated in place
-template <class PB>
-__device__ __forceinline__ void tcn_conv1(const PB& prm, int wo, const float (&x)[2][16], float (&y1)[2][16]) {
+// One TCN for P positions held by a thread.  Every weight is loaded once (LDCU) and used for P FFMAs; conv3 accumulates
+// straight into x (bias + residual + sum) and the depthwise stage overwrites y1 in place, so the live state is 2*P*16 floats.
+template <int P, class PB>
+__device__ __forceinline__ void tcn_conv1(const PB& prm, int wo, const float (&x)[P][16], float (&y1)[P][16]) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) y1[0][c] = y1[1][c] = prm.w[wo + blob::TCN_B1 + c];
+    for (int c = 0; c < 16; ++c) {
+        const float bb = prm.w[wo + blob::TCN_B1 + c];
+#pragma unroll
+        for (int s = 0; s < P; ++s) y1[s][c] = bb;
+    }
 #pragma unroll
     for (int ci = 0; ci < 16; ++ci)
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
             const float ww = prm.w[wo + blob::TCN_W1 + ci * 16 + c];
-            y1[0][c] = fmaf(x[0][ci], ww, y1[0][c]);
-            y1[1][c] = fmaf(x[1][ci], ww, y1[1][c]);
+#pragma unroll
+            for (int s = 0; s < P; ++s) y1[s][c] = fmaf(x[s][ci], ww, y1[s][c]);
         }
     const float a1 = prm.w[wo + blob::TCN_SLOPE + 0];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) { y1[0][c] = prelu(y1[0][c], a1); y1[1][c] = prelu(y1[1][c], a1); }
+    for (int s = 0; s < P; ++s)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) y1[s][c] = prelu(y1[s][c], a1);
 }
+// depthwise dilated temporal conv, in place: y[c] <- PReLU(b2 + w0 * tap(t-2d) + w1 * tap(t-d) + w2 * y[c])
 template <class PB>
-__device__ __forceinline__ void tcn_dw(const PB& prm, int wo, const float4 (&ta)[4], const float4 (&tb)[4], const float (&y1)[16], float (&y2)[16]) {
+__device__ __forceinline__ void tcn_dw(const PB& prm, int wo, const float4 (&ta)[4], const float4 (&tb)[4], float (&y)[16]) {
     const float a2 = prm.w[wo + blob::TCN_SLOPE + 1];
 #pragma unroll
     for (int qd = 0; qd < 4; ++qd) {
@@ -721,111 +818,122 @@ __device__ __forceinline__ void tcn_dw(const PB& prm, int wo, const float4 (&ta)
             float v = prm.w[wo + blob::TCN_B2 + c];
             v = fmaf(prm.w[wo + blob::TCN_W2 + c], f4get(ta[qd], i), v);
             v = fmaf(prm.w[wo + blob::TCN_W2 + 16 + c], f4get(tb[qd], i), v);
-            v = fmaf(prm.w[wo + blob::TCN_W2 + 32 + c], y1[c], v);
-            y2[c] = prelu(v, a2);
+            v = fmaf(prm.w[wo + blob::TCN_W2 + 32 + c], y[c], v);
+            y[c] = prelu(v, a2);
         }
     }
 }
-template <class PB>
-__device__ __forceinline__ void tcn_conv3(const PB& prm, int wo, const float (&y2)[2][16], float (&x)[2][16]) {
-    float o[2][16];
+template <int P, class PB>
+__device__ __forceinline__ void tcn_conv3(const PB& prm, int wo, const float (&y2)[P][16], float (&x)[P][16]) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) { const float bb = prm.w[wo + blob::TCN_B3 + c]; o[0][c] = bb + x[0][c]; o[1][c] = bb + x[1][c]; }
+    for (int c = 0; c < 16; ++c) {
+        const float bb = prm.w[wo + blob::TCN_B3 + c];
+#pragma unroll
+        for (int s = 0; s < P; ++s) x[s][c] += bb;
+    }
 #pragma unroll
     for (int ci = 0; ci < 16; ++ci)
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
             const float ww = prm.w[wo + blob::TCN_W3 + ci * 16 + c];
-            o[0][c] = fmaf(y2[0][ci], ww, o[0][c]);
-            o[1][c] = fmaf(y2[1][ci], ww, o[1][c]);
+#pragma unroll
+            for (int s = 0; s < P; ++s) x[s][c] = fmaf(y2[s][ci], ww, x[s][c]);
         }
     const float a3 = prm.w[wo + blob::TCN_SLOPE + 2];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) { x[0][c] = prelu(o[0][c], a3); x[1][c] = prelu(o[1][c], a3); }
+    for (int s = 0; s < P; ++s)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) x[s][c] = prelu(x[s][c], a3);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
-k_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_constant__ ParamBlock<4 * blob::TCN_SIZE> prm, int T, int seg_len) {
-    extern __shared__ float4 smem4[];
-    float4* Y = smem4;                               // [TC_NT rows]
-    float4* H = Y + TC_NT * TC_ROW4;                 // [2 parities][30 rows]
+// GTCN walking kernel, one WARP per (utterance, bin) column: a lane owns frame slots lane, lane+32, .. (P of them) of a
+// 32*P-frame tile, keeps x in registers through the four TCNs and exchanges conv1 outputs with the other lanes through the
+// warp's private shared memory -- only __syncwarp, no CTA barrier, every lane busy (the CTA-tiled v2 kernel lost 21 % of its
+// stall samples to barriers and 8 % of its lanes to 264/288 occupancy).
+// grid (ceil(B*33 / WC_WARPS), nseg), WC_WARPS*32 threads.
+constexpr int WC_WARPS = 8;
+__host__ __device__ constexpr int wc_nt(int P) { return 32 * P; }
+__host__ __device__ constexpr int wc_warp4(int P) { return 4 * wc_nt(P) + 2 * 4 * 30; }       // float4 per warp: Y[q][row] + H[par][q][30]
+__host__ __device__ constexpr int wc_smem_floats(int P) { return WC_WARPS * wc_warp4(P) * 4; }
 
-    const int tid = threadIdx.x, b = blockIdx.y;
-    const int seg = blockIdx.x / 3, col0 = (blockIdx.x - seg * 3) * TC_FC;
-    const int s0 = seg * seg_len, s1 = min(T, s0 + seg_len);
+template <int P>
+__global__ void __launch_bounds__(WC_WARPS * 32, (P <= 2 ? 2 : 1))
+k_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_constant__ ParamBlock<4 * blob::TCN_SIZE> prm,
+       int T, int seg_len, int64_t ncols) {
+    constexpr int NT = wc_nt(P);
+    extern __shared__ float4 smem4[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* Y = smem4 + warp * wc_warp4(P);
+    float4* H = Y + 4 * NT;
+    const int64_t colid = (int64_t)blockIdx.x * WC_WARPS + warp;
+    if (colid >= ncols) return;                                   // whole warp exits together (no CTA barrier below)
+    const int64_t b = colid / kF2;
+    const int f = (int)(colid - b * kF2);
+    const int s0 = blockIdx.y * seg_len, s1 = min(T, s0 + seg_len);
     if (s0 >= s1) return;
     const int tw0 = max(0, s0 - TC_WARMUP);
-    zero_f4(reinterpret_cast<float*>(Y), TC_SMEM_FLOATS, tid, TC_THREADS);
-    __syncthreads();
-
-    const bool act = tid < TC_ACTIVE;
-    const int sp2 = tid / TC_FC, col = tid - sp2 * TC_FC;
-    const int64_t ubase = (int64_t)b * T * kF2 * 16;
+    for (int i = lane; i < 240; i += 32) H[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    const float* xcol = xin + (b * T * kF2 + f) * 16;
+    float* ocol = out + (b * T * kF2 + f) * 16;
     int par = 0;
 
-    for (int t0 = tw0; t0 < s1; t0 += TC_NT, par ^= 1) {
-        float x[2][16];
-        if (act) {
+    for (int t0 = tw0; t0 < s1; t0 += NT, par ^= 1) {
+        float x[P][16];
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int t = t0 + 2 * sp2 + s;
-                if (t < s1) {
-                    const float4* px = reinterpret_cast<const float4*>(xin + ubase + ((int64_t)t * kF2 + col0 + col) * 16);
+        for (int s = 0; s < P; ++s) {
+            const int t = t0 + lane + 32 * s;
+            if (t < s1) {
+                const float4* px = reinterpret_cast<const float4*>(xcol + (int64_t)t * (kF2 * 16));
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const float4 u = px[v];
-                        x[s][4 * v] = u.x; x[s][4 * v + 1] = u.y; x[s][4 * v + 2] = u.z; x[s][4 * v + 3] = u.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) x[s][c] = 0.f;
+                for (int v = 0; v < 4; ++v) {
+                    const float4 u = px[v];
+                    x[s][4 * v] = u.x; x[s][4 * v + 1] = u.y; x[s][4 * v + 2] = u.z; x[s][4 * v + 3] = u.w;
                 }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) x[s][c] = 0.f;
             }
         }
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
             const int d = 1 << k, coff = (2 << k) - 2, wo = k * blob::TCN_SIZE;   // history rows of TCN k start at 2^(k+1) - 2
-            const float4* Hc = H + (par * 30 + coff) * TC_ROW4;                    // frames t0-2d .. t0-1 (from the previous tile)
-            float4* Hn = H + ((par ^ 1) * 30 + coff) * TC_ROW4;
-            float y1[2][16];
-            if (act) {
-                tcn_conv1(prm, wo, x, y1);
+            const float4* Hc = H + par * 120 + coff;                               // [q] stride 30: frames t0-2d .. t0-1
+            float4* Hn = H + (par ^ 1) * 120 + coff;
+            float y[P][16];
+            tcn_conv1<P>(prm, wo, x, y);
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    float4* row = Y + (2 * sp2 + s) * TC_ROW4 + col;
+            for (int s = 0; s < P; ++s)
 #pragma unroll
-                    for (int qd = 0; qd < 4; ++qd)
-                        row[qd * 12] = make_float4(y1[s][4 * qd], y1[s][4 * qd + 1], y1[s][4 * qd + 2], y1[s][4 * qd + 3]);
+                for (int qd = 0; qd < 4; ++qd)
+                    Y[qd * NT + lane + 32 * s] = make_float4(y[s][4 * qd], y[s][4 * qd + 1], y[s][4 * qd + 2], y[s][4 * qd + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < P; ++s) {
+                const int sl = lane + 32 * s;
+                float4 ta[4], tb[4];
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    ta[qd] = sl >= 2 * d ? Y[qd * NT + sl - 2 * d] : Hc[qd * 30 + sl];
+                    tb[qd] = sl >= d ? Y[qd * NT + sl - d] : Hc[qd * 30 + sl + d];
                 }
+                tcn_dw(prm, wo, ta, tb, y[s]);
             }
-            __syncthreads();
-            if (act) {
-                float y2[2][16];
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int sl = 2 * sp2 + s;
-                    const float4* rA = (sl >= 2 * d ? Y + (sl - 2 * d) * TC_ROW4 : Hc + sl * TC_ROW4) + col;
-                    const float4* rB = (sl >= d ? Y + (sl - d) * TC_ROW4 : Hc + (sl + d) * TC_ROW4) + col;
-                    float4 ta[4], tb[4];
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) { ta[qd] = rA[qd * 12]; tb[qd] = rB[qd * 12]; }
-                    tcn_dw(prm, wo, ta, tb, y1[s], y2[s]);
-                }
-                tcn_conv3(prm, wo, y2, x);
+            tcn_conv3<P>(prm, wo, y, x);
+            // history for the next tile <- last 2d rows of this tile (other parity, so this tile's tap readers are undisturbed)
+            for (int i = lane; i < 8 * d; i += 32) {
+                const int qd = i / (2 * d), j = i - qd * 2 * d;
+                Hn[qd * 30 + j] = Y[qd * NT + NT - 2 * d + j];
             }
-            // history for the next tile <- last 2d rows of this tile (other parity: tap readers of Hc are not disturbed)
-            for (int i = tid; i < 2 * d * TC_ROW4; i += TC_THREADS) Hn[i] = Y[(TC_NT - 2 * d) * TC_ROW4 + i];
-            __syncthreads();
+            __syncwarp();
         }
-        if (act) {
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int t = t0 + 2 * sp2 + s;
-                if (t >= s0 && t < s1) {
-                    float4* po = reinterpret_cast<float4*>(out + ubase + ((int64_t)t * kF2 + col0 + col) * 16);
+        for (int s = 0; s < P; ++s) {
+            const int t = t0 + lane + 32 * s;
+            if (t >= s0 && t < s1) {
+                float4* po = reinterpret_cast<float4*>(ocol + (int64_t)t * (kF2 * 16));
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) po[v] = make_float4(x[s][4 * v], x[s][4 * v + 1], x[s][4 * v + 2], x[s][4 * v + 3]);
-                }
+                for (int v = 0; v < 4; ++v) po[v] = make_float4(x[s][4 * v], x[s][4 * v + 1], x[s][4 * v + 2], x[s][4 * v + 3]);
             }
         }
     }
@@ -844,16 +952,25 @@ constexpr int BK_X4 = 4 * 35;                    // float4 per slot: [q][f + 1]
 constexpr int BK_Y4 = 4 * 67;                    // float4 per slot: [q][g + 1]
 constexpr int BK_M = 130 * 2;                    // floats per slot: [h][2] -- overlays X (dead after de3)
 static_assert(BK_M <= BK_X4 * 4, "mask buffer must fit in the dead input tile");
-constexpr int BK_SMEM_FLOATS = blob::BACK_SIZE + BK_NF * (BK_X4 * 4 + BK_Y4 * 4);
+constexpr int BK_FFT_FLOATS = FR_FFT_FLOATS + 256;        // FftTables + 1/envelope
+__host__ __device__ constexpr int bk_smem_floats(bool to_wav) { return blob::BACK_SIZE + BK_NF * (BK_X4 * 4 + BK_Y4 * 4) + (to_wav ? BK_FFT_FLOATS : 0); }
 
+// TO_WAV = false: the enhanced spectrum goes to `outp` (element strides ob, of, ot, oc).
+// TO_WAV = true : the iSTFT is fused in: the masked spectrum stays in shared memory, is inverted (256-point FFT through the
+//                 conjugation trick), windowed and overlap-added straight into `wav_out` [B][256 (T-1)] with vector RED.ADD.
+//                 Every output sample receives exactly two addends on top of a zeroed buffer, so the result does not depend
+//                 on their order (bitwise deterministic).  The caller zeroes wav_out first.
+template <bool TO_WAV>
 __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict__ de2, const float* __restrict__ en1,
                                                         const float* __restrict__ en0, const float* __restrict__ spec,
                                                         int64_t sb, int64_t sf, int64_t st, int64_t sc,
                                                         float* __restrict__ outp, int64_t ob, int64_t of, int64_t ot, int64_t oc,
+                                                        float* __restrict__ wav_out, int64_t wav_stride,
                                                         int T, int64_t nframes, const float* __restrict__ blobp) {
     extern __shared__ float4 smem4[];
     float* W = reinterpret_cast<float*>(smem4);
     float4* X = reinterpret_cast<float4*>(W + blob::BACK_SIZE);
+    float4* const X4all = X;
     float4* Y3 = X + BK_NF * BK_X4;
     float* M = reinterpret_cast<float*>(X);          // stride BK_X4 * 4 floats per slot
     constexpr int M_STRIDE = BK_X4 * 4;
@@ -975,9 +1092,67 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
             }
             const float* p = spec + b * sb + t * st + (int64_t)i * sf;
             const float re = p[0], im = p[sc];
-            float* o = outp + b * ob + t * ot + (int64_t)i * of;
-            o[0] = re * m0 - im * m1;
-            o[oc] = im * m0 + re * m1;
+            if (TO_WAV) {
+                reinterpret_cast<float2*>(Y3 + slot * BK_Y4)[i] = make_float2(re * m0 - im * m1, im * m0 + re * m1);   // Y3 is dead: reuse as spectrum
+            } else {
+                float* o = outp + b * ob + t * ot + (int64_t)i * of;
+                o[0] = re * m0 - im * m1;
+                o[oc] = im * m0 + re * m1;
+            }
+        }
+    }
+    if (TO_WAV) {
+        // ---- e (fused iSTFT): per slot the dead Y3 region (1072 floats) holds [0,514) spectrum | [544,1056) FFT buffer A;
+        //      FFT buffer B (512 floats) lives in the slot's X region (560 floats; the mask stored there is dead after stage d)
+        static_assert(BK_Y4 * 4 >= 544 + 512 && BK_X4 * 4 >= 512, "fused iSTFT buffers must fit in the dead slot regions");
+        FftTables& tb = *reinterpret_cast<FftTables*>(W + bk_smem_floats(false));
+        float* inv_env = reinterpret_cast<float*>(&tb) + FR_FFT_FLOATS;
+        load_fft_tables(tb, blobp, tid, BK_THREADS);
+        if (tid < 256) inv_env[tid] = blobp[blob::FFT_OFF + blob::FFT_INV_ENV + tid];
+        __syncthreads();
+        const int fr = tid >> 6, j = tid & 63;
+        const bool fft_thread = tid < 256;
+#pragma unroll 1
+        for (int r = 0; r < BK_NF / 4; ++r) {
+            const int slot = r * 4 + (fft_thread ? fr : 0);
+            const int64_t fi = fi0 + slot;
+            const bool valid = fft_thread && fi < nframes;
+            float* base = reinterpret_cast<float*>(Y3 + slot * BK_Y4);
+            const float2* X = reinterpret_cast<const float2*>(base);
+            float2* A = reinterpret_cast<float2*>(base + 544);
+            float2* Bf = reinterpret_cast<float2*>(reinterpret_cast<float*>(X4all + slot * BK_X4));
+            if (fft_thread) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k = j + 64 * q;                       // 0..255
+                    float2 xk = X[k], xc = X[256 - k];
+                    xc.y = -xc.y;
+                    if (k == 0) { xk.y = 0.f; xc.y = 0.f; }         // imag of DC / Nyquist ignored (C2R semantics)
+                    const float2 w = tb.tw512[k];
+                    const float dx = xk.x - xc.x, dy = xk.y - xc.y;
+                    const float a = w.x * dx + w.y * dy, bq = w.x * dy - w.y * dx;   // conj(w) * D
+                    A[k] = valid ? make_float2(0.5f * (xk.x + xc.x) - 0.5f * bq, -(0.5f * (xk.y + xc.y) + 0.5f * a)) : make_float2(0.f, 0.f);
+                }
+            }
+            __syncthreads();
+            fft256_masked(A, Bf, tb.tw256, j, fft_thread);
+            if (valid) {
+                const int64_t b = fi / T;
+                const int t = (int)(fi - b * T);
+                float* o = wav_out + b * wav_stride + (int64_t)(t - 1) * kHop;      // frame t covers output samples 256 (t-1) .. 256 (t+1)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int m = j + 64 * q;                       // frame samples 2m, 2m+1
+                    const float2 z = A[m];
+                    const int i = 2 * m;
+                    const bool keep = i < 256 ? t > 0 : t < T - 1;  // first half of frame 0 / second half of the last frame are trimmed
+                    if (keep) {
+                        const float v0 = tb.win[i] * (z.x * (1.0f / 256.0f)) * inv_env[i & 255];
+                        const float v1 = tb.win[i + 1] * (-z.y * (1.0f / 256.0f)) * inv_env[(i + 1) & 255];
+                        atomicAdd(reinterpret_cast<float2*>(o + i), make_float2(v0, v1));
+                    }
+                }
+            }
         }
     }
 }

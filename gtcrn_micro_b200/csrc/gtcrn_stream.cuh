@@ -232,8 +232,8 @@ ks_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_con
         const int g = gk_ >> 2, k = gk_ & 3, d = 1 << k, row0 = g * 30 + (2 << k) - 2, wo = gk_ * blob::TCN_SIZE;
         const int slotA = (int)(step & (2 * d - 1));          // frame t-2d, overwritten with frame t
         const int slotB = (int)((step + d) & (2 * d - 1));    // frame t-d
-        float y1[2][16], y2[2][16];
-        tcn_conv1(prm, wo, x, y1);
+        float y1[2][16];
+        tcn_conv1<2>(prm, wo, x, y1);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             float4* rA = reinterpret_cast<float4*>(ybase[s] + (row0 + slotA) * (kF2 * 16));
@@ -245,9 +245,9 @@ ks_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_con
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) rA[qd] = make_float4(y1[s][4 * qd], y1[s][4 * qd + 1], y1[s][4 * qd + 2], y1[s][4 * qd + 3]);
             }
-            tcn_dw(prm, wo, ta, tb, y1[s], y2[s]);
+            tcn_dw(prm, wo, ta, tb, y1[s]);
         }
-        tcn_conv3(prm, wo, y2, x);
+        tcn_conv3<2>(prm, wo, y1, x);
     }
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
@@ -468,7 +468,7 @@ inline int model_step(const float* blobp, const HostParams& hp, void* state, con
     const unsigned gfr = (unsigned)((N + FR_NF - 1) / FR_NF);
     // T = 1: strides {b: 514, f: 2, t: 0, c: 1}.  k_front / k_back do not know about `skip`; on the skipped call
     // (first wav hop) they run on a zero spectrum and their outputs are simply never consumed.
-    k_front<<<gfr, FR_THREADS, FR_SMEM_FLOATS * sizeof(float), st>>>(spec, kSpecFrame, 2, 0, 1, 1, N, blobp, ws.en0, ws.act[0]);
+    k_front<false><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, kSpecFrame, 2, 0, 1, nullptr, 0, 0, nullptr, 1, N, blobp, ws.en0, ws.act[0]);
     ++launches;
     const unsigned gsg = (unsigned)((N + SG_NS - 1) / SG_NS);
     for (int i = 0; i < 3; ++i) {
@@ -481,8 +481,8 @@ inline int model_step(const float* blobp, const HostParams& hp, void* state, con
         ks_gtconv<true><<<gsg, SG_THREADS, SG_SMEM_FLOATS * sizeof(float), st>>>(ws.act[5 + i], ws.act[3 - i], ws.act[6 + i], hp.dec[i], state, 3 + i, N);
         ++launches;
     }
-    k_back<<<gfr, BK_THREADS, BK_SMEM_FLOATS * sizeof(float), st>>>(ws.act[8], ws.act[0], ws.en0, spec, kSpecFrame, 2, 0, 1,
-                                                                    out, kSpecFrame, 2, 0, 1, 1, N, blobp);
+    k_back<false><<<gfr, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(ws.act[8], ws.act[0], ws.en0, spec, kSpecFrame, 2, 0, 1,
+                                                                                  out, kSpecFrame, 2, 0, 1, nullptr, 0, 1, N, blobp);
     ++launches;
     return launches;
 }

@@ -175,11 +175,14 @@ static float* d_out; static float* d_W;
 static int g_blocks;
 
 template <int P, int NL, bool U>
-static void run_const(const char* tag, int threads) {
+static void run_const(const char* tag, int threads, int smem_limit_kb = 0) {
     int iters = 12000 / (NL * P) + 1;
-    float ms = time_ms([&] { k_const<P, NL, U><<<g_blocks, threads>>>(d_out, iters); });
+    // smem_limit_kb > 0: request that much dynamic shared memory per block to cap the number of resident blocks per SM
+    if (smem_limit_kb) CK(cudaFuncSetAttribute(k_const<P, NL, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit_kb * 1024));
+    float ms = time_ms([&] { k_const<P, NL, U><<<g_blocks, threads, smem_limit_kb * 1024>>>(d_out, iters); });
     double flop = 2.0 * 256 * P * NL * (double)iters * g_blocks * threads;
-    printf("const  %-8s P=%d NL=%2d (%2d KB) thr=%3d : %7.3f ms  %6.2f TFLOP/s\n", tag, P, NL, NL, threads, ms, flop / ms * 1e-9);
+    int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_const<P, NL, U>, threads, smem_limit_kb * 1024);
+    printf("const  %-8s P=%d NL=%2d (%2d KB) thr=%3d warps/SM=%2d : %7.3f ms  %6.2f TFLOP/s\n", tag, P, NL, NL, threads, occ * threads / 32, ms, flop / ms * 1e-9);
 }
 template <int P, int NL, bool G>
 static void run_ld(int threads) {
@@ -223,6 +226,15 @@ int main() {
     run_const<2, 32, false>("loop", 256);
     run_const<2, 60, false>("loop", 256);
     run_const<4, 60, false>("loop", 128);
+    // occupancy sensitivity of the constant-bank feed (LDCU + FFMA.UR): 64 / 32 / 16 / 8 warps per SM
+    run_const<2, 8, false>("loop", 256, 0);
+    run_const<2, 8, false>("loop", 256, 50);
+    run_const<2, 8, false>("loop", 256, 100);
+    run_const<2, 8, false>("loop", 256, 200);
+    run_const<4, 8, false>("loop", 256, 100);
+    run_const<4, 8, false>("loop", 256, 200);
+    run_const<1, 8, false>("loop", 256, 0);
+    run_const<1, 8, false>("loop", 256, 50);
     // broadcast LDS.128
     run_ld<1, 8, false>(256);
     run_ld<2, 8, false>(256);
