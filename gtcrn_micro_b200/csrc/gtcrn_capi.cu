@@ -162,10 +162,10 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
         ProfScope ps(h, KC_FRONT, nframes, st);
         if (fused)
             k_front<true><<<gfr, FR_THREADS, fr_smem_floats(true) * sizeof(float), st>>>(nullptr, 0, 0, 0, 0, wav, wav_stride, L, h->spec_in,
-                                                                                         Ti, nframes, h->blob, h->en0, h->act[0]);
+                                                                                         Ti, nframes, h->blob, h->hp->front, h->en0, h->act[0]);
         else
             k_front<false><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, is[0], is[1], is[2], is[3], nullptr, 0, 0, nullptr,
-                                                                                           Ti, nframes, h->blob, h->en0, h->act[0]);
+                                                                                           Ti, nframes, h->blob, h->hp->front, h->en0, h->act[0]);
     }
     h->launches++;
     {
@@ -208,10 +208,10 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
         if (fused) {
             const int64_t ss[4] = {T * kSpecFrame, 2, kSpecFrame, 1};
             k_back<true><<<gfr, BK_THREADS, bk_smem_floats(true) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, h->spec_in, ss[0], ss[1], ss[2], ss[3],
-                                                                                        nullptr, 0, 0, 0, 0, wav_out, wav_out_stride, Ti, nframes, h->blob);
+                                                                                        nullptr, 0, 0, 0, 0, wav_out, wav_out_stride, Ti, nframes, h->blob, h->hp->back);
         } else {
             k_back<false><<<gfr, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, spec, is[0], is[1], is[2], is[3],
-                                                                                          out, os[0], os[1], os[2], os[3], nullptr, 0, Ti, nframes, h->blob);
+                                                                                          out, os[0], os[1], os[2], os[3], nullptr, 0, Ti, nframes, h->blob, h->hp->back);
         }
     }
     h->launches++;

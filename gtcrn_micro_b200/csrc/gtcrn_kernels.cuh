@@ -253,16 +253,61 @@ __global__ void __launch_bounds__(256) k_istft(const float* __restrict__ spec, i
 // (the streaming path calls the same kernel with T = 1).  Writes en0 [B][T][65][16], en1 [B][T][33][16].
 // ================================================================================================
 constexpr int FR_NF = 8;
-constexpr int FR_THREADS = 288;
-constexpr int FR_FEAT = 3 * 260;           // per slot
-constexpr int FR_ERB = 3 * 132;            // [c][1 + j], zero at 0 and 130
-constexpr int FR_SFE = 133 * 4;            // [f + 2][4]
-constexpr int FR_A0 = 4 * 69 * 4;          // [q][f' + 2][4]  -- aliases feat|erb (dead once SFE is done)
+constexpr int FR_THREADS = 320;            // en1 runs its two output-channel halves on warps 0-4 / 5-9 (warp-uniform weights)
+constexpr int FR_FEAT = 260 * 4;           // per slot: one float4 (mag, re, im, 0) per bin, 257 bins
+constexpr int FR_ERB = 64 * 4;             // per slot: one float4 per ERB band (bins 65.. of the compressed axis); low 65 bins stay in feat
+// sfe and a0 are stored PARITY-SPLIT along the (padded) bin index c: the stride-2 convolutions read c = 2 f' + k, i.e.
+// plane (k & 1), entry f' + (k >> 1) -- consecutive lanes hit consecutive 16-byte entries (no 2-way bank conflict)
+constexpr int FR_SFE4 = 2 * 67;            // float4: [parity][67], c = f + 2 in [0,133)
+constexpr int FR_SFE = FR_SFE4 * 4;
+constexpr int FR_A0_4 = 4 * 2 * 35;        // float4: [q][parity][35], c = f' + 2 in [0,69) -- overlays feat|erb (dead once SFE is done)
+constexpr int FR_A0 = FR_A0_4 * 4;
+constexpr int FR_W_FLOATS = blob::FRONT_EN0_W;     // only the ERB / SFE tables go to shared memory; conv weights are kernel params
 constexpr int FR_SLOT = FR_FEAT + FR_ERB + FR_SFE;
 static_assert(FR_A0 <= FR_FEAT + FR_ERB, "a0 must fit in the dead feat|erb region");
 constexpr int FR_FFT_FLOATS = 1540;         // FftTables: tw256 (512) + tw512 (516) + win (512)
 static_assert(sizeof(FftTables) == FR_FFT_FLOATS * 4, "FftTables layout");
-__host__ __device__ constexpr int fr_smem_floats(bool from_wav) { return blob::FRONT_SIZE + FR_NF * FR_SLOT + (from_wav ? FR_FFT_FLOATS : 0); }
+__host__ __device__ constexpr int fr_smem_floats(bool from_wav) { return FR_W_FLOATS + FR_NF * FR_SLOT + (from_wav ? FR_FFT_FLOATS : 0); }
+
+// en1 for one output-channel half H (compile-time so the weight indices stay warp-uniform): thread = 2 slots x 8 co at one f''
+template <int H, class PB>
+__device__ __forceinline__ void front_en1(const PB& prm, const float* slots, int r, int64_t fi0, int64_t nframes, float* __restrict__ en1) {
+    const int sp2 = r / kF2, f = r - sp2 * kF2, s0 = 2 * sp2, s1 = s0 + 1;
+    float acc0[8], acc1[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc0[c] = acc1[c] = prm.w[blob::FRONT_EN1_B + 8 * H + c];
+    const float4* i0p = reinterpret_cast<const float4*>(slots + s0 * FR_SLOT) + f;
+    const float4* i1p = reinterpret_cast<const float4*>(slots + s1 * FR_SLOT) + f;
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {
+        const int po = (k & 1) * 35 + (k >> 1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 x0 = i0p[q * 70 + po], x1 = i1p[q * 70 + po];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float ww = prm.w[blob::FRONT_EN1_W + (k * 16 + 4 * q + i) * 16 + 8 * H + c];
+                    acc0[c] = fmaf(f4get(x0, i), ww, acc0[c]);
+                    acc1[c] = fmaf(f4get(x1, i), ww, acc1[c]);
+                }
+        }
+    }
+    const float a = prm.w[blob::FRONT_SLOPE + 1];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { acc0[c] = prelu(acc0[c], a); acc1[c] = prelu(acc1[c], a); }
+    if (fi0 + s0 < nframes) {
+        float4* g = reinterpret_cast<float4*>(en1 + ((fi0 + s0) * kF2 + f) * 16 + 8 * H);
+        g[0] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+        g[1] = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
+    }
+    if (fi0 + s1 < nframes) {
+        float4* g = reinterpret_cast<float4*>(en1 + ((fi0 + s1) * kF2 + f) * 16 + 8 * H);
+        g[0] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+        g[1] = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
+    }
+}
 
 // FROM_WAV = false: `spec` is the input spectrum (element strides sb, sf, st, sc), `wav`/`spec_out` unused.
 // FROM_WAV = true : the STFT is fused in: frames are cut from `wav` [B][L] (reflect padding, sqrt-Hann), transformed in
@@ -272,10 +317,11 @@ template <bool FROM_WAV>
 __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict__ spec, int64_t sb, int64_t sf, int64_t st, int64_t sc,
                                                          const float* __restrict__ wav, int64_t wav_stride, int L, float* __restrict__ spec_out,
                                                          int T, int64_t nframes, const float* __restrict__ blobp,
+                                                         const __grid_constant__ ParamBlock<blob::FRONT_SIZE> prm,
                                                          float* __restrict__ en0, float* __restrict__ en1) {
     extern __shared__ float4 smem4[];
     float* W = reinterpret_cast<float*>(smem4);
-    float* slots = W + blob::FRONT_SIZE;       // per slot: [feat | erb | sfe]; a0 overlays feat|erb
+    float* slots = W + FR_W_FLOATS;            // per slot: [feat | erb | sfe]; a0 overlays feat|erb
     const int tid = threadIdx.x;
     const int64_t fi0 = (int64_t)blockIdx.x * FR_NF;              // first flattened frame (b * T + t) of this CTA
 
@@ -283,11 +329,7 @@ __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict
         // ---- a (fused STFT): 4 frames per round, 64 threads per 256-point FFT.  A = slot's sfe region, B = slot's feat region.
         FftTables& tb = *reinterpret_cast<FftTables*>(slots + FR_NF * FR_SLOT);
         load_fft_tables(tb, blobp, tid, FR_THREADS);
-        copy_f4(W, blobp + blob::FRONT_OFF, blob::FRONT_SIZE, tid, FR_THREADS);
-        for (int i = tid; i < FR_NF * 3; i += FR_THREADS) {       // zero pads of erb (idx 0, 130, 131 per channel)
-            float* e = slots + (i / 3) * FR_SLOT + FR_FEAT + (i % 3) * 132;
-            e[0] = 0.f; e[130] = 0.f; e[131] = 0.f;
-        }
+        copy_f4(W, blobp + blob::FRONT_OFF, FR_W_FLOATS, tid, FR_THREADS);
         __syncthreads();
         const int fr = tid >> 6, j = tid & 63;
         const bool fft_thread = tid < 256;
@@ -318,7 +360,7 @@ __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict
             __syncthreads();
             fft256_masked(A, Bf, tb.tw256, j, fft_thread);
             if (fft_thread) {
-                float* fs = slots + slot * FR_SLOT;                // feat region (B is dead now)
+                float4* fs = reinterpret_cast<float4*>(slots + slot * FR_SLOT);   // feat region (B is dead now)
                 float2* o = valid ? reinterpret_cast<float2*>(spec_out + fi * kSpecFrame) : nullptr;
                 for (int k = j; k <= 256; k += 64) {
                     const float2 zk = A[k & 255];
@@ -329,9 +371,7 @@ __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict
                     const float re = 0.5f * (zk.x + zc.x) + 0.5f * (w.x * dy + w.y * dx);
                     const float im = 0.5f * (zk.y + zc.y) - 0.5f * (w.x * dx - w.y * dy);
                     if (valid) o[k] = make_float2(re, im);
-                    fs[k] = sqrtf(re * re + im * im + 1e-12f);
-                    fs[260 + k] = re;
-                    fs[520 + k] = im;
+                    fs[k] = make_float4(sqrtf(re * re + im * im + 1e-12f), re, im, 0.f);
                 }
             }
             // no barrier needed between rounds: round r+1 touches other slots; the barrier below orders everything
@@ -339,8 +379,8 @@ __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict
         __syncthreads();
         for (int i = tid; i < FR_NF * 4; i += FR_THREADS) {       // sfe pad columns (its region held FFT buffer A until now)
             float4* sfe4 = reinterpret_cast<float4*>(slots + (i >> 2) * FR_SLOT + FR_FEAT + FR_ERB);
-            const int c = i & 3;
-            sfe4[c < 2 ? c : 129 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int c = i & 3;                                  // padded bins 0, 1, 131, 132 -> (parity, entry)
+            sfe4[c == 0 ? 0 : c == 1 ? 67 : c == 2 ? 67 + 65 : 66] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     } else
     // ---- a: features.  All global loads of the tile are issued first (8 independent loads per thread in flight).
@@ -360,93 +400,98 @@ __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict
                 else { re[i] = p[0]; im[i] = p[sc]; }
             }
         }
-        copy_f4(W, blobp + blob::FRONT_OFF, blob::FRONT_SIZE, tid, FR_THREADS);
-        for (int i = tid; i < FR_NF * 3; i += FR_THREADS) {       // zero pads of erb (idx 0, 130, 131 per channel) and sfe (4 columns)
-            float* e = slots + (i / 3) * FR_SLOT + FR_FEAT + (i % 3) * 132;
-            e[0] = 0.f; e[130] = 0.f; e[131] = 0.f;
-        }
+        copy_f4(W, blobp + blob::FRONT_OFF, FR_W_FLOATS, tid, FR_THREADS);
         for (int i = tid; i < FR_NF * 4; i += FR_THREADS) {
             float4* sfe4 = reinterpret_cast<float4*>(slots + (i >> 2) * FR_SLOT + FR_FEAT + FR_ERB);
-            const int c = i & 3;
-            sfe4[c < 2 ? c : 129 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int c = i & 3;                                  // padded bins 0, 1, 131, 132 -> (parity, entry)
+            sfe4[c == 0 ? 0 : c == 1 ? 67 : c == 2 ? 67 + 65 : 66] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int idx = tid + i * FR_THREADS;
             if (idx < FR_NF * kBins) {
                 const int slot = idx / kBins, k = idx - slot * kBins;
-                float* fs = slots + slot * FR_SLOT;
-                fs[k] = sqrtf(re[i] * re[i] + im[i] * im[i] + 1e-12f);
-                fs[260 + k] = re[i];
-                fs[520 + k] = im[i];
+                reinterpret_cast<float4*>(slots + slot * FR_SLOT)[k] = make_float4(sqrtf(re[i] * re[i] + im[i] * im[i] + 1e-12f), re[i], im[i], 0.f);
             }
         }
     }
     __syncthreads();
-    // ---- b: ERB compress (sparse triangular bank)
-    {
-        const int* estart = reinterpret_cast<const int*>(W + blob::FRONT_ERB_START);
-        const int* ecnt = reinterpret_cast<const int*>(W + blob::FRONT_ERB_CNT);
-        const float* ew = W + blob::FRONT_ERB_W;
-        for (int idx = tid; idx < FR_NF * 3 * kErb; idx += FR_THREADS) {
-            const int slot = idx / (3 * kErb), r = idx - slot * 3 * kErb, c = r / kErb, jb = r - c * kErb;
-            const float* fs = slots + slot * FR_SLOT + c * 260;
-            float v;
-            if (jb < 65) {
-                v = fs[jb];
-            } else {
-                const int bnd = jb - 65, s = estart[bnd], n = ecnt[bnd];
-                v = 0.f;
-                for (int i = 0; i < n; ++i) v = fmaf(ew[bnd * blob::kErbMaxTap + i], fs[65 + s + i], v);
-            }
-            slots[slot * FR_SLOT + FR_FEAT + c * 132 + 1 + jb] = v;
+    // ---- b: ERB compress (sparse triangular bank, <= 12 contiguous taps per band): thread = (band, slot pair); each tap weight
+    //      is loaded once and applied to the (mag, re, im) float4 of two slots.  The 65 low bins are used in place (no copy).
+    if (tid < 64 * (FR_NF / 2)) {
+        const int bnd = tid & 63, sp2 = tid >> 6;
+        const int s = reinterpret_cast<const int*>(W + blob::FRONT_ERB_START)[bnd], n = reinterpret_cast<const int*>(W + blob::FRONT_ERB_CNT)[bnd];
+        const float* ew = W + blob::FRONT_ERB_W + bnd * blob::kErbMaxTap;
+        const float4* f0 = reinterpret_cast<const float4*>(slots + (2 * sp2) * FR_SLOT) + 65 + s;
+        const float4* f1 = reinterpret_cast<const float4*>(slots + (2 * sp2 + 1) * FR_SLOT) + 65 + s;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        for (int i = 0; i < n; ++i) {
+            const float w = ew[i];
+            const float4 x0 = f0[i], x1 = f1[i];
+            a0.x = fmaf(w, x0.x, a0.x); a0.y = fmaf(w, x0.y, a0.y); a0.z = fmaf(w, x0.z, a0.z);
+            a1.x = fmaf(w, x1.x, a1.x); a1.y = fmaf(w, x1.y, a1.y); a1.z = fmaf(w, x1.z, a1.z);
         }
+        reinterpret_cast<float4*>(slots + (2 * sp2) * FR_SLOT + FR_FEAT)[bnd] = a0;
+        reinterpret_cast<float4*>(slots + (2 * sp2 + 1) * FR_SLOT + FR_FEAT)[bnd] = a1;
     }
     __syncthreads();
-    // ---- c: SFE-Lite (depthwise 3-tap along F, no bias)
+    // ---- c: SFE-Lite (depthwise 3-tap along the 129 compressed bins, zero padded, no bias)
     {
-        const float* sw = W + blob::FRONT_SFE_W;
+        const float* sw = W + blob::FRONT_SFE_W;                   // [c][k]
         for (int idx = tid; idx < FR_NF * kErb; idx += FR_THREADS) {
             const int slot = idx / kErb, f = idx - slot * kErb;
-            const float* e = slots + slot * FR_SLOT + FR_FEAT + f;
+            const float4* lo = reinterpret_cast<const float4*>(slots + slot * FR_SLOT);            // compressed bins 0..64 = spectrum bins
+            const float4* hi = reinterpret_cast<const float4*>(slots + slot * FR_SLOT + FR_FEAT);  // compressed bins 65..128 = ERB bands
+            float4 t[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int j = f + k - 1;
+                t[k] = (j < 0 || j > 128) ? make_float4(0.f, 0.f, 0.f, 0.f) : (j < 65 ? lo[j] : hi[j - 65]);
+            }
             float4 v;
-            v.x = sw[0] * e[0] + sw[1] * e[1] + sw[2] * e[2];
-            v.y = sw[3] * e[132] + sw[4] * e[133] + sw[5] * e[134];
-            v.z = sw[6] * e[264] + sw[7] * e[265] + sw[8] * e[266];
+            v.x = sw[0] * t[0].x + sw[1] * t[1].x + sw[2] * t[2].x;
+            v.y = sw[3] * t[0].y + sw[4] * t[1].y + sw[5] * t[2].y;
+            v.z = sw[6] * t[0].z + sw[7] * t[1].z + sw[8] * t[2].z;
             v.w = 0.f;
-            reinterpret_cast<float4*>(slots + slot * FR_SLOT + FR_FEAT + FR_ERB)[f + 2] = v;
+            const int c = f + 2;
+            reinterpret_cast<float4*>(slots + slot * FR_SLOT + FR_FEAT + FR_ERB)[(c & 1) * 67 + (c >> 1)] = v;
         }
     }
     __syncthreads();
-    // ---- d: en0  (thread = 2 slots x 16 co at one f').  Output a0 overlays the dead feat|erb region; its pad columns are zeroed here.
+    // ---- d: en0  (thread = 2 slots x 16 co at one f').  Output a0 overlays the dead feat|erb region; its pad bins are zeroed here.
     if (tid >= 160 && tid < 160 + FR_NF * 16) {
-        const int i = tid - 160, slot = i >> 4, q = (i >> 2) & 3, c = i & 3;
-        reinterpret_cast<float4*>(slots + slot * FR_SLOT)[q * 69 + (c < 2 ? c : 65 + c)] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int i = tid - 160, slot = i >> 4, q = (i >> 2) & 3, c = i & 3;   // padded bins 0, 1, 67, 68
+        reinterpret_cast<float4*>(slots + slot * FR_SLOT)[q * 70 + (c == 0 ? 0 : c == 1 ? 35 : c == 2 ? 35 + 33 : 34)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (tid < (FR_NF / 2) * kF1) {
         const int sp2 = tid / kF1, f = tid - sp2 * kF1, s0 = 2 * sp2, s1 = s0 + 1;
         float acc0[16], acc1[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = W[blob::FRONT_EN0_B + c];
-        const float4* i0p = reinterpret_cast<const float4*>(slots + s0 * FR_SLOT + FR_FEAT + FR_ERB) + 2 * f;
-        const float4* i1p = reinterpret_cast<const float4*>(slots + s1 * FR_SLOT + FR_FEAT + FR_ERB) + 2 * f;
+        for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = prm.w[blob::FRONT_EN0_B + c];
+        const float4* i0p = reinterpret_cast<const float4*>(slots + s0 * FR_SLOT + FR_FEAT + FR_ERB) + f;
+        const float4* i1p = reinterpret_cast<const float4*>(slots + s1 * FR_SLOT + FR_FEAT + FR_ERB) + f;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            const float4 x0 = i0p[k], x1 = i1p[k];
-            const float* w = W + blob::FRONT_EN0_W + k * 48;
-            axpy2<16>(acc0, acc1, x0.x, x1.x, w);
-            axpy2<16>(acc0, acc1, x0.y, x1.y, w + 16);
-            axpy2<16>(acc0, acc1, x0.z, x1.z, w + 32);
+            const float4 x0 = i0p[(k & 1) * 67 + (k >> 1)], x1 = i1p[(k & 1) * 67 + (k >> 1)];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float ww = prm.w[blob::FRONT_EN0_W + k * 48 + i * 16 + c];
+                    acc0[c] = fmaf(f4get(x0, i), ww, acc0[c]);
+                    acc1[c] = fmaf(f4get(x1, i), ww, acc1[c]);
+                }
         }
-        const float a = W[blob::FRONT_SLOPE + 0];
+        const float a = prm.w[blob::FRONT_SLOPE + 0];
 #pragma unroll
         for (int c = 0; c < 16; ++c) { acc0[c] = prelu(acc0[c], a); acc1[c] = prelu(acc1[c], a); }
         float4* o0 = reinterpret_cast<float4*>(slots + s0 * FR_SLOT);
         float4* o1 = reinterpret_cast<float4*>(slots + s1 * FR_SLOT);
+        const int cp = f + 2, po = (cp & 1) * 35 + (cp >> 1);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            o0[q * 69 + f + 2] = make_float4(acc0[4 * q], acc0[4 * q + 1], acc0[4 * q + 2], acc0[4 * q + 3]);
-            o1[q * 69 + f + 2] = make_float4(acc1[4 * q], acc1[4 * q + 1], acc1[4 * q + 2], acc1[4 * q + 3]);
+            o0[q * 70 + po] = make_float4(acc0[4 * q], acc0[4 * q + 1], acc0[4 * q + 2], acc0[4 * q + 3]);
+            o1[q * 70 + po] = make_float4(acc1[4 * q], acc1[4 * q + 1], acc1[4 * q + 2], acc1[4 * q + 3]);
         }
         if (fi0 + s0 < nframes) {
             float4* g = reinterpret_cast<float4*>(en0 + ((fi0 + s0) * kF1 + f) * 16);
@@ -460,39 +505,12 @@ __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict
         }
     }
     __syncthreads();
-    // ---- e: en1  (thread = 2 slots x 8 co at one f'')
-    if (tid < 2 * (FR_NF / 2) * kF2) {
-        const int h = tid / ((FR_NF / 2) * kF2), r = tid - h * (FR_NF / 2) * kF2;
-        const int sp2 = r / kF2, f = r - sp2 * kF2, s0 = 2 * sp2, s1 = s0 + 1;
-        float acc0[8], acc1[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc0[c] = acc1[c] = W[blob::FRONT_EN1_B + 8 * h + c];
-        const float4* i0p = reinterpret_cast<const float4*>(slots + s0 * FR_SLOT) + 2 * f;
-        const float4* i1p = reinterpret_cast<const float4*>(slots + s1 * FR_SLOT) + 2 * f;
-#pragma unroll 1
-        for (int k = 0; k < 5; ++k) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 x0 = i0p[q * 69 + k], x1 = i1p[q * 69 + k];
-                const float* w = W + blob::FRONT_EN1_W + (k * 16 + 4 * q) * 16 + 8 * h;
-                axpy2<8>(acc0, acc1, x0.x, x1.x, w);
-                axpy2<8>(acc0, acc1, x0.y, x1.y, w + 16);
-                axpy2<8>(acc0, acc1, x0.z, x1.z, w + 32);
-                axpy2<8>(acc0, acc1, x0.w, x1.w, w + 48);
-            }
-        }
-        const float a = W[blob::FRONT_SLOPE + 1];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) { acc0[c] = prelu(acc0[c], a); acc1[c] = prelu(acc1[c], a); }
-        if (fi0 + s0 < nframes) {
-            float4* g = reinterpret_cast<float4*>(en1 + ((fi0 + s0) * kF2 + f) * 16 + 8 * h);
-            g[0] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
-            g[1] = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
-        }
-        if (fi0 + s1 < nframes) {
-            float4* g = reinterpret_cast<float4*>(en1 + ((fi0 + s1) * kF2 + f) * 16 + 8 * h);
-            g[0] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
-            g[1] = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
+    // ---- e: en1: output-channel half 0 on warps 0-4, half 1 on warps 5-9 (132 of 160 lanes each)
+    {
+        const int half = tid >= 160, r = tid - half * 160;
+        if (r < (FR_NF / 2) * kF2) {
+            if (half == 0) front_en1<0>(prm, slots, r, fi0, nframes, en1);
+            else front_en1<1>(prm, slots, r, fi0, nframes, en1);
         }
     }
 }
@@ -953,7 +971,53 @@ constexpr int BK_Y4 = 4 * 67;                    // float4 per slot: [q][g + 1]
 constexpr int BK_M = 130 * 2;                    // floats per slot: [h][2] -- overlays X (dead after de3)
 static_assert(BK_M <= BK_X4 * 4, "mask buffer must fit in the dead input tile");
 constexpr int BK_FFT_FLOATS = FR_FFT_FLOATS + 256;        // FftTables + 1/envelope
-__host__ __device__ constexpr int bk_smem_floats(bool to_wav) { return blob::BACK_SIZE + BK_NF * (BK_X4 * 4 + BK_Y4 * 4) + (to_wav ? BK_FFT_FLOATS : 0); }
+constexpr int BK_W_OFF = blob::BACK_DE4_W;                 // only de4 / inverse-ERB tables go to shared memory (non-uniform indices);
+constexpr int BK_W_FLOATS = blob::BACK_SIZE - BK_W_OFF;    // the de3 weights are a kernel parameter
+__host__ __device__ constexpr int bk_smem_floats(bool to_wav) { return BK_W_FLOATS + BK_NF * (BK_X4 * 4 + BK_Y4 * 4) + (to_wav ? BK_FFT_FLOATS : 0); }
+
+// de3 for output bins of one parity (compile-time, so tap set and weight indices are warp-uniform): thread = 2 slots x 16 co.
+// transposed conv in gather form: even g = 2m uses taps k = 0,2,4 on input bins m+1, m, m-1; odd g = 2m+1 taps k = 1,3 on m+1, m.
+template <int ODD, class PB>
+__device__ __forceinline__ void back_de3(const PB& prm, const float4* X, float4* Y3, int sp2, int m, int64_t fi0, int64_t nframes,
+                                         const float* __restrict__ en0) {
+    const int g = 2 * m + ODD;
+    float acc0[16], acc1[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = prm.w[blob::BACK_DE3_B + c];
+    const float4* x0 = X + (2 * sp2) * BK_X4;
+    const float4* x1 = x0 + BK_X4;
+#pragma unroll 1
+    for (int j = 0; j < 3 - ODD; ++j) {
+        const int colx = m + 2 - j;                            // input bin f = m + 1 - j, stored at col f + 1
+        const int wb = blob::BACK_DE3_W + (2 * j + ODD) * 256;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            const float4 i0 = x0[qd * 35 + colx], i1 = x1[qd * 35 + colx];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float ww = prm.w[wb + (4 * qd + i) * 16 + c];
+                    acc0[c] = fmaf(f4get(i0, i), ww, acc0[c]);
+                    acc1[c] = fmaf(f4get(i1, i), ww, acc1[c]);
+                }
+        }
+    }
+    const float a = prm.w[blob::BACK_SLOPE + 0];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int slot = 2 * sp2 + s;
+        float* acc = s ? acc1 : acc0;
+        const bool ok = fi0 + slot < nframes;
+        const float4* pe = reinterpret_cast<const float4*>(en0 + ((fi0 + (ok ? slot : 0)) * kF1 + g) * 16);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            const float4 e = pe[qd];
+            Y3[slot * BK_Y4 + qd * 67 + g + 1] = make_float4(prelu(acc[4 * qd], a) + e.x, prelu(acc[4 * qd + 1], a) + e.y,
+                                                             prelu(acc[4 * qd + 2], a) + e.z, prelu(acc[4 * qd + 3], a) + e.w);
+        }
+    }
+}
 
 // TO_WAV = false: the enhanced spectrum goes to `outp` (element strides ob, of, ot, oc).
 // TO_WAV = true : the iSTFT is fused in: the masked spectrum stays in shared memory, is inverted (256-point FFT through the
@@ -966,10 +1030,12 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
                                                         int64_t sb, int64_t sf, int64_t st, int64_t sc,
                                                         float* __restrict__ outp, int64_t ob, int64_t of, int64_t ot, int64_t oc,
                                                         float* __restrict__ wav_out, int64_t wav_stride,
-                                                        int T, int64_t nframes, const float* __restrict__ blobp) {
+                                                        int T, int64_t nframes, const float* __restrict__ blobp,
+                                                        const __grid_constant__ ParamBlock<blob::BACK_SIZE> prm) {
     extern __shared__ float4 smem4[];
-    float* W = reinterpret_cast<float*>(smem4);
-    float4* X = reinterpret_cast<float4*>(W + blob::BACK_SIZE);
+    float* Wsm = reinterpret_cast<float*>(smem4);
+    float* W = Wsm - BK_W_OFF;                       // so that W[blob::BACK_xxx] addresses the copied sub-range
+    float4* X = reinterpret_cast<float4*>(Wsm + BK_W_FLOATS);
     float4* const X4all = X;
     float4* Y3 = X + BK_NF * BK_X4;
     float* M = reinterpret_cast<float*>(X);          // stride BK_X4 * 4 floats per slot
@@ -999,52 +1065,19 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
                 X[slot * BK_X4 + qd * 35 + f + 1] = make_float4(u[s][qd].x + v[s][qd].x, u[s][qd].y + v[s][qd].y, u[s][qd].z + v[s][qd].z, u[s][qd].w + v[s][qd].w);
         }
     }
-    copy_f4(W, blobp + blob::BACK_OFF, blob::BACK_SIZE, tid, BK_THREADS);
+    copy_f4(Wsm, blobp + blob::BACK_OFF + BK_W_OFF, BK_W_FLOATS, tid, BK_THREADS);
     for (int i = tid; i < BK_NF * 8; i += BK_THREADS) {            // zero pad columns of X (0, 34) and Y3 (0, 66)
         const int slot = i >> 3, q = (i >> 1) & 3, side = i & 1;
         X[slot * BK_X4 + q * 35 + (side ? 34 : 0)] = make_float4(0.f, 0.f, 0.f, 0.f);
         Y3[slot * BK_Y4 + q * 67 + (side ? 66 : 0)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    // ---- b: de3 (thread = 2 slots x 16 co at one output bin g; even bins first so warps are parity-uniform)
-    if (tid < (BK_NF / 2) * kF1) {
-        const int sp2 = tid / kF1, pg = tid - sp2 * kF1;
-        const int g = pg < 33 ? 2 * pg : 2 * (pg - 33) + 1;
-        const int m = g >> 1, odd = g & 1, ntap = 3 - odd;
-        float acc0[16], acc1[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = W[blob::BACK_DE3_B + c];
-        const float4* x0 = X + (2 * sp2) * BK_X4;
-        const float4* x1 = x0 + BK_X4;
-#pragma unroll 1
-        for (int j = 0; j < ntap; ++j) {
-            const int k = 2 * j + odd, colx = m + 2 - j;       // input bin f = m + 1 - j, stored at col f + 1
-            const float* wk = W + blob::BACK_DE3_W + k * 256;
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
-                const float4 i0 = x0[qd * 35 + colx], i1 = x1[qd * 35 + colx];
-                axpy2<16>(acc0, acc1, i0.x, i1.x, wk + (4 * qd + 0) * 16);
-                axpy2<16>(acc0, acc1, i0.y, i1.y, wk + (4 * qd + 1) * 16);
-                axpy2<16>(acc0, acc1, i0.z, i1.z, wk + (4 * qd + 2) * 16);
-                axpy2<16>(acc0, acc1, i0.w, i1.w, wk + (4 * qd + 3) * 16);
-            }
-        }
-        const float a = W[blob::BACK_SLOPE + 0];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const int slot = 2 * sp2 + s;
-            float* acc = s ? acc1 : acc0;
-            {
-                const bool ok = fi0 + slot < nframes;
-                const float4* pe = reinterpret_cast<const float4*>(en0 + ((fi0 + (ok ? slot : 0)) * kF1 + g) * 16);
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    const float4 e = pe[qd];
-                    Y3[slot * BK_Y4 + qd * 67 + g + 1] = make_float4(prelu(acc[4 * qd], a) + e.x, prelu(acc[4 * qd + 1], a) + e.y,
-                                                                     prelu(acc[4 * qd + 2], a) + e.z, prelu(acc[4 * qd + 3], a) + e.w);
-                }
-            }
-        }
+    // ---- b: de3: even output bins on warps 0-4 (132 of 160 lanes), odd bins on warps 5-8 (128 lanes)
+    if (tid < 160) {
+        if (tid < (BK_NF / 2) * 33) back_de3<0>(prm, X, Y3, tid / 33, tid % 33, fi0, nframes, en0);
+    } else {
+        const int r = tid - 160;
+        back_de3<1>(prm, X, Y3, r >> 5, r & 31, fi0, nframes, en0);
     }
     __syncthreads();
     // ---- c: de4 (16 -> 2) + tanh -> mask on the 129 ERB bins
@@ -1105,7 +1138,7 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
         // ---- e (fused iSTFT): per slot the dead Y3 region (1072 floats) holds [0,514) spectrum | [544,1056) FFT buffer A;
         //      FFT buffer B (512 floats) lives in the slot's X region (560 floats; the mask stored there is dead after stage d)
         static_assert(BK_Y4 * 4 >= 544 + 512 && BK_X4 * 4 >= 512, "fused iSTFT buffers must fit in the dead slot regions");
-        FftTables& tb = *reinterpret_cast<FftTables*>(W + bk_smem_floats(false));
+        FftTables& tb = *reinterpret_cast<FftTables*>(Wsm + bk_smem_floats(false));
         float* inv_env = reinterpret_cast<float*>(&tb) + FR_FFT_FLOATS;
         load_fft_tables(tb, blobp, tid, BK_THREADS);
         if (tid < 256) inv_env[tid] = blobp[blob::FFT_OFF + blob::FFT_INV_ENV + tid];

@@ -451,7 +451,11 @@ struct HostParams {
     gk::ParamBlock<blob::DECGT_SIZE> dec[3];
     gk::ParamBlock<4 * blob::TCN_SIZE> gtcn[2];
     gk::ParamBlock<8 * blob::TCN_SIZE> tcn8;
+    gk::ParamBlock<blob::FRONT_SIZE> front;
+    gk::ParamBlock<blob::BACK_SIZE> back;
     void load(const float* blob_host) {
+        memcpy(front.w, blob_host + blob::FRONT_OFF, sizeof(front.w));
+        memcpy(back.w, blob_host + blob::BACK_OFF, sizeof(back.w));
         for (int i = 0; i < 3; ++i) {
             memcpy(enc[i].w, blob_host + blob::ENCGT_OFF + i * blob::ENCGT_SIZE, sizeof(enc[i].w));
             memcpy(dec[i].w, blob_host + blob::DECGT_OFF + i * blob::DECGT_SIZE, sizeof(dec[i].w));
@@ -468,7 +472,7 @@ inline int model_step(const float* blobp, const HostParams& hp, void* state, con
     const unsigned gfr = (unsigned)((N + FR_NF - 1) / FR_NF);
     // T = 1: strides {b: 514, f: 2, t: 0, c: 1}.  k_front / k_back do not know about `skip`; on the skipped call
     // (first wav hop) they run on a zero spectrum and their outputs are simply never consumed.
-    k_front<false><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, kSpecFrame, 2, 0, 1, nullptr, 0, 0, nullptr, 1, N, blobp, ws.en0, ws.act[0]);
+    k_front<false><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, kSpecFrame, 2, 0, 1, nullptr, 0, 0, nullptr, 1, N, blobp, hp.front, ws.en0, ws.act[0]);
     ++launches;
     const unsigned gsg = (unsigned)((N + SG_NS - 1) / SG_NS);
     for (int i = 0; i < 3; ++i) {
@@ -482,7 +486,7 @@ inline int model_step(const float* blobp, const HostParams& hp, void* state, con
         ++launches;
     }
     k_back<false><<<gfr, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(ws.act[8], ws.act[0], ws.en0, spec, kSpecFrame, 2, 0, 1,
-                                                                                  out, kSpecFrame, 2, 0, 1, nullptr, 0, 1, N, blobp);
+                                                                                  out, kSpecFrame, 2, 0, 1, nullptr, 0, 1, N, blobp, hp.back);
     ++launches;
     return launches;
 }
