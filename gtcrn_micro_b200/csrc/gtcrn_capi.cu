@@ -61,7 +61,12 @@ struct gtcrnb_handle {
     float* stage_in[2] = {nullptr, nullptr};
     float* stage_out[2] = {nullptr, nullptr};
     size_t stage_in_floats = 0, stage_out_floats = 0;
-    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_comp2 = nullptr, s_d2h = nullptr;
+    // second activation workspace for the host pipeline: consecutive chunks run on two compute streams so that the tail of one
+    // chunk's kernels overlaps the head of the next (the fields above are the currently selected workspace)
+    struct WsSet { int64_t cap_frames = 0; float* en0 = nullptr; float* act[kNumAct33] = {}; float* spec_in = nullptr; float* spec_out = nullptr; };
+    WsSet parked;                                 // the workspace that is NOT currently selected
+    int ws_cur = 0;
     cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
     // occupancy (resident CTAs per SM) of the walking kernels, for segment selection
     int occ_gt_enc = 1, occ_gt_dec = 1, occ_tcn = 1;
@@ -129,6 +134,17 @@ struct ProfScope {
         h->prof_events.push_back(ev);
     }
 };
+
+void select_workspace(gtcrnb_handle* h, int idx) {
+    if (h->ws_cur == idx) return;
+    gtcrnb_handle::WsSet tmp;
+    tmp.cap_frames = h->cap_frames; tmp.en0 = h->en0; tmp.spec_in = h->spec_in; tmp.spec_out = h->spec_out;
+    for (int i = 0; i < kNumAct33; ++i) tmp.act[i] = h->act[i];
+    h->cap_frames = h->parked.cap_frames; h->en0 = h->parked.en0; h->spec_in = h->parked.spec_in; h->spec_out = h->parked.spec_out;
+    for (int i = 0; i < kNumAct33; ++i) h->act[i] = h->parked.act[i];
+    h->parked = tmp;
+    h->ws_cur = idx;
+}
 
 // Split T frames into `nseg` equal segments for a walking kernel: minimise waves * (segment work + warm-up + per-CTA overhead).
 // Segments need not be tile aligned (tiles start at the segment's own warm-up frame and slot groups past the end are skipped);
@@ -309,6 +325,8 @@ void gtcrnb_destroy(gtcrnb_handle* h) {
     cudaSetDevice(h->device);
     auto freep = [](float* p) { if (p) cudaFree(p); };
     freep(h->blob); freep(h->en0); freep(h->spec_in); freep(h->spec_out);
+    freep(h->parked.en0); freep(h->parked.spec_in); freep(h->parked.spec_out);
+    for (auto p : h->parked.act) freep(p);
     delete h->hp;
     for (auto p : h->act) freep(p);
     for (int i = 0; i < 2; ++i) {
@@ -319,6 +337,7 @@ void gtcrnb_destroy(gtcrnb_handle* h) {
     }
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    if (h->s_comp2) cudaStreamDestroy(h->s_comp2);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     delete h;
 }
@@ -414,6 +433,7 @@ int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int6
     if (!h->s_h2d) {
         CU(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->s_comp2, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             CU(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
@@ -450,17 +470,21 @@ int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int6
         if (c >= 2) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[i], 0));      // input buffer i consumed
         CU(cudaMemcpyAsync(h->stage_in[i], wav_host + b0 * L, sizeof(float) * nb * L, cudaMemcpyHostToDevice, h->s_h2d));
         CU(cudaEventRecord(h->ev_h2d[i], h->s_h2d));
-        CU(cudaStreamWaitEvent(h->s_comp, h->ev_h2d[i], 0));
-        if (c >= 2) CU(cudaStreamWaitEvent(h->s_comp, h->ev_d2h[i], 0));      // output buffer i drained
-        int rc = gtcrnb_enhance(h, h->stage_in[i], nb, L, L, h->stage_out[i], Lout, h->s_comp);
-        if (rc) return rc;
-        CU(cudaEventRecord(h->ev_comp[i], h->s_comp));
+        cudaStream_t sc = i ? h->s_comp2 : h->s_comp;                         // chunk parity -> compute stream + workspace
+        select_workspace(h, i);
+        CU(cudaStreamWaitEvent(sc, h->ev_h2d[i], 0));
+        if (c >= 2) CU(cudaStreamWaitEvent(sc, h->ev_d2h[i], 0));             // output buffer i drained
+        int rc = gtcrnb_enhance(h, h->stage_in[i], nb, L, L, h->stage_out[i], Lout, sc);
+        if (rc) { select_workspace(h, 0); return rc; }
+        CU(cudaEventRecord(h->ev_comp[i], sc));
         CU(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[i], 0));
         CU(cudaMemcpyAsync(out_host + b0 * Lout, h->stage_out[i], sizeof(float) * nb * Lout, cudaMemcpyDeviceToHost, h->s_d2h));
         CU(cudaEventRecord(h->ev_d2h[i], h->s_d2h));
     }
+    select_workspace(h, 0);
     CU(cudaStreamSynchronize(h->s_d2h));
     CU(cudaStreamSynchronize(h->s_comp));
+    CU(cudaStreamSynchronize(h->s_comp2));
     return GTCRNB_OK;
 }
 

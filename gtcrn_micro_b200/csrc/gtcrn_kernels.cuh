@@ -916,6 +916,8 @@ k_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_cons
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
             const int d = 1 << k, coff = (2 << k) - 2, wo = k * blob::TCN_SIZE;   // history rows of TCN k start at 2^(k+1) - 2
+            static_assert(blob::TCN_SIZE % 4 == 0, "16-byte aligned weight chunks");
+            __builtin_assume((wo & 3) == 0);                                       // lets ptxas use 128-bit uniform constant loads
             const float4* Hc = H + par * 120 + coff;                               // [q] stride 30: frames t0-2d .. t0-1
             float4* Hn = H + (par ^ 1) * 120 + coff;
             float y[P][16];

@@ -2,7 +2,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 python -m pytest tests/test_gpu_offline.py -q -x -m gpu -k "host or layer" 2>&1 | tail -2
-for c in 64 128 256 512; do
+for c in 64 128 256; do
   GTCRNB_HOST_CHUNK=$c python bench.py --steps 5 --warmup 3 --no-cpu --no-stream > gpurun_out/bench_cfg.json 2> gpurun_out/bench_cfg.err; tail -2 gpurun_out/bench_cfg.err
   python - <<PY
 import json
