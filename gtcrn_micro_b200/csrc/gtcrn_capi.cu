@@ -49,6 +49,7 @@ struct gtcrnb_handle {
     float* blob = nullptr;
     gs::HostParams* hp = nullptr;                 // host copies of the weight chunks passed as kernel parameters
     bool fuse_fft = true;                         // fuse STFT / iSTFT into the front / back kernels in gtcrnb_enhance
+    bool tcn_smem_w = true;                       // GTCN weights from shared memory instead of the constant bank
     int tcn_p = 2;                                // frame slots per lane of the GTCN kernel (2..4)
     int gt_enc = 0, gt_dec = 0;                   // index into kGtVariants for the encoder / decoder GTConv kernels
     // activation workspace for one chunk of utterances
@@ -102,21 +103,32 @@ int ensure_workspace(gtcrnb_handle* h, int64_t frames) {
 }
 
 // GTConv walking-kernel variants (frame slots per thread PS, slot groups per CTA G)
-struct GtVariant { int ps, g, threads, smem_bytes; const void* enc; const void* dec; };
-template <int PS, int G> GtVariant make_gt_variant() {
-    return {PS, G, gk::gt_threads(G), gk::gt_smem_floats(PS, G) * (int)sizeof(float),
-            (const void*)gk::k_gtconv<false, PS, G>, (const void*)gk::k_gtconv<true, PS, G>};
+struct GtVariant { int ps, g, smem_w, threads, smem_enc, smem_dec; const void* enc; const void* dec; };
+template <int PS, int G, bool SW> GtVariant make_gt_variant() {
+    return {PS, G, SW ? 1 : 0, gk::gt_threads(G),
+            gk::gt_smem_floats(PS, G, SW ? gk::gt_chunk<false>() : 0) * (int)sizeof(float),
+            gk::gt_smem_floats(PS, G, SW ? gk::gt_chunk<true>() : 0) * (int)sizeof(float),
+            (const void*)gk::k_gtconv<false, PS, G, SW>, (const void*)gk::k_gtconv<true, PS, G, SW>};
 }
-const GtVariant kGtVariants[] = {make_gt_variant<2, 8>(), make_gt_variant<3, 8>(), make_gt_variant<4, 7>()};
-constexpr int kNumGtVariants = 3;
+// index: 0 (2,8,const) 1 (3,8,const) 2 (4,7,const) 3 (2,8,smem) 4 (3,8,smem) 5 (4,7,smem)
+const GtVariant kGtVariants[] = {make_gt_variant<2, 8, false>(), make_gt_variant<3, 8, false>(), make_gt_variant<4, 7, false>(),
+                                 make_gt_variant<2, 8, true>(), make_gt_variant<3, 8, true>(), make_gt_variant<4, 7, true>()};
+constexpr int kNumGtVariants = 6;
 
 template <bool DEC>
 void launch_gtconv(const GtVariant& v, dim3 grid, cudaStream_t st, const float* x, const float* skip, float* out,
                    const gk::ParamBlock<gk::gt_chunk<DEC>()>& prm, int T, int seg) {
     using namespace gk;
-    if (v.ps == 2) k_gtconv<DEC, 2, 8><<<grid, v.threads, v.smem_bytes, st>>>(x, skip, out, prm, T, seg);
-    else if (v.ps == 3) k_gtconv<DEC, 3, 8><<<grid, v.threads, v.smem_bytes, st>>>(x, skip, out, prm, T, seg);
-    else k_gtconv<DEC, 4, 7><<<grid, v.threads, v.smem_bytes, st>>>(x, skip, out, prm, T, seg);
+    const int sm = DEC ? v.smem_dec : v.smem_enc;
+    if (v.smem_w) {
+        if (v.ps == 2) k_gtconv<DEC, 2, 8, true><<<grid, v.threads, sm, st>>>(x, skip, out, prm, T, seg);
+        else if (v.ps == 3) k_gtconv<DEC, 3, 8, true><<<grid, v.threads, sm, st>>>(x, skip, out, prm, T, seg);
+        else k_gtconv<DEC, 4, 7, true><<<grid, v.threads, sm, st>>>(x, skip, out, prm, T, seg);
+    } else {
+        if (v.ps == 2) k_gtconv<DEC, 2, 8, false><<<grid, v.threads, sm, st>>>(x, skip, out, prm, T, seg);
+        else if (v.ps == 3) k_gtconv<DEC, 3, 8, false><<<grid, v.threads, sm, st>>>(x, skip, out, prm, T, seg);
+        else k_gtconv<DEC, 4, 7, false><<<grid, v.threads, sm, st>>>(x, skip, out, prm, T, seg);
+    }
 }
 
 // RAII: brackets a kernel launch with two events when profiling is on
@@ -197,14 +209,12 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
     {
         const int64_t ncols = B * kF2;
         const int64_t ctas = (ncols + WC_WARPS - 1) / WC_WARPS;
-        const int P = h->tcn_p;
         const int seg = pick_seg_len(ctas, Ti, 32, TC_WARMUP, h->sm_count * h->occ_tcn);
         const dim3 g((unsigned)ctas, (unsigned)((Ti + seg - 1) / seg));
         for (int i = 0; i < 2; ++i) {
             ProfScope ps(h, KC_GTCN, nframes, st);
-            if (P == 4) k_gtcn<4><<<g, WC_WARPS * 32, wc_smem_floats(4) * sizeof(float), st>>>(h->act[3 + i], h->act[4 + i], h->hp->gtcn[i], Ti, seg, ncols);
-            else if (P == 3) k_gtcn<3><<<g, WC_WARPS * 32, wc_smem_floats(3) * sizeof(float), st>>>(h->act[3 + i], h->act[4 + i], h->hp->gtcn[i], Ti, seg, ncols);
-            else k_gtcn<2><<<g, WC_WARPS * 32, wc_smem_floats(2) * sizeof(float), st>>>(h->act[3 + i], h->act[4 + i], h->hp->gtcn[i], Ti, seg, ncols);
+            if (h->tcn_smem_w) k_gtcn<2, true><<<g, WC_WARPS * 32, wc_smem_floats(2, true) * sizeof(float), st>>>(h->act[3 + i], h->act[4 + i], h->hp->gtcn[i], Ti, seg, ncols);
+            else k_gtcn<2, false><<<g, WC_WARPS * 32, wc_smem_floats(2) * sizeof(float), st>>>(h->act[3 + i], h->act[4 + i], h->hp->gtcn[i], Ti, seg, ncols);
             h->launches++;
         }
     }
@@ -282,10 +292,13 @@ int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) 
     using namespace gk;
     struct { const void* fn; int floats; } attrs[] = {
         {(const void*)k_front<false>, fr_smem_floats(false)}, {(const void*)k_front<true>, fr_smem_floats(true)},
-        {kGtVariants[0].enc, kGtVariants[0].smem_bytes / 4}, {kGtVariants[0].dec, kGtVariants[0].smem_bytes / 4},
-        {kGtVariants[1].enc, kGtVariants[1].smem_bytes / 4}, {kGtVariants[1].dec, kGtVariants[1].smem_bytes / 4},
-        {kGtVariants[2].enc, kGtVariants[2].smem_bytes / 4}, {kGtVariants[2].dec, kGtVariants[2].smem_bytes / 4},
-        {(const void*)k_gtcn<2>, wc_smem_floats(2)}, {(const void*)k_gtcn<3>, wc_smem_floats(3)}, {(const void*)k_gtcn<4>, wc_smem_floats(4)},
+        {kGtVariants[0].enc, kGtVariants[0].smem_enc / 4}, {kGtVariants[0].dec, kGtVariants[0].smem_dec / 4},
+        {kGtVariants[1].enc, kGtVariants[1].smem_enc / 4}, {kGtVariants[1].dec, kGtVariants[1].smem_dec / 4},
+        {kGtVariants[2].enc, kGtVariants[2].smem_enc / 4}, {kGtVariants[2].dec, kGtVariants[2].smem_dec / 4},
+        {kGtVariants[3].enc, kGtVariants[3].smem_enc / 4}, {kGtVariants[3].dec, kGtVariants[3].smem_dec / 4},
+        {kGtVariants[4].enc, kGtVariants[4].smem_enc / 4}, {kGtVariants[4].dec, kGtVariants[4].smem_dec / 4},
+        {kGtVariants[5].enc, kGtVariants[5].smem_enc / 4}, {kGtVariants[5].dec, kGtVariants[5].smem_dec / 4},
+        {(const void*)k_gtcn<2, false>, wc_smem_floats(2)}, {(const void*)k_gtcn<2, true>, wc_smem_floats(2, true)},
         {(const void*)k_back<false>, bk_smem_floats(false)}, {(const void*)k_back<true>, bk_smem_floats(true)},
         {(const void*)k_stft, 0},
         {(const void*)k_istft, 0},
@@ -303,18 +316,18 @@ int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) 
     auto pick = [](const char* env, int dflt) {
         const char* e = getenv(env);
         if (!e) return dflt;
-        for (int i = 0; i < kNumGtVariants; ++i) if (kGtVariants[i].ps == atoi(e)) return i;
+        const int v = atoi(e);                                  // e.g. 4 = (PS 4, constant bank), 14 = (PS 4, shared-memory weights)
+        for (int i = 0; i < kNumGtVariants; ++i) if (kGtVariants[i].ps == v % 10 && kGtVariants[i].smem_w == v / 10) return i;
         return dflt;
     };
     h->gt_enc = pick("GTCRNB_GT_PS_ENC", 0);
     h->gt_dec = pick("GTCRNB_GT_PS_DEC", 2);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_gt_enc, kGtVariants[h->gt_enc].enc, kGtVariants[h->gt_enc].threads, kGtVariants[h->gt_enc].smem_bytes);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_gt_dec, kGtVariants[h->gt_dec].dec, kGtVariants[h->gt_dec].threads, kGtVariants[h->gt_dec].smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_gt_enc, kGtVariants[h->gt_enc].enc, kGtVariants[h->gt_enc].threads, kGtVariants[h->gt_enc].smem_enc);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_gt_dec, kGtVariants[h->gt_dec].dec, kGtVariants[h->gt_dec].threads, kGtVariants[h->gt_dec].smem_dec);
     if (const char* e = getenv("GTCRNB_FUSE_FFT")) h->fuse_fft = atoi(e) != 0;
-    if (const char* e = getenv("GTCRNB_TCN_P")) h->tcn_p = std::min(4, std::max(2, atoi(e)));
-    if (h->tcn_p == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn<4>, WC_WARPS * 32, wc_smem_floats(4) * sizeof(float));
-    else if (h->tcn_p == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn<3>, WC_WARPS * 32, wc_smem_floats(3) * sizeof(float));
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn<2>, WC_WARPS * 32, wc_smem_floats(2) * sizeof(float));
+    if (const char* e = getenv("GTCRNB_TCN_SMEMW")) h->tcn_smem_w = atoi(e) != 0;
+    if (h->tcn_smem_w) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn<2, true>, WC_WARPS * 32, wc_smem_floats(2, true) * sizeof(float));
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn<2, false>, WC_WARPS * 32, wc_smem_floats(2) * sizeof(float));
     h->occ_gt_enc = std::max(1, h->occ_gt_enc); h->occ_gt_dec = std::max(1, h->occ_gt_dec); h->occ_tcn = std::max(1, h->occ_tcn);
     *out = h;
     return GTCRNB_OK;

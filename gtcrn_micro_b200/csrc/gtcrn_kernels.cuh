@@ -78,6 +78,7 @@ __device__ __forceinline__ void axpy2c(float (&a0)[N], float (&a1)[N], float x0,
 }
 
 template <int NF> struct alignas(16) ParamBlock { float w[NF]; };
+struct SmemWeights { const float* __restrict__ w; };      // same .w[] interface as ParamBlock, backed by shared memory
 
 // ================================================================================================
 // 256-point complex FFT, radix-4 Stockham autosort, 64 threads per transform, 4 stages.
@@ -533,8 +534,8 @@ constexpr int GT_WARMUP = 4;
 template <bool DEC> __host__ __device__ constexpr int gt_chunk() { return DEC ? blob::DECGT_SIZE : blob::ENCGT_SIZE; }
 // PS frame slots per thread, G slot groups per CTA: NT = G*PS frames per tile, G*33 active threads
 __host__ __device__ constexpr int gt_threads(int G) { return (G * kF2 + 31) / 32 * 32; }
-__host__ __device__ constexpr int gt_smem_floats(int PS, int G) {
-    return (G * PS + 2) * GT_ROW4 * 4 + G * PS * kF2 * 8 + (G * PS + 2) * 8;
+__host__ __device__ constexpr int gt_smem_floats(int PS, int G, int w_floats = 0) {
+    return (G * PS + 2) * GT_ROW4 * 4 + G * PS * kF2 * 8 + (G * PS + 2) * 8 + w_floats;
 }
 __host__ __device__ constexpr int gt_min_blocks(int PS) { return PS >= 4 ? 2 : (PS == 3 ? 2 : 3); }
 
@@ -640,10 +641,10 @@ __device__ __forceinline__ float gt_energy(const float* e2_slot_c) {
     return s / 33.0f;
 }
 
-template <bool DEC, int PS, int G>
+template <bool DEC, int PS, int G, bool SMEM_W>
 __global__ void __launch_bounds__(gt_threads(G), gt_min_blocks(PS))
 k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* __restrict__ out,
-         const __grid_constant__ ParamBlock<gt_chunk<DEC>()> prm, int T, int seg_len) {
+         const __grid_constant__ ParamBlock<gt_chunk<DEC>()> prm_c, int T, int seg_len) {
     constexpr int NT = G * PS, R = NT + 2, GT_THREADS = gt_threads(G), GT_ACTIVE = G * kF2;
     static_assert(NT * 8 <= GT_THREADS, "phase 3 needs one thread per (slot, channel)");
     extern __shared__ float4 smem4[];
@@ -656,6 +657,12 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
     if (s0 >= s1) return;
     const int tw0 = max(0, s0 - GT_WARMUP);
     zero_f4(reinterpret_cast<float*>(Pb), gt_smem_floats(PS, G), tid, GT_THREADS);
+    // weight source: kernel parameter (constant bank) or a shared-memory copy read with broadcast LDS.128
+    float* wsm = Ev + R * 8;
+    if (SMEM_W)
+        for (int i = tid; i < gt_chunk<DEC>(); i += GT_THREADS) wsm[i] = prm_c.w[i];
+    const SmemWeights prm_s{static_cast<const float*>(__builtin_assume_aligned(wsm, 16))};
+    auto& prm = [&]() -> auto& { if constexpr (SMEM_W) return prm_s; else return prm_c; }();
     __syncthreads();
 
     const bool act = tid < GT_ACTIVE;
@@ -872,17 +879,25 @@ __device__ __forceinline__ void tcn_conv3(const PB& prm, int wo, const float (&y
 constexpr int WC_WARPS = 8;
 __host__ __device__ constexpr int wc_nt(int P) { return 32 * P; }
 __host__ __device__ constexpr int wc_warp4(int P) { return 4 * wc_nt(P) + 2 * 4 * 30; }       // float4 per warp: Y[q][row] + H[par][q][30]
-__host__ __device__ constexpr int wc_smem_floats(int P) { return WC_WARPS * wc_warp4(P) * 4; }
+__host__ __device__ constexpr int wc_smem_floats(int P, bool smem_w = false) { return WC_WARPS * wc_warp4(P) * 4 + (smem_w ? 4 * blob::TCN_SIZE : 0); }
 
-template <int P>
+template <int P, bool SMEM_W>
 __global__ void __launch_bounds__(WC_WARPS * 32, (P <= 2 ? 2 : 1))
-k_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_constant__ ParamBlock<4 * blob::TCN_SIZE> prm,
+k_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_constant__ ParamBlock<4 * blob::TCN_SIZE> prm_c,
        int T, int seg_len, int64_t ncols) {
     constexpr int NT = wc_nt(P);
     extern __shared__ float4 smem4[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* Y = smem4 + warp * wc_warp4(P);
     float4* H = Y + 4 * NT;
+    // weight source: kernel parameter (constant bank, LDCU) or a shared-memory copy (broadcast LDS)
+    float* wsm = reinterpret_cast<float*>(smem4 + WC_WARPS * wc_warp4(P));
+    if (SMEM_W) {
+        for (int i = threadIdx.x; i < 4 * blob::TCN_SIZE; i += WC_WARPS * 32) wsm[i] = prm_c.w[i];
+        __syncthreads();
+    }
+    const SmemWeights prm_s{static_cast<const float*>(__builtin_assume_aligned(wsm, 16))};
+    auto& prm = [&]() -> auto& { if constexpr (SMEM_W) return prm_s; else return prm_c; }();
     const int64_t colid = (int64_t)blockIdx.x * WC_WARPS + warp;
     if (colid >= ncols) return;                                   // whole warp exits together (no CTA barrier below)
     const int64_t b = colid / kF2;
