@@ -535,7 +535,7 @@ template <bool DEC> __host__ __device__ constexpr int gt_chunk() { return DEC ? 
 // PS frame slots per thread, G slot groups per CTA: NT = G*PS frames per tile, G*33 active threads
 __host__ __device__ constexpr int gt_threads(int G) { return (G * kF2 + 31) / 32 * 32; }
 __host__ __device__ constexpr int gt_smem_floats(int PS, int G, int w_floats = 0) {
-    return (G * PS + 2) * GT_ROW4 * 4 + G * PS * kF2 * 8 + (G * PS + 2) * 8 + w_floats;
+    return (G * PS + 2) * GT_ROW4 * 4 + G * PS * kF2 * 8 + (G * PS + 2) * 8 + G * PS * 8 + w_floats;
 }
 __host__ __device__ constexpr int gt_min_blocks(int PS) { return PS >= 4 ? 2 : (PS == 3 ? 2 : 3); }
 
@@ -612,26 +612,22 @@ __device__ __forceinline__ void gt_pc2(const PB& prm, float (&d)[16], float (&q)
 #pragma unroll
         for (int c = 0; c < 8; ++c) q[c] = fmaf(d[ci], prm.w[O::PC2_W + ci * 8 + c], q[c]);
 }
-// TRALite gate from the energies of frames t-2, t-1, t (e0, e1, e2 point at 8 floats each)
+// TRALite gate of channel c from the energies of frames t-2, t-1, t (e0, e1, e2 point at 8 floats each).  Evaluated by ONE
+// thread per (frame, channel) and shared through shared memory: doing it per bin-thread (33x redundant, 8 expf each) cost 22 %
+// of the GTConv kernels' stall samples (ncu r1_v8).
 template <bool DEC, class PB>
-__device__ __forceinline__ void gt_gate(const PB& prm, const float* e0, const float* e1, const float* e2, float (&g)[8]) {
+__device__ __forceinline__ float gt_gate1(const PB& prm, const float* e0, const float* e1, const float* e2, int c) {
     using O = GtOff<DEC>;
-    float y[8];
+    float v = prm.w[O::TPW_B + c];
 #pragma unroll
     for (int ci = 0; ci < 8; ++ci) {
-        float v = prm.w[O::TDW_B + ci];
-        v = fmaf(prm.w[O::TDW_W + 0 * 8 + ci], e0[ci], v);
-        v = fmaf(prm.w[O::TDW_W + 1 * 8 + ci], e1[ci], v);
-        v = fmaf(prm.w[O::TDW_W + 2 * 8 + ci], e2[ci], v);
-        y[ci] = v;
+        float y = prm.w[O::TDW_B + ci];
+        y = fmaf(prm.w[O::TDW_W + 0 * 8 + ci], e0[ci], y);
+        y = fmaf(prm.w[O::TDW_W + 1 * 8 + ci], e1[ci], y);
+        y = fmaf(prm.w[O::TDW_W + 2 * 8 + ci], e2[ci], y);
+        v = fmaf(prm.w[O::TPW_W + ci * 8 + c], y, v);
     }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float v = prm.w[O::TPW_B + c];
-#pragma unroll
-        for (int ci = 0; ci < 8; ++ci) v = fmaf(prm.w[O::TPW_W + ci * 8 + c], y[ci], v);
-        g[c] = 1.0f / (1.0f + expf(-v));
-    }
+    return 1.0f / (1.0f + expf(-v));
 }
 // fixed-order energy sum over the 33 bins of one frame slot: E2 [33][8] -> mean
 __device__ __forceinline__ float gt_energy(const float* e2_slot_c) {
@@ -658,7 +654,8 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
     const int tw0 = max(0, s0 - GT_WARMUP);
     zero_f4(reinterpret_cast<float*>(Pb), gt_smem_floats(PS, G), tid, GT_THREADS);
     // weight source: kernel parameter (constant bank) or a shared-memory copy read with broadcast LDS.128
-    float* wsm = Ev + R * 8;
+    float* Gt = Ev + R * 8;                                           // [NT][8] TRALite gates of the current tile
+    float* wsm = Gt + NT * 8;
     if (SMEM_W)
         for (int i = tid; i < gt_chunk<DEC>(); i += GT_THREADS) wsm[i] = prm_c.w[i];
     const SmemWeights prm_s{static_cast<const float*>(__builtin_assume_aligned(wsm, 16))};
@@ -758,15 +755,23 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
             }
         }
         __syncthreads();
-        // ---- phase 3: TRALite energies, fixed summation order (bitwise deterministic / causal)
+        // ---- phase 3: TRALite energies (fixed summation order: bitwise deterministic / causal), then one gate per (slot, channel)
+        int erow = 0;
         if (tid < NT * 8) {
             const int slot = tid >> 3, c = tid & 7;
-            int v = rb + slot;
-            v -= (v >= R) ? R : 0;
-            Ev[v * 8 + c] = gt_energy(E2 + slot * kF2 * 8 + c);
+            erow = rb + slot;
+            erow -= (erow >= R) ? R : 0;
+            Ev[erow * 8 + c] = gt_energy(E2 + slot * kF2 * 8 + c);
         }
         __syncthreads();
-        // ---- phase 4: gate (per thread), channel shuffle [q0,x2_0,q1,x2_1,...], store
+        if (tid < NT * 8) {
+            const int slot = tid >> 3, c = tid & 7;
+            int r1 = erow - 1; r1 += (r1 < 0) ? R : 0;
+            int r2 = r1 - 1; r2 += (r2 < 0) ? R : 0;
+            Gt[slot * 8 + c] = gt_gate1<DEC>(prm, Ev + r2 * 8, Ev + r1 * 8, Ev + erow * 8, c);
+        }
+        __syncthreads();
+        // ---- phase 4: gate, channel shuffle [q0,x2_0,q1,x2_1,...], store
         if (act) {
 #pragma unroll
             for (int s = 0; s < PS; ++s) {
@@ -780,20 +785,20 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
                         v2.x += u2.x; v2.y += u2.y; v2.z += u2.z; v2.w += u2.w;
                         v3.x += u3.x; v3.y += u3.y; v3.z += u3.z; v3.w += u3.w;
                     }
-                    float gate[8];
-                    gt_gate<DEC>(prm, Ev + rrow[s] * 8, Ev + rrow[s + 1] * 8, Ev + rrow[s + 2] * 8, gate);
+                    const float4 g0 = reinterpret_cast<const float4*>(Gt + (g * PS + s) * 8)[0];
+                    const float4 g1 = reinterpret_cast<const float4*>(Gt + (g * PS + s) * 8)[1];
                     float4* po = reinterpret_cast<float4*>(out + ubase + ((int64_t)t * kF2 + f) * 16);
-                    po[0] = make_float4(q[s][0] * gate[0], v2.x, q[s][1] * gate[1], v2.y);
-                    po[1] = make_float4(q[s][2] * gate[2], v2.z, q[s][3] * gate[3], v2.w);
-                    po[2] = make_float4(q[s][4] * gate[4], v3.x, q[s][5] * gate[5], v3.y);
-                    po[3] = make_float4(q[s][6] * gate[6], v3.z, q[s][7] * gate[7], v3.w);
+                    po[0] = make_float4(q[s][0] * g0.x, v2.x, q[s][1] * g0.y, v2.y);
+                    po[1] = make_float4(q[s][2] * g0.z, v2.z, q[s][3] * g0.w, v2.w);
+                    po[2] = make_float4(q[s][4] * g1.x, v3.x, q[s][5] * g1.y, v3.y);
+                    po[3] = make_float4(q[s][6] * g1.z, v3.z, q[s][7] * g1.w, v3.w);
                 }
             }
         }
         rb += NT;
         rb -= (rb >= R) ? R : 0;
         // no barrier needed here: the next phase 1 only writes ring rows whose readers finished before the
-        // barrier after phase 2, and every later writer of E2 / Ev is separated from this tile's readers by >= 1 barrier
+        // barrier after phase 2, and every later writer of E2 / Ev / Gt is separated from this tile's readers by >= 2 barriers
     }
 }
 

@@ -69,7 +69,7 @@ constexpr int SG_NS = 8;
 constexpr int SG_THREADS = 288;
 constexpr int SG_ACTIVE = SG_NS * kF2;
 constexpr int SG_ROW4 = gk::GT_ROW4;
-constexpr int SG_SMEM_FLOATS = SG_NS * 3 * SG_ROW4 * 4 + SG_NS * kF2 * 8 + SG_NS * 3 * 8;
+constexpr int SG_SMEM_FLOATS = SG_NS * 3 * SG_ROW4 * 4 + SG_NS * kF2 * 8 + SG_NS * 3 * 8 + SG_NS * 8;
 
 template <bool DEC>
 __global__ void __launch_bounds__(SG_THREADS, 2)
@@ -85,6 +85,7 @@ ks_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* 
     float4* Pb = smem4;                                               // [stream][3 rows: t-2, t-1, t][q][col]
     float* E2 = reinterpret_cast<float*>(Pb + SG_NS * 3 * SG_ROW4);   // [stream][33][8]
     float* Ev = E2 + SG_NS * kF2 * 8;                                 // [stream][3][8]
+    float* Gt = Ev + SG_NS * 3 * 8;                                   // [stream][8]
 
     const int tid = threadIdx.x;
     const int64_t n0 = (int64_t)blockIdx.x * SG_NS;
@@ -173,6 +174,11 @@ ks_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* 
         if (n2 < N) stream_base(state, n2)[kTraE + blk * 16 + slot_old * 8 + c] = e;
     }
     __syncthreads();
+    if (tid < SG_NS * 8) {
+        const int l2 = tid >> 3, c = tid & 7;
+        Gt[l2 * 8 + c] = gt_gate1<DEC>(prm, Ev + (l2 * 3) * 8, Ev + (l2 * 3 + 1) * 8, Ev + (l2 * 3 + 2) * 8, c);
+    }
+    __syncthreads();
     // ---- phase 4: gate, shuffle, store
     if (act) {
         const float4* px = reinterpret_cast<const float4*>(xin + (n * kF2 + f) * 16);
@@ -183,8 +189,7 @@ ks_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* 
             v2.x += u2.x; v2.y += u2.y; v2.z += u2.z; v2.w += u2.w;
             v3.x += u3.x; v3.y += u3.y; v3.z += u3.z; v3.w += u3.w;
         }
-        float gate[8];
-        gt_gate<DEC>(prm, Ev + (ls * 3) * 8, Ev + (ls * 3 + 1) * 8, Ev + (ls * 3 + 2) * 8, gate);
+        const float* gate = Gt + ls * 8;
         float4* po = reinterpret_cast<float4*>(out + (n * kF2 + f) * 16);
         po[0] = make_float4(q[0] * gate[0], v2.x, q[1] * gate[1], v2.y);
         po[1] = make_float4(q[2] * gate[2], v2.z, q[3] * gate[3], v2.w);
