@@ -8,17 +8,18 @@
 //   weights    one packed blob (blob_layout.h): BN folded, every contraction stored [k][ci][co]
 //
 // Kernel design: the layers are tiny channel contractions (K = 8..144, N = 16) applied to
-// B*T*F independent positions, so the path is FP32-FMA bound, not HBM or tensor-core bound.  Every
-// contraction uses the same register tile: one thread owns TWO frame slots x 16 (or 8) output channels at
-// one frequency bin, activations come from shared memory as LDS.128 in a [row][ci/4][col][4] layout
-// (conflict-free for consecutive bins) and the warp-uniform weight vectors as broadcast LDS.128.  That
-// feed was measured at 47 TFLOP/s (64 % of the 73.4 TFLOP/s FFMA peak) in tools/microbench/ffma_feed.cu.
+// B*T*F independent positions, so the path is FP32-FMA bound, not HBM or tensor-core bound (a tcgen05 3xTF32
+// prototype was measured and rejected: tools/microbench/umma_tf32_test.cu).  Every contraction uses the same
+// register tile: one thread owns P frame slots x 16 (or 8) output channels at one frequency bin; activations come
+// from registers or from shared memory as LDS.128 in a [row][ci/4][bin][4] layout (consecutive bins -> consecutive
+// 16 bytes, parity-split for the stride-2 convs), and the warp-uniform weights from the constant bank (kernel
+// parameters: LDCU + FFMA R,R,UR,R) or, in the GTCN kernel, from shared memory as broadcast LDS.128.
 //
-// Temporal layers (GTConv 3x3 + TRALite, dilated TCNs) are computed by CTAs that WALK along time over one
-// utterance segment, carrying their causal history (2 frames of point-conv output, 2 TRA energies, 2d
-// frames per TCN) in shared memory between tiles -- the same role the reference's streaming caches play
-// (gtcrn_micro_stream.py:416-429, :490-500) -- so no halo is recomputed except a short warm-up when an
-// utterance is split into several segments for occupancy.
+// Temporal layers (GTConv 3x3 + TRALite, dilated TCNs) are computed by CTAs / warps that WALK along time over one
+// utterance segment, carrying their causal history (2 frames of point-conv output, 2 TRA energies, 2d frames per
+// TCN) in shared-memory rings between tiles -- the same role the reference's streaming caches play
+// (gtcrn_micro_stream.py:416-429, :490-500) -- so no halo is recomputed except a short warm-up when an utterance
+// is split into several segments for occupancy.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -700,6 +701,13 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
                 float4* row = Pb + rrow[s + 2] * GT_ROW4 + f + 1;
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) row[qd * 35] = make_float4(p[4 * qd], p[4 * qd + 1], p[4 * qd + 2], p[4 * qd + 3]);
+                // pull the same position of the NEXT tile towards L2 while this tile computes (phase-1 loads were 8-17 % of the
+                // kernel's stall samples as long_scoreboard, ncu r1_v8)
+                const int tn = t + NT;
+                if (tn < s1) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xin + ubase + ((int64_t)tn * kF2 + f) * 16));
+                    if (DEC) asm volatile("prefetch.global.L2 [%0];" ::"l"(skip + ubase + ((int64_t)tn * kF2 + f) * 16));
+                }
             }
         }
         __syncthreads();
