@@ -125,6 +125,15 @@ __device__ __forceinline__ void fft256_masked(float2* a, float2* b, const float2
     __syncthreads();
 }
 
+// one WARP per transform: every lane does two radix-4 butterflies per stage; only __syncwarp between stages, so 8 frames can
+// be transformed by 8 warps without a single CTA barrier (the 64-thread version cost k_front 35 % of its samples in barriers)
+__device__ __forceinline__ void fft256_warp(float2* a, float2* b, const float2* tw, int lane) {
+    fft256_stage(a, b, tw, lane, 1);  fft256_stage(a, b, tw, lane + 32, 1);  __syncwarp();
+    fft256_stage(b, a, tw, lane, 4);  fft256_stage(b, a, tw, lane + 32, 4);  __syncwarp();
+    fft256_stage(a, b, tw, lane, 16); fft256_stage(a, b, tw, lane + 32, 16); __syncwarp();
+    fft256_stage(b, a, tw, lane, 64); fft256_stage(b, a, tw, lane + 32, 64); __syncwarp();
+}
+
 __device__ __forceinline__ int reflect_idx(int i, int L) {
     if (i < 0) i = -i;
     if (i >= L) i = 2 * (L - 1) - i;
@@ -333,50 +342,43 @@ __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict
         load_fft_tables(tb, blobp, tid, FR_THREADS);
         copy_f4(W, blobp + blob::FRONT_OFF, FR_W_FLOATS, tid, FR_THREADS);
         __syncthreads();
-        const int fr = tid >> 6, j = tid & 63;
-        const bool fft_thread = tid < 256;
-#pragma unroll 1
-        for (int r = 0; r < FR_NF / 4; ++r) {
-            const int slot = r * 4 + (fft_thread ? fr : 0);
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp < FR_NF) {                                        // warp w transforms frame slot w (only __syncwarp inside)
+            const int slot = warp;
             const int64_t fi = fi0 + slot;
-            const bool valid = fft_thread && fi < nframes;
+            const bool valid = fi < nframes;
             float2* A = reinterpret_cast<float2*>(slots + slot * FR_SLOT + FR_FEAT + FR_ERB);
             float2* Bf = reinterpret_cast<float2*>(slots + slot * FR_SLOT);
             int64_t b = 0; int t = 0;
             if (valid) { b = fi / T; t = (int)(fi - b * T); }
-            if (fft_thread) {
-                if (valid) {
-                    const float* x = wav + b * wav_stride;
-                    const int base = kHop * t - kHop;
+            if (valid) {
+                const float* x = wav + b * wav_stride;
+                const int base = kHop * t - kHop;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int n = j + 64 * q;
-                        const int i0 = reflect_idx(base + 2 * n, L), i1 = reflect_idx(base + 2 * n + 1, L);
-                        A[n] = make_float2(tb.win[2 * n] * x[i0], tb.win[2 * n + 1] * x[i1]);
-                    }
-                } else {
+                for (int q = 0; q < 8; ++q) {
+                    const int n = lane + 32 * q;
+                    const int i0 = reflect_idx(base + 2 * n, L), i1 = reflect_idx(base + 2 * n + 1, L);
+                    A[n] = make_float2(tb.win[2 * n] * x[i0], tb.win[2 * n + 1] * x[i1]);
+                }
+            } else {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) A[j + 64 * q] = make_float2(0.f, 0.f);
-                }
+                for (int q = 0; q < 8; ++q) A[lane + 32 * q] = make_float2(0.f, 0.f);
             }
-            __syncthreads();
-            fft256_masked(A, Bf, tb.tw256, j, fft_thread);
-            if (fft_thread) {
-                float4* fs = reinterpret_cast<float4*>(slots + slot * FR_SLOT);   // feat region (B is dead now)
-                float2* o = valid ? reinterpret_cast<float2*>(spec_out + fi * kSpecFrame) : nullptr;
-                for (int k = j; k <= 256; k += 64) {
-                    const float2 zk = A[k & 255];
-                    float2 zc = A[(256 - k) & 255];
-                    zc.y = -zc.y;
-                    const float2 w = tb.tw512[k];
-                    const float dx = zk.x - zc.x, dy = zk.y - zc.y;
-                    const float re = 0.5f * (zk.x + zc.x) + 0.5f * (w.x * dy + w.y * dx);
-                    const float im = 0.5f * (zk.y + zc.y) - 0.5f * (w.x * dx - w.y * dy);
-                    if (valid) o[k] = make_float2(re, im);
-                    fs[k] = make_float4(sqrtf(re * re + im * im + 1e-12f), re, im, 0.f);
-                }
+            __syncwarp();
+            fft256_warp(A, Bf, tb.tw256, lane);
+            float4* fs = reinterpret_cast<float4*>(slots + slot * FR_SLOT);   // feat region (B is dead now)
+            float2* o = valid ? reinterpret_cast<float2*>(spec_out + fi * kSpecFrame) : nullptr;
+            for (int k = lane; k <= 256; k += 32) {
+                const float2 zk = A[k & 255];
+                float2 zc = A[(256 - k) & 255];
+                zc.y = -zc.y;
+                const float2 w = tb.tw512[k];
+                const float dx = zk.x - zc.x, dy = zk.y - zc.y;
+                const float re = 0.5f * (zk.x + zc.x) + 0.5f * (w.x * dy + w.y * dx);
+                const float im = 0.5f * (zk.y + zc.y) - 0.5f * (w.x * dx - w.y * dy);
+                if (valid) o[k] = make_float2(re, im);
+                fs[k] = make_float4(sqrtf(re * re + im * im + 1e-12f), re, im, 0.f);
             }
-            // no barrier needed between rounds: round r+1 touches other slots; the barrier below orders everything
         }
         __syncthreads();
         for (int i = tid; i < FR_NF * 4; i += FR_THREADS) {       // sfe pad columns (its region held FFT buffer A until now)
@@ -1054,6 +1056,36 @@ __device__ __forceinline__ void back_de3(const PB& prm, const float4* X, float4*
 //                 conjugation trick), windowed and overlap-added straight into `wav_out` [B][256 (T-1)] with vector RED.ADD.
 //                 Every output sample receives exactly two addends on top of a zeroed buffer, so the result does not depend
 //                 on their order (bitwise deterministic).  The caller zeroes wav_out first.
+// de4 (16 -> 2) + tanh for output bins of one parity: thread = 4 slots x 2 co at bin h = 2m + ODD; every weight pair (one LDCU.64)
+// feeds 8 FFMAs.  Same gather form as de3.  Result: mask on the compressed axis, M[slot][h][2].
+template <int ODD, class PB>
+__device__ __forceinline__ void back_de4(const PB& prm, const float4* Y3, float* M, int m_stride, int sg, int m) {
+    const int h = 2 * m + ODD;
+    float a0[4], a1[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) { a0[s] = prm.w[blob::BACK_DE4_B + 0]; a1[s] = prm.w[blob::BACK_DE4_B + 1]; }
+    const float4* y = Y3 + (4 * sg) * BK_Y4;
+#pragma unroll
+    for (int j = 0; j < 3 - ODD; ++j) {
+        const int colx = m + 2 - j, wb = blob::BACK_DE4_W + (2 * j + ODD) * 32;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            float4 in[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) in[s] = y[s * BK_Y4 + qd * 67 + colx];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float w0 = prm.w[wb + (4 * qd + i) * 2], w1 = prm.w[wb + (4 * qd + i) * 2 + 1];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) { a0[s] = fmaf(f4get(in[s], i), w0, a0[s]); a1[s] = fmaf(f4get(in[s], i), w1, a1[s]); }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+        *reinterpret_cast<float2*>(M + (4 * sg + s) * m_stride + 2 * h) = make_float2(tanhf(a0[s]), tanhf(a1[s]));
+}
+
 template <bool TO_WAV>
 __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict__ de2, const float* __restrict__ en1,
                                                         const float* __restrict__ en0, const float* __restrict__ spec,
@@ -1096,6 +1128,11 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
         }
     }
     copy_f4(Wsm, blobp + blob::BACK_OFF + BK_W_OFF, BK_W_FLOATS, tid, BK_THREADS);
+    if (TO_WAV) {                                                  // iSTFT tables (needed last) are fetched first so their latency is hidden
+        FftTables& tb0 = *reinterpret_cast<FftTables*>(Wsm + bk_smem_floats(false));
+        load_fft_tables(tb0, blobp, tid, BK_THREADS);
+        if (tid < 256) (reinterpret_cast<float*>(&tb0) + FR_FFT_FLOATS)[tid] = blobp[blob::FFT_OFF + blob::FFT_INV_ENV + tid];
+    }
     for (int i = tid; i < BK_NF * 8; i += BK_THREADS) {            // zero pad columns of X (0, 34) and Y3 (0, 66)
         const int slot = i >> 3, q = (i >> 1) & 3, side = i & 1;
         X[slot * BK_X4 + q * 35 + (side ? 34 : 0)] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1110,102 +1147,100 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
         back_de3<1>(prm, X, Y3, r >> 5, r & 31, fi0, nframes, en0);
     }
     __syncthreads();
-    // ---- c: de4 (16 -> 2) + tanh -> mask on the 129 ERB bins
-    for (int idx = tid; idx < BK_NF * kErb; idx += BK_THREADS) {
-        const int slot = idx / kErb, h = idx - slot * kErb;
-        const int m = h >> 1, odd = h & 1, ntap = 3 - odd;
-        float m0 = W[blob::BACK_DE4_B + 0], m1 = W[blob::BACK_DE4_B + 1];
-        const float4* y = Y3 + slot * BK_Y4;
-        for (int j = 0; j < ntap; ++j) {
-            const int k = 2 * j + odd, colx = m + 2 - j;
-            const float4* w4 = reinterpret_cast<const float4*>(W + blob::BACK_DE4_W + k * 32);
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
-                const float4 i = y[qd * 67 + colx];
-                const float4 wa = w4[2 * qd], wb = w4[2 * qd + 1];   // (ci,co): (4q,0) (4q,1) (4q+1,0) (4q+1,1) | (4q+2,..) (4q+3,..)
-                m0 = fmaf(i.x, wa.x, m0); m1 = fmaf(i.x, wa.y, m1);
-                m0 = fmaf(i.y, wa.z, m0); m1 = fmaf(i.y, wa.w, m1);
-                m0 = fmaf(i.z, wb.x, m0); m1 = fmaf(i.z, wb.y, m1);
-                m0 = fmaf(i.w, wb.z, m0); m1 = fmaf(i.w, wb.w, m1);
-            }
-        }
-        M[slot * M_STRIDE + 2 * h] = tanhf(m0);
-        M[slot * M_STRIDE + 2 * h + 1] = tanhf(m1);
+    // ---- c: de4 (16 -> 2) + tanh -> mask on the 129 compressed bins: even bins (65) on warps 0-4, odd bins (64) on warps 5-8
+    static_assert(BK_NF == 8, "de4 mapping assumes two groups of four slots");
+    if (tid < 160) {
+        if (tid < 130) back_de4<0>(prm, Y3, M, M_STRIDE, tid / 65, tid % 65);
+    } else {
+        const int r = tid - 160;
+        back_de4<1>(prm, Y3, M, M_STRIDE, r >> 6, r & 63);
     }
     __syncthreads();
-    // ---- d: ERB expand + complex ratio mask
-    {
-        const int* ib0 = reinterpret_cast<const int*>(W + blob::BACK_IERB_B0);
-        const float* iw = W + blob::BACK_IERB_W;
+    // ---- d: ERB expand + complex ratio mask (+ e: fused iSTFT).  mask(i) on the 257 spectrum bins from the 129 compressed ones.
+    const int* ib0 = reinterpret_cast<const int*>(W + blob::BACK_IERB_B0);
+    const float* iw = W + blob::BACK_IERB_W;
+    auto mask_at = [&](const float* ms, int i, float& m0, float& m1) {
+        if (i < 65) {
+            m0 = ms[2 * i];
+            m1 = ms[2 * i + 1];
+        } else {
+            const int j = i - 65, bb = 65 + ib0[j];
+            const float w0 = iw[2 * j], w1 = iw[2 * j + 1];
+            m0 = w0 * ms[2 * bb] + w1 * ms[2 * bb + 2];
+            m1 = w0 * ms[2 * bb + 1] + w1 * ms[2 * bb + 3];
+        }
+    };
+    if (!TO_WAV) {
         for (int idx = tid; idx < BK_NF * kBins; idx += BK_THREADS) {
             const int slot = idx / kBins, i = idx - slot * kBins;
             const int64_t fi = fi0 + slot;
             if (fi >= nframes) continue;
             const int64_t b = fi / T, t = fi - b * T;
-            const float* ms = M + slot * M_STRIDE;
             float m0, m1;
-            if (i < 65) {
-                m0 = ms[2 * i];
-                m1 = ms[2 * i + 1];
-            } else {
-                const int j = i - 65, bb = 65 + ib0[j];
-                const float w0 = iw[2 * j], w1 = iw[2 * j + 1];
-                m0 = w0 * ms[2 * bb] + w1 * ms[2 * bb + 2];
-                m1 = w0 * ms[2 * bb + 1] + w1 * ms[2 * bb + 3];
-            }
+            mask_at(M + slot * M_STRIDE, i, m0, m1);
             const float* p = spec + b * sb + t * st + (int64_t)i * sf;
             const float re = p[0], im = p[sc];
-            if (TO_WAV) {
-                reinterpret_cast<float2*>(Y3 + slot * BK_Y4)[i] = make_float2(re * m0 - im * m1, im * m0 + re * m1);   // Y3 is dead: reuse as spectrum
-            } else {
-                float* o = outp + b * ob + t * ot + (int64_t)i * of;
-                o[0] = re * m0 - im * m1;
-                o[oc] = im * m0 + re * m1;
-            }
+            float* o = outp + b * ob + t * ot + (int64_t)i * of;
+            o[0] = re * m0 - im * m1;
+            o[oc] = im * m0 + re * m1;
         }
-    }
-    if (TO_WAV) {
-        // ---- e (fused iSTFT): per slot the dead Y3 region (1072 floats) holds [0,514) spectrum | [544,1056) FFT buffer A;
-        //      FFT buffer B (512 floats) lives in the slot's X region (560 floats; the mask stored there is dead after stage d)
+    } else {
+        // warp w owns frame slot w from here on: mask its spectrum into shared memory, invert it, window, overlap-add.
+        // Per slot the dead Y3 region (1072 floats) holds [0,514) spectrum | [544,1056) FFT buffer A; FFT buffer B (512 floats)
+        // lives in the slot's X region -- but that region still holds the mask M until this warp has consumed it, so B is only
+        // touched after the __syncwarp that follows the masking loop.
         static_assert(BK_Y4 * 4 >= 544 + 512 && BK_X4 * 4 >= 512, "fused iSTFT buffers must fit in the dead slot regions");
         FftTables& tb = *reinterpret_cast<FftTables*>(Wsm + bk_smem_floats(false));
-        float* inv_env = reinterpret_cast<float*>(&tb) + FR_FFT_FLOATS;
-        load_fft_tables(tb, blobp, tid, BK_THREADS);
-        if (tid < 256) inv_env[tid] = blobp[blob::FFT_OFF + blob::FFT_INV_ENV + tid];
-        __syncthreads();
-        const int fr = tid >> 6, j = tid & 63;
-        const bool fft_thread = tid < 256;
-#pragma unroll 1
-        for (int r = 0; r < BK_NF / 4; ++r) {
-            const int slot = r * 4 + (fft_thread ? fr : 0);
+        const float* inv_env = reinterpret_cast<const float*>(&tb) + FR_FFT_FLOATS;
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp < BK_NF) {
+            const int slot = warp;
             const int64_t fi = fi0 + slot;
-            const bool valid = fft_thread && fi < nframes;
+            const bool valid = fi < nframes;
+            int64_t b = 0; int t = 0;
+            if (valid) { b = fi / T; t = (int)(fi - b * T); }
             float* base = reinterpret_cast<float*>(Y3 + slot * BK_Y4);
-            const float2* X = reinterpret_cast<const float2*>(base);
+            float2* Ys = reinterpret_cast<float2*>(base);       // masked spectrum of this slot
             float2* A = reinterpret_cast<float2*>(base + 544);
             float2* Bf = reinterpret_cast<float2*>(reinterpret_cast<float*>(X4all + slot * BK_X4));
-            if (fft_thread) {
+            {
+                const float2* sp = reinterpret_cast<const float2*>(spec + b * sb + (int64_t)t * st);   // fused mode: internal layout (sf = 2, sc = 1)
+                float2 x[9];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int k = j + 64 * q;                       // 0..255
-                    float2 xk = X[k], xc = X[256 - k];
-                    xc.y = -xc.y;
-                    if (k == 0) { xk.y = 0.f; xc.y = 0.f; }         // imag of DC / Nyquist ignored (C2R semantics)
-                    const float2 w = tb.tw512[k];
-                    const float dx = xk.x - xc.x, dy = xk.y - xc.y;
-                    const float a = w.x * dx + w.y * dy, bq = w.x * dy - w.y * dx;   // conj(w) * D
-                    A[k] = valid ? make_float2(0.5f * (xk.x + xc.x) - 0.5f * bq, -(0.5f * (xk.y + xc.y) + 0.5f * a)) : make_float2(0.f, 0.f);
+                for (int q = 0; q < 9; ++q) {
+                    const int i = lane + 32 * q;
+                    x[q] = (valid && i <= 256) ? sp[i] : make_float2(0.f, 0.f);
+                }
+                const float* ms = M + slot * M_STRIDE;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    const int i = lane + 32 * q;
+                    if (i <= 256) {
+                        float m0, m1;
+                        mask_at(ms, i, m0, m1);
+                        Ys[i] = make_float2(x[q].x * m0 - x[q].y * m1, x[q].y * m0 + x[q].x * m1);
+                    }
                 }
             }
-            __syncthreads();
-            fft256_masked(A, Bf, tb.tw256, j, fft_thread);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k = lane + 32 * q;                        // 0..255
+                float2 xk = Ys[k], xc = Ys[256 - k];
+                xc.y = -xc.y;
+                if (k == 0) { xk.y = 0.f; xc.y = 0.f; }             // imag of DC / Nyquist ignored (C2R semantics)
+                const float2 w = tb.tw512[k];
+                const float dx = xk.x - xc.x, dy = xk.y - xc.y;
+                const float a = w.x * dx + w.y * dy, bq = w.x * dy - w.y * dx;   // conj(w) * D
+                A[k] = valid ? make_float2(0.5f * (xk.x + xc.x) - 0.5f * bq, -(0.5f * (xk.y + xc.y) + 0.5f * a)) : make_float2(0.f, 0.f);
+            }
+            __syncwarp();
+            fft256_warp(A, Bf, tb.tw256, lane);
             if (valid) {
-                const int64_t b = fi / T;
-                const int t = (int)(fi - b * T);
                 float* o = wav_out + b * wav_stride + (int64_t)(t - 1) * kHop;      // frame t covers output samples 256 (t-1) .. 256 (t+1)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int m = j + 64 * q;                       // frame samples 2m, 2m+1
+                for (int q = 0; q < 8; ++q) {
+                    const int m = lane + 32 * q;                    // frame samples 2m, 2m+1
                     const float2 z = A[m];
                     const int i = 2 * m;
                     const bool keep = i < 256 ? t > 0 : t < T - 1;  // first half of frame 0 / second half of the last frame are trimmed
