@@ -108,3 +108,22 @@ def test_capi_library_exports_every_declared_symbol(b200_lib):
     assert b200_lib.gtcrnb_abi_version() == 1
     assert b200_lib.gtcrnb_blob_floats() == pack.blob_size()
     assert b200_lib.gtcrnb_stream_state_bytes(4) > 4 * 38112 * 4
+
+
+def test_load_checkpoint_layouts(tmp_path, weights_dns3):
+    # reference checkpoint dict {"epoch","optimizer","scheduler","model"} (train.py:206-211; consumer infer.py:38-39), plus the
+    # variants its export scripts tolerate (stream_onnx.py:38-47): bare state_dict, "state_dict" key, DDP "module." prefix
+    ref = pack.pack_state_dict(weights_dns3)
+    p1 = str(tmp_path / "model_157.tar")
+    torch.save({"epoch": 157, "optimizer": {}, "scheduler": {}, "model": dict(weights_dns3)}, p1)
+    p2 = str(tmp_path / "bare.pt")
+    torch.save(dict(weights_dns3), p2)
+    p3 = str(tmp_path / "ddp.pt")
+    torch.save({"state_dict": {"module." + k: v for k, v in weights_dns3.items()}}, p3)
+    for path in (p1, p2, p3):
+        m = G.load_checkpoint(path)
+        assert isinstance(m, G.GTCRNMicro)
+        assert np.array_equal(pack.pack_state_dict(m.state_dict()), ref)
+    s = G.load_checkpoint(p1, stream=True)
+    assert isinstance(s, G.StreamGTCRNMicro)
+    assert np.array_equal(pack.pack_state_dict(s.state_dict()), ref)
