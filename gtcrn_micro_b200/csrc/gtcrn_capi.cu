@@ -59,8 +59,9 @@ struct gtcrnb_handle {
     float* spec_in = nullptr;
     float* spec_out = nullptr;
     // host pipeline staging
-    float* stage_in[2] = {nullptr, nullptr};
-    float* stage_out[2] = {nullptr, nullptr};
+    static constexpr int kStage = 3;                 // staging buffers in flight per direction (workspaces / compute streams: 2)
+    float* stage_in[kStage] = {};
+    float* stage_out[kStage] = {};
     size_t stage_in_floats = 0, stage_out_floats = 0;
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_comp2 = nullptr, s_d2h = nullptr;
     // second activation workspace for the host pipeline: consecutive chunks run on two compute streams so that the tail of one
@@ -68,7 +69,7 @@ struct gtcrnb_handle {
     struct WsSet { int64_t cap_frames = 0; float* en0 = nullptr; float* act[kNumAct33] = {}; float* spec_in = nullptr; float* spec_out = nullptr; };
     WsSet parked;                                 // the workspace that is NOT currently selected
     int ws_cur = 0;
-    cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
+    cudaEvent_t ev_h2d[kStage] = {}, ev_comp[kStage] = {}, ev_d2h[kStage] = {};
     // occupancy (resident CTAs per SM) of the walking kernels, for segment selection
     int occ_gt_enc = 1, occ_gt_dec = 1, occ_tcn = 1;
     int64_t launches = 0;
@@ -342,7 +343,7 @@ void gtcrnb_destroy(gtcrnb_handle* h) {
     for (auto p : h->parked.act) freep(p);
     delete h->hp;
     for (auto p : h->act) freep(p);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
         freep(h->stage_in[i]); freep(h->stage_out[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
         if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
@@ -448,26 +449,27 @@ int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int6
         CU(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&h->s_comp2, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
             CU(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
         }
     }
-    // chunks of ~64 utterance-equivalents of 10 s keep the three engines (H2D, SMs, D2H) overlapped
+    // three engines (H2D copy, SMs, D2H copy) run overlapped over chunks; three staging buffers per direction decouple the copies
+    // from the two compute streams / workspaces (measured on B200, 1024 x 10 s: 2 buffers 326k, 3 buffers 346k audio-s/s)
     // chunk size trades pipeline fill/drain (first H2D and last D2H are exposed) against per-chunk kernel efficiency
-    int64_t chunk_units = 128;                                     // in 10-second-utterance equivalents
+    int64_t chunk_units = 192;                                     // in 10-second-utterance equivalents
     if (const char* e = getenv("GTCRNB_HOST_CHUNK")) chunk_units = std::max(1, atoi(e));
     const int64_t Bc = std::max<int64_t>(1, std::min<int64_t>(B, (chunk_units * 160000) / L));
     const size_t need_in = (size_t)Bc * L, need_out = (size_t)Bc * Lout;
     if (need_in > h->stage_in_floats || need_out > h->stage_out_floats) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
             if (h->stage_in[i]) cudaFree(h->stage_in[i]);
             if (h->stage_out[i]) cudaFree(h->stage_out[i]);
             h->stage_in[i] = h->stage_out[i] = nullptr;
         }
         h->stage_in_floats = h->stage_out_floats = 0;
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
             if (cudaMalloc(&h->stage_in[i], need_in * sizeof(float)) != cudaSuccess ||
                 cudaMalloc(&h->stage_out[i], need_out * sizeof(float)) != cudaSuccess) {
                 cudaGetLastError();
@@ -476,28 +478,64 @@ int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int6
         }
         h->stage_in_floats = need_in; h->stage_out_floats = need_out;
     }
-    int64_t c = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += Bc, ++c) {
-        const int i = (int)(c & 1);
-        const int64_t nb = std::min(Bc, B - b0);
-        if (c >= 2) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[i], 0));      // input buffer i consumed
+    // Chunk schedule: the first H2D and the last D2H cannot overlap with anything, so the pipeline ramps up and down through
+    // chunks of Bc/2^ramp .. Bc/2 (the two compute streams hide the small chunks' partial waves behind their neighbours).
+    int ramp = 3;
+    if (const char* e = getenv("GTCRNB_HOST_RAMP")) ramp = std::max(0, std::min(4, atoi(e)));
+    std::vector<int64_t> sizes;
+    {
+        std::vector<int64_t> head;
+        int64_t used = 0;
+        for (int r = ramp; r >= 1; --r) {
+            const int64_t n = Bc >> r;
+            if (n < 1 || used + 2 * n + Bc > B) continue;              // keep at least one full chunk in the middle
+            head.push_back(n); used += 2 * n;
+        }
+        sizes = head;
+        for (int64_t left = B - used; left > 0;) { const int64_t n = std::min(Bc, left); sizes.push_back(n); left -= n; }
+        for (auto it = head.rbegin(); it != head.rend(); ++it) sizes.push_back(*it);
+    }
+    // GTCRNB_HOST_TRACE=1: per-chunk engine timeline on stderr (diagnostic; adds timing events, not for benchmarking)
+    const bool trace = getenv("GTCRNB_HOST_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+    int64_t b0 = 0;
+    for (size_t c = 0; c < sizes.size(); b0 += sizes[c], ++c) {
+        const int i = (int)(c % gtcrnb_handle::kStage), ws = (int)(c & 1);   // staging slot, workspace / compute stream
+        const int64_t nb = sizes[c];
+        if (c >= (size_t)gtcrnb_handle::kStage) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[i], 0));      // input buffer i consumed
+        mark(h->s_h2d);
         CU(cudaMemcpyAsync(h->stage_in[i], wav_host + b0 * L, sizeof(float) * nb * L, cudaMemcpyHostToDevice, h->s_h2d));
+        mark(h->s_h2d);
         CU(cudaEventRecord(h->ev_h2d[i], h->s_h2d));
-        cudaStream_t sc = i ? h->s_comp2 : h->s_comp;                         // chunk parity -> compute stream + workspace
-        select_workspace(h, i);
+        cudaStream_t sc = ws ? h->s_comp2 : h->s_comp;                         // chunk parity -> compute stream + workspace
+        select_workspace(h, ws);
         CU(cudaStreamWaitEvent(sc, h->ev_h2d[i], 0));
-        if (c >= 2) CU(cudaStreamWaitEvent(sc, h->ev_d2h[i], 0));             // output buffer i drained
+        if (c >= (size_t)gtcrnb_handle::kStage) CU(cudaStreamWaitEvent(sc, h->ev_d2h[i], 0));             // output buffer i drained
+        mark(sc);
         int rc = gtcrnb_enhance(h, h->stage_in[i], nb, L, L, h->stage_out[i], Lout, sc);
         if (rc) { select_workspace(h, 0); return rc; }
+        mark(sc);
         CU(cudaEventRecord(h->ev_comp[i], sc));
         CU(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[i], 0));
+        mark(h->s_d2h);
         CU(cudaMemcpyAsync(out_host + b0 * Lout, h->stage_out[i], sizeof(float) * nb * Lout, cudaMemcpyDeviceToHost, h->s_d2h));
+        mark(h->s_d2h);
         CU(cudaEventRecord(h->ev_d2h[i], h->s_d2h));
     }
     select_workspace(h, 0);
     CU(cudaStreamSynchronize(h->s_d2h));
     CU(cudaStreamSynchronize(h->s_comp));
     CU(cudaStreamSynchronize(h->s_comp2));
+    if (trace) {
+        fprintf(stderr, "chunk  utts   h2d[start,end]      compute[start,end]   d2h[start,end]  (ms from first H2D)\n");
+        for (size_t c = 0; c < sizes.size(); ++c) {
+            float t[6];
+            for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], tev[0], tev[6 * c + k]);
+            fprintf(stderr, "%5zu %5lld   %7.3f %7.3f     %7.3f %7.3f      %7.3f %7.3f\n", c, (long long)sizes[c], t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
+        for (auto e : tev) cudaEventDestroy(e);
+    }
     return GTCRNB_OK;
 }
 
@@ -512,6 +550,22 @@ int gtcrnb_debug_activation(gtcrnb_handle* h, const char* name, float* out_dev, 
     const size_t have = per_frame * (size_t)(h->last_B * h->last_T);
     if (n_floats > have) return fail(GTCRNB_E_INVALID, "activation '%s' holds %zu floats, %zu requested", name, have, n_floats);
     CU(cudaMemcpyAsync(out_dev, src, n_floats * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return GTCRNB_OK;
+}
+
+// ---------------------------------------------------------------- on-device quality metrics
+int gtcrnb_pair_metrics(gtcrnb_handle* h, const float* ref_dev, int64_t ref_stride, const float* inf_dev, int64_t inf_stride,
+                        int64_t B, int64_t L, float* out_dev, void* stream) {
+    if (B < 0 || L <= 0) return fail(GTCRNB_E_INVALID, "gtcrnb_pair_metrics: bad shape");
+    if (h && B == 0) return GTCRNB_OK;
+    if (!h || !ref_dev || !inf_dev || !out_dev) return fail(GTCRNB_E_INVALID, "gtcrnb_pair_metrics: NULL argument");
+    for (int64_t b0 = 0; b0 < B; b0 += 65535) {
+        const int64_t nb = std::min<int64_t>(65535, B - b0);
+        gk::k_pair_metrics<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(ref_dev + b0 * ref_stride, ref_stride, inf_dev + b0 * inf_stride,
+                                                                           inf_stride, L, out_dev + 2 * b0);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
     return GTCRNB_OK;
 }
 

@@ -1255,4 +1255,40 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
     }
 }
 
+// ================================================================================================
+// On-device quality metrics of (reference, enhanced) waveform pairs: SI-SNR and SDR exactly as the reference's evaluation
+// script defines them (eval/eval_intrusive_metrics.py:74-82 sisnr_metric, :85-94 sdr_metric), from five raw moments per
+// utterance accumulated in fp64 with a fixed reduction order (deterministic).  grid B, 256 threads; out [B][2] = (si_snr, sdr) dB.
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_pair_metrics(const float* __restrict__ ref, int64_t ref_stride, const float* __restrict__ inf,
+                                                      int64_t inf_stride, int64_t L, float* __restrict__ out) {
+    __shared__ double red[8][5];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* r = ref + (int64_t)blockIdx.x * ref_stride;
+    const float* x = inf + (int64_t)blockIdx.x * inf_stride;
+    double s[5] = {0, 0, 0, 0, 0};                       // sum r, sum x, sum r^2, sum x^2, sum r x
+    for (int64_t i = tid; i < L; i += 256) {
+        const double a = r[i], b = x[i];
+        s[0] += a; s[1] += b; s[2] += a * a; s[3] += b * b; s[4] += a * b;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_down_sync(0xffffffffu, s[k], o);
+        if (lane == 0) red[warp][k] = s[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double t[5];
+        for (int k = 0; k < 5; ++k) { t[k] = 0; for (int w = 0; w < 8; ++w) t[k] += red[w][k]; }
+        const double n = (double)L, mr = t[0] / n, mx = t[1] / n;
+        const double rr = t[2] - n * mr * mr, xx = t[3] - n * mx * mx, rx = t[4] - n * mr * mx;   // centred second moments
+        const double a = rx / (rr + n * 1e-8);            // np.sum(ref**2 + 1e-8)
+        const double tgt = a * a * rr, res = xx - 2.0 * a * rx + a * a * rr;
+        out[2 * blockIdx.x] = (float)(10.0 * log10((tgt + 1e-8) / (fmax(res, 0.0) + 1e-8)));
+        const double err = xx - 2.0 * rx + rr;            // sum (inf_c - ref_c)^2
+        out[2 * blockIdx.x + 1] = (float)(10.0 * log10((rr + 1e-8) / (fmax(err, 0.0) + 1e-8)));
+    }
+}
+
 }  // namespace gk

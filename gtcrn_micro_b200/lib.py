@@ -20,7 +20,7 @@ SYMBOLS = [
     "gtcrnb_stream_reset", "gtcrnb_stream_step_spec", "gtcrnb_stream_step_wav", "gtcrnb_stream_import_caches",
     "gtcrnb_stream_export_caches", "gtcrnb_debug_activation", "gtcrnb_launch_count", "gtcrnb_host_alloc",
     "gtcrnb_host_free", "gtcrnb_last_error", "gtcrnb_profile_enable", "gtcrnb_profile_read",
-    "gtcrnb_profile_num_classes", "gtcrnb_profile_class_name",
+    "gtcrnb_profile_num_classes", "gtcrnb_profile_class_name", "gtcrnb_pair_metrics",
 ]
 
 
@@ -69,6 +69,7 @@ def load() -> C.CDLL:
             "gtcrnb_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), i64p, i64p]),
             "gtcrnb_profile_num_classes": (C.c_int, []),
             "gtcrnb_profile_class_name": (cp, [C.c_int]),
+            "gtcrnb_pair_metrics": (C.c_int, [vp, vp, i64, vp, i64, i64, i64, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)

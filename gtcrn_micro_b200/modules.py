@@ -160,7 +160,10 @@ class _B200Module(nn.Module):
             self._handle_key = None
 
     def __del__(self):
-        self._release()
+        try:
+            self._release()
+        except Exception:       # interpreter shutdown: torch's module machinery may already be torn down
+            pass
 
     def profile(self, on: bool) -> None:
         """Bracket every kernel launch of this model with CUDA events (see `profile_read`)."""
@@ -239,6 +242,21 @@ class GTCRNMicro(_B200Module):
         L = _lib.load()
         with torch.cuda.device(dev):
             _lib.check(L.gtcrnb_enhance_host(h, wav.data_ptr(), B, Ls, out.data_ptr()), "gtcrnb_enhance_host")
+        return out
+
+    @torch.no_grad()
+    def pair_metrics(self, ref: torch.Tensor, inf: torch.Tensor) -> torch.Tensor:
+        """SI-SNR and SDR (dB) of waveform pairs on the device, as eval_intrusive_metrics.py:74-94 defines them.
+        ref, inf [B,L] float32 CUDA -> [B,2] = (si_snr, sdr)."""
+        if ref.shape != inf.shape or ref.dim() != 2 or ref.dtype != torch.float32 or inf.dtype != torch.float32:
+            raise ValueError("ref and inf must be float32 [B,L] of the same shape")
+        ref = ref if ref.stride(1) == 1 else ref.contiguous()
+        inf = inf if inf.stride(1) == 1 else inf.contiguous()
+        h = self._ensure_handle(ref.device)
+        out = torch.empty((ref.shape[0], 2), dtype=torch.float32, device=ref.device)
+        with torch.cuda.device(ref.device):
+            _lib.check(_lib.load().gtcrnb_pair_metrics(h, ref.data_ptr(), ref.stride(0), inf.data_ptr(), inf.stride(0), ref.shape[0],
+                                                       ref.shape[1], out.data_ptr(), torch.cuda.current_stream().cuda_stream), "gtcrnb_pair_metrics")
         return out
 
     @torch.no_grad()

@@ -90,6 +90,12 @@ int gtcrnb_stream_import_caches(gtcrnb_handle* h, void* state_dev, int64_t N, co
 int gtcrnb_stream_export_caches(gtcrnb_handle* h, const void* state_dev, int64_t N, float* conv_cache_dev,
                                 float* tra_cache_dev, float* const tcn_cache_dev[8], void* stream);
 
+/* ---- on-device quality metrics ---------------------------------------------------
+ * SI-SNR and SDR of B (reference, enhanced) waveform pairs of L samples, as defined by the reference's evaluation script
+ * (gtcrn_micro/eval/eval_intrusive_metrics.py:74-82 sisnr_metric, :85-94 sdr_metric).  out_dev [B][2] = (si_snr_db, sdr_db). */
+int gtcrnb_pair_metrics(gtcrnb_handle* h, const float* ref_dev, int64_t ref_stride, const float* inf_dev, int64_t inf_stride,
+                        int64_t B, int64_t L, float* out_dev, void* stream);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 /* Copy an intermediate activation of the LAST gtcrnb_forward_spec / gtcrnb_enhance call (first
  * workspace chunk) to a device buffer, channel-last [B][T][F][16].  name: "en0" (F=65), "en1".."en4",

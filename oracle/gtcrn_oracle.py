@@ -377,6 +377,16 @@ def si_snr(ref: np.ndarray, inf: np.ndarray) -> float:
     return float(10 * np.log10((np.sum(tgt ** 2) + 1e-8) / (np.sum(res ** 2) + 1e-8)))
 
 
+def sdr(ref: np.ndarray, inf: np.ndarray) -> float:
+    """eval_intrusive_metrics.py:85-94"""
+    ref = np.asarray(ref, dtype=np.float64)
+    inf = np.asarray(inf, dtype=np.float64)
+    inf = inf - inf.mean()
+    ref = ref - ref.mean()
+    res = inf - ref
+    return float(10 * np.log10((np.sum(ref ** 2) + 1e-8) / (np.sum(res ** 2) + 1e-8)))
+
+
 # --------------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8d)
 # --------------------------------------------------------------------------------------------

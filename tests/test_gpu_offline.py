@@ -179,9 +179,14 @@ def test_strided_inputs_and_empty(oracle, weights_dns3, b200_lib):
         m.enhance(torch.zeros(2, 256, device=DEV))                    # reflect padding needs L > 256 (torch.stft raises too)
 
 
-def test_enhance_host_matches_device(oracle, weights_dns3, b200_lib):
+@pytest.mark.parametrize("chunk,ramp", [(None, None), ("1", "0"), ("2", "2"), ("4", "3")])
+def test_enhance_host_matches_device(oracle, weights_dns3, b200_lib, monkeypatch, chunk, ramp):
+    # the pipelined host path (ramped chunk schedule over two workspaces) must equal one device call, whatever the chunking
+    if chunk is not None:
+        monkeypatch.setenv("GTCRNB_HOST_CHUNK", chunk)                # in 10 s units: 1 -> 3 utterances of 3 s per chunk
+        monkeypatch.setenv("GTCRNB_HOST_RAMP", ramp)
     m = make_model(weights_dns3, b200_lib)
-    x = oracle.synth_batch(70, 16000 * 3 + 5, seed=21)                # > 1 staging chunk
+    x = oracle.synth_batch(70, 16000 * 3 + 5, seed=21)
     xp = x.pin_memory()
     out_h = m.enhance_host(xp)
     out_d = m.enhance(x.to(DEV)).cpu()
