@@ -49,7 +49,8 @@ struct gtcrnb_handle {
     float* blob = nullptr;
     gs::HostParams* hp = nullptr;                 // host copies of the weight chunks passed as kernel parameters
     bool fuse_fft = true;                         // fuse STFT / iSTFT into the front / back kernels in gtcrnb_enhance
-    bool tcn_smem_w = true;                       // GTCN weights from shared memory instead of the constant bank
+    bool tcn_smem_w = false;                      // GTCN weights from shared memory (LDS.128) instead of the constant bank; with FFMA2 the
+                                                  // constant-bank feed wins (B200: 4.73 vs 5.67 ms per 1024 x 10 s), before FFMA2 smem won (6.4 vs 7.3)
     int tcn_p = 2;                                // frame slots per lane of the GTCN kernel (2..4)
     int gt_enc = 0, gt_dec = 0;                   // index into kGtVariants for the encoder / decoder GTConv kernels
     // activation workspace for one chunk of utterances

@@ -23,6 +23,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <utility>
 
 #include "blob_layout.h"
 
@@ -42,6 +43,34 @@ __device__ __forceinline__ float prelu(float v, float a) { const float m = a * v
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float f4get(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) { (f(std::integral_constant<int, I>{}), ...); }
+// compile-time loop: f(integral_constant<int, 0>) .. f(integral_constant<int, N-1>), guaranteed unrolled
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
+
+// Packed fp32 FMA (sm_100 FFMA2, fma.rn.f32x2): two IEEE fmas in one issue slot.  The convolutions here are
+// acc[c] += x * w[c] with x per thread and w[c] warp-uniform, which maps to `FFMA2 Racc, Rx.F32, URw.F32x2, Racc` (scalar
+// x broadcast, weight pair in uniform registers fed by LDCU.128): half the FMA issue slots and half the constant loads of
+// the FFMA form, results bit-identical (same fma per lane).  -DGTCRNB_NO_FFMA2 restores the scalar form for A/B runs.
+__device__ __forceinline__ void fma_pair(float& a0, float& a1, float x, float w0, float w1) {
+#ifndef GTCRNB_NO_FFMA2
+    const float2 r = __ffma2_rn(make_float2(x, x), make_float2(w0, w1), make_float2(a0, a1));
+    a0 = r.x; a1 = r.y;
+#else
+    a0 = fmaf(x, w0, a0); a1 = fmaf(x, w1, a1);
+#endif
+}
+// a0 += x0 * w0, a1 += x1 * w1 (distinct inputs: depthwise taps, adjacent channels of one float4)
+__device__ __forceinline__ void fma_pair2(float& a0, float& a1, float x0, float x1, float w0, float w1) {
+#ifndef GTCRNB_NO_FFMA2
+    const float2 r = __ffma2_rn(make_float2(x0, x1), make_float2(w0, w1), make_float2(a0, a1));
+    a0 = r.x; a1 = r.y;
+#else
+    a0 = fmaf(x0, w0, a0); a1 = fmaf(x1, w1, a1);
+#endif
+}
+
 __device__ __forceinline__ void copy_f4(float* dst, const float* __restrict__ src, int n_floats, int tid, int nthr) {
     float4* d4 = reinterpret_cast<float4*>(dst);
     const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -59,10 +88,8 @@ __device__ __forceinline__ void axpy2(float (&a0)[N], float (&a1)[N], float x0, 
 #pragma unroll
     for (int v = 0; v < N / 4; ++v) {
         const float4 ww = w4[v];
-        a0[4 * v + 0] = fmaf(x0, ww.x, a0[4 * v + 0]); a1[4 * v + 0] = fmaf(x1, ww.x, a1[4 * v + 0]);
-        a0[4 * v + 1] = fmaf(x0, ww.y, a0[4 * v + 1]); a1[4 * v + 1] = fmaf(x1, ww.y, a1[4 * v + 1]);
-        a0[4 * v + 2] = fmaf(x0, ww.z, a0[4 * v + 2]); a1[4 * v + 2] = fmaf(x1, ww.z, a1[4 * v + 2]);
-        a0[4 * v + 3] = fmaf(x0, ww.w, a0[4 * v + 3]); a1[4 * v + 3] = fmaf(x1, ww.w, a1[4 * v + 3]);
+        fma_pair(a0[4 * v + 0], a0[4 * v + 1], x0, ww.x, ww.y); fma_pair(a1[4 * v + 0], a1[4 * v + 1], x1, ww.x, ww.y);
+        fma_pair(a0[4 * v + 2], a0[4 * v + 3], x0, ww.z, ww.w); fma_pair(a1[4 * v + 2], a1[4 * v + 3], x1, ww.z, ww.w);
     }
 }
 
@@ -71,12 +98,19 @@ __device__ __forceinline__ void axpy2(float (&a0)[N], float (&a1)[N], float x0, 
 template <int N>
 __device__ __forceinline__ void axpy2c(float (&a0)[N], float (&a1)[N], float x0, float x1, const float* w) {
 #pragma unroll
-    for (int c = 0; c < N; ++c) {
-        const float ww = w[c];
-        a0[c] = fmaf(x0, ww, a0[c]);
-        a1[c] = fmaf(x1, ww, a1[c]);
+    for (int c = 0; c < N; c += 2) {
+        const float w0 = w[c], w1 = w[c + 1];
+        fma_pair(a0[c], a0[c + 1], x0, w0, w1);
+        fma_pair(a1[c], a1[c + 1], x1, w0, w1);
     }
 }
+
+#ifndef GTCRNB_DEC_UNROLL
+#define GTCRNB_DEC_UNROLL 1      // decoder 3x3 (kf, ci-quad) loop: 0 rolled (12 iterations), 1 kf rolled, 2 fully unrolled
+#endif
+#ifndef GTCRNB_EN1_UNROLL
+#define GTCRNB_EN1_UNROLL 1      // front en1 tap loop: 0 rolled, 1 unrolled
+#endif
 
 template <int NF> struct alignas(16) ParamBlock { float w[NF]; };
 struct SmemWeights { const float* __restrict__ w; };      // same .w[] interface as ParamBlock, backed by shared memory
@@ -289,7 +323,11 @@ __device__ __forceinline__ void front_en1(const PB& prm, const float* slots, int
     for (int c = 0; c < 8; ++c) acc0[c] = acc1[c] = prm.w[blob::FRONT_EN1_B + 8 * H + c];
     const float4* i0p = reinterpret_cast<const float4*>(slots + s0 * FR_SLOT) + f;
     const float4* i1p = reinterpret_cast<const float4*>(slots + s1 * FR_SLOT) + f;
+#if GTCRNB_EN1_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int k = 0; k < 5; ++k) {
         const int po = (k & 1) * 35 + (k >> 1);
 #pragma unroll
@@ -298,10 +336,11 @@ __device__ __forceinline__ void front_en1(const PB& prm, const float* slots, int
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float ww = prm.w[blob::FRONT_EN1_W + (k * 16 + 4 * q + i) * 16 + 8 * H + c];
-                    acc0[c] = fmaf(f4get(x0, i), ww, acc0[c]);
-                    acc1[c] = fmaf(f4get(x1, i), ww, acc1[c]);
+                for (int c = 0; c < 8; c += 2) {
+                    const float w0 = prm.w[blob::FRONT_EN1_W + (k * 16 + 4 * q + i) * 16 + 8 * H + c];
+                    const float w1 = prm.w[blob::FRONT_EN1_W + (k * 16 + 4 * q + i) * 16 + 8 * H + c + 1];
+                    fma_pair(acc0[c], acc0[c + 1], f4get(x0, i), w0, w1);
+                    fma_pair(acc1[c], acc1[c + 1], f4get(x1, i), w0, w1);
                 }
         }
     }
@@ -480,10 +519,10 @@ __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const float ww = prm.w[blob::FRONT_EN0_W + k * 48 + i * 16 + c];
-                    acc0[c] = fmaf(f4get(x0, i), ww, acc0[c]);
-                    acc1[c] = fmaf(f4get(x1, i), ww, acc1[c]);
+                for (int c = 0; c < 16; c += 2) {
+                    const float w0 = prm.w[blob::FRONT_EN0_W + k * 48 + i * 16 + c], w1 = prm.w[blob::FRONT_EN0_W + k * 48 + i * 16 + c + 1];
+                    fma_pair(acc0[c], acc0[c + 1], f4get(x0, i), w0, w1);
+                    fma_pair(acc1[c], acc1[c + 1], f4get(x1, i), w0, w1);
                 }
         }
         const float a = prm.w[blob::FRONT_SLOPE + 0];
@@ -566,7 +605,7 @@ __device__ __forceinline__ void gt_pc1(const PB& prm, const float (&x1)[8], floa
 #pragma unroll
     for (int ci = 0; ci < 8; ++ci)
 #pragma unroll
-        for (int c = 0; c < 16; ++c) p[c] = fmaf(x1[ci], prm.w[O::PC1_W + ci * 16 + c], p[c]);
+        for (int c = 0; c < 16; c += 2) fma_pair(p[c], p[c + 1], x1[ci], prm.w[O::PC1_W + ci * 16 + c], prm.w[O::PC1_W + ci * 16 + c + 1]);
     const float a1 = prm.w[O::SLOPE + 0];
 #pragma unroll
     for (int c = 0; c < 16; ++c) p[c] = prelu(p[c], a1);
@@ -582,10 +621,15 @@ __device__ __forceinline__ void gt_mid_step(const PB& prm, int kf, int qd, const
             for (int i = 0; i < 4; ++i) {
                 const int wb = O::MID_W + ((kt * 3 + kf) * 16 + 4 * qd + i) * 16;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const float ww = prm.w[wb + c];
+                for (int c = 0; c < 16; c += 2) {
+                    const float w0 = prm.w[wb + c], w1 = prm.w[wb + c + 1];
+#ifdef GTCRNB_DECMID_SCALAR
 #pragma unroll
-                    for (int s = 0; s < PS; ++s) acc[s][c] = fmaf(f4get(in[s + kt], i), ww, acc[s][c]);
+                    for (int s = 0; s < PS; ++s) { acc[s][c] = fmaf(f4get(in[s + kt], i), w0, acc[s][c]); acc[s][c + 1] = fmaf(f4get(in[s + kt], i), w1, acc[s][c + 1]); }
+#else
+#pragma unroll
+                    for (int s = 0; s < PS; ++s) fma_pair(acc[s][c], acc[s][c + 1], f4get(in[s + kt], i), w0, w1);
+#endif
                 }
             }
         }
@@ -593,10 +637,11 @@ __device__ __forceinline__ void gt_mid_step(const PB& prm, int kf, int qd, const
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float ww = prm.w[O::MID_W + (kt * 3 + kf) * 16 + 4 * qd + i];
+            for (int i = 0; i < 4; i += 2) {
+                const float w0 = prm.w[O::MID_W + (kt * 3 + kf) * 16 + 4 * qd + i], w1 = prm.w[O::MID_W + (kt * 3 + kf) * 16 + 4 * qd + i + 1];
 #pragma unroll
-                for (int s = 0; s < PS; ++s) acc[s][4 * qd + i] = fmaf(f4get(in[s + kt], i), ww, acc[s][4 * qd + i]);
+                for (int s = 0; s < PS; ++s)
+                    fma_pair2(acc[s][4 * qd + i], acc[s][4 * qd + i + 1], f4get(in[s + kt], i), f4get(in[s + kt], i + 1), w0, w1);
             }
         }
     }
@@ -613,7 +658,7 @@ __device__ __forceinline__ void gt_pc2(const PB& prm, float (&d)[16], float (&q)
 #pragma unroll
     for (int ci = 0; ci < 16; ++ci)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) q[c] = fmaf(d[ci], prm.w[O::PC2_W + ci * 8 + c], q[c]);
+        for (int c = 0; c < 8; c += 2) fma_pair(q[c], q[c + 1], d[ci], prm.w[O::PC2_W + ci * 8 + c], prm.w[O::PC2_W + ci * 8 + c + 1]);
 }
 // TRALite gate of channel c from the energies of frames t-2, t-1, t (e0, e1, e2 point at 8 floats each).  Evaluated by ONE
 // thread per (frame, channel) and shared through shared memory: doing it per bin-thread (33x redundant, 8 expf each) cost 22 %
@@ -736,6 +781,7 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
             // (kf, ci-quad) loop kept rolled: the body (3 kt x 4 ci x 16 co x PS FFMAs) is ~8 KB of code; fully unrolled
             // it was 32 KB per kf and the kernel stalled 23 % of the time on instruction fetch (ncu r1_v2: no_inst)
             if (DEC) {
+#if GTCRNB_DEC_UNROLL == 0
 #pragma unroll 1
                 for (int kq = 0; kq < 12; ++kq) {
                     const int kf = kq >> 2, qd = kq & 3;
@@ -744,6 +790,30 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
                     for (int j = 0; j < PS + 2; ++j) in[j] = Pb[rrow[j] * GT_ROW4 + qd * 35 + f + kf];
                     gt_mid_step<DEC, PS>(prm, kf, qd, in, acc);
                 }
+#elif GTCRNB_DEC_UNROLL == 1
+#pragma unroll 1
+                for (int kf = 0; kf < 3; ++kf) {
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        float4 in[PS + 2];
+#pragma unroll
+                        for (int j = 0; j < PS + 2; ++j) in[j] = Pb[rrow[j] * GT_ROW4 + qd * 35 + f + kf];
+                        gt_mid_step<DEC, PS>(prm, kf, qd, in, acc);
+                    }
+                }
+#else
+                // forced full unroll (a plain `#pragma unroll` is declined at this body size): every weight index becomes an
+                // immediate, so the loads are LDCU.128 through the uniform datapath instead of register-indexed LDC.64
+                // through the indexed constant cache, whose ~0.5 requests/clk/SM ceiling bound the rolled loop (ncu r1_v12:
+                // idc__request_cycles_active 62 %, pipe_adu 64 %, fma pipe 58 %)
+                static_for<12>([&](auto kq_) {
+                    constexpr int kq = decltype(kq_)::value, kf = kq >> 2, qd = kq & 3;
+                    float4 in[PS + 2];
+#pragma unroll
+                    for (int j = 0; j < PS + 2; ++j) in[j] = Pb[rrow[j] * GT_ROW4 + qd * 35 + f + kf];
+                    gt_mid_step<DEC, PS>(prm, kf, qd, in, acc);
+                });
+#endif
             } else {
 #pragma unroll 1
                 for (int kf = 0; kf < 3; ++kf) {
@@ -835,10 +905,10 @@ __device__ __forceinline__ void tcn_conv1(const PB& prm, int wo, const float (&x
 #pragma unroll
     for (int ci = 0; ci < 16; ++ci)
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const float ww = prm.w[wo + blob::TCN_W1 + ci * 16 + c];
+        for (int c = 0; c < 16; c += 2) {
+            const float w0 = prm.w[wo + blob::TCN_W1 + ci * 16 + c], w1 = prm.w[wo + blob::TCN_W1 + ci * 16 + c + 1];
 #pragma unroll
-            for (int s = 0; s < P; ++s) y1[s][c] = fmaf(x[s][ci], ww, y1[s][c]);
+            for (int s = 0; s < P; ++s) fma_pair(y1[s][c], y1[s][c + 1], x[s][ci], w0, w1);
         }
     const float a1 = prm.w[wo + blob::TCN_SLOPE + 0];
 #pragma unroll
@@ -874,10 +944,10 @@ __device__ __forceinline__ void tcn_conv3(const PB& prm, int wo, const float (&y
 #pragma unroll
     for (int ci = 0; ci < 16; ++ci)
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const float ww = prm.w[wo + blob::TCN_W3 + ci * 16 + c];
+        for (int c = 0; c < 16; c += 2) {
+            const float w0 = prm.w[wo + blob::TCN_W3 + ci * 16 + c], w1 = prm.w[wo + blob::TCN_W3 + ci * 16 + c + 1];
 #pragma unroll
-            for (int s = 0; s < P; ++s) x[s][c] = fmaf(y2[s][ci], ww, x[s][c]);
+            for (int s = 0; s < P; ++s) fma_pair(x[s][c], x[s][c + 1], y2[s][ci], w0, w1);
         }
     const float a3 = prm.w[wo + blob::TCN_SLOPE + 2];
 #pragma unroll
@@ -1028,10 +1098,10 @@ __device__ __forceinline__ void back_de3(const PB& prm, const float4* X, float4*
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const float ww = prm.w[wb + (4 * qd + i) * 16 + c];
-                    acc0[c] = fmaf(f4get(i0, i), ww, acc0[c]);
-                    acc1[c] = fmaf(f4get(i1, i), ww, acc1[c]);
+                for (int c = 0; c < 16; c += 2) {
+                    const float w0 = prm.w[wb + (4 * qd + i) * 16 + c], w1 = prm.w[wb + (4 * qd + i) * 16 + c + 1];
+                    fma_pair(acc0[c], acc0[c + 1], f4get(i0, i), w0, w1);
+                    fma_pair(acc1[c], acc1[c + 1], f4get(i1, i), w0, w1);
                 }
         }
     }
@@ -1077,7 +1147,7 @@ __device__ __forceinline__ void back_de4(const PB& prm, const float4* Y3, float*
             for (int i = 0; i < 4; ++i) {
                 const float w0 = prm.w[wb + (4 * qd + i) * 2], w1 = prm.w[wb + (4 * qd + i) * 2 + 1];
 #pragma unroll
-                for (int s = 0; s < 4; ++s) { a0[s] = fmaf(f4get(in[s], i), w0, a0[s]); a1[s] = fmaf(f4get(in[s], i), w1, a1[s]); }
+                for (int s = 0; s < 4; ++s) fma_pair(a0[s], a1[s], f4get(in[s], i), w0, w1);
             }
         }
     }

@@ -138,25 +138,16 @@ ks_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* 
 #pragma unroll
         for (int c = 0; c < 16; ++c) acc[0][c] = prm.w[GtOff<DEC>::MID_B + c];
         const float4* r0 = Pb + (ls * 3) * SG_ROW4 + f;
-        if (DEC) {
+        // kf rolled, ci-quads unrolled (same shape as the offline kernel): keeps the weight loads on the uniform datapath
+        // (UR-indexed LDCU) instead of per-thread-indexed LDC through the indexed constant cache
 #pragma unroll 1
-            for (int kq = 0; kq < 12; ++kq) {
-                const int kf = kq >> 2, qd = kq & 3;
+        for (int kf = 0; kf < 3; ++kf) {
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
                 float4 in[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j) in[j] = r0[j * SG_ROW4 + qd * 35 + kf];
                 gt_mid_step<DEC, 1>(prm, kf, qd, in, acc);
-            }
-        } else {
-#pragma unroll 1
-            for (int kf = 0; kf < 3; ++kf) {
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    float4 in[3];
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) in[j] = r0[j * SG_ROW4 + qd * 35 + kf];
-                    gt_mid_step<DEC, 1>(prm, kf, qd, in, acc);
-                }
             }
         }
         gt_pc2<DEC>(prm, acc[0], q);

@@ -11,7 +11,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgtcrn_b200.so")
+LIB_PATH = os.environ.get("GTCRNB_LIB") or os.path.join(HERE, "libgtcrn_b200.so")   # GTCRNB_LIB: A/B builds of the same ABI
 
 # every symbol include/gtcrn_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
