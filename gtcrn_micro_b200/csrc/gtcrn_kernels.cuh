@@ -61,6 +61,24 @@ __device__ __forceinline__ void fma_pair(float& a0, float& a1, float x, float w0
     a0 = fmaf(x, w0, a0); a1 = fmaf(x, w1, a1);
 #endif
 }
+// PReLU of two values with one packed multiply (FMUL2) + two FMNMX; bit-identical to prelu() per element
+__device__ __forceinline__ void prelu_pair(float& v0, float& v1, float a) {
+#ifndef GTCRNB_NO_FFMA2
+    const float2 m = __fmul2_rn(make_float2(v0, v1), make_float2(a, a));
+    v0 = a <= 1.f ? fmaxf(v0, m.x) : fminf(v0, m.x);
+    v1 = a <= 1.f ? fmaxf(v1, m.y) : fminf(v1, m.y);
+#else
+    v0 = prelu(v0, a); v1 = prelu(v1, a);
+#endif
+}
+__device__ __forceinline__ void add_pair(float& a0, float& a1, float b0, float b1) {
+#ifndef GTCRNB_NO_FFMA2
+    const float2 r = __fadd2_rn(make_float2(a0, a1), make_float2(b0, b1));
+    a0 = r.x; a1 = r.y;
+#else
+    a0 += b0; a1 += b1;
+#endif
+}
 // a0 += x0 * w0, a1 += x1 * w1 (distinct inputs: depthwise taps, adjacent channels of one float4)
 __device__ __forceinline__ void fma_pair2(float& a0, float& a1, float x0, float x1, float w0, float w1) {
 #ifndef GTCRNB_NO_FFMA2
@@ -107,6 +125,9 @@ __device__ __forceinline__ void axpy2c(float (&a0)[N], float (&a1)[N], float x0,
 
 #ifndef GTCRNB_DEC_UNROLL
 #define GTCRNB_DEC_UNROLL 1      // decoder 3x3 (kf, ci-quad) loop: 0 rolled (12 iterations), 1 kf rolled, 2 fully unrolled
+#endif
+#ifndef GTCRNB_TCN_UNROLL
+#define GTCRNB_TCN_UNROLL 0      // GTCN: 0 loop over the four TCNs rolled (weights at a uniform-register offset), 1 unrolled
 #endif
 #ifndef GTCRNB_EN1_UNROLL
 #define GTCRNB_EN1_UNROLL 1      // front en1 tap loop: 0 rolled, 1 unrolled
@@ -346,7 +367,7 @@ __device__ __forceinline__ void front_en1(const PB& prm, const float* slots, int
     }
     const float a = prm.w[blob::FRONT_SLOPE + 1];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { acc0[c] = prelu(acc0[c], a); acc1[c] = prelu(acc1[c], a); }
+    for (int c = 0; c < 8; c += 2) { prelu_pair(acc0[c], acc0[c + 1], a); prelu_pair(acc1[c], acc1[c + 1], a); }
     if (fi0 + s0 < nframes) {
         float4* g = reinterpret_cast<float4*>(en1 + ((fi0 + s0) * kF2 + f) * 16 + 8 * H);
         g[0] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
@@ -527,7 +548,7 @@ __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict
         }
         const float a = prm.w[blob::FRONT_SLOPE + 0];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) { acc0[c] = prelu(acc0[c], a); acc1[c] = prelu(acc1[c], a); }
+        for (int c = 0; c < 16; c += 2) { prelu_pair(acc0[c], acc0[c + 1], a); prelu_pair(acc1[c], acc1[c + 1], a); }
         float4* o0 = reinterpret_cast<float4*>(slots + s0 * FR_SLOT);
         float4* o1 = reinterpret_cast<float4*>(slots + s1 * FR_SLOT);
         const int cp = f + 2, po = (cp & 1) * 35 + (cp >> 1);
@@ -608,7 +629,7 @@ __device__ __forceinline__ void gt_pc1(const PB& prm, const float (&x1)[8], floa
         for (int c = 0; c < 16; c += 2) fma_pair(p[c], p[c + 1], x1[ci], prm.w[O::PC1_W + ci * 16 + c], prm.w[O::PC1_W + ci * 16 + c + 1]);
     const float a1 = prm.w[O::SLOPE + 0];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) p[c] = prelu(p[c], a1);
+    for (int c = 0; c < 16; ++c) p[c] = prelu(p[c], a1);      // scalar on purpose: pairing here costs the GTConv kernels spills
 }
 // one (kf, ci-quad) step of the 3x3 conv for PS slots: in[j] = tap row j (slot s uses rows s, s+1, s+2 for kt = 0,1,2)
 template <bool DEC, int PS, class PB>
@@ -914,7 +935,7 @@ __device__ __forceinline__ void tcn_conv1(const PB& prm, int wo, const float (&x
 #pragma unroll
     for (int s = 0; s < P; ++s)
 #pragma unroll
-        for (int c = 0; c < 16; ++c) y1[s][c] = prelu(y1[s][c], a1);
+        for (int c = 0; c < 16; c += 2) prelu_pair(y1[s][c], y1[s][c + 1], a1);
 }
 // depthwise dilated temporal conv, in place: y[c] <- PReLU(b2 + w0 * tap(t-2d) + w1 * tap(t-d) + w2 * y[c])
 template <class PB>
@@ -923,8 +944,8 @@ __device__ __forceinline__ void tcn_dw(const PB& prm, int wo, const float4 (&ta)
 #pragma unroll
     for (int qd = 0; qd < 4; ++qd) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = 4 * qd + i;
+        for (int i = 0; i < 4; ++i) {                        // scalar on purpose: pairing these per-channel taps makes ptxas fetch ALL
+            const int c = 4 * qd + i;                        // of the TCN's weights with per-thread-indexed LDC (tools/sass_check.sh), 2x slower
             float v = prm.w[wo + blob::TCN_B2 + c];
             v = fmaf(prm.w[wo + blob::TCN_W2 + c], f4get(ta[qd], i), v);
             v = fmaf(prm.w[wo + blob::TCN_W2 + 16 + c], f4get(tb[qd], i), v);
@@ -936,10 +957,10 @@ __device__ __forceinline__ void tcn_dw(const PB& prm, int wo, const float4 (&ta)
 template <int P, class PB>
 __device__ __forceinline__ void tcn_conv3(const PB& prm, int wo, const float (&y2)[P][16], float (&x)[P][16]) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        const float bb = prm.w[wo + blob::TCN_B3 + c];
+    for (int c = 0; c < 16; c += 2) {
+        const float b0 = prm.w[wo + blob::TCN_B3 + c], b1 = prm.w[wo + blob::TCN_B3 + c + 1];
 #pragma unroll
-        for (int s = 0; s < P; ++s) x[s][c] += bb;
+        for (int s = 0; s < P; ++s) add_pair(x[s][c], x[s][c + 1], b0, b1);
     }
 #pragma unroll
     for (int ci = 0; ci < 16; ++ci)
@@ -953,7 +974,7 @@ __device__ __forceinline__ void tcn_conv3(const PB& prm, int wo, const float (&y
 #pragma unroll
     for (int s = 0; s < P; ++s)
 #pragma unroll
-        for (int c = 0; c < 16; ++c) x[s][c] = prelu(x[s][c], a3);
+        for (int c = 0; c < 16; c += 2) prelu_pair(x[s][c], x[s][c + 1], a3);
 }
 
 // GTCN walking kernel, one WARP per (utterance, bin) column: a lane owns frame slots lane, lane+32, .. (P of them) of a
@@ -1013,11 +1034,15 @@ k_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_cons
                 for (int c = 0; c < 16; ++c) x[s][c] = 0.f;
             }
         }
+#if GTCRNB_TCN_UNROLL
+        static_for<4>([&](auto k_) {
+            constexpr int k = decltype(k_)::value;
+#else
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
+#endif
             const int d = 1 << k, coff = (2 << k) - 2, wo = k * blob::TCN_SIZE;   // history rows of TCN k start at 2^(k+1) - 2
             static_assert(blob::TCN_SIZE % 4 == 0, "16-byte aligned weight chunks");
-            __builtin_assume((wo & 3) == 0);                                       // lets ptxas use 128-bit uniform constant loads
             const float4* Hc = H + par * 120 + coff;                               // [q] stride 30: frames t0-2d .. t0-1
             float4* Hn = H + (par ^ 1) * 120 + coff;
             float y[P][16];
@@ -1046,7 +1071,11 @@ k_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_cons
                 Hn[qd * 30 + j] = Y[qd * NT + NT - 2 * d + j];
             }
             __syncwarp();
+#if GTCRNB_TCN_UNROLL
+        });
+#else
         }
+#endif
 #pragma unroll
         for (int s = 0; s < P; ++s) {
             const int t = t0 + lane + 32 * s;

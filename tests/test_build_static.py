@@ -1,0 +1,76 @@
+"""Static checks of the built library's SASS (no GPU needed): the properties the measured speed depends on and that a small
+source edit can silently flip, because ptxas chooses the instruction forms.
+
+ * weights reach the FMA pipe through the uniform datapath (LDCU, immediate or uniform-register offset).  Per-thread
+   register-indexed constant loads (LDC c[0x0][Rn+imm]) go through the indexed constant cache, whose ~0.5 requests/clk/SM
+   bound the decoder 3x3 kernel at 9.1 ms instead of 7.5 ms and the GTCN kernel at 8.7 ms instead of 4.5 ms (B200, round 1).
+ * the convolutions are packed FFMA2 (fma.rn.f32x2), not scalar FFMA.
+ * no kernel on the default path spills more than a couple of registers (<= 16 bytes of stack).
+"""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+import gtcrn_micro_b200.build as B
+
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+# kernels launched with the default tuning (gtcrn_capi.cu): offline + streaming
+HOT = ["k_frontILb0", "k_frontILb1", "k_backILb0", "k_backILb1", "k_gtconvILb0ELi2ELi8ELb0", "k_gtconvILb1ELi4ELi7ELb0",
+       "k_gtcnILi2ELb0", "ks_gtconvILb0", "ks_gtconvILb1", "ks_gtcn"]
+
+
+@pytest.fixture(scope="module")
+def sass():
+    if not os.path.exists(CUOBJDUMP):
+        pytest.skip("cuobjdump not available")
+    lib = B.build()
+    out = subprocess.run([CUOBJDUMP, "-sass", lib], capture_output=True, text=True, check=True).stdout
+    per, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1); per[name] = []
+        elif name and re.search(r"/\*[0-9a-f]{4,}\*/\s+\S", line):
+            per[name].append(line)
+    return per
+
+
+def _find(per, key):
+    hits = [n for n in per if key in n]
+    assert len(hits) == 1, (key, hits)
+    return per[hits[0]]
+
+
+@pytest.mark.parametrize("key", HOT)
+def test_weights_use_the_uniform_datapath(sass, key):
+    body = _find(sass, key)
+    r_indexed = sum(1 for l in body if re.search(r"c\[0x0\]\[R\d", l))
+    assert r_indexed <= 16, f"{key}: {r_indexed} per-thread-indexed constant loads (LDC c[0x0][R..]) -- see tools/sass_check.sh"
+
+
+@pytest.mark.parametrize("key", HOT)
+def test_convolutions_are_packed_ffma2(sass, key):
+    body = _find(sass, key)
+    f2 = sum(1 for l in body if "FFMA2" in l)
+    f1 = sum(1 for l in body if re.search(r"\sFFMA\s", l))
+    assert f2 >= 100 and f2 >= 1.5 * f1, (key, f2, f1)
+
+
+def test_default_kernels_do_not_spill():
+    if not os.path.exists(CUOBJDUMP):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([CUOBJDUMP, "-res-usage", B.build()], capture_output=True, text=True, check=True).stdout
+    fn = None
+    seen = 0
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            fn = m.group(1); continue
+        m = re.search(r"STACK:(\d+)", line)
+        if m and fn and any(k in fn for k in HOT):
+            seen += 1
+            assert int(m.group(1)) <= 16, (fn, line.strip())
+    assert seen == len(HOT)
