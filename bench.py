@@ -43,7 +43,7 @@ FRAMES_PER_UTT = 1 + L_UTT // 256
 MAC_PER_FRAME = 614_530                   # conv/linear MACs of the reference's own ops
 DEC_GT_MAC_PER_FRAME = 84_582             # one decoder GTConvBlock
 FP32_PEAK_TFLOPS = 73.4                   # measured on this pool's B200: tools/microbench/ffma_feed.cu -> profiles/ffma_feed_r1.txt
-DEC_GT_DRAM_BYTES_PER_FRAME = 8739        # ncu --set full, dram__bytes_read+write of one k_gtconv<DEC> launch / frames (profiles/ncu_r1_v10_summary.txt)
+DEC_GT_DRAM_BYTES_PER_FRAME = 8555        # ncu --set full, dram__bytes_read+write of one k_gtconv<DEC> launch / frames (profiles/ncu_r1_v13_summary.txt)
 DEC_GT_ALG_BYTES_PER_FRAME = 3 * 33 * 16 * 4   # read x + skip, write out: 6,336 B
 WEIGHTS = os.path.join(ROOT, "tests", "golden", "weights_dns3.npz")
 
@@ -326,9 +326,13 @@ def run_b200(args):
         "peak_source": "measured FFMA micro-benchmark on this pool's B200 (tools/microbench/ffma_feed.cu, profiles/ffma_feed_r1.txt); "
                        "MEASURED_PEAKS.json carries HBM and bf16-tensor peaks only and this path is FP32-FMA bound (SURVEY 8d)",
         "traffic": DEC_GT_DRAM_BYTES_PER_FRAME * (dk["frames"] // max(1, dk["launches"])),
-        "traffic_note": "DRAM bytes per launch from ncu (8,739 B/frame, profiles/ncu_r1_v10_summary.txt) vs 6,336 algorithmic B/frame: "
+        "traffic_note": "DRAM bytes per launch from ncu (8,555 B/frame, profiles/ncu_r1_v13_summary.txt) vs 6,336 algorithmic B/frame: "
                         "the untouched channel half is re-read in the store phase instead of being held in 32 registers",
         "algorithmic_bytes_per_launch": DEC_GT_ALG_BYTES_PER_FRAME * (dk["frames"] // max(1, dk["launches"])),
+        # the same kernel against the HBM roof (it is not the binding one: arithmetic intensity 84,582 MAC / 6,336 B = 26.7 flop/B)
+        "hbm_view": {"bound": "hbm", "achieved": round(DEC_GT_ALG_BYTES_PER_FRAME * dk["frames"] / (dk["ms"] * 1e-3) / 1e9, 1) if dk["ms"] > 0 else 0.0,
+                     "peak": hbm_peak, "unit": "GB/s",
+                     "frac": round(DEC_GT_ALG_BYTES_PER_FRAME * dk["frames"] / (dk["ms"] * 1e-3) / 1e9 / hbm_peak, 4) if dk["ms"] > 0 else 0.0},
         "ms_per_launch": round(dk["ms"] / max(1, dk["launches"]), 4), "launches": dk["launches"],
         "share_of_step": round(dk["ms"] / step_kernel_ms, 4) if step_kernel_ms else None,
         "dominant_class_by_time": dom,
