@@ -146,15 +146,22 @@ __device__ __forceinline__ void fft256_stage(const float2* __restrict__ in, floa
     const int k = j & (Ns - 1);
     float2 v0 = in[j], v1 = in[j + 64], v2 = in[j + 128], v3 = in[j + 192];
     if (Ns > 1) {
-        const int m = k * (64 / Ns);
-        v1 = cmul(v1, tw[m]);
-        v2 = cmul(v2, tw[2 * m]);
-        v3 = cmul(v3, tw[3 * m]);
+        // stage-major table, three twiddles per butterfly at consecutive float2s (pack.py _fft_tables): conflict-free
+        const float2* tws = tw + (Ns == 4 ? 0 : Ns == 16 ? 12 : 60) + 3 * k;
+        v1 = cmul(v1, tws[0]);
+        v2 = cmul(v2, tws[1]);
+        v3 = cmul(v3, tws[2]);
     }
     const float2 s0 = make_float2(v0.x + v2.x, v0.y + v2.y), s1 = make_float2(v0.x - v2.x, v0.y - v2.y);
     const float2 s2 = make_float2(v1.x + v3.x, v1.y + v3.y), d = make_float2(v1.x - v3.x, v1.y - v3.y);
     const float2 s3 = make_float2(d.y, -d.x);   // d * (-i)
     const int j0 = ((j - k) << 2) + k;
+    if (Ns == 1) {                                          // the four outputs are contiguous: two 128-bit stores (half the wavefronts)
+        float4* o4 = reinterpret_cast<float4*>(out + 4 * j);
+        o4[0] = make_float4(s0.x + s2.x, s0.y + s2.y, s1.x + s3.x, s1.y + s3.y);
+        o4[1] = make_float4(s0.x - s2.x, s0.y - s2.y, s1.x - s3.x, s1.y - s3.y);
+        return;
+    }
     out[j0] = make_float2(s0.x + s2.x, s0.y + s2.y);
     out[j0 + Ns] = make_float2(s1.x + s3.x, s1.y + s3.y);
     out[j0 + 2 * Ns] = make_float2(s0.x - s2.x, s0.y - s2.y);
@@ -215,7 +222,7 @@ constexpr int STFT_FPB = 4;
 __global__ void __launch_bounds__(256) k_stft(const float* __restrict__ wav, int64_t in_stride, int L, int T,
                                               const float* __restrict__ blobp, float* __restrict__ spec) {
     __shared__ FftTables tb;
-    __shared__ float2 buf[STFT_FPB][2][256];
+    __shared__ __align__(16) float2 buf[STFT_FPB][2][256];
     const int tid = threadIdx.x, fr = tid >> 6, j = tid & 63;
     const int t = blockIdx.x * STFT_FPB + fr, b = blockIdx.y;
     const bool valid = t < T;
@@ -260,7 +267,7 @@ constexpr int ISTFT_HOPS = 7;
 __global__ void __launch_bounds__(256) k_istft(const float* __restrict__ spec, int64_t sb, int64_t sf, int64_t st, int64_t sc,
                                                int T, const float* __restrict__ blobp, float* __restrict__ wav, int64_t out_stride) {
     __shared__ FftTables tb;
-    __shared__ float2 buf[4][2][256];
+    __shared__ __align__(16) float2 buf[4][2][256];
     __shared__ float frames[ISTFT_HOPS + 1][512];
     __shared__ float inv_env[256];
     const int tid = threadIdx.x, fr = tid >> 6, j = tid & 63;

@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) ks_stft_step(void* state, const float* __
                                                     float* __restrict__ spec, int64_t N) {
     using namespace gk;
     __shared__ FftTables tb;
-    __shared__ float2 buf[4][2][256];
+    __shared__ __align__(16) float2 buf[4][2][256];
     Header* hdr = reinterpret_cast<Header*>(state);
     const long long k = hdr->wav_calls;
     const int tid = threadIdx.x, fr = tid >> 6, j = tid & 63;
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(256) ks_istft_step(void* state, const float* _
                                                      float* __restrict__ hop_out, int64_t N) {
     using namespace gk;
     __shared__ FftTables tb;
-    __shared__ float2 buf[4][2][256];
+    __shared__ __align__(16) float2 buf[4][2][256];
     __shared__ float inv_env[256];
     const Header* hdr = reinterpret_cast<const Header*>(state);
     const long long k = hdr->wav_calls;

@@ -36,7 +36,7 @@ def prelu(x, a):
 # ---------------------------------------------------------------------------------- FFT
 def fft256_stockham(z, tw):
     """Forward 256-point complex FFT, radix-4 Stockham autosort, exactly the kernel's index map.
-    z [..., 256] complex; tw [256] complex = exp(-2*pi*i*m/256)."""
+    z [..., 256] complex; tw [256] complex = the blob's stage-major twiddle table."""
     N, R = 256, 4
     a = z.copy()
     Ns = 1
@@ -44,7 +44,8 @@ def fft256_stockham(z, tw):
         out = np.empty_like(a)
         for j in range(N // R):
             k = j % Ns
-            v = [a[..., j + r * (N // R)] * tw[(k * r * (N // (Ns * R))) % N] for r in range(R)]
+            base = {1: 0, 4: 0, 16: 12, 64: 60}[Ns]               # stage-major twiddle table, 3 per butterfly (pack._fft_tables)
+            v = [a[..., j + r * (N // R)] * (tw[base + 3 * k + (r - 1)] if (r > 0 and Ns > 1) else 1.0) for r in range(R)]
             # radix-4 butterfly (forward)
             s0, s1 = v[0] + v[2], v[0] - v[2]
             s2, s3 = v[1] + v[3], (v[1] - v[3]) * (-1j)
