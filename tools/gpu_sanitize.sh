@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-cat > /tmp/san_case.py <<'PY'
+cat > gpurun_out/san_case.py <<'PY'
 import sys, torch
 sys.path.insert(0, 'oracle'); sys.path.insert(0, '.')
 import gtcrn_oracle as O, gtcrn_micro_b200 as G
@@ -13,9 +13,11 @@ sm = G.StreamGTCRNMicro(); G.convert_to_stream(sm, m)
 st = sm.new_state(5, 'cuda:0')
 for k in range(6):
     o = sm.step_wav(x[:1, 256 * k:256 * (k + 1)].repeat(5, 1).contiguous(), st)
-torch.cuda.synchronize(); print('ok', y.shape, float((y - z).abs().max()))
+pm = m.pair_metrics(x[:, :y.shape[1]].contiguous(), y)
+yh = m.enhance_host(x.cpu().pin_memory())
+torch.cuda.synchronize(); print('ok', y.shape, float((y - z).abs().max()), bool(torch.equal(yh, y.cpu())), pm.shape)
 PY
 for tool in memcheck racecheck; do
-  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san_case.py > gpurun_out/sanitize_$tool.log 2>&1
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python gpurun_out/san_case.py > gpurun_out/sanitize_$tool.log 2>&1
   echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|ok " gpurun_out/sanitize_$tool.log | tail -3
 done
