@@ -193,7 +193,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = best_B * SECONDS * args.steps / dt
     sample = f"{best_B} x {SECONDS} s utterances per step (bounded sample of the 1024-utterance batch), torch {torch.__version__} CPU, {cores} threads"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -201,7 +201,7 @@ def run_reference(args):
         "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------
@@ -247,6 +247,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
@@ -369,9 +370,21 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"oracle port (torch {torch.__version__} CPU, same ATen ops as the reference), {SECONDS} s utterances, "
                                           f"best of B in {detail} (1 warm-up + best of 2 each); 1024-utterance batch extrapolated from this sample"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.buffer.write(data); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -384,6 +397,12 @@ def main():
     ap.add_argument("--no-stream", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: park the real stdout and point fd 1 at stderr while the libraries run
+    # (NCCL prints its version banner on stdout), then hand the real stdout back to emit().
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
