@@ -112,10 +112,11 @@ template <int PS, int G, bool SW> GtVariant make_gt_variant() {
             gk::gt_smem_floats(PS, G, SW ? gk::gt_chunk<true>() : 0) * (int)sizeof(float),
             (const void*)gk::k_gtconv<false, PS, G, SW>, (const void*)gk::k_gtconv<true, PS, G, SW>};
 }
-// index: 0 (2,8,const) 1 (3,8,const) 2 (4,7,const) 3 (2,8,smem) 4 (3,8,smem) 5 (4,7,smem)
+// index: 0 (2,8,const) 1 (3,8,const) 2 (4,7,const) 3 (2,8,smem) 4 (3,8,smem) 5 (4,7,smem) 6 (1,8,const)
 const GtVariant kGtVariants[] = {make_gt_variant<2, 8, false>(), make_gt_variant<3, 8, false>(), make_gt_variant<4, 7, false>(),
-                                 make_gt_variant<2, 8, true>(), make_gt_variant<3, 8, true>(), make_gt_variant<4, 7, true>()};
-constexpr int kNumGtVariants = 6;
+                                 make_gt_variant<2, 8, true>(), make_gt_variant<3, 8, true>(), make_gt_variant<4, 7, true>(),
+                                 make_gt_variant<1, 8, false>()};
+constexpr int kNumGtVariants = 7;
 
 template <bool DEC>
 void launch_gtconv(const GtVariant& v, dim3 grid, cudaStream_t st, const float* x, const float* skip, float* out,
@@ -127,7 +128,8 @@ void launch_gtconv(const GtVariant& v, dim3 grid, cudaStream_t st, const float* 
         else if (v.ps == 3) k_gtconv<DEC, 3, 8, true><<<grid, v.threads, sm, st>>>(x, skip, out, prm, T, seg);
         else k_gtconv<DEC, 4, 7, true><<<grid, v.threads, sm, st>>>(x, skip, out, prm, T, seg);
     } else {
-        if (v.ps == 2) k_gtconv<DEC, 2, 8, false><<<grid, v.threads, sm, st>>>(x, skip, out, prm, T, seg);
+        if (v.ps == 1) k_gtconv<DEC, 1, 8, false><<<grid, v.threads, sm, st>>>(x, skip, out, prm, T, seg);
+        else if (v.ps == 2) k_gtconv<DEC, 2, 8, false><<<grid, v.threads, sm, st>>>(x, skip, out, prm, T, seg);
         else if (v.ps == 3) k_gtconv<DEC, 3, 8, false><<<grid, v.threads, sm, st>>>(x, skip, out, prm, T, seg);
         else k_gtconv<DEC, 4, 7, false><<<grid, v.threads, sm, st>>>(x, skip, out, prm, T, seg);
     }
@@ -300,6 +302,7 @@ int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) 
         {kGtVariants[3].enc, kGtVariants[3].smem_enc / 4}, {kGtVariants[3].dec, kGtVariants[3].smem_dec / 4},
         {kGtVariants[4].enc, kGtVariants[4].smem_enc / 4}, {kGtVariants[4].dec, kGtVariants[4].smem_dec / 4},
         {kGtVariants[5].enc, kGtVariants[5].smem_enc / 4}, {kGtVariants[5].dec, kGtVariants[5].smem_dec / 4},
+        {kGtVariants[6].enc, kGtVariants[6].smem_enc / 4}, {kGtVariants[6].dec, kGtVariants[6].smem_dec / 4},
         {(const void*)k_gtcn<2, false>, wc_smem_floats(2)}, {(const void*)k_gtcn<2, true>, wc_smem_floats(2, true)},
         {(const void*)k_back<false>, bk_smem_floats(false)}, {(const void*)k_back<true>, bk_smem_floats(true)},
         {(const void*)k_stft, 0},
@@ -481,7 +484,7 @@ int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int6
     }
     // Chunk schedule: the first H2D and the last D2H cannot overlap with anything, so the pipeline ramps up and down through
     // chunks of Bc/2^ramp .. Bc/2 (the two compute streams hide the small chunks' partial waves behind their neighbours).
-    int ramp = 3;
+    int ramp = 4;
     if (const char* e = getenv("GTCRNB_HOST_RAMP")) ramp = std::max(0, std::min(4, atoi(e)));
     std::vector<int64_t> sizes;
     {

@@ -607,7 +607,7 @@ __host__ __device__ constexpr int gt_threads(int G) { return (G * kF2 + 31) / 32
 __host__ __device__ constexpr int gt_smem_floats(int PS, int G, int w_floats = 0) {
     return (G * PS + 2) * GT_ROW4 * 4 + G * PS * kF2 * 8 + (G * PS + 2) * 8 + G * PS * 8 + w_floats;
 }
-__host__ __device__ constexpr int gt_min_blocks(int PS) { return PS >= 4 ? 2 : (PS == 3 ? 2 : 3); }
+__host__ __device__ constexpr int gt_min_blocks(int PS) { return PS >= 4 ? 2 : (PS == 3 ? 2 : (PS == 2 ? 3 : 4)); }
 
 template <bool DEC> struct GtOff {
     static constexpr int PC1_W = DEC ? blob::DECGT_PC1_W : blob::ENCGT_PC1_W;
