@@ -346,7 +346,7 @@ def run_b200(args):
     }
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"GTCRN-Micro offline batched inference, {B} x {SECONDS} s synthetic 16 kHz utterances per GPU (BASELINE configs[1]), "
                                f"STFT+model+iSTFT, shipped DNS3 checkpoint weights",
@@ -396,7 +396,17 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="utterances per GPU per step (BASELINE configs[1]: 1024)")
     ap.add_argument("--no-stream", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sweep-utterances", type=int, default=0,
+                    help="BASELINE configs[4]: a fixed job of this many 10 s utterances (65536) sharded over the ranks in contiguous "
+                         "blocks (shard.shard_range); sets --steps to the rank's share / --batch and reports scaling 'strong'")
     args = ap.parse_args()
+    args.scaling = "weak"
+    if args.sweep_utterances:
+        from gtcrn_micro_b200.shard import shard_range
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        lo, hi = shard_range(args.sweep_utterances, 0, world)          # rank 0 holds the largest shard
+        args.steps = max(1, -(-(hi - lo) // args.batch))
+        args.scaling = "strong"
     # stdout carries exactly ONE JSON line: park the real stdout and point fd 1 at stderr while the libraries run
     # (NCCL prints its version banner on stdout), then hand the real stdout back to emit().
     global _REAL_STDOUT

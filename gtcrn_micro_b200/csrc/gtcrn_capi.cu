@@ -274,6 +274,11 @@ void* gtcrnb_host_alloc(size_t bytes) {
     if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
+void* gtcrnb_host_alloc_wc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
 void gtcrnb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) {

@@ -20,7 +20,7 @@ SYMBOLS = [
     "gtcrnb_stream_reset", "gtcrnb_stream_step_spec", "gtcrnb_stream_step_wav", "gtcrnb_stream_import_caches",
     "gtcrnb_stream_export_caches", "gtcrnb_debug_activation", "gtcrnb_launch_count", "gtcrnb_host_alloc",
     "gtcrnb_host_free", "gtcrnb_last_error", "gtcrnb_profile_enable", "gtcrnb_profile_read",
-    "gtcrnb_profile_num_classes", "gtcrnb_profile_class_name", "gtcrnb_pair_metrics",
+    "gtcrnb_profile_num_classes", "gtcrnb_profile_class_name", "gtcrnb_pair_metrics", "gtcrnb_host_alloc_wc",
 ]
 
 
@@ -63,6 +63,7 @@ def load() -> C.CDLL:
             "gtcrnb_debug_activation": (C.c_int, [vp, cp, vp, sz, vp]),
             "gtcrnb_launch_count": (i64, [vp]),
             "gtcrnb_host_alloc": (vp, [sz]),
+            "gtcrnb_host_alloc_wc": (vp, [sz]),
             "gtcrnb_host_free": (None, [vp]),
             "gtcrnb_last_error": (cp, []),
             "gtcrnb_profile_enable": (C.c_int, [vp, C.c_int]),

@@ -413,6 +413,38 @@ def convert_to_stream(stream_model: nn.Module, model: nn.Module) -> None:
     stream_model.load_state_dict(dst)
 
 
+class _HostBlock:
+    """Owns one gtcrnb_host_alloc block; freed when the last tensor viewing it goes away."""
+    def __init__(self, ptr: int):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.load().gtcrnb_host_free(C.c_void_p(self.ptr))
+                self.ptr = 0
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, write_combined: bool = False) -> torch.Tensor:
+    """float32 page-locked host tensor from the library's allocator (`gtcrnb_host_alloc[_wc]`) for `enhance_host`.
+    write_combined=True is for INPUT buffers that the CPU fills sequentially and never reads: the copy engine reads them
+    without cache snooping.  CPU reads of such a tensor are very slow."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    L = _lib.load()
+    ptr = (L.gtcrnb_host_alloc_wc if write_combined else L.gtcrnb_host_alloc)(max(4, 4 * n))
+    if not ptr:
+        raise GtcrnB200Error(f"page-locked allocation of {4 * n} bytes failed")
+    block = _HostBlock(int(ptr))
+    buf = (C.c_float * n).from_address(block.ptr)
+    buf._gtcrnb_owner = block                                   # ctypes array keeps the block alive; torch keeps the array alive
+    t = torch.frombuffer(buf, dtype=torch.float32, count=n) if n else torch.empty(0)
+    return t.view(*shape)
+
+
 def load_checkpoint(path: str, stream: bool = False, map_location="cpu") -> nn.Module:
     """Build a model from a reference training checkpoint `{"epoch","optimizer","scheduler","model"}`
     (train.py:206-211); also tolerates a bare state_dict, `state_dict`/`model_state_dict` keys and a DDP

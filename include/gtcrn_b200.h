@@ -112,6 +112,9 @@ const char* gtcrnb_profile_class_name(int i);
 int64_t gtcrnb_launch_count(const gtcrnb_handle* h);
 /* Pinned host memory helpers for the *_host entry points. */
 void* gtcrnb_host_alloc(size_t bytes);
+/* write-combined page-locked memory for INPUT buffers the CPU only writes sequentially (never reads back): the DMA engine
+ * reads it without snooping the CPU caches.  Free with gtcrnb_host_free. */
+void* gtcrnb_host_alloc_wc(size_t bytes);
 void gtcrnb_host_free(void* p);
 const char* gtcrnb_last_error(void);
 
