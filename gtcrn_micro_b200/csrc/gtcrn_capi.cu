@@ -64,6 +64,9 @@ struct gtcrnb_handle {
     float* stage_in[kStage] = {};
     float* stage_out[kStage] = {};
     size_t stage_in_floats = 0, stage_out_floats = 0;
+    int16_t* pcm_in[kStage] = {};                    // PCM16 wire buffers of gtcrnb_enhance_host_pcm16
+    int16_t* pcm_out[kStage] = {};
+    size_t pcm_in_elems = 0, pcm_out_elems = 0;
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_comp2 = nullptr, s_d2h = nullptr;
     // second activation workspace for the host pipeline: consecutive chunks run on two compute streams so that the tail of one
     // chunk's kernels overlaps the head of the next (the fields above are the currently selected workspace)
@@ -354,6 +357,8 @@ void gtcrnb_destroy(gtcrnb_handle* h) {
     for (auto p : h->act) freep(p);
     for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
         freep(h->stage_in[i]); freep(h->stage_out[i]);
+        if (h->pcm_in[i]) cudaFree(h->pcm_in[i]);
+        if (h->pcm_out[i]) cudaFree(h->pcm_out[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
         if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
         if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
@@ -448,10 +453,15 @@ int gtcrnb_enhance(gtcrnb_handle* h, const float* wav_dev, int64_t B, int64_t L,
     return GTCRNB_OK;
 }
 
-int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int64_t L, float* out_host) {
-    if (!h || !wav_host || !out_host) return fail(GTCRNB_E_INVALID, "gtcrnb_enhance_host: NULL argument");
+}  // extern "C" (reopened below): the shared host pipeline is a C++ function
+
+namespace {
+// H2D / compute / D2H pipeline behind gtcrnb_enhance_host (float32 samples) and gtcrnb_enhance_host_pcm16 (PCM16 samples on the
+// wire, converted on the device: x / 32768 in, floor(y * 32768) clamped out -- half the PCIe bytes of the float contract).
+int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, void* out_host, bool pcm) {
     if (L <= 256 || B < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_enhance_host: need L > 256");
-    if (B == 0) return GTCRNB_OK;
+    if (h && B == 0) return GTCRNB_OK;                            // empty batch: torch hands out NULL data pointers
+    if (!h || !wav_host || !out_host) return fail(GTCRNB_E_INVALID, "gtcrnb_enhance_host: NULL argument");
     const int64_t T = 1 + L / gk::kHop, Lout = gk::kHop * (T - 1);
     if (!h->s_h2d) {
         CU(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
@@ -487,6 +497,23 @@ int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int6
         }
         h->stage_in_floats = need_in; h->stage_out_floats = need_out;
     }
+    if (pcm && (need_in > h->pcm_in_elems || need_out > h->pcm_out_elems)) {
+        for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
+            if (h->pcm_in[i]) cudaFree(h->pcm_in[i]);
+            if (h->pcm_out[i]) cudaFree(h->pcm_out[i]);
+            h->pcm_in[i] = h->pcm_out[i] = nullptr;
+        }
+        h->pcm_in_elems = h->pcm_out_elems = 0;
+        for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
+            if (cudaMalloc(&h->pcm_in[i], need_in * sizeof(int16_t)) != cudaSuccess ||
+                cudaMalloc(&h->pcm_out[i], need_out * sizeof(int16_t)) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(GTCRNB_E_NOMEM, "PCM16 staging allocation failed");
+            }
+        }
+        h->pcm_in_elems = need_in; h->pcm_out_elems = need_out;
+    }
+    const size_t esz = pcm ? sizeof(int16_t) : sizeof(float);
     // Chunk schedule: the first H2D and the last D2H cannot overlap with anything, so the pipeline ramps up and down through
     // chunks of Bc/2^ramp .. Bc/2 (the two compute streams hide the small chunks' partial waves behind their neighbours).
     int ramp = 4;
@@ -514,7 +541,8 @@ int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int6
         const int64_t nb = sizes[c];
         if (c >= (size_t)gtcrnb_handle::kStage) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[i], 0));      // input buffer i consumed
         mark(h->s_h2d);
-        CU(cudaMemcpyAsync(h->stage_in[i], wav_host + b0 * L, sizeof(float) * nb * L, cudaMemcpyHostToDevice, h->s_h2d));
+        CU(cudaMemcpyAsync(pcm ? (void*)h->pcm_in[i] : (void*)h->stage_in[i], (const char*)wav_host + b0 * L * esz, esz * nb * L,
+                           cudaMemcpyHostToDevice, h->s_h2d));
         mark(h->s_h2d);
         CU(cudaEventRecord(h->ev_h2d[i], h->s_h2d));
         cudaStream_t sc = ws ? h->s_comp2 : h->s_comp;                         // chunk parity -> compute stream + workspace
@@ -522,13 +550,22 @@ int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int6
         CU(cudaStreamWaitEvent(sc, h->ev_h2d[i], 0));
         if (c >= (size_t)gtcrnb_handle::kStage) CU(cudaStreamWaitEvent(sc, h->ev_d2h[i], 0));             // output buffer i drained
         mark(sc);
+        if (pcm) {
+            gk::k_pcm16_to_f32<<<h->sm_count * 8, 256, 0, sc>>>(h->pcm_in[i], h->stage_in[i], nb * L);
+            h->launches++;
+        }
         int rc = gtcrnb_enhance(h, h->stage_in[i], nb, L, L, h->stage_out[i], Lout, sc);
         if (rc) { select_workspace(h, 0); return rc; }
+        if (pcm) {
+            gk::k_f32_to_pcm16<<<h->sm_count * 8, 256, 0, sc>>>(h->stage_out[i], h->pcm_out[i], nb * Lout);
+            h->launches++;
+        }
         mark(sc);
         CU(cudaEventRecord(h->ev_comp[i], sc));
         CU(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[i], 0));
         mark(h->s_d2h);
-        CU(cudaMemcpyAsync(out_host + b0 * Lout, h->stage_out[i], sizeof(float) * nb * Lout, cudaMemcpyDeviceToHost, h->s_d2h));
+        CU(cudaMemcpyAsync((char*)out_host + b0 * Lout * esz, pcm ? (const void*)h->pcm_out[i] : (const void*)h->stage_out[i], esz * nb * Lout,
+                           cudaMemcpyDeviceToHost, h->s_d2h));
         mark(h->s_d2h);
         CU(cudaEventRecord(h->ev_d2h[i], h->s_d2h));
     }
@@ -546,6 +583,15 @@ int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int6
         for (auto e : tev) cudaEventDestroy(e);
     }
     return GTCRNB_OK;
+}
+}  // namespace
+
+extern "C" {
+int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int64_t L, float* out_host) {
+    return host_pipeline(h, wav_host, B, L, out_host, false);
+}
+int gtcrnb_enhance_host_pcm16(gtcrnb_handle* h, const int16_t* wav_host, int64_t B, int64_t L, int16_t* out_host) {
+    return host_pipeline(h, wav_host, B, L, out_host, true);
 }
 
 int gtcrnb_debug_activation(gtcrnb_handle* h, const char* name, float* out_dev, size_t n_floats, void* stream) {

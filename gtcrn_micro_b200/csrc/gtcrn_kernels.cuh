@@ -1362,6 +1362,44 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
 }
 
 // ================================================================================================
+// PCM16 <-> float32 on the device (wav files are PCM16: the host pipeline can ship 2 bytes per sample over PCIe).
+// Decode x / 32768 (what soundfile / the reference's sf.read(dtype="float32") produce, infer.py:52); encode floor(y * 32768)
+// clamped, the rule the reference's shipped *_enh.wav files follow (tests/golden/pairs.npz: 99.98 % exact, rint 50 %).
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_pcm16_to_f32(const int16_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n8 = ((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? n / 8 : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const int4 v = reinterpret_cast<const int4*>(in)[i];
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[2 * k] = (float)(short)(w[k] & 0xffff) * (1.0f / 32768.0f);
+            o[2 * k + 1] = (float)(short)(w[k] >> 16) * (1.0f / 32768.0f);
+        }
+        reinterpret_cast<float4*>(out)[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    for (int64_t i = n8 * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (float)in[i] * (1.0f / 32768.0f);
+}
+__device__ __forceinline__ int pcm16_of(float v) { return (int)fminf(fmaxf(floorf(v * 32768.0f), -32768.0f), 32767.0f); }
+__global__ void __launch_bounds__(256) k_f32_to_pcm16(const float* __restrict__ in, int16_t* __restrict__ out, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n8 = ((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? n / 8 : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const float4 a = reinterpret_cast<const float4*>(in)[2 * i], b = reinterpret_cast<const float4*>(in)[2 * i + 1];
+        int4 v;
+        v.x = (pcm16_of(a.x) & 0xffff) | (pcm16_of(a.y) << 16);
+        v.y = (pcm16_of(a.z) & 0xffff) | (pcm16_of(a.w) << 16);
+        v.z = (pcm16_of(b.x) & 0xffff) | (pcm16_of(b.y) << 16);
+        v.w = (pcm16_of(b.z) & 0xffff) | (pcm16_of(b.w) << 16);
+        reinterpret_cast<int4*>(out)[i] = v;
+    }
+    for (int64_t i = n8 * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (int16_t)pcm16_of(in[i]);
+}
+
+// ================================================================================================
 // On-device quality metrics of (reference, enhanced) waveform pairs: SI-SNR and SDR exactly as the reference's evaluation
 // script defines them (eval/eval_intrusive_metrics.py:74-82 sisnr_metric, :85-94 sdr_metric), from five raw moments per
 // utterance accumulated in fp64 with a fixed reduction order (deterministic).  grid B, 256 threads; out [B][2] = (si_snr, sdr) dB.

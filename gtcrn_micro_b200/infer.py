@@ -4,9 +4,9 @@ Mirrors /root/reference/gtcrn_micro/infer.py:26-119: same inp
 clean references matched by DNS3 `fileid_N`), same outputs (`<uid>_enh.wav` PCM16 files, `inf.scp`, `ref.scp`), same
 length fix-up against the clean reference (pad / truncate, infer.py:97-102), same YAML keys when driven by `-C`.
 What changes is the schedule: files are bucketed by exact length (no padding, so results are bit-identical to running each
-file alone), each bucket travels as PCM16 to the GPU, is converted, enhanced by the fused wav->wav kernels in one call, length
-fixed, quantised back to PCM16 on the device (floor(x * 32768), the rule the reference's shipped *_enh.wav files follow) and
-written out.  Optionally scores the pairs on the device (eval/eval_intrusive_metrics.py SI-SNR / SDR).
+file alone); a bucket of PCM16 files goes through `enhance_host_pcm16` (C ABI gtcrnb_enhance_host_pcm16): PCM16 over PCIe in
+both directions, decoded, enhanced by the fused wav->wav kernels and quantised on the device (floor(y * 32768), the rule the
+reference's shipped *_enh.wav files follow), then length-fixed and written out.  Optionally scores the pairs on the device (eval/eval_intrusive_metrics.py SI-SNR / SDR).
 
     python -m gtcrn_micro_b200.infer --noisy-dir N --clean-dir C --enh-dir E --checkpoint ckpt.tar [--metrics]
     python -m gtcrn_micro_b200.infer -C infer.yaml            # reference layout: test_dataset.{noisy_dir,clean_dir}, network.{enh_folder,checkpoint}
@@ -138,38 +138,38 @@ def run(model, jobs: Sequence[Job], enh_dir: str, max_batch: int = 256, device: 
     lengths = [wav_num_samples(j.noisy_path) for j in jobs]
     enh_paths: List[Optional[str]] = [None] * len(jobs)
     scores: Dict[str, Tuple[float, float]] = {}
+    def to_f32(a: np.ndarray) -> np.ndarray:
+        return a.astype(np.float32) / 32768.0 if a.dtype == np.int16 else a
+
+    def fix_np(y: np.ndarray, n: Optional[int]) -> np.ndarray:           # infer.py:97-102 on one PCM16 row
+        if n is None or n == len(y):
+            return y
+        return np.pad(y, (0, n - len(y))) if len(y) < n else y[:n]
+
     for batch in bucket_by_length(lengths, max_batch):
         raw = [read_wav(jobs[i].noisy_path) for i in batch]
-        if all(r.dtype == np.int16 for r in raw):
-            pcm_in = torch.from_numpy(np.stack(raw))
-            if dev.type == "cuda":
-                pcm_in = pcm_in.pin_memory()
-            x = pcm_in.to(dev, non_blocking=True).to(torch.float32).mul_(1.0 / 32768.0)
-        else:
-            x = torch.from_numpy(np.stack([r.astype(np.float32) / 32768.0 if r.dtype == np.int16 else r for r in raw])).to(dev)
-        enh = model.enhance(x)                                                   # fused STFT -> model -> iSTFT + overlap-add
         refs = [read_wav(jobs[i].ref_path) if jobs[i].ref_path else None for i in batch]
-        ref_len = {len(r) for r in refs if r is not None}
-        if len(ref_len) == 1 and all(r is not None for r in refs):               # common case: one clean length per bucket
-            n = ref_len.pop()
-            enh_fixed = fix_length(enh, n)
-            pcm = to_pcm16(enh_fixed).cpu().numpy()
-            outs = [pcm[k] for k in range(len(batch))]
-            if metrics:
-                r = torch.from_numpy(np.stack([q.astype(np.float32) / 32768.0 if q.dtype == np.int16 else q for q in refs])).to(dev)
-                sc = model.pair_metrics(r, enh_fixed.contiguous()).cpu().numpy()
-                for k, i in enumerate(batch):
-                    scores[jobs[i].uid] = (float(sc[k, 0]), float(sc[k, 1]))
+        ref_n = [None if r is None else len(r) for r in refs]
+        if all(r.dtype == np.int16 for r in raw) and dev.type == "cuda" and hasattr(model, "enhance_host_pcm16"):
+            # PCM16 end to end: 2 bytes per sample each way over PCIe, decode / enhance / quantise on the device
+            pcm_in = torch.from_numpy(np.stack(raw)).pin_memory()
+            pcm = model.enhance_host_pcm16(pcm_in, device=dev).numpy()
         else:
-            outs = []
-            for k, i in enumerate(batch):
-                e = enh[k:k + 1] if refs[k] is None else fix_length(enh[k:k + 1], len(refs[k]))
-                outs.append(to_pcm16(e)[0].cpu().numpy())
-                if metrics and refs[k] is not None:
-                    q = refs[k]
-                    r = torch.from_numpy(q.astype(np.float32) / 32768.0 if q.dtype == np.int16 else q)[None].to(dev)
-                    sc = model.pair_metrics(r, e.contiguous()).cpu().numpy()
-                    scores[jobs[i].uid] = (float(sc[0, 0]), float(sc[0, 1]))
+            x = torch.from_numpy(np.stack([to_f32(r) for r in raw])).to(dev)
+            pcm = to_pcm16(model.enhance(x)).cpu().numpy()
+        outs = [fix_np(pcm[k], ref_n[k]) for k in range(len(batch))]
+        if metrics:
+            # scored on what was written (the evaluation script reads the PCM16 files back): group rows of equal length
+            by_len: Dict[int, List[int]] = {}
+            for k in range(len(batch)):
+                if refs[k] is not None:
+                    by_len.setdefault(len(outs[k]), []).append(k)
+            for ks in by_len.values():
+                r = torch.from_numpy(np.stack([to_f32(refs[k]) for k in ks])).to(dev)
+                e = torch.from_numpy(np.stack([outs[k] for k in ks])).to(dev).to(torch.float32).mul_(1.0 / 32768.0)
+                sc = model.pair_metrics(r, e).cpu().numpy()
+                for row, k in enumerate(ks):
+                    scores[jobs[batch[k]].uid] = (float(sc[row, 0]), float(sc[row, 1]))
         for k, i in enumerate(batch):
             enh_paths[i] = os.path.join(enh_dir, jobs[i].uid + "_enh.wav")
             wavfile.write(enh_paths[i], FS, outs[k])

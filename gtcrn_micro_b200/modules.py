@@ -245,6 +245,23 @@ class GTCRNMicro(_B200Module):
         return out
 
     @torch.no_grad()
+    def enhance_host_pcm16(self, wav: torch.Tensor, out: Optional[torch.Tensor] = None, device: Optional[torch.device] = None) -> torch.Tensor:
+        """`enhance_host` for PCM16 audio: wav int16 [B,L] on the host (ideally pinned) -> int16 [B,256*(L//256)].
+        Samples cross PCIe as 2 bytes; decode (x/32768) and encode (floor(y*32768), clamped) run on the device."""
+        if wav.is_cuda or wav.dim() != 2 or wav.dtype != torch.int16 or not wav.is_contiguous():
+            raise ValueError("wav must be a contiguous int16 CPU tensor [B,L]")
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        h = self._ensure_handle(dev)
+        B, Ls = wav.shape
+        if out is None:
+            out = torch.empty((B, 256 * (Ls // 256)), dtype=torch.int16, pin_memory=True)
+        elif out.dtype != torch.int16 or not out.is_contiguous() or tuple(out.shape) != (B, 256 * (Ls // 256)):
+            raise ValueError("out must be a contiguous int16 CPU tensor [B,256*(L//256)]")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().gtcrnb_enhance_host_pcm16(h, wav.data_ptr(), B, Ls, out.data_ptr()), "gtcrnb_enhance_host_pcm16")
+        return out
+
+    @torch.no_grad()
     def pair_metrics(self, ref: torch.Tensor, inf: torch.Tensor) -> torch.Tensor:
         """SI-SNR and SDR (dB) of waveform pairs on the device, as eval_intrusive_metrics.py:74-94 defines them.
         ref, inf [B,L] float32 CUDA -> [B,2] = (si_snr, sdr)."""

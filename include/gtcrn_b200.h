@@ -62,6 +62,13 @@ int gtcrnb_enhance(gtcrnb_handle* h, const float* wav_dev, int64_t B, int64_t L,
 int gtcrnb_enhance_host(gtcrnb_handle* h, const float* wav_host, int64_t B, int64_t L,
                         float* out_host);
 
+/* The same pipeline with PCM16 samples on the wire (wav files are PCM16; half the PCIe bytes): the device decodes
+ * x / 32768 -- what the reference's sf.read(..., dtype="float32") yields, infer.py:52 -- and encodes
+ * floor(y * 32768) clamped to int16, the quantisation of the reference's sf.write(enh_path, enhanced, fs) outputs
+ * (infer.py:107; the shipped *_enh.wav examples).  out_host [B, 256*(L/256)] int16. */
+int gtcrnb_enhance_host_pcm16(gtcrnb_handle* h, const int16_t* wav_host, int64_t B, int64_t L,
+                              int16_t* out_host);
+
 /* STFT / iSTFT on their own (torch.stft / torch.istft call sites infer.py:60-67, :73-76).
  * spec is contiguous [B][T][257][2], T = 1 + L/256; istft writes [B][256*(T-1)]. */
 int gtcrnb_stft(gtcrnb_handle* h, const float* wav_dev, int64_t B, int64_t L, int64_t in_stride,

@@ -210,3 +210,28 @@ def test_full_size_properties(oracle, weights_dns3, b200_lib):
     # (4) oracle spot check on one utterance
     ref = oracle.enhance(weights_dns3, x[7:8].cpu())
     assert float((y[7:8].cpu() - ref).abs().max()) <= WAV_TOL
+
+
+@pytest.mark.parametrize("chunk", [None, "1"])
+def test_enhance_host_pcm16_matches_float_path(oracle, weights_dns3, pairs, b200_lib, monkeypatch, chunk):
+    # PCM16 on the wire: decode x/32768 and floor(y*32768) encode on the device must equal doing both on the host around the
+    # float path, bit for bit; and it reproduces the reference's shipped enhanced example
+    if chunk is not None:
+        monkeypatch.setenv("GTCRNB_HOST_CHUNK", chunk)
+    m = make_model(weights_dns3, b200_lib)
+    g = torch.Generator().manual_seed(3)
+    for B, L in ((5, 16000 * 2 + 3), (37, 256 * 90 + 201), (2, 257)):
+        x16 = torch.randint(-20000, 20000, (B, L), generator=g, dtype=torch.int16)
+        x16[0, :10] = torch.tensor([-32768, 32767, 0, 1, -1, 12345, -12345, 300, -300, 7], dtype=torch.int16)
+        got = m.enhance_host_pcm16(x16.pin_memory())
+        y = m.enhance((x16.float() / 32768.0).to(DEV)).cpu()
+        want = torch.floor(y * 32768.0).clamp_(-32768, 32767).to(torch.int16)
+        assert got.dtype == torch.int16 and got.shape == want.shape
+        assert torch.equal(got, want), (B, L)
+    n = torch.from_numpy(pairs["noisy1"].copy())[None]
+    out = m.enhance_host_pcm16(n)[0].numpy()
+    enh = pairs["enh1"]
+    assert np.abs(out[:len(enh)].astype(np.int32) - enh).max() <= 1 and np.mean(out[:len(enh)] == enh) > 0.995
+    assert m.enhance_host_pcm16(torch.zeros(0, 1000, dtype=torch.int16)).shape == (0, 768)
+    with pytest.raises(ValueError):
+        m.enhance_host_pcm16(torch.zeros(2, 1000))
