@@ -80,6 +80,14 @@ struct gtcrnb_handle {
     int64_t last_B = 0, last_T = 0;
     // optional per-kernel-class timing with CUDA events on the launching stream (gtcrnb_profile_*)
     bool profiling = false;
+    // CUDA graphs of the streaming hop (10-12 kernels whose by-value weight blocks, up to 20 KB each, make the hop launch-bound
+    // at small stream counts): instantiated the second consecutive time the same (state, in, out, N) is stepped, replayed after
+    struct StepGraph { int kind; const void* state; const void* in; const void* out; int64_t n; cudaGraphExec_t exec; int launches; uint64_t used; };
+    std::vector<StepGraph> step_graphs;
+    StepGraph last_step{-1, nullptr, nullptr, nullptr, 0, nullptr, 0, 0};
+    cudaStream_t s_cap = nullptr;
+    uint64_t step_tick = 0;
+    bool stream_graphs = true;                       // GTCRNB_STREAM_GRAPH=0 disables
     std::vector<ProfEvent> prof_events;
     double prof_ms[kNumKernelClasses] = {};
     int64_t prof_launches[kNumKernelClasses] = {};
@@ -88,8 +96,15 @@ struct gtcrnb_handle {
 
 namespace {
 
+void drop_step_graphs(gtcrnb_handle* h) {
+    for (auto& g : h->step_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->step_graphs.clear();
+    h->last_step.kind = -1;
+}
+
 int ensure_workspace(gtcrnb_handle* h, int64_t frames) {
     if (frames <= h->cap_frames) return GTCRNB_OK;
+    drop_step_graphs(h);                              // cached hop graphs point into the old workspace
     auto freep = [](float*& p) { if (p) cudaFree(p); p = nullptr; };
     freep(h->en0); freep(h->spec_in); freep(h->spec_out);
     for (auto& p : h->act) freep(p);
@@ -339,6 +354,7 @@ int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) 
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_gt_dec, kGtVariants[h->gt_dec].dec, kGtVariants[h->gt_dec].threads, kGtVariants[h->gt_dec].smem_dec);
     if (const char* e = getenv("GTCRNB_FUSE_FFT")) h->fuse_fft = atoi(e) != 0;
     if (const char* e = getenv("GTCRNB_TCN_SMEMW")) h->tcn_smem_w = atoi(e) != 0;
+    if (const char* e = getenv("GTCRNB_STREAM_GRAPH")) h->stream_graphs = atoi(e) != 0;
     if (h->tcn_smem_w) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn<2, true>, WC_WARPS * 32, wc_smem_floats(2, true) * sizeof(float));
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn<2, false>, WC_WARPS * 32, wc_smem_floats(2) * sizeof(float));
     h->occ_gt_enc = std::max(1, h->occ_gt_enc); h->occ_gt_dec = std::max(1, h->occ_gt_dec); h->occ_tcn = std::max(1, h->occ_tcn);
@@ -349,6 +365,8 @@ int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) 
 void gtcrnb_destroy(gtcrnb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    drop_step_graphs(h);
+    if (h->s_cap) cudaStreamDestroy(h->s_cap);
     auto freep = [](float* p) { if (p) cudaFree(p); };
     freep(h->blob); freep(h->en0); freep(h->spec_in); freep(h->spec_out);
     freep(h->parked.en0); freep(h->parked.spec_in); freep(h->parked.spec_out);
@@ -663,24 +681,76 @@ int gtcrnb_stream_reset(gtcrnb_handle* h, void* state_dev, int64_t N, void* stre
     return GTCRNB_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// kind 0: spectral frame in / out, kind 1: waveform hop in / out
+int stream_step(gtcrnb_handle* h, int kind, void* state, const float* in, float* out, int64_t N, cudaStream_t st) {
+    int rc = ensure_workspace(h, N);
+    if (rc) return rc;
+    auto direct = [&](cudaStream_t s) {
+        return kind ? gs::step_wav(h->blob, *h->hp, state, stream_ws(h), in, out, N, s) : gs::step_spec(h->blob, *h->hp, state, stream_ws(h), in, out, N, s);
+    };
+    if (!h->stream_graphs || h->profiling || h->ws_cur != 0) {
+        h->launches += direct(st);
+        CU(cudaGetLastError());
+        return GTCRNB_OK;
+    }
+    ++h->step_tick;
+    for (auto& g : h->step_graphs)
+        if (g.kind == kind && g.state == state && g.in == in && g.out == out && g.n == N) {
+            g.used = h->step_tick;
+            CU(cudaGraphLaunch(g.exec, st));
+            h->launches += g.launches;
+            return GTCRNB_OK;
+        }
+    auto& l = h->last_step;
+    const bool repeat = l.kind == kind && l.state == state && l.in == in && l.out == out && l.n == N;
+    l.kind = kind; l.state = state; l.in = in; l.out = out; l.n = N;
+    if (!repeat) {                                    // pointers that change every hop never pay for a capture
+        h->launches += direct(st);
+        CU(cudaGetLastError());
+        return GTCRNB_OK;
+    }
+    if (!h->s_cap) CU(cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking));
+    CU(cudaStreamBeginCapture(h->s_cap, cudaStreamCaptureModeThreadLocal));
+    const int n_launch = direct(h->s_cap);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->s_cap, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {                           // capture is an optimisation: fall back to plain launches
+        cudaGetLastError();
+        h->stream_graphs = false;
+        h->launches += direct(st);
+        CU(cudaGetLastError());
+        return GTCRNB_OK;
+    }
+    if (h->step_graphs.size() >= 8) {                 // small LRU
+        size_t victim = 0;
+        for (size_t i = 1; i < h->step_graphs.size(); ++i) if (h->step_graphs[i].used < h->step_graphs[victim].used) victim = i;
+        cudaGraphExecDestroy(h->step_graphs[victim].exec);
+        h->step_graphs.erase(h->step_graphs.begin() + victim);
+    }
+    h->step_graphs.push_back({kind, state, in, out, N, exec, n_launch, h->step_tick});
+    CU(cudaGraphLaunch(exec, st));
+    h->launches += n_launch;
+    return GTCRNB_OK;
+}
+}  // namespace
+
+extern "C" {
 int gtcrnb_stream_step_spec(gtcrnb_handle* h, void* state_dev, const float* spec_dev, float* out_dev, int64_t N, void* stream) {
     if (!h || !state_dev || !spec_dev || !out_dev || N < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_step_spec: bad argument");
     if (N == 0) return GTCRNB_OK;
-    int rc = ensure_workspace(h, N);
-    if (rc) return rc;
-    h->launches += gs::step_spec(h->blob, *h->hp, state_dev, stream_ws(h), spec_dev, out_dev, N, (cudaStream_t)stream);
-    CU(cudaGetLastError());
-    return GTCRNB_OK;
+    return stream_step(h, 0, state_dev, spec_dev, out_dev, N, (cudaStream_t)stream);
 }
 
 int gtcrnb_stream_step_wav(gtcrnb_handle* h, void* state_dev, const float* hop_in_dev, float* hop_out_dev, int64_t N, void* stream) {
     if (!h || !state_dev || !hop_in_dev || !hop_out_dev || N < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_step_wav: bad argument");
     if (N == 0) return GTCRNB_OK;
-    int rc = ensure_workspace(h, N);
-    if (rc) return rc;
-    h->launches += gs::step_wav(h->blob, *h->hp, state_dev, stream_ws(h), hop_in_dev, hop_out_dev, N, (cudaStream_t)stream);
-    CU(cudaGetLastError());
-    return GTCRNB_OK;
+    return stream_step(h, 1, state_dev, hop_in_dev, hop_out_dev, N, (cudaStream_t)stream);
 }
 
 int gtcrnb_stream_import_caches(gtcrnb_handle* h, void* state_dev, int64_t N, const float* conv_cache_dev, const float* tra_cache_dev,

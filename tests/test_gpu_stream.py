@@ -122,3 +122,39 @@ def test_long_stream_ring_wraparound(oracle, weights_dns3, b200_lib):
     spec = m.stft(oracle.synth_batch(2, 256 * 199 + 3, seed=8).to(DEV))
     ys = run_stream(s, spec)
     assert rel_err(ys, m(spec)) <= 1e-5
+
+
+def test_hop_graphs_replay_bitwise(oracle, weights_dns3, b200_lib, monkeypatch):
+    # With static in/out buffers the library replays a CUDA graph of the hop from the third call on (the 10-12 launches with
+    # by-value weight blocks make small hops launch-bound).  Graph replay, plain launches and changing buffers must agree bit for bit,
+    # for both step flavours, also after the state was reset and after an offline call grew the shared workspace.
+    m, s = models(weights_dns3)
+    s.step(torch.zeros(1, 257, 2, device=DEV), s.new_state(1, DEV))    # create the handle (reads the env) while graphs are on
+    monkeypatch.setenv("GTCRNB_STREAM_GRAPH", "0")
+    m0, s0 = models(weights_dns3)
+    s0.step(torch.zeros(1, 257, 2, device=DEV), s0.new_state(1, DEV))
+    monkeypatch.delenv("GTCRNB_STREAM_GRAPH")
+    N, HOPS = 5, 24
+    g = torch.Generator().manual_seed(12)
+    wav = (0.1 * torch.randn(HOPS, N, 256, generator=g)).to(DEV)
+    spec = torch.randn(HOPS, N, 257, 2, generator=g).to(DEV)
+    st_g, st_p, st_v = s.new_state(N, DEV), s0.new_state(N, DEV), s.new_state(N, DEV)
+    hop_in, hop_out = torch.empty(N, 256, device=DEV), torch.empty(N, 256, device=DEV)
+    l0 = s.launch_count()
+    for k in range(HOPS):
+        hop_in.copy_(wav[k])
+        s.step_wav(hop_in, st_g, hop_out)                              # stable pointers -> graph
+        ref = s0.step_wav(wav[k].contiguous(), st_p)                   # graphs disabled
+        var = s.step_wav(wav[k].clone(), st_v)                         # graphs enabled, pointers change every hop
+        assert torch.equal(hop_out, ref) and torch.equal(var, ref), k
+        if k == 11:                                                    # a bigger stream set grows the workspace under the cached graph
+            s.step_wav(torch.zeros(64, 256, device=DEV), s.new_state(64, DEV))
+    assert s.launch_count() - l0 >= 2 * HOPS * 12                      # replayed hops are counted like launched ones (12 kernels per hop)
+    st_g2, st_p2 = s.new_state(N, DEV), s0.new_state(N, DEV)
+    f_in, f_out = torch.empty(N, 257, 2, device=DEV), torch.empty(N, 257, 2, device=DEV)
+    for k in range(HOPS):
+        f_in.copy_(spec[k])
+        s.step(f_in, st_g2, f_out)
+        assert torch.equal(f_out, s0.step(spec[k].contiguous(), st_p2)), k
+        if k == 9:
+            s.reset(st_g2); s0.reset(st_p2)
