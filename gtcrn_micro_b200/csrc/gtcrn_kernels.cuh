@@ -135,6 +135,11 @@ __device__ __forceinline__ void axpy2c(float (&a0)[N], float (&a1)[N], float x0,
 
 template <int NF> struct alignas(16) ParamBlock { float w[NF]; };
 struct SmemWeights { const float* __restrict__ w; };      // same .w[] interface as ParamBlock, backed by shared memory
+// compile-time choice of the weight source of a kernel (shared-memory copy or the kernel-parameter block itself)
+template <bool SMEM, class S, class C>
+__device__ __forceinline__ const auto& pick_weights(const S& smem, const C& cbank) {
+    if constexpr (SMEM) return smem; else return cbank;
+}
 
 // ================================================================================================
 // 256-point complex FFT, radix-4 Stockham autosort, 64 threads per transform, 4 stages.
@@ -735,7 +740,7 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
     if (SMEM_W)
         for (int i = tid; i < gt_chunk<DEC>(); i += GT_THREADS) wsm[i] = prm_c.w[i];
     const SmemWeights prm_s{static_cast<const float*>(__builtin_assume_aligned(wsm, 16))};
-    auto& prm = [&]() -> auto& { if constexpr (SMEM_W) return prm_s; else return prm_c; }();
+    const auto& prm = pick_weights<SMEM_W>(prm_s, prm_c);
     __syncthreads();
 
     const bool act = tid < GT_ACTIVE;
@@ -1010,7 +1015,7 @@ k_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_cons
         __syncthreads();
     }
     const SmemWeights prm_s{static_cast<const float*>(__builtin_assume_aligned(wsm, 16))};
-    auto& prm = [&]() -> auto& { if constexpr (SMEM_W) return prm_s; else return prm_c; }();
+    const auto& prm = pick_weights<SMEM_W>(prm_s, prm_c);
     const int64_t colid = (int64_t)blockIdx.x * WC_WARPS + warp;
     if (colid >= ncols) return;                                   // whole warp exits together (no CTA barrier below)
     const int64_t b = colid / kF2;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of build variants (GTCRNB_LIB) and env knobs.  Usage: tools/gpu_perf12.sh "ENV1=a ENV2=b" "..." ...
+# A/B of build variants (GTCRNB_LIB) and env knobs.  Usage: tools/gpu_ab.sh "ENV1=a ENV2=b" "..." ...
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 for cfg in "$@"; do
