@@ -35,6 +35,20 @@ def import_reference():
     return GTCRNMicro, StreamGTCRNMicro, convert_to_stream
 
 
+def reference_metric_functions():
+    """The reference's own sisnr_metric / sdr_metric (eval/eval_intrusive_metrics.py:74-94), compiled from its source file in
+    isolation: the module itself imports pesq / pystoi / p_tqdm, which this image does not have."""
+    import ast
+    import numpy as np
+    path = os.path.join(REF, "gtcrn_micro/eval/eval_intrusive_metrics.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    ns = {"np": np}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("sisnr_metric", "sdr_metric"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns["sisnr_metric"], ns["sdr_metric"]
+
+
 def randomise(model, seed):
     """Random weights with non-trivial BN statistics and PReLU slopes (ERB buffers untouched)."""
     g = torch.Generator().manual_seed(seed)
@@ -79,6 +93,16 @@ def main():
     GTCRNMicro, StreamGTCRNMicro, convert_to_stream = import_reference()
     ckpt = torch.load(os.path.join(REF, "gtcrn_micro/ckpts/best_model_dns3.tar"), map_location="cpu")
     win = torch.hann_window(512).pow(0.5)
+
+    # --- evaluation metrics (on-device SI-SNR / SDR are checked against these restatements)
+    import numpy as np
+    sisnr_ref, sdr_ref = reference_metric_functions()
+    g = np.random.default_rng(5)
+    for n, noise in ((16000, 0.3), (160000, 0.05), (777, 1.5)):
+        r = g.standard_normal(n) * 0.1
+        x = 0.8 * r + noise * 0.1 * g.standard_normal(n) + 0.01
+        check(f"si_snr n={n}", abs(sisnr_ref(r, x) - O.si_snr(r, x)), 1e-9)
+        check(f"sdr n={n}", abs(sdr_ref(r, x) - O.sdr(r, x)), 1e-9)
 
     # --- ERB bank == checkpoint buffers
     bank = torch.from_numpy(O.erb_filter_bank())

@@ -54,6 +54,12 @@ def pairs():
 
 
 @pytest.fixture(scope="session")
+def metrics_golden():
+    """waveform pairs with the reference's own SI-SNR / SDR values (tests/golden/make_golden.py make_metrics)"""
+    return dict(np.load(os.path.join(GOLDEN, "metrics.npz")))
+
+
+@pytest.fixture(scope="session")
 def b200_lib():
     """Build (if stale) and load the C-ABI library; the GPU tests go through it."""
     from gtcrn_micro_b200 import build, lib

@@ -10,6 +10,7 @@ Writes into tests/golden/:
                        < 256(t+1), so output[:256*311] of the cropped input equals the full-file output.
   ref_outputs.npz      seeded input + the reference's own outputs (offline spec, streaming spec, wav)
                        for both weight sets.
+  metrics.npz          waveform pairs with the reference's own SI-SNR / SDR values (eval_intrusive_metrics.py:74-94)
 Nothing from the reference's sources is copied; only its weights / audio data and its outputs.
 """
 from __future__ import annotations
@@ -23,14 +24,33 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
-from check_against_reference import REF, import_reference, randomise, read_wav_int16  # noqa: E402
+from check_against_reference import REF, import_reference, randomise, read_wav_int16, reference_metric_functions  # noqa: E402
 
 
 def sd_to_np(sd):
     return {k: v.detach().cpu().numpy() for k, v in sd.items()}
 
 
+def make_metrics():
+    """metrics.npz: float32 (reference, degraded) pairs and the reference's own SI-SNR / SDR for them."""
+    sisnr_ref, sdr_ref = reference_metric_functions()
+    g = np.random.default_rng(20261017)
+    out = {}
+    for i, (n, gain, noise, dc) in enumerate(((4000, 0.8, 0.3, 0.01), (16000, 1.0, 0.02, 0.0), (16000, 0.5, 1.0, -0.02), (257, 1.2, 0.1, 0.0))):
+        t = np.arange(n) / 16000.0
+        r = (0.1 * np.sin(2 * np.pi * 220 * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 3 * t)) + 0.01 * g.standard_normal(n)).astype(np.float32)
+        x = (gain * r + noise * 0.05 * g.standard_normal(n) + dc).astype(np.float32)
+        out[f"ref{i}"], out[f"inf{i}"] = r, x
+        out[f"si_snr{i}"] = np.float64(sisnr_ref(r.astype(np.float64), x.astype(np.float64)))
+        out[f"sdr{i}"] = np.float64(sdr_ref(r.astype(np.float64), x.astype(np.float64)))
+    np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)
+
+
 def main():
+    if "--only-metrics" in sys.argv:
+        make_metrics()
+        return
+    make_metrics()
     GTCRNMicro, StreamGTCRNMicro, convert_to_stream = import_reference()
     ckpt = torch.load(os.path.join(REF, "gtcrn_micro/ckpts/best_model_dns3.tar"), map_location="cpu")
     win = torch.hann_window(512).pow(0.5)

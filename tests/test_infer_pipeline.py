@@ -119,3 +119,15 @@ def test_pair_metrics_vs_oracle(oracle, b200_lib):
     big = torch.zeros(8, 40000, device="cuda:0")
     assert m.pair_metrics(big[:, ::2], big[:, ::2]).shape == (8, 2)              # strided views
     assert m.pair_metrics(big[:0], big[:0]).shape == (0, 2)
+
+
+@pytest.mark.gpu
+def test_pair_metrics_vs_reference_values(metrics_golden, b200_lib):
+    import gtcrn_micro_b200 as G
+    m = G.GTCRNMicro()
+    for i in range(4):
+        r = torch.from_numpy(metrics_golden[f"ref{i}"])[None].to("cuda:0")
+        x = torch.from_numpy(metrics_golden[f"inf{i}"])[None].to("cuda:0")
+        out = m.pair_metrics(r, x).cpu().numpy()[0]
+        assert abs(out[0] - float(metrics_golden[f"si_snr{i}"])) <= 1e-3, (i, out)
+        assert abs(out[1] - float(metrics_golden[f"sdr{i}"])) <= 1e-3, (i, out)

@@ -72,3 +72,11 @@ def test_stream_conv_primitives(oracle):
                 o, cc, tc = oracle.gt_conv_block(x[:, :, t:t + 1], W, p, dec, cc, tc)
                 outs.append(o)
             assert (torch.cat(outs, 2) - off).abs().max() <= 1e-5
+
+
+def test_metrics_match_reference_values(oracle, metrics_golden):
+    # oracle restatement of eval_intrusive_metrics.py:74-94 against values computed by the reference's own functions
+    for i in range(4):
+        r, x = metrics_golden[f"ref{i}"], metrics_golden[f"inf{i}"]
+        assert abs(oracle.si_snr(r, x) - float(metrics_golden[f"si_snr{i}"])) <= 1e-9
+        assert abs(oracle.sdr(r, x) - float(metrics_golden[f"sdr{i}"])) <= 1e-9
