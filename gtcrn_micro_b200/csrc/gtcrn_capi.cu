@@ -612,6 +612,25 @@ int gtcrnb_enhance_host_pcm16(gtcrnb_handle* h, const int16_t* wav_host, int64_t
     return host_pipeline(h, wav_host, B, L, out_host, true);
 }
 
+int gtcrnb_pcm16_to_f32(gtcrnb_handle* h, const int16_t* in_dev, float* out_dev, int64_t n, void* stream) {
+    if (n < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_pcm16_to_f32: bad size");
+    if (h && n == 0) return GTCRNB_OK;
+    if (!h || !in_dev || !out_dev) return fail(GTCRNB_E_INVALID, "gtcrnb_pcm16_to_f32: NULL argument");
+    gk::k_pcm16_to_f32<<<h->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(in_dev, out_dev, n);
+    h->launches++;
+    CU(cudaGetLastError());
+    return GTCRNB_OK;
+}
+int gtcrnb_f32_to_pcm16(gtcrnb_handle* h, const float* in_dev, int16_t* out_dev, int64_t n, void* stream) {
+    if (n < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_f32_to_pcm16: bad size");
+    if (h && n == 0) return GTCRNB_OK;
+    if (!h || !in_dev || !out_dev) return fail(GTCRNB_E_INVALID, "gtcrnb_f32_to_pcm16: NULL argument");
+    gk::k_f32_to_pcm16<<<h->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(in_dev, out_dev, n);
+    h->launches++;
+    CU(cudaGetLastError());
+    return GTCRNB_OK;
+}
+
 int gtcrnb_debug_activation(gtcrnb_handle* h, const char* name, float* out_dev, size_t n_floats, void* stream) {
     if (!h || !name || !out_dev) return fail(GTCRNB_E_INVALID, "gtcrnb_debug_activation: NULL argument");
     const float* src = nullptr;

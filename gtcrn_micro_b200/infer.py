@@ -156,7 +156,8 @@ def run(model, jobs: Sequence[Job], enh_dir: str, max_batch: int = 256, device: 
             pcm = model.enhance_host_pcm16(pcm_in, device=dev).numpy()
         else:
             x = torch.from_numpy(np.stack([to_f32(r) for r in raw])).to(dev)
-            pcm = to_pcm16(model.enhance(x)).cpu().numpy()
+            y = model.enhance(x)
+            pcm = (model.float_to_pcm16(y) if hasattr(model, "float_to_pcm16") and dev.type == "cuda" else to_pcm16(y)).cpu().numpy()
         outs = [fix_np(pcm[k], ref_n[k]) for k in range(len(batch))]
         if metrics:
             # scored on what was written (the evaluation script reads the PCM16 files back): group rows of equal length
@@ -166,7 +167,8 @@ def run(model, jobs: Sequence[Job], enh_dir: str, max_batch: int = 256, device: 
                     by_len.setdefault(len(outs[k]), []).append(k)
             for ks in by_len.values():
                 r = torch.from_numpy(np.stack([to_f32(refs[k]) for k in ks])).to(dev)
-                e = torch.from_numpy(np.stack([outs[k] for k in ks])).to(dev).to(torch.float32).mul_(1.0 / 32768.0)
+                e16 = torch.from_numpy(np.stack([outs[k] for k in ks])).to(dev)
+                e = model.pcm16_to_float(e16) if hasattr(model, "pcm16_to_float") and dev.type == "cuda" else e16.to(torch.float32).mul_(1.0 / 32768.0)
                 sc = model.pair_metrics(r, e).cpu().numpy()
                 for row, k in enumerate(ks):
                     scores[jobs[batch[k]].uid] = (float(sc[row, 0]), float(sc[row, 1]))

@@ -21,7 +21,7 @@ SYMBOLS = [
     "gtcrnb_stream_export_caches", "gtcrnb_debug_activation", "gtcrnb_launch_count", "gtcrnb_host_alloc",
     "gtcrnb_host_free", "gtcrnb_last_error", "gtcrnb_profile_enable", "gtcrnb_profile_read",
     "gtcrnb_profile_num_classes", "gtcrnb_profile_class_name", "gtcrnb_pair_metrics", "gtcrnb_host_alloc_wc",
-    "gtcrnb_enhance_host_pcm16",
+    "gtcrnb_enhance_host_pcm16", "gtcrnb_pcm16_to_f32", "gtcrnb_f32_to_pcm16",
 ]
 
 
@@ -54,6 +54,8 @@ def load() -> C.CDLL:
             "gtcrnb_enhance": (C.c_int, [vp, vp, i64, i64, i64, vp, i64, vp]),
             "gtcrnb_enhance_host": (C.c_int, [vp, vp, i64, i64, vp]),
             "gtcrnb_enhance_host_pcm16": (C.c_int, [vp, vp, i64, i64, vp]),
+            "gtcrnb_pcm16_to_f32": (C.c_int, [vp, vp, vp, i64, vp]),
+            "gtcrnb_f32_to_pcm16": (C.c_int, [vp, vp, vp, i64, vp]),
             "gtcrnb_stft": (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),
             "gtcrnb_istft": (C.c_int, [vp, vp, i64, i64, vp, i64, vp]),
             "gtcrnb_stream_state_bytes": (sz, [i64]),

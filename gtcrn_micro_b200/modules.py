@@ -262,6 +262,30 @@ class GTCRNMicro(_B200Module):
         return out
 
     @torch.no_grad()
+    def pcm16_to_float(self, pcm: torch.Tensor) -> torch.Tensor:
+        """int16 CUDA tensor -> float32 (x / 32768, what sf.read(dtype="float32") gives, infer.py:52)."""
+        if not pcm.is_cuda or pcm.dtype != torch.int16:
+            raise ValueError("pcm must be an int16 CUDA tensor")
+        pcm = pcm.contiguous()
+        out = torch.empty(pcm.shape, dtype=torch.float32, device=pcm.device)
+        h = self._ensure_handle(pcm.device)
+        with torch.cuda.device(pcm.device):
+            _lib.check(_lib.load().gtcrnb_pcm16_to_f32(h, pcm.data_ptr(), out.data_ptr(), pcm.numel(), torch.cuda.current_stream().cuda_stream), "gtcrnb_pcm16_to_f32")
+        return out
+
+    @torch.no_grad()
+    def float_to_pcm16(self, x: torch.Tensor) -> torch.Tensor:
+        """float32 CUDA tensor -> int16 with the quantisation of the reference's written wav files: floor(x * 32768), clamped."""
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise ValueError("x must be a float32 CUDA tensor")
+        x = x.contiguous()
+        out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+        h = self._ensure_handle(x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().gtcrnb_f32_to_pcm16(h, x.data_ptr(), out.data_ptr(), x.numel(), torch.cuda.current_stream().cuda_stream), "gtcrnb_f32_to_pcm16")
+        return out
+
+    @torch.no_grad()
     def pair_metrics(self, ref: torch.Tensor, inf: torch.Tensor) -> torch.Tensor:
         """SI-SNR and SDR (dB) of waveform pairs on the device, as eval_intrusive_metrics.py:74-94 defines them.
         ref, inf [B,L] float32 CUDA -> [B,2] = (si_snr, sdr)."""

@@ -97,6 +97,11 @@ int gtcrnb_stream_import_caches(gtcrnb_handle* h, void* state_dev, int64_t N, co
 int gtcrnb_stream_export_caches(gtcrnb_handle* h, const void* state_dev, int64_t N, float* conv_cache_dev,
                                 float* tra_cache_dev, float* const tcn_cache_dev[8], void* stream);
 
+/* PCM16 <-> float32 on device buffers of n samples (the conversions gtcrnb_enhance_host_pcm16 applies): decode x / 32768,
+ * encode floor(y * 32768) clamped to [-32768, 32767]. */
+int gtcrnb_pcm16_to_f32(gtcrnb_handle* h, const int16_t* in_dev, float* out_dev, int64_t n, void* stream);
+int gtcrnb_f32_to_pcm16(gtcrnb_handle* h, const float* in_dev, int16_t* out_dev, int64_t n, void* stream);
+
 /* ---- on-device quality metrics ---------------------------------------------------
  * SI-SNR and SDR of B (reference, enhanced) waveform pairs of L samples, as defined by the reference's evaluation script
  * (gtcrn_micro/eval/eval_intrusive_metrics.py:74-82 sisnr_metric, :85-94 sdr_metric).  out_dev [B][2] = (si_snr_db, sdr_db). */

@@ -131,3 +131,30 @@ def test_pair_metrics_vs_reference_values(metrics_golden, b200_lib):
         out = m.pair_metrics(r, x).cpu().numpy()[0]
         assert abs(out[0] - float(metrics_golden[f"si_snr{i}"])) <= 1e-3, (i, out)
         assert abs(out[1] - float(metrics_golden[f"sdr{i}"])) <= 1e-3, (i, out)
+
+
+@pytest.mark.gpu
+def test_pcm16_conversions_and_float_wav_files(tmp_path, weights_dns3, pairs, b200_lib):
+    import gtcrn_micro_b200 as G
+    m = G.GTCRNMicro(); m.load_state_dict(weights_dns3)
+    g = torch.Generator().manual_seed(1)
+    for n in (1, 7, 8, 1000, 40003):
+        q = torch.randint(-32768, 32768, (n,), generator=g, dtype=torch.int32).to(torch.int16).to("cuda:0")
+        f = m.pcm16_to_float(q)
+        assert torch.equal(f.cpu(), q.cpu().float() / 32768.0)
+        assert torch.equal(m.float_to_pcm16(f), q)                                   # exact round trip
+        x = (torch.randn(n, generator=g) * 0.7).to("cuda:0")
+        want = torch.floor(x * 32768.0).clamp_(-32768, 32767).to(torch.int16)
+        assert torch.equal(m.float_to_pcm16(x), want)
+        assert torch.equal(m.float_to_pcm16(x[1:]), want[1:])                        # unaligned view -> scalar tail path
+    # float32 wav files take the float branch of the pipeline and must give the same PCM16 output as PCM16 files
+    dn, de1, de2 = tmp_path / "n16", tmp_path / "e16", tmp_path / "e32"; dn.mkdir()
+    dn32 = tmp_path / "n32"; dn32.mkdir()
+    for i in (1, 2):
+        wavfile.write(dn / f"noisy_fileid_{i}.wav", 16000, pairs[f"noisy{i}"])
+        wavfile.write(dn32 / f"noisy_fileid_{i}.wav", 16000, pairs[f"noisy{i}"].astype(np.float32) / 32768.0)
+    I.run(m, I.list_jobs(str(dn), None), str(de1), max_batch=4)
+    I.run(m, I.list_jobs(str(dn32), None), str(de2), max_batch=4)
+    for i in (1, 2):
+        a = wavfile.read(de1 / f"noisy_fileid_{i}_enh.wav")[1]; b = wavfile.read(de2 / f"noisy_fileid_{i}_enh.wav")[1]
+        assert a.dtype == np.int16 and np.array_equal(a, b)
