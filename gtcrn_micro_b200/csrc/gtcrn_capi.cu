@@ -206,7 +206,7 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
     using namespace gk;
     const int Ti = (int)T;
     const int64_t nframes = B * T;
-    const dim3 gfr((unsigned)((nframes + FR_NF - 1) / FR_NF));
+    const dim3 gfr((unsigned)((nframes + FR_NF - 1) / FR_NF)), gbk((unsigned)((nframes + BK_NF - 1) / BK_NF));
     const bool fused = wav != nullptr;
     {
         ProfScope ps(h, KC_FRONT, nframes, st);
@@ -255,10 +255,10 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
         ProfScope ps(h, KC_BACK, nframes, st);
         if (fused) {
             const int64_t ss[4] = {T * kSpecFrame, 2, kSpecFrame, 1};
-            k_back<true><<<gfr, BK_THREADS, bk_smem_floats(true) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, h->spec_in, ss[0], ss[1], ss[2], ss[3],
+            k_back<true><<<gbk, BK_THREADS, bk_smem_floats(true) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, h->spec_in, ss[0], ss[1], ss[2], ss[3],
                                                                                         nullptr, 0, 0, 0, 0, wav_out, wav_out_stride, Ti, nframes, h->blob, h->hp->back);
         } else {
-            k_back<false><<<gfr, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, spec, is[0], is[1], is[2], is[3],
+            k_back<false><<<gbk, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, spec, is[0], is[1], is[2], is[3],
                                                                                           out, os[0], os[1], os[2], os[3], nullptr, 0, Ti, nframes, h->blob, h->hp->back);
         }
     }

@@ -330,8 +330,14 @@ __global__ void __launch_bounds__(256) k_istft(const float* __restrict__ spec, i
 // Frames are independent here, so (b,t) is flattened: grid ceil(B*T/8), 288 threads, 8 frames per CTA
 // (the streaming path calls the same kernel with T = 1).  Writes en0 [B][T][65][16], en1 [B][T][33][16].
 // ================================================================================================
-constexpr int FR_NF = 8;
-constexpr int FR_THREADS = 320;            // en1 runs its two output-channel halves on warps 0-4 / 5-9 (warp-uniform weights)
+#ifndef GTCRNB_FR_NF
+#define GTCRNB_FR_NF 8
+#endif
+constexpr int FR_NF = GTCRNB_FR_NF;        // frames per CTA (even)
+constexpr int FR_HALF = ((FR_NF / 2) * kF2 + 31) / 32 * 32;   // en1 runs its two output-channel halves on separate warps (warp-uniform weights)
+constexpr int FR_THREADS = 2 * FR_HALF;    // 320 at 8 frames (warps 0-4 / 5-9), 192 at 4
+constexpr int FR_MIN_BLOCKS = FR_NF >= 8 ? 3 : 5;
+static_assert(FR_NF % 2 == 0 && FR_THREADS >= (FR_NF / 2) * kF1 && FR_THREADS / 32 >= FR_NF && 8 * FR_THREADS >= FR_NF * kBins, "k_front thread map");
 constexpr int FR_FEAT = 260 * 4;           // per slot: one float4 (mag, re, im, 0) per bin, 257 bins
 constexpr int FR_ERB = 64 * 4;             // per slot: one float4 per ERB band (bins 65.. of the compressed axis); low 65 bins stay in feat
 // sfe and a0 are stored PARITY-SPLIT along the (padded) bin index c: the stride-2 convolutions read c = 2 f' + k, i.e.
@@ -397,7 +403,7 @@ __device__ __forceinline__ void front_en1(const PB& prm, const float* slots, int
 //                   shared memory (the FFT ping-pong buffers overlay the slot's own feat / sfe regions) and the spectrum is
 //                   written once to `spec_out` [B][T][257][2] for the mask stage; it is never read back here.
 template <bool FROM_WAV>
-__global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict__ spec, int64_t sb, int64_t sf, int64_t st, int64_t sc,
+__global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float* __restrict__ spec, int64_t sb, int64_t sf, int64_t st, int64_t sc,
                                                          const float* __restrict__ wav, int64_t wav_stride, int L, float* __restrict__ spec_out,
                                                          int T, int64_t nframes, const float* __restrict__ blobp,
                                                          const __grid_constant__ ParamBlock<blob::FRONT_SIZE> prm,
@@ -411,30 +417,40 @@ __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict
     if (FROM_WAV) {
         // ---- a (fused STFT): 4 frames per round, 64 threads per 256-point FFT.  A = slot's sfe region, B = slot's feat region.
         FftTables& tb = *reinterpret_cast<FftTables*>(slots + FR_NF * FR_SLOT);
+        // warp w owns frame slot w.  Its 512 samples are requested first, so their latency hides behind the table copy and the
+        // barrier (the loads were 8 % of the kernel's samples as long_scoreboard and made the FFT warps finish unevenly: 15 % of
+        // all samples sat in the barrier after this phase, ncu r1_v13)
+        const int warp = tid >> 5, lane = tid & 31;
+        const int64_t fi_w = fi0 + warp;
+        const bool valid = warp < FR_NF && fi_w < nframes;
+        float xr0[8], xr1[8];
+        if (valid) {
+            const int64_t b = fi_w / T;
+            const int t = (int)(fi_w - b * T);
+            const float* x = wav + b * wav_stride;
+            const int base = kHop * t - kHop;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int n = lane + 32 * q;
+                xr0[q] = x[reflect_idx(base + 2 * n, L)];
+                xr1[q] = x[reflect_idx(base + 2 * n + 1, L)];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) xr0[q] = xr1[q] = 0.f;
+        }
         load_fft_tables(tb, blobp, tid, FR_THREADS);
         copy_f4(W, blobp + blob::FRONT_OFF, FR_W_FLOATS, tid, FR_THREADS);
         __syncthreads();
-        const int warp = tid >> 5, lane = tid & 31;
-        if (warp < FR_NF) {                                        // warp w transforms frame slot w (only __syncwarp inside)
+        if (warp < FR_NF) {                                        // (only __syncwarp inside)
             const int slot = warp;
-            const int64_t fi = fi0 + slot;
-            const bool valid = fi < nframes;
+            const int64_t fi = fi_w;
             float2* A = reinterpret_cast<float2*>(slots + slot * FR_SLOT + FR_FEAT + FR_ERB);
             float2* Bf = reinterpret_cast<float2*>(slots + slot * FR_SLOT);
-            int64_t b = 0; int t = 0;
-            if (valid) { b = fi / T; t = (int)(fi - b * T); }
-            if (valid) {
-                const float* x = wav + b * wav_stride;
-                const int base = kHop * t - kHop;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int n = lane + 32 * q;
-                    const int i0 = reflect_idx(base + 2 * n, L), i1 = reflect_idx(base + 2 * n + 1, L);
-                    A[n] = make_float2(tb.win[2 * n] * x[i0], tb.win[2 * n + 1] * x[i1]);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) A[lane + 32 * q] = make_float2(0.f, 0.f);
+            for (int q = 0; q < 8; ++q) {
+                const int n = lane + 32 * q;
+                A[n] = make_float2(tb.win[2 * n] * xr0[q], tb.win[2 * n + 1] * xr1[q]);
             }
             __syncwarp();
             fft256_warp(A, Bf, tb.tw256, lane);
@@ -535,8 +551,8 @@ __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict
     }
     __syncthreads();
     // ---- d: en0  (thread = 2 slots x 16 co at one f').  Output a0 overlays the dead feat|erb region; its pad bins are zeroed here.
-    if (tid >= 160 && tid < 160 + FR_NF * 16) {
-        const int i = tid - 160, slot = i >> 4, q = (i >> 2) & 3, c = i & 3;   // padded bins 0, 1, 67, 68
+    if (tid >= FR_HALF && tid < FR_HALF + FR_NF * 16) {
+        const int i = tid - FR_HALF, slot = i >> 4, q = (i >> 2) & 3, c = i & 3;   // padded bins 0, 1, 67, 68
         reinterpret_cast<float4*>(slots + slot * FR_SLOT)[q * 70 + (c == 0 ? 0 : c == 1 ? 35 : c == 2 ? 35 + 33 : 34)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (tid < (FR_NF / 2) * kF1) {
@@ -583,7 +599,7 @@ __global__ void __launch_bounds__(FR_THREADS, 3) k_front(const float* __restrict
     __syncthreads();
     // ---- e: en1: output-channel half 0 on warps 0-4, half 1 on warps 5-9 (132 of 160 lanes each)
     {
-        const int half = tid >= 160, r = tid - half * 160;
+        const int half = tid >= FR_HALF, r = tid - half * FR_HALF;
         if (r < (FR_NF / 2) * kF2) {
             if (half == 0) front_en1<0>(prm, slots, r, fi0, nframes, en1);
             else front_en1<1>(prm, slots, r, fi0, nframes, en1);

@@ -465,7 +465,7 @@ struct HostParams {
 inline int model_step(const float* blobp, const HostParams& hp, void* state, const Ws& ws, const float* spec, float* out, int64_t N, cudaStream_t st) {
     using namespace gk;
     int launches = 0;
-    const unsigned gfr = (unsigned)((N + FR_NF - 1) / FR_NF);
+    const unsigned gfr = (unsigned)((N + FR_NF - 1) / FR_NF), gbk = (unsigned)((N + BK_NF - 1) / BK_NF);
     // T = 1: strides {b: 514, f: 2, t: 0, c: 1}.  k_front / k_back do not know about `skip`; on the skipped call
     // (first wav hop) they run on a zero spectrum and their outputs are simply never consumed.
     k_front<false><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, kSpecFrame, 2, 0, 1, nullptr, 0, 0, nullptr, 1, N, blobp, hp.front, ws.en0, ws.act[0]);
@@ -481,7 +481,7 @@ inline int model_step(const float* blobp, const HostParams& hp, void* state, con
         ks_gtconv<true><<<gsg, SG_THREADS, SG_SMEM_FLOATS * sizeof(float), st>>>(ws.act[5 + i], ws.act[3 - i], ws.act[6 + i], hp.dec[i], state, 3 + i, N);
         ++launches;
     }
-    k_back<false><<<gfr, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(ws.act[8], ws.act[0], ws.en0, spec, kSpecFrame, 2, 0, 1,
+    k_back<false><<<gbk, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(ws.act[8], ws.act[0], ws.en0, spec, kSpecFrame, 2, 0, 1,
                                                                                   out, kSpecFrame, 2, 0, 1, nullptr, 0, 1, N, blobp, hp.back);
     ++launches;
     return launches;
