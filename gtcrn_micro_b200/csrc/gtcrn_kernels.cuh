@@ -1232,33 +1232,46 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
     const int tid = threadIdx.x;
     const int64_t fi0 = (int64_t)blockIdx.x * BK_NF;
 
-    // ---- a: x = de2 + en1 into X (loads issued before the weight copy so their latency overlaps it)
-    if (tid < (BK_NF / 2) * kF2) {
-        const int sp2 = tid / kF2, f = tid - sp2 * kF2;
-        float4 u[2][4], v[2][4];
+    // ---- a: x = de2 + en1 into X.  The loads are issued first, the table copies run while they are in flight, and the
+    //      operands this CTA needs much later (en0 skip rows for de3, the spectrum for the mask) are pulled towards L2 now
+    //      (ncu r1_v13: 12 % of the kernel's samples were long_scoreboard on exactly those three consumers).
+    const bool loader = tid < (BK_NF / 2) * kF2;
+    const int sp2_a = tid / kF2, f_a = tid - sp2_a * kF2;
+    float4 u[2][4], v[2][4];
+    if (loader) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            const int slot = 2 * sp2 + s;
+            const int slot = 2 * sp2_a + s;
             const bool ok = fi0 + slot < nframes;
-            const int64_t off = ((fi0 + (ok ? slot : 0)) * kF2 + f) * 16;
+            const int64_t off = ((fi0 + (ok ? slot : 0)) * kF2 + f_a) * 16;
             const float4* pa = reinterpret_cast<const float4*>(de2 + off);
             const float4* pb = reinterpret_cast<const float4*>(en1 + off);
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) { u[s][qd] = pa[qd]; v[s][qd] = pb[qd]; }
         }
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const int slot = 2 * sp2 + s;
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd)
-                X[slot * BK_X4 + qd * 35 + f + 1] = make_float4(u[s][qd].x + v[s][qd].x, u[s][qd].y + v[s][qd].y, u[s][qd].z + v[s][qd].z, u[s][qd].w + v[s][qd].w);
-        }
+    }
+    {
+        const int nf = (int)min((int64_t)BK_NF, nframes - fi0);                      // frames of this CTA (contiguous rows)
+        static_assert(BK_THREADS * 128 >= BK_NF * kF1 * 64 && BK_THREADS * 128 >= BK_NF * kSpecFrame * 4, "one 128-byte line per thread covers the rows");
+        if (tid * 128 < nf * kF1 * 64)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(en0 + fi0 * kF1 * 16) + tid * 128));
+        if (TO_WAV && tid * 128 < nf * kSpecFrame * 4)                               // fused mode: spec is the contiguous [frame][257][2] buffer
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(spec + fi0 * kSpecFrame) + tid * 128));
     }
     copy_f4(Wsm, blobp + blob::BACK_OFF + BK_W_OFF, BK_W_FLOATS, tid, BK_THREADS);
     if (TO_WAV) {                                                  // iSTFT tables (needed last) are fetched first so their latency is hidden
         FftTables& tb0 = *reinterpret_cast<FftTables*>(Wsm + bk_smem_floats(false));
         load_fft_tables(tb0, blobp, tid, BK_THREADS);
         if (tid < 256) (reinterpret_cast<float*>(&tb0) + FR_FFT_FLOATS)[tid] = blobp[blob::FFT_OFF + blob::FFT_INV_ENV + tid];
+    }
+    if (loader) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int slot = 2 * sp2_a + s;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd)
+                X[slot * BK_X4 + qd * 35 + f_a + 1] = make_float4(u[s][qd].x + v[s][qd].x, u[s][qd].y + v[s][qd].y, u[s][qd].z + v[s][qd].z, u[s][qd].w + v[s][qd].w);
+        }
     }
     for (int i = tid; i < BK_NF * 8; i += BK_THREADS) {            // zero pad columns of X (0, 34) and Y3 (0, 66)
         const int slot = i >> 3, q = (i >> 1) & 3, side = i & 1;
