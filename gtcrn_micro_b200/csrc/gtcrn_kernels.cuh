@@ -94,6 +94,16 @@ __device__ __forceinline__ void copy_f4(float* dst, const float* __restrict__ sr
     const float4* s4 = reinterpret_cast<const float4*>(src);
     for (int i = tid; i < (n_floats >> 2); i += nthr) d4[i] = s4[i];
 }
+// asynchronous variant (cp.async, LDGSTS): global -> shared without staging registers, so the copy overlaps whatever the thread
+// does next; complete it with cp_async_wait_all() before the barrier that publishes the data
+__device__ __forceinline__ void copy_f4_async(float* dst, const float* __restrict__ src, int n_floats, int tid, int nthr) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    for (int i = tid; i < (n_floats >> 2); i += nthr)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * i), "l"(src + 4 * i) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void zero_f4(float* dst, int n_floats, int tid, int nthr) {
     float4* d4 = reinterpret_cast<float4*>(dst);
     for (int i = tid; i < (n_floats >> 2); i += nthr) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -217,6 +227,12 @@ __device__ __forceinline__ void load_fft_tables(FftTables& t, const float* __res
     copy_f4(reinterpret_cast<float*>(t.tw256), f + blob::FFT_TW256, 512, tid, nthr);
     copy_f4(reinterpret_cast<float*>(t.tw512), f + blob::FFT_TW512, 516, tid, nthr);
     copy_f4(t.win, f + blob::FFT_WIN, 512, tid, nthr);
+}
+__device__ __forceinline__ void load_fft_tables_async(FftTables& t, const float* __restrict__ blobp, int tid, int nthr) {
+    const float* f = blobp + blob::FFT_OFF;
+    copy_f4_async(reinterpret_cast<float*>(t.tw256), f + blob::FFT_TW256, 512, tid, nthr);
+    copy_f4_async(reinterpret_cast<float*>(t.tw512), f + blob::FFT_TW512, 516, tid, nthr);
+    copy_f4_async(t.win, f + blob::FFT_WIN, 512, tid, nthr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -439,8 +455,11 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
 #pragma unroll
             for (int q = 0; q < 8; ++q) xr0[q] = xr1[q] = 0.f;
         }
-        load_fft_tables(tb, blobp, tid, FR_THREADS);
-        copy_f4(W, blobp + blob::FRONT_OFF, FR_W_FLOATS, tid, FR_THREADS);
+        load_fft_tables_async(tb, blobp, tid, FR_THREADS);         // needed by the FFT right after the barrier
+        cp_async_commit();
+        copy_f4_async(W, blobp + blob::FRONT_OFF, FR_W_FLOATS, tid, FR_THREADS);   // ERB / SFE tables: needed after the FFT phase
+        cp_async_commit();
+        cp_async_wait_group<1>();
         __syncthreads();
         if (warp < FR_NF) {                                        // (only __syncwarp inside)
             const int slot = warp;
@@ -468,6 +487,7 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
                 fs[k] = make_float4(sqrtf(re * re + im * im + 1e-12f), re, im, 0.f);
             }
         }
+        cp_async_wait_group<0>();                                  // ERB / SFE tables
         __syncthreads();
         for (int i = tid; i < FR_NF * 4; i += FR_THREADS) {       // sfe pad columns (its region held FFT buffer A until now)
             float4* sfe4 = reinterpret_cast<float4*>(slots + (i >> 2) * FR_SLOT + FR_FEAT + FR_ERB);
@@ -492,7 +512,7 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
                 else { re[i] = p[0]; im[i] = p[sc]; }
             }
         }
-        copy_f4(W, blobp + blob::FRONT_OFF, FR_W_FLOATS, tid, FR_THREADS);
+        copy_f4_async(W, blobp + blob::FRONT_OFF, FR_W_FLOATS, tid, FR_THREADS);
         for (int i = tid; i < FR_NF * 4; i += FR_THREADS) {
             float4* sfe4 = reinterpret_cast<float4*>(slots + (i >> 2) * FR_SLOT + FR_FEAT + FR_ERB);
             const int c = i & 3;                                  // padded bins 0, 1, 131, 132 -> (parity, entry)
@@ -506,6 +526,7 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
                 reinterpret_cast<float4*>(slots + slot * FR_SLOT)[k] = make_float4(sqrtf(re[i] * re[i] + im[i] * im[i] + 1e-12f), re[i], im[i], 0.f);
             }
         }
+        cp_async_wait_all();
     }
     __syncthreads();
     // ---- b: ERB compress (sparse triangular bank, <= 12 contiguous taps per band): thread = (band, slot pair); each tap weight
@@ -1258,11 +1279,12 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
         if (TO_WAV && tid * 128 < nf * kSpecFrame * 4)                               // fused mode: spec is the contiguous [frame][257][2] buffer
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(spec + fi0 * kSpecFrame) + tid * 128));
     }
-    copy_f4(Wsm, blobp + blob::BACK_OFF + BK_W_OFF, BK_W_FLOATS, tid, BK_THREADS);
-    if (TO_WAV) {                                                  // iSTFT tables (needed last) are fetched first so their latency is hidden
+    // tables (de4 / inverse-ERB weights, iSTFT tables) are not needed before de4: asynchronous copies that land during de3
+    copy_f4_async(Wsm, blobp + blob::BACK_OFF + BK_W_OFF, BK_W_FLOATS, tid, BK_THREADS);
+    if (TO_WAV) {
         FftTables& tb0 = *reinterpret_cast<FftTables*>(Wsm + bk_smem_floats(false));
-        load_fft_tables(tb0, blobp, tid, BK_THREADS);
-        if (tid < 256) (reinterpret_cast<float*>(&tb0) + FR_FFT_FLOATS)[tid] = blobp[blob::FFT_OFF + blob::FFT_INV_ENV + tid];
+        load_fft_tables_async(tb0, blobp, tid, BK_THREADS);
+        copy_f4_async(reinterpret_cast<float*>(&tb0) + FR_FFT_FLOATS, blobp + blob::FFT_OFF + blob::FFT_INV_ENV, 256, tid, BK_THREADS);
     }
     if (loader) {
 #pragma unroll
@@ -1286,6 +1308,7 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
         const int r = tid - 160;
         back_de3<1>(prm, X, Y3, r >> 5, r & 31, fi0, nframes, en0);
     }
+    cp_async_wait_all();                                           // this thread's share of the table copies has landed
     __syncthreads();
     // ---- c: de4 (16 -> 2) + tanh -> mask on the 129 compressed bins: even bins (65) on warps 0-4, odd bins (64) on warps 5-8
     static_assert(BK_NF == 8, "de4 mapping assumes two groups of four slots");
