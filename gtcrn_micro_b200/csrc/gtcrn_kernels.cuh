@@ -1031,13 +1031,17 @@ __device__ __forceinline__ void tcn_conv3(const PB& prm, int wo, const float (&y
 // warp's private shared memory -- only __syncwarp, no CTA barrier, every lane busy (the CTA-tiled v2 kernel lost 21 % of its
 // stall samples to barriers and 8 % of its lanes to 264/288 occupancy).
 // grid (ceil(B*33 / WC_WARPS), nseg), WC_WARPS*32 threads.
-constexpr int WC_WARPS = 8;
+#ifndef GTCRNB_WC_WARPS
+#define GTCRNB_WC_WARPS 8
+#endif
+constexpr int WC_WARPS = GTCRNB_WC_WARPS;           // columns (warps) per CTA
+constexpr int WC_MIN_BLOCKS = WC_WARPS >= 8 ? 2 : 18 / WC_WARPS;
 __host__ __device__ constexpr int wc_nt(int P) { return 32 * P; }
 __host__ __device__ constexpr int wc_warp4(int P) { return 4 * wc_nt(P) + 2 * 4 * 30; }       // float4 per warp: Y[q][row] + H[par][q][30]
 __host__ __device__ constexpr int wc_smem_floats(int P, bool smem_w = false) { return WC_WARPS * wc_warp4(P) * 4 + (smem_w ? 4 * blob::TCN_SIZE : 0); }
 
 template <int P, bool SMEM_W>
-__global__ void __launch_bounds__(WC_WARPS * 32, (P <= 2 ? 2 : 1))
+__global__ void __launch_bounds__(WC_WARPS * 32, (P <= 2 ? WC_MIN_BLOCKS : 1))
 k_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_constant__ ParamBlock<4 * blob::TCN_SIZE> prm_c,
        int T, int seg_len, int64_t ncols) {
     constexpr int NT = wc_nt(P);
