@@ -649,7 +649,10 @@ __host__ __device__ constexpr int gt_threads(int G) { return (G * kF2 + 31) / 32
 __host__ __device__ constexpr int gt_smem_floats(int PS, int G, int w_floats = 0) {
     return (G * PS + 2) * GT_ROW4 * 4 + G * PS * kF2 * 8 + (G * PS + 2) * 8 + G * PS * 8 + w_floats;
 }
-__host__ __device__ constexpr int gt_min_blocks(int PS) { return PS >= 4 ? 2 : (PS == 3 ? 2 : (PS == 2 ? 3 : 4)); }
+// CTAs per SM the register budget should allow: PS frame slots per thread need about 56 / 72 / 96 / 128 registers
+__host__ __device__ constexpr int gt_min_blocks(int PS, int G = 8) {
+    return 65536 / (gt_threads(G) * (PS >= 4 ? 128 : PS == 3 ? 96 : PS == 2 ? 72 : 56));
+}
 
 template <bool DEC> struct GtOff {
     static constexpr int PC1_W = DEC ? blob::DECGT_PC1_W : blob::ENCGT_PC1_W;
@@ -756,7 +759,7 @@ __device__ __forceinline__ float gt_energy(const float* e2_slot_c) {
 }
 
 template <bool DEC, int PS, int G, bool SMEM_W>
-__global__ void __launch_bounds__(gt_threads(G), gt_min_blocks(PS))
+__global__ void __launch_bounds__(gt_threads(G), gt_min_blocks(PS, G))
 k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* __restrict__ out,
          const __grid_constant__ ParamBlock<gt_chunk<DEC>()> prm_c, int T, int seg_len) {
     constexpr int NT = G * PS, R = NT + 2, GT_THREADS = gt_threads(G), GT_ACTIVE = G * kF2;

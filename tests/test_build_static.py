@@ -18,7 +18,7 @@ import gtcrn_micro_b200.build as B
 
 CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 # kernels launched with the default tuning (gtcrn_capi.cu): offline + streaming
-HOT = ["k_frontILb0", "k_frontILb1", "k_backILb0", "k_backILb1", "k_gtconvILb0ELi2ELi8ELb0", "k_gtconvILb1ELi4ELi7ELb0",
+HOT = ["k_frontILb0", "k_frontILb1", "k_backILb0", "k_backILb1", "k_gtconvILb0ELi2ELi4ELb0", "k_gtconvILb1ELi4ELi7ELb0",
        "k_gtcnILi2ELb0", "ks_gtconvILb0", "ks_gtconvILb1", "ks_gtcn"]
 
 
