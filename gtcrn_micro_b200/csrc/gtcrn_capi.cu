@@ -74,6 +74,12 @@ struct gtcrnb_handle {
     WsSet parked;                                 // the workspace that is NOT currently selected
     int ws_cur = 0;
     cudaEvent_t ev_h2d[kStage] = {}, ev_comp[kStage] = {}, ev_d2h[kStage] = {};
+    // Ordering between the caller's stream and the host pipeline's internal streams: both use the handle's activation workspace.
+    // Every entry point that launches on a caller stream records ev_user there; the host pipeline makes its compute streams wait
+    // on it before touching the workspace (the pipeline itself is synchronous, so nothing is needed in the other direction).
+    cudaEvent_t ev_user = nullptr;
+    bool user_pending = false;
+    bool in_pipeline = false;
     // occupancy (resident CTAs per SM) of the walking kernels, for segment selection
     int occ_gt_enc = 1, occ_gt_dec = 1, occ_tcn = 1;
     int64_t launches = 0;
@@ -161,6 +167,13 @@ struct ProfScope {
         h->prof_events.push_back(ev);
     }
 };
+
+// called after launching on a caller-owned stream (see gtcrnb_handle::ev_user)
+void note_user_work(gtcrnb_handle* h, cudaStream_t st) {
+    if (h->in_pipeline) return;
+    if (!h->ev_user && cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); h->ev_user = nullptr; return; }
+    if (cudaEventRecord(h->ev_user, st) == cudaSuccess) h->user_pending = true; else cudaGetLastError();
+}
 
 void select_workspace(gtcrnb_handle* h, int idx) {
     if (h->ws_cur == idx) return;
@@ -376,6 +389,7 @@ void gtcrnb_destroy(gtcrnb_handle* h) {
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     if (h->s_comp2) cudaStreamDestroy(h->s_comp2);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    if (h->ev_user) cudaEventDestroy(h->ev_user);
     delete h;
 }
 
@@ -394,6 +408,7 @@ int gtcrnb_forward_spec(gtcrnb_handle* h, const float* spec_dev, const int64_t i
         rc = run_model(h, spec_dev + b0 * in_strides[0], in_strides, nb, T, out_dev + b0 * out_strides[0], out_strides, st);
         if (rc) return rc;
     }
+    note_user_work(h, st);
     return GTCRNB_OK;
 }
 
@@ -459,6 +474,7 @@ int gtcrnb_enhance(gtcrnb_handle* h, const float* wav_dev, int64_t B, int64_t L,
         rc = gtcrnb_istft(h, h->spec_out, nb, T, out_dev + b0 * out_stride, out_stride, stream);
         if (rc) return rc;
     }
+    note_user_work(h, (cudaStream_t)stream);
     return GTCRNB_OK;
 }
 
@@ -541,6 +557,12 @@ int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, 
         for (auto it = head.rbegin(); it != head.rend(); ++it) sizes.push_back(*it);
     }
     // GTCRNB_HOST_TRACE=1: per-chunk engine timeline on stderr (diagnostic; adds timing events, not for benchmarking)
+    if (h->user_pending) {                                        // work queued on a caller stream still owns the workspaces
+        CU(cudaStreamWaitEvent(h->s_comp, h->ev_user, 0));
+        CU(cudaStreamWaitEvent(h->s_comp2, h->ev_user, 0));
+        h->user_pending = false;
+    }
+    struct PipelineFlag { gtcrnb_handle* h; PipelineFlag(gtcrnb_handle* h_) : h(h_) { h->in_pipeline = true; } ~PipelineFlag() { h->in_pipeline = false; } } pflag(h);
     const bool trace = getenv("GTCRNB_HOST_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;
     auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
@@ -695,7 +717,13 @@ int gtcrnb_stream_reset(gtcrnb_handle* h, void* state_dev, int64_t N, void* stre
 
 namespace {
 // kind 0: spectral frame in / out, kind 1: waveform hop in / out
+int stream_step_impl(gtcrnb_handle* h, int kind, void* state, const float* in, float* out, int64_t N, cudaStream_t st);
 int stream_step(gtcrnb_handle* h, int kind, void* state, const float* in, float* out, int64_t N, cudaStream_t st) {
+    const int rc = stream_step_impl(h, kind, state, in, out, N, st);
+    if (rc == GTCRNB_OK) note_user_work(h, st);
+    return rc;
+}
+int stream_step_impl(gtcrnb_handle* h, int kind, void* state, const float* in, float* out, int64_t N, cudaStream_t st) {
     int rc = ensure_workspace(h, N);
     if (rc) return rc;
     auto direct = [&](cudaStream_t s) {
@@ -761,6 +789,19 @@ int gtcrnb_stream_step_wav(gtcrnb_handle* h, void* state_dev, const float* hop_i
     if (!h || !state_dev || !hop_in_dev || !hop_out_dev || N < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_step_wav: bad argument");
     if (N == 0) return GTCRNB_OK;
     return stream_step(h, 1, state_dev, hop_in_dev, hop_out_dev, N, (cudaStream_t)stream);
+}
+
+int gtcrnb_stream_flush_wav(gtcrnb_handle* h, void* state_dev, const float* tail_dev, int64_t tail_len, float* out_dev, int64_t N, void* stream) {
+    if (!h || !state_dev || !out_dev || N < 0 || tail_len < 0 || tail_len > 255 || (tail_len > 0 && !tail_dev))
+        return fail(GTCRNB_E_INVALID, "gtcrnb_stream_flush_wav: bad argument (0 <= tail_len <= 255, tail_dev required when tail_len > 0)");
+    if (N == 0) return GTCRNB_OK;
+    if (N > 2147483647LL) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_flush_wav: too many streams");
+    int rc = ensure_workspace(h, N);
+    if (rc) return rc;
+    h->launches += gs::flush_wav(h->blob, *h->hp, state_dev, stream_ws(h), tail_dev, (int)tail_len, out_dev, N, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    note_user_work(h, (cudaStream_t)stream);
+    return GTCRNB_OK;
 }
 
 int gtcrnb_stream_import_caches(gtcrnb_handle* h, void* state_dev, int64_t N, const float* conv_cache_dev, const float* tra_cache_dev,

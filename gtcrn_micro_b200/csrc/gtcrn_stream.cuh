@@ -378,6 +378,32 @@ __global__ void __launch_bounds__(256) ks_istft_step(void* state, const float* _
     }
 }
 
+// End of stream (gtcrnb_stream_flush_wav): after K full hops (and `tail_len` < 256 trailing samples) the offline path still has
+// two frames to go -- frame K-1 = [hop K-2 | hop K-1] and frame K = [hop K-1 | v], v = the "virtual hop K" that torch.stft's
+// reflect padding creates past the end of the signal (infer.py:60-67; L = 256 K + tail_len, x[i >= L] = x[2 (L-1) - i]).
+// This kernel builds v [N][256] from the trailing samples and the two hops in the WAV_IN ring; two ordinary step_wav calls
+// with v as the new hop then emit the last two offline hops.
+__global__ void __launch_bounds__(256) ks_reflect_tail(const void* state, const float* __restrict__ tail, int tail_len,
+                                                       float* __restrict__ v, int64_t N) {
+    const Header* hdr = reinterpret_cast<const Header*>(state);
+    const long long K = hdr->wav_calls;
+    const int64_t n = blockIdx.x;
+    const int j = threadIdx.x;
+    if (n >= N) return;
+    const float* ring = reinterpret_cast<const float*>(state) + kHdrFloats + n * (int64_t)kPerStream + kWavIn;
+    const float* h1 = ring + ((K - 1) & 1) * 256;              // hop K-1
+    const float* h2 = ring + (K & 1) * 256;                    // hop K-2
+    float val = 0.f;
+    if (K >= 2) {
+        if (j < tail_len) val = tail[n * tail_len + j];
+        else {
+            const int r = 2 * tail_len - 2 - j;                // position relative to sample 256 K
+            val = r >= 0 ? tail[n * tail_len + r] : (r >= -256 ? h1[256 + r] : h2[512 + r]);
+        }
+    }
+    v[n * 256 + j] = val;
+}
+
 __global__ void ks_advance(void* state, int wav_mode) {
     Header* hdr = reinterpret_cast<Header*>(state);
     if (!hdr->skip) hdr->frame_step += 1;
@@ -500,6 +526,15 @@ inline int step_wav(const float* blobp, const HostParams& hp, void* state, const
     ks_istft_step<<<g4, 256, 0, st>>>(state, ws.spec_out, blobp, hop_out, N);
     ks_advance<<<1, 1, 0, st>>>(state, 1);
     return launches + 2;
+}
+
+// the last two offline hops; out [2][N][256] (out[1] doubles as the buffer of the virtual hop).  Returns the number of launches.
+inline int flush_wav(const float* blobp, const HostParams& hp, void* state, const Ws& ws, const float* tail, int tail_len, float* out, int64_t N, cudaStream_t st) {
+    float* v = out + N * 256;
+    ks_reflect_tail<<<(unsigned)N, 256, 0, st>>>(state, tail, tail_len, v, N);
+    int launches = 1 + step_wav(blobp, hp, state, ws, v, out, N, st);
+    launches += step_wav(blobp, hp, state, ws, v, v, N, st);
+    return launches;
 }
 
 inline int convert_caches(bool import, void* state, int64_t N, float* conv_cache, float* tra_cache, float* const* tcn, cudaStream_t st) {

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import argparse
 import os
+import re
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -183,6 +184,49 @@ def run(model, jobs: Sequence[Job], enh_dir: str, max_batch: int = 256, device: 
     return inf_rows, ref_rows, scores
 
 
+_INTERP = re.compile(r"\$\{([^${}]+)\}")
+
+
+def load_config(path: str) -> dict:
+    """Reference-style YAML with OmegaConf `${a.b.c}` interpolations resolved (the reference reads cfg_infer.yaml with
+    OmegaConf.load, infer.py:27; its `checkpoint` / `enh_folder` entries interpolate `network.exp_path` / `network.ckpt_name`).
+    Absolute dotted keys only (what the reference's configs use); nested references resolve recursively; cycles raise."""
+    import yaml
+    with open(path) as f:
+        cfg = yaml.safe_load(f) or {}
+
+    def lookup(key: str):
+        node = cfg
+        for part in key.strip().split("."):
+            if not isinstance(node, dict) or part not in node:
+                raise KeyError(f"{path}: interpolation key '{key}' not found")
+            node = node[part]
+        return node
+
+    def resolve(v, stack=()):
+        if isinstance(v, dict):
+            return {k: resolve(x, stack) for k, x in v.items()}
+        if isinstance(v, list):
+            return [resolve(x, stack) for x in v]
+        if not isinstance(v, str) or "${" not in v:
+            return v
+        whole = _INTERP.fullmatch(v)
+        if whole:                                                   # "${a.b}" alone keeps the referenced value's type
+            key = whole.group(1)
+            if key in stack:
+                raise ValueError(f"{path}: interpolation cycle through '{key}'")
+            return resolve(lookup(key), stack + (key,))
+
+        def sub(m):
+            key = m.group(1)
+            if key in stack:
+                raise ValueError(f"{path}: interpolation cycle through '{key}'")
+            return str(resolve(lookup(key), stack + (key,)))
+        return _INTERP.sub(sub, v)
+
+    return resolve(cfg)
+
+
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("-C", "--config", default=None, help="reference-style infer YAML")
@@ -192,9 +236,7 @@ def main(argv=None) -> int:
     ap.add_argument("--metrics", action="store_true", help="score SI-SNR / SDR on the device against the clean references")
     args = ap.parse_args(argv)
     if args.config:
-        import yaml
-        with open(args.config) as f:
-            cfg = yaml.safe_load(f)
+        cfg = load_config(args.config)
         args.noisy_dir = args.noisy_dir or cfg["test_dataset"]["noisy_dir"]
         args.clean_dir = args.clean_dir or cfg["test_dataset"].get("clean_dir")
         args.enh_dir = args.enh_dir or cfg["network"]["enh_folder"]

@@ -21,7 +21,7 @@ SYMBOLS = [
     "gtcrnb_stream_export_caches", "gtcrnb_debug_activation", "gtcrnb_launch_count", "gtcrnb_host_alloc",
     "gtcrnb_host_free", "gtcrnb_last_error", "gtcrnb_profile_enable", "gtcrnb_profile_read",
     "gtcrnb_profile_num_classes", "gtcrnb_profile_class_name", "gtcrnb_pair_metrics", "gtcrnb_host_alloc_wc",
-    "gtcrnb_enhance_host_pcm16", "gtcrnb_pcm16_to_f32", "gtcrnb_f32_to_pcm16",
+    "gtcrnb_enhance_host_pcm16", "gtcrnb_pcm16_to_f32", "gtcrnb_f32_to_pcm16", "gtcrnb_stream_flush_wav",
 ]
 
 
@@ -62,6 +62,7 @@ def load() -> C.CDLL:
             "gtcrnb_stream_reset": (C.c_int, [vp, vp, i64, vp]),
             "gtcrnb_stream_step_spec": (C.c_int, [vp, vp, vp, vp, i64, vp]),
             "gtcrnb_stream_step_wav": (C.c_int, [vp, vp, vp, vp, i64, vp]),
+            "gtcrnb_stream_flush_wav": (C.c_int, [vp, vp, vp, i64, vp, i64, vp]),
             "gtcrnb_stream_import_caches": (C.c_int, [vp, vp, i64, vp, vp, C.POINTER(vp), vp]),
             "gtcrnb_stream_export_caches": (C.c_int, [vp, vp, i64, vp, vp, C.POINTER(vp), vp]),
             "gtcrnb_debug_activation": (C.c_int, [vp, cp, vp, sz, vp]),

@@ -234,9 +234,11 @@ class GTCRNMicro(_B200Module):
         """Same as `enhance` for HOST tensors (ideally pinned): chunked H2D / compute / D2H pipeline inside the library."""
         if wav.is_cuda or wav.dim() != 2 or wav.dtype != torch.float32 or not wav.is_contiguous():
             raise ValueError("wav must be a contiguous float32 CPU tensor [B,L]")
+        B, Ls = wav.shape
+        if out is not None and (out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != (B, 256 * (Ls // 256))):
+            raise ValueError("out must be a contiguous float32 CPU tensor [B,256*(L//256)]")   # the library writes B*256*(L//256) floats through this pointer
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         h = self._ensure_handle(dev)
-        B, Ls = wav.shape
         if out is None:
             out = torch.empty((B, 256 * (Ls // 256)), dtype=torch.float32, pin_memory=True)
         L = _lib.load()
@@ -250,13 +252,13 @@ class GTCRNMicro(_B200Module):
         Samples cross PCIe as 2 bytes; decode (x/32768) and encode (floor(y*32768), clamped) run on the device."""
         if wav.is_cuda or wav.dim() != 2 or wav.dtype != torch.int16 or not wav.is_contiguous():
             raise ValueError("wav must be a contiguous int16 CPU tensor [B,L]")
+        B, Ls = wav.shape
+        if out is not None and (out.is_cuda or out.dtype != torch.int16 or not out.is_contiguous() or tuple(out.shape) != (B, 256 * (Ls // 256))):
+            raise ValueError("out must be a contiguous int16 CPU tensor [B,256*(L//256)]")
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         h = self._ensure_handle(dev)
-        B, Ls = wav.shape
         if out is None:
             out = torch.empty((B, 256 * (Ls // 256)), dtype=torch.int16, pin_memory=True)
-        elif out.dtype != torch.int16 or not out.is_contiguous() or tuple(out.shape) != (B, 256 * (Ls // 256)):
-            raise ValueError("out must be a contiguous int16 CPU tensor [B,256*(L//256)]")
         with torch.cuda.device(dev):
             _lib.check(_lib.load().gtcrnb_enhance_host_pcm16(h, wav.data_ptr(), B, Ls, out.data_ptr()), "gtcrnb_enhance_host_pcm16")
         return out
@@ -370,15 +372,23 @@ class StreamGTCRNMicro(_B200Module):
                 assert tuple(tcn_cache[g][k].shape) == (B, 16, 2 * d, 33), tcn_cache[g][k].shape
         h = self._ensure_handle(spec.device)
         L = _lib.load()
-        st = StreamState(B, spec.device)
         cc, tc = conv_cache.contiguous(), tra_cache.contiguous()
         nc = [[tcn_cache[g][k].contiguous() for k in range(4)] for g in range(2)]
         ptrs = (C.c_void_p * 8)(*[nc[g][k].data_ptr() for g in range(2) for k in range(4)])
+        # The native ring-buffer state is kept between calls and re-imported only when the caller hands in cache tensors other
+        # than the ones this module exported last time (or modified them through torch: `_version` moves).  The usual loop
+        # (gtcrn_micro_stream.py:626-636) feeds the returned objects straight back, so it pays for one import in total.
+        cached = getattr(self, "_fwd_state", None)
+        key = (int(h.value), B, spec.device, tuple((t.data_ptr(), t._version) for t in [cc, tc] + [nc[g][k] for g in range(2) for k in range(4)]))
         frame = spec[:, :, 0, :].contiguous()
         out = torch.empty_like(frame)
         with torch.cuda.device(spec.device):
             s = torch.cuda.current_stream().cuda_stream
-            _lib.check(L.gtcrnb_stream_import_caches(h, st.ptr, B, cc.data_ptr(), tc.data_ptr(), ptrs, s), "gtcrnb_stream_import_caches")
+            if cached is not None and cached[0] == key:
+                st = cached[1]
+            else:
+                st = StreamState(B, spec.device)
+                _lib.check(L.gtcrnb_stream_import_caches(h, st.ptr, B, cc.data_ptr(), tc.data_ptr(), ptrs, s), "gtcrnb_stream_import_caches")
             _lib.check(L.gtcrnb_stream_step_spec(h, st.ptr, frame.data_ptr(), out.data_ptr(), B, s), "gtcrnb_stream_step_spec")
             _lib.check(L.gtcrnb_stream_export_caches(h, st.ptr, B, cc.data_ptr(), tc.data_ptr(), ptrs, s), "gtcrnb_stream_export_caches")
         if cc.data_ptr() != conv_cache.data_ptr():
@@ -386,6 +396,9 @@ class StreamGTCRNMicro(_B200Module):
         if tc.data_ptr() != tra_cache.data_ptr():
             tra_cache.copy_(tc)
         new_tcn = [[nc[g][k] for k in range(4)] for g in range(2)]
+        # valid for the next call only if the caller passes back exactly what we return (raw-pointer writes do not move _version)
+        nkey = (int(h.value), B, spec.device, tuple((t.data_ptr(), t._version) for t in [conv_cache, tra_cache] + [new_tcn[g][k] for g in range(2) for k in range(4)]))
+        self._fwd_state = (nkey, st) if (cc.data_ptr() == conv_cache.data_ptr() and tc.data_ptr() == tra_cache.data_ptr()) else None
         return out[:, :, None, :], conv_cache, tra_cache, new_tcn
 
     # ---- native API: state stays on the device as ring buffers ------------------------------------
@@ -425,6 +438,24 @@ class StreamGTCRNMicro(_B200Module):
             _lib.check(_lib.load().gtcrnb_stream_step_wav(h, state.ptr, hop.data_ptr(), out.data_ptr(), state.n,
                                                           torch.cuda.current_stream().cuda_stream), "gtcrnb_stream_step_wav")
         return out
+
+
+    @torch.no_grad()
+    def flush_wav(self, state: StreamState, tail: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """End of stream: returns [N,512], the two enhanced hops `step_wav`'s 32 ms latency still holds back, computed with the
+        end-of-signal reflect padding of torch.stft -- concatenated after the `step_wav` outputs (minus the two leading zero
+        hops) this is exactly `GTCRNMicro.enhance` of the whole signal.  tail [N,r], r < 256: trailing samples that did not
+        fill a hop (they shape the last frame, infer.py:60-67).  The state must be reset before it is used again."""
+        r = 0 if tail is None else int(tail.shape[1])
+        if tail is not None and (tuple(tail.shape) != (state.n, r) or r > 255 or tail.dtype != torch.float32 or not tail.is_contiguous()):
+            raise ValueError(f"tail must be contiguous float32 [{state.n}, r < 256]")
+        dev = state.buf.device
+        h = self._ensure_handle(dev)
+        out = torch.empty((2, state.n, 256), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().gtcrnb_stream_flush_wav(h, state.ptr, tail.data_ptr() if r else None, r, out.data_ptr(), state.n,
+                                                           torch.cuda.current_stream().cuda_stream), "gtcrnb_stream_flush_wav")
+        return out.permute(1, 0, 2).reshape(state.n, 512)
 
 
 def convert_to_stream(stream_model: nn.Module, model: nn.Module) -> None:
@@ -469,7 +500,7 @@ class _HostBlock:
 
 
 def pinned_empty(shape, write_combined: bool = False) -> torch.Tensor:
-    """float32 page-locked host tensor from the library's allocator (`gtcrnb_host_alloc[_wc]`) for `enhance_host`.
+    """float32 (only) page-locked host tensor from the library's allocator (`gtcrnb_host_alloc[_wc]`) for `enhance_host`.
     write_combined=True is for INPUT buffers that the CPU fills sequentially and never reads: the copy engine reads them
     without cache snooping.  CPU reads of such a tensor are very slow."""
     n = 1
@@ -478,7 +509,7 @@ def pinned_empty(shape, write_combined: bool = False) -> torch.Tensor:
     L = _lib.load()
     ptr = (L.gtcrnb_host_alloc_wc if write_combined else L.gtcrnb_host_alloc)(max(4, 4 * n))
     if not ptr:
-        raise GtcrnB200Error(f"page-locked allocation of {4 * n} bytes failed")
+        raise _lib.GtcrnB200Error(f"page-locked allocation of {4 * n} bytes failed")
     block = _HostBlock(int(ptr))
     buf = (C.c_float * n).from_address(block.ptr)
     buf._gtcrnb_owner = block                                   # ctypes array keeps the block alive; torch keeps the array alive
@@ -486,11 +517,14 @@ def pinned_empty(shape, write_combined: bool = False) -> torch.Tensor:
     return t.view(*shape)
 
 
-def load_checkpoint(path: str, stream: bool = False, map_location="cpu") -> nn.Module:
+def load_checkpoint(path: str, stream: bool = False, map_location="cpu", unsafe: bool = False) -> nn.Module:
     """Build a model from a reference training checkpoint `{"epoch","optimizer","scheduler","model"}`
     (train.py:206-211); also tolerates a bare state_dict, `state_dict`/`model_state_dict` keys and a DDP
-    `module.` prefix like the reference's export scripts (stream_onnx.py:38-47)."""
-    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    `module.` prefix like the reference's export scripts (stream_onnx.py:38-47).
+    The file is read with `weights_only=True` (tensors and plain containers only -- the shipped best_model_dns3.tar loads
+    that way); `unsafe=True` opts into full unpickling for checkpoints that carry custom objects, and must only be used
+    on trusted files."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=not unsafe)
     sd = ckpt
     for k in ("model", "state_dict", "model_state_dict"):
         if isinstance(ckpt, dict) and k in ckpt and isinstance(ckpt[k], dict):

@@ -89,6 +89,13 @@ int gtcrnb_stream_step_spec(gtcrnb_handle* h, void* state_dev, const float* spec
  * one hop of overlap-add); the first two hops are zeros; see DESIGN.md. */
 int gtcrnb_stream_step_wav(gtcrnb_handle* h, void* state_dev, const float* hop_in_dev, float* hop_out_dev,
                            int64_t N, void* stream);
+/* End of stream for the wav entry point: after K calls of gtcrnb_stream_step_wav (K >= 2 full hops) plus `tail_len` (0..255)
+ * trailing samples tail_dev [N][tail_len] (NULL when 0), emit the two hops the 32 ms latency still holds back:
+ * out_dev [2][N][256] = offline output hops K-2 and K-1 of a signal of L = 256 K + tail_len samples, including torch.stft's
+ * reflect padding at the end of the signal (infer.py:60-67) -- with it the streamed output equals gtcrnb_enhance's
+ * 256*(L/256) samples exactly.  The state is finished afterwards (gtcrnb_stream_reset before reuse). */
+int gtcrnb_stream_flush_wav(gtcrnb_handle* h, void* state_dev, const float* tail_dev, int64_t tail_len,
+                            float* out_dev, int64_t N, void* stream);
 /* Import / export the model caches of a stream batch in the reference's own tensor layout
  * (gtcrn_micro_stream.py:618-623): conv_cache [2,N,16,6,33], tra_cache [2,3,N,8,2],
  * tcn_cache[g][k] [N,16,2*d_k,33] passed as 8 pointers (g-major).  All device pointers. */

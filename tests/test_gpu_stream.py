@@ -158,3 +158,78 @@ def test_hop_graphs_replay_bitwise(oracle, weights_dns3, b200_lib, monkeypatch):
         assert torch.equal(f_out, s0.step(spec[k].contiguous(), st_p2)), k
         if k == 9:
             s.reset(st_g2); s0.reset(st_p2)
+
+
+@pytest.mark.parametrize("tail", [0, 1, 77, 255])
+def test_stream_flush_completes_offline_output(oracle, weights_dns3, b200_lib, tail):
+    # SURVEY 8(f)1 "OLA tail flush": step_wav + flush_wav == enhance of the whole signal (infer.py:60-76), including the
+    # end-of-signal reflect padding and trailing samples that do not fill a hop
+    m, s = models(weights_dns3)
+    N, hops = 3, 11
+    x = oracle.synth_batch(N, 256 * hops + tail, seed=32 + tail).to(DEV)
+    off = m.enhance(x)                                                        # [N, 256*hops]
+    st = s.new_state(N, DEV)
+    outs = [s.step_wav(x[:, 256 * k:256 * (k + 1)].contiguous(), st) for k in range(hops)]
+    outs.append(s.flush_wav(st, x[:, 256 * hops:].contiguous() if tail else None))
+    y = torch.cat(outs, dim=1)[:, 512:]
+    assert y.shape == off.shape
+    err = float((y - off).abs().max())
+    print(f"stream wav + flush (tail {tail}) vs offline: max-abs {err:.2e}")
+    assert err <= 1e-6
+    assert float((y.cpu() - oracle.enhance(weights_dns3, x.cpu())).abs().max()) <= WAV_TOL
+    with pytest.raises(ValueError):
+        s.flush_wav(st, torch.zeros(N, 256, device=DEV))
+
+
+def test_reference_forward_reuses_native_state(oracle, weights_dns3, ref_outputs, b200_lib):
+    # the drop-in forward keeps its ring-buffer state between calls when the caller feeds the returned caches back
+    # (one import in total), and re-imports when the caches were replaced or modified through torch
+    _, s = models(weights_dns3)
+    spec = torch.from_numpy(ref_outputs["spec"]).to(DEV)
+    B = spec.shape[0]
+
+    def fresh():
+        return (torch.zeros(2, B, 16, 6, 33, device=DEV), torch.zeros(2, 3, B, 8, 2, device=DEV),
+                [[torch.zeros(B, 16, 2 * d, 33, device=DEV) for d in (1, 2, 4, 8)] for _ in range(2)])
+    cc, tc, nc = fresh()
+    l0 = s.launch_count()
+    ys = []
+    for t in range(12):
+        yi, cc, tc, nc = s(spec[:, :, t:t + 1], cc, tc, nc)
+        ys.append(yi)
+    assert s.launch_count() - l0 == 1 + 12 * (10 + 1)             # one import, then step + export per frame
+    want = torch.from_numpy(ref_outputs["dns3.stream_spec_out"][:, :, :12])
+    assert rel_err(torch.cat(ys, dim=2), want) <= REL_TOL
+    # restart from zero caches (new tensors): must re-import and reproduce frame 0
+    cc2, tc2, nc2 = fresh()
+    y0, cc2, tc2, nc2 = s(spec[:, :, 0:1], cc2, tc2, nc2)
+    assert torch.equal(y0, ys[0])
+    # in-place edit of a returned cache through torch is honoured
+    cc2.zero_(); tc2.zero_()
+    for g in range(2):
+        for k in range(4):
+            nc2[g][k].zero_()
+    y0b, *_ = s(spec[:, :, 0:1], cc2, tc2, nc2)
+    assert torch.equal(y0b, ys[0])
+
+
+def test_stream_parity_at_scale_16384(oracle, weights_dns3, b200_lib):
+    # BASELINE configs[2] size: 16,384 concurrent streams x 100 hops; a 16-stream subset is compared with the oracle's
+    # frame-by-frame loop and every stream with its bitwise twin (streams 0..15 are repeated at the end of the batch)
+    _, s = models(weights_dns3)
+    N, T, K = 16384, 100, 16
+    g = torch.Generator(device=DEV).manual_seed(77)
+    st = s.new_state(N, DEV)
+    sub_in, sub_out = [], []
+    for t in range(T):
+        f = torch.randn(N, 257, 2, device=DEV, generator=g)
+        f[N - K:] = f[:K]
+        o = s.step(f, st)
+        assert torch.equal(o[N - K:], o[:K]), t
+        sub_in.append(f[:K].cpu()); sub_out.append(o[:K].cpu())
+    spec = torch.stack(sub_in, dim=2)                                 # [K,257,T,2]
+    with torch.inference_mode():
+        ref = oracle.stream_spec(weights_dns3, spec)
+    e = rel_err(torch.stack(sub_out, dim=2), ref)
+    print(f"16384 streams x {T} hops: subset rel err vs oracle stream loop {e:.2e}")
+    assert e <= REL_TOL

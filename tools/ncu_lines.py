@@ -8,11 +8,15 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(raw.splitlines()))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Line No")
 H = rows[hi]
-si, wi, xi, ii = H.index("# Samples"), H.index("L1 Wavefronts Shared"), H.index("L1 Wavefronts Shared Excessive"), H.index("Instructions Executed")
+def col(name):
+    return H.index(name) if name in H else None
+si, wi, xi, ii = col("# Samples"), col("L1 Wavefronts Shared"), col("L1 Wavefronts Shared Excessive"), col("Instructions Executed")
+def geti(r, i):
+    return int(r[i]) if i is not None and r[i].strip() else 0
 stall_cols = [(n[6:], i) for i, n in enumerate(H) if n.startswith("stall_") and "Not Issued" not in n]
 lines = [r for r in rows[hi + 1:] if r and r[0].strip().isdigit()]
-tot = sum(int(r[si]) for r in lines); twf = sum(int(r[wi]) for r in lines)
+tot = sum(geti(r, si) for r in lines); twf = sum(geti(r, wi) for r in lines)
 print(rows[1][1][:100]); print("total samples", tot, "smem wavefronts", twf)
-for r in sorted(lines, key=lambda r: -int(r[si]))[:top]:
-    st = sorted(((n, int(r[i])) for n, i in stall_cols if int(r[i]) > 0), key=lambda x: -x[1])[:3]
-    print(f"{100*int(r[si])/tot:5.1f}%  wf {100*int(r[wi])/max(1,twf):4.1f}% (x{int(r[xi])/max(1,int(r[wi])):.2f})  inst {int(r[ii]):>11d}  L{r[0]:>4s}  {r[1].strip()[:84]:84s} {st}")
+for r in sorted(lines, key=lambda r: -geti(r, si))[:top]:
+    st = sorted(((n, geti(r, i)) for n, i in stall_cols if geti(r, i) > 0), key=lambda x: -x[1])[:3]
+    print(f"{100*geti(r, si)/max(1,tot):5.1f}%  wf {100*geti(r, wi)/max(1,twf):4.1f}% (x{geti(r, xi)/max(1,geti(r, wi)):.2f})  inst {geti(r, ii):>11d}  L{r[0]:>4s}  {r[1].strip()[:84]:84s} {st}")
