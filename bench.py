@@ -11,12 +11,19 @@ process N such batches with no collective (weak scaling).  One JSON line is prin
   e2e           same metric through `GTCRNMicro.enhance_host` (C ABI gtcrnb_enhance_host): pinned HOST
                 buffers in, pinned HOST buffers out, H2D / D2H inside the timed region
   roofline      dominant kernel (decoder GTConv 3x3), timed live with CUDA events inside the library
-  cpu_baseline  the oracle (torch-CPU port of the reference, same ATen ops) on this box's host cores
-  streaming     frame-by-frame path: per-hop latency for N concurrent streams vs the 16 ms deadline
+  cpu_baseline  the reference's own CPU implementation (baseline/_ref; oracle port if absent) on this box's host
+                cores: offline audio-s/s and, per BASELINE.md section 3, max real-time streams of its frame-by-frame model
+  streaming     frame-by-frame path (BASELINE configs[2]): p50/p99/max hop latency over 625 hops for 4,096 / 16,384
+                streams, wav in / wav out through pinned host buffers (copies inside the hop), HBM roofline of the hop,
+                and the largest stream count whose worst hop meets the 16 ms deadline (searched, then confirmed)
 
-`--impl reference` times the reference's CPU implementation of the same path.  The reference is pure
-Python/PyTorch and is not present on the GPU box, so this arm runs the oracle port (oracle/gtcrn_oracle.py,
-pinned against the reference by oracle/check_against_reference.py) with all host threads.
+  parity        a fixed 16-utterance subset of the TIMED batch's output compared with the oracle (checker only,
+                outside the timed region): waveform max-abs <= 1e-4 and SI-SNR delta <= 0.01 dB or the run fails
+
+`--impl reference` times the reference's own CPU implementation of the same path: the unmodified bglid/GTCRN-Micro
+package installed into the git-ignored baseline/_ref by oracle/install_reference.sh (kind "reference": its
+GTCRNMicro between torch.stft / torch.istft exactly as infer.py:60-76, its StreamGTCRNMicro + convert_to_stream for
+the streaming figure).  When baseline/_ref is absent the arm falls back to the oracle port (kind "port").
 """
 from __future__ import annotations
 
@@ -56,7 +63,7 @@ def measured_peaks():
         return {}
 
 
-def synth_on_device(B: int, L: int, device, seed: int) -> torch.Tensor:
+def synth_on_device(B: int, L: int, device, seed: int, keep_clean=None):
     """Same recipe as oracle.synth_batch generated on the device in fp32: 5 harmonics of
     f0~U(90,250) Hz, 4 Hz syllable envelope, RMS 0.05, white noise at SNR~U(0,15) dB, clipped."""
     g = torch.Generator(device=device).manual_seed(seed)
@@ -75,6 +82,10 @@ def synth_on_device(B: int, L: int, device, seed: int) -> torch.Tensor:
         snr = 15 * torch.rand(nb, 1, generator=g, device=device)
         noise = torch.randn(nb, L, generator=g, device=device) * (0.05 / 10 ** (snr / 20))
         out[b0:b0 + nb] = (clean + noise).clamp_(-1, 1)
+        if keep_clean is not None:
+            for j, i in enumerate(keep_clean[0]):
+                if b0 <= i < b0 + nb:
+                    keep_clean[1][j] = clean[i - b0].cpu()
     return out
 
 
@@ -144,19 +155,97 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_throughput(batches, reps: int, budget_s: float):
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+class CpuReference:
+    """The reference's CPU implementation of the path.  kind "reference": the unmodified package from baseline/_ref
+    (oracle/install_reference.sh) driven exactly like infer.py:60-76 and gtcrn_micro_stream.py:618-636; kind "port": the
+    oracle restatement (same ATen ops), used only when baseline/_ref is missing."""
+
+    def __init__(self):
+        import gtcrn_oracle as O
+        self.O = O
+        self.W = O.load_weights_npz(WEIGHTS)
+        self.kind = "port"
+        self.model = self.smodel = None
+        if os.path.isdir(os.path.join(REF_DIR, "gtcrn_micro")):
+            try:
+                import types
+                if REF_DIR not in sys.path:
+                    sys.path.insert(0, REF_DIR)
+                sys.modules.setdefault("soundfile", types.ModuleType("soundfile"))   # gtcrn_micro_stream.py:8 imports it; only __main__ uses it
+                from gtcrn_micro.models.gtcrn_micro import GTCRNMicro
+                from gtcrn_micro.streaming.conversion.convert import convert_to_stream
+                from gtcrn_micro.streaming.gtcrn_micro_stream import StreamGTCRNMicro
+                ck = os.path.join(REF_DIR, "gtcrn_micro", "ckpts", "best_model_dns3.tar")
+                sd = torch.load(ck, map_location="cpu", weights_only=True)["model"] if os.path.exists(ck) else self.W
+                self.model = GTCRNMicro().eval()
+                self.model.load_state_dict(sd)
+                self.smodel = StreamGTCRNMicro().eval()
+                convert_to_stream(self.smodel, self.model)
+                self.kind = "reference"
+            except Exception as e:      # a broken install must not sink the bench: fall back to the port and say so
+                sys.stderr.write(f"bench: reference package in {REF_DIR} unusable ({type(e).__name__}: {e}); using the oracle port\n")
+                self.model = self.smodel = None
+
+    def enhance(self, x: torch.Tensor) -> torch.Tensor:
+        if self.model is None:
+            return self.O.enhance(self.W, x)
+        with torch.inference_mode():                                               # infer.py:60-76, batched
+            win = torch.hann_window(512).pow(0.5)
+            spec = torch.stft(x, 512, 256, 512, win, return_complex=False)
+            out = self.model(spec)
+            return torch.istft(torch.view_as_complex(out.contiguous()), 512, 256, 512, win)
+
+    def stream_hop_seconds(self, B: int, warm: int = 3, hops: int = 10) -> float:
+        """Mean seconds per hop of the frame-by-frame model batched over B streams."""
+        g = torch.Generator().manual_seed(B)
+        frames = [torch.randn(B, 257, 1, 2, generator=g) for _ in range(4)]
+        with torch.inference_mode():
+            if self.smodel is None:
+                st = self.O.StreamState(B)
+                step = lambda f: self.O.forward_spec(self.W, f, st)
+            else:
+                caches = [torch.zeros(2, B, 16, 6, 33), torch.zeros(2, 3, B, 8, 2),
+                          [[torch.zeros(B, 16, 2 * d, 33) for d in (1, 2, 4, 8)] for _ in range(2)]]   # gtcrn_micro_stream.py:618-623
+
+                def step(f):
+                    y, caches[0], caches[1], caches[2] = self.smodel(f, caches[0], caches[1], caches[2])
+                    return y
+            for i in range(warm):
+                step(frames[i % 4])
+            t0 = time.perf_counter()
+            for i in range(hops):
+                step(frames[i % 4])
+            return (time.perf_counter() - t0) / hops
+
+
+def cpu_streaming(ref: "CpuReference", budget_s: float = 20.0) -> dict:
+    """max real-time streams on the host CPU = B * 16 ms / t_hop, maximised over B."""
+    t_start, detail, best = time.perf_counter(), {}, 0.0
+    for B in (1, 64, 512, 2048):
+        t = ref.stream_hop_seconds(B)
+        detail[str(B)] = {"hop_ms": round(t * 1e3, 3), "realtime_streams": int(B * 0.016 / t)}
+        best = max(best, B * 0.016 / t)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    return {"max_realtime_streams": int(best), "deadline_ms": 16.0, "by_batch": detail,
+            "protocol": "frame-by-frame model (spectral frames in/out, zero caches), 3 warm-up + 10 timed hops per B, B*16ms/t_hop"}
+
+
+def cpu_throughput(ref: "CpuReference", batches, reps: int, budget_s: float):
     """Best audio-s/s over batch sizes (SURVEY 8d protocol: 1 warm-up + best of `reps` per B)."""
-    import gtcrn_oracle as O
-    W = O.load_weights_npz(WEIGHTS)
+    O = ref.O
     torch.set_num_threads(os.cpu_count() or 1)
     best, detail, t_start = 0.0, {}, time.perf_counter()
     for B in batches:
         x = O.synth_batch(B, L_UTT, seed=4321)
-        O.enhance(W, x[:1])
+        ref.enhance(x[:1])
         times = []
         for _ in range(reps + 1):
             t0 = time.perf_counter()
-            O.enhance(W, x)
+            ref.enhance(x)
             times.append(time.perf_counter() - t0)
             if time.perf_counter() - t_start > budget_s:
                 break
@@ -172,33 +261,36 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import gtcrn_oracle as O
-    W = O.load_weights_npz(WEIGHTS)
+    ref = CpuReference()
+    O = ref.O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     # pick the batch size that suits this host (bounded sample of the 1024-utterance workload)
     best_B, best_v = 16, 0.0
     for B in (4, 16, 64):
         x = O.synth_batch(B, L_UTT, seed=4321)
-        O.enhance(W, x[:1])
-        t0 = time.perf_counter(); O.enhance(W, x); dt = time.perf_counter() - t0
+        ref.enhance(x[:1])
+        t0 = time.perf_counter(); ref.enhance(x); dt = time.perf_counter() - t0
         if B * SECONDS / dt > best_v:
             best_B, best_v = B, B * SECONDS / dt
     x = O.synth_batch(best_B, L_UTT, seed=4321)
     for _ in range(args.warmup):
-        O.enhance(W, x)
+        ref.enhance(x)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.enhance(W, x)
+        ref.enhance(x)
     dt = time.perf_counter() - t0
     value = best_B * SECONDS * args.steps / dt
-    sample = f"{best_B} x {SECONDS} s utterances per step (bounded sample of the 1024-utterance batch), torch {torch.__version__} CPU, {cores} threads"
+    what = "the reference's own GTCRNMicro between torch.stft / torch.istft (baseline/_ref)" if ref.kind == "reference" else "oracle port of the reference"
+    sample = (f"{what}: {best_B} x {SECONDS} s utterances per step (bounded sample of the 1024-utterance batch), "
+              f"torch {torch.__version__} CPU, {cores} threads")
     emit({
         "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"GTCRN-Micro offline batched inference, 1024 x {SECONDS} s synthetic 16 kHz utterances per GPU (configs[1]); CPU arm times a bounded sample"},
-        "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": ref.kind, "sample": sample,
+                         "streaming": cpu_streaming(ref)},
         "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
@@ -207,40 +299,132 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def bench_streaming(G, model, device, n_list=(4096, 16384, 65536), hops=60, warm=10):
-    """Per-hop latency of the frame-by-frame path (spectral frames in, spectral frames out)."""
-    res = {}
+STREAM_HOP_BYTES = 93_000                 # minimal HBM bytes per stream-hop (2 KB audio + 88.7 KB ring-buffer state + activations)
+
+
+def _hop_stats(ms):
+    ms = sorted(ms)
+    return {"hop_ms_p50": round(ms[len(ms) // 2], 4), "hop_ms_p99": round(ms[min(len(ms) - 1, int(0.99 * len(ms)))], 4), "hop_ms_max": round(ms[-1], 4)}
+
+
+def _stream_wav_hops(smodel, N, device, hops, warm=10):
+    """`hops` real-time hops for N streams, wav in / wav out through PINNED HOST buffers: per hop H2D of [N,256] new samples,
+    gtcrnb_stream_step_wav, D2H of [N,256] enhanced samples, all inside the hop's CUDA-event bracket."""
+    st = smodel.new_state(N, device)
+    g = torch.Generator().manual_seed(N)
+    hin = [torch.empty(N, 256, pin_memory=True).copy_(0.1 * torch.randn(N, 256, generator=g)) for _ in range(4)]
+    hout = torch.empty(N, 256, pin_memory=True)
+    din, dout = torch.empty(N, 256, device=device), torch.empty(N, 256, device=device)
+
+    def hop(i):
+        din.copy_(hin[i % 4], non_blocking=True)
+        smodel.step_wav(din, st, dout)
+        hout.copy_(dout, non_blocking=True)
+    for i in range(warm):
+        hop(i)
+    torch.cuda.synchronize(device)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(hops)]
+    for i in range(hops):
+        evs[i][0].record()
+        hop(i)
+        evs[i][1].record()
+    torch.cuda.synchronize(device)
+    ok = bool(torch.isfinite(hout).all())
+    del st
+    return [a.elapsed_time(b) for a, b in evs], ok
+
+
+def _stream_spec_hops(smodel, N, device, hops, warm=10):
+    """device-resident view: spectral frames in / out, no copies (kernel time of one hop)."""
+    st = smodel.new_state(N, device)
+    g = torch.Generator(device=device).manual_seed(99)
+    frames = [torch.randn(N, 257, 2, device=device, generator=g) for _ in range(4)]
+    out = torch.empty(N, 257, 2, device=device)
+    for i in range(warm):
+        smodel.step(frames[i % 4], st, out)
+    torch.cuda.synchronize(device)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(hops)]
+    for i in range(hops):
+        evs[i][0].record()
+        smodel.step(frames[i % 4], st, out)
+        evs[i][1].record()
+    torch.cuda.synchronize(device)
+    del st
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def bench_streaming(G, model, device, hbm_peak, n_list=(4096, 16384), hops=625, max_search=True):
+    """BASELINE configs[2]: per-hop latency (p50 / p99 / max over >= 625 hops) of the frame-by-frame path against the 16 ms
+    deadline, wav-in / wav-out with the host<->device copies inside every hop, plus the device-resident kernel view and the
+    largest stream count whose WORST hop still meets the deadline (doubling + bisection, confirmed over `hops` hops)."""
+    res = {"deadline_ms": 16.0, "hops": hops, "io": "wav in / wav out, pinned host buffers, H2D + D2H of N x 256 samples inside every hop",
+           "latency_contract": "output lags input by 512 samples (32 ms); gtcrnb_stream_flush_wav emits the last two hops"}
     smodel = G.StreamGTCRNMicro()
     G.convert_to_stream(smodel, model)
-    g = torch.Generator(device=device).manual_seed(99)
     for N in n_list:
-        st = smodel.new_state(N, device)
-        frames = [torch.randn(N, 257, 2, device=device, generator=g) for _ in range(4)]
-        out = torch.empty(N, 257, 2, device=device)
-        for i in range(warm):
-            smodel.step(frames[i % 4], st, out)
-        torch.cuda.synchronize(device)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(hops)]
-        for i in range(hops):
-            evs[i][0].record()
-            smodel.step(frames[i % 4], st, out)
-            evs[i][1].record()
-        torch.cuda.synchronize(device)
-        ms = sorted(a.elapsed_time(b) for a, b in evs)
-        res[str(N)] = {"hop_ms_p50": round(ms[len(ms) // 2], 4), "hop_ms_p99": round(ms[min(len(ms) - 1, int(0.99 * len(ms)))], 4),
-                       "hop_ms_max": round(ms[-1], 4), "realtime": ms[-1] < 16.0,
-                       "streams_at_deadline_est": int(N * 16.0 / ms[-1])}
-        del st, frames, out
+        ms, ok = _stream_wav_hops(smodel, N, device, hops)
+        r = _hop_stats(ms)
+        r["realtime"] = r["hop_ms_max"] < 16.0 and ok
+        spec_ms = sorted(_stream_spec_hops(smodel, N, device, 100))
+        r["device_resident_spec_hop_ms_p50"] = round(spec_ms[len(spec_ms) // 2], 4)
+        r["ns_per_frame"] = round(1e6 * r["device_resident_spec_hop_ms_p50"] / N, 2)
+        gbs = STREAM_HOP_BYTES * N / (r["device_resident_spec_hop_ms_p50"] * 1e-3) / 1e9
+        r["roofline"] = {"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
+                         "bytes_per_stream_hop": STREAM_HOP_BYTES}
+        res[str(N)] = r
         torch.cuda.empty_cache()
-    ok = [int(n) for n, v in res.items() if v["realtime"]]
-    res["max_realtime_streams_tested"] = max(ok) if ok else 0
-    res["deadline_ms"] = 16.0
+    if max_search:
+        def worst(N, h):
+            ms, ok = _stream_wav_hops(smodel, N, device, h, warm=5)
+            torch.cuda.empty_cache()
+            return max(ms) if ok else float("inf")
+        free = torch.cuda.mem_get_info(device)[0]
+        cap = int(free * 0.7 // (38880 * 4 + 27 * 1024 + 4096))          # state + per-hop workspace per stream
+        lo, hi = max(n_list), None
+        n = lo * 2
+        while hi is None and n <= cap:
+            if worst(n, 40) < 16.0:
+                lo, n = n, n * 2
+            else:
+                hi = n
+        if hi is None:
+            hi = min(cap, n)
+        while hi - lo > max(1024, lo // 32):
+            mid = (lo + hi) // 2 // 256 * 256
+            if worst(mid, 40) < 16.0:
+                lo = mid
+            else:
+                hi = mid
+        ms, ok = _stream_wav_hops(smodel, lo, device, hops)
+        while (max(ms) >= 16.0 or not ok) and lo > max(n_list):          # confirmation over the full hop count; back off 3 % at a time
+            lo = int(lo * 0.97) // 256 * 256
+            ms, ok = _stream_wav_hops(smodel, lo, device, hops)
+        r = _hop_stats(ms)
+        r["streams"] = lo
+        r["memory_cap_streams"] = cap
+        res["max_realtime_streams"] = r
+        torch.cuda.empty_cache()
     return res
+
+
+PARITY_IDX = [0, 1, 63, 64, 127, 128, 255, 256, 511, 512, 700, 767, 768, 900, 1022, 1023]
+
+
+def parity_of_timed_batch(x_sub: torch.Tensor, clean_sub: torch.Tensor, y_sub: torch.Tensor) -> dict:
+    """CHECKER leg (the only place the B200 arm touches oracle/): the oracle's CPU restatement of the reference run on a fixed
+    16-utterance subset of the batch that was just timed, compared with the timed run's own output rows."""
+    import gtcrn_oracle as O
+    W = O.load_weights_npz(WEIGHTS)
+    ref = O.enhance(W, x_sub)
+    n = ref.shape[1]
+    err = float((y_sub - ref).abs().max())
+    d = max(abs(O.si_snr(clean_sub[i, :n].numpy(), y_sub[i].numpy()) - O.si_snr(clean_sub[i, :n].numpy(), ref[i].numpy())) for i in range(ref.shape[0]))
+    return {"max_abs": err, "si_snr_delta_db": round(d, 6), "n": int(ref.shape[0]), "tolerance": {"max_abs": 1e-4, "si_snr_delta_db": 0.01},
+            "against": "oracle/gtcrn_oracle.py on the same 16 utterances of the timed batch", "ok": bool(err <= 1e-4 and d <= 0.01)}
 
 
 def run_b200(args):
     import gtcrn_micro_b200 as G
-    import gtcrn_oracle as O
     from gtcrn_micro_b200 import build
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -255,12 +439,13 @@ def run_b200(args):
         build.build()
     if world > 1:
         dist.barrier()
-    W = O.load_weights_npz(WEIGHTS)                      # weights only; the oracle's compute is not used on this arm
     model = G.GTCRNMicro()
-    model.load_state_dict(W)
+    model.load_state_dict(G.load_state_dict_npz(WEIGHTS))
 
     B = args.batch
-    x = synth_on_device(B, L_UTT, device, seed=1234 + rank * B)      # 655 MB per rank, > L2 (126 MB)
+    pidx = [i for i in PARITY_IDX if i < B]
+    clean_rows = [None] * len(pidx)
+    x = synth_on_device(B, L_UTT, device, seed=1234 + rank * B, keep_clean=(pidx, clean_rows))      # 655 MB per rank, > L2 (126 MB)
     # warm-up (also sizes the workspace) ----------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         y = model.enhance(x)
@@ -286,6 +471,7 @@ def run_b200(args):
     prof = model.profile_read(reset=True)
     model.profile(False)
     assert bool(torch.isfinite(y).all())
+    x_sub, y_sub = x[pidx].cpu(), y[pidx].cpu()            # rows of the batch that was timed / of the last timed step's output
 
     # e2e: pinned host buffers through the C-ABI host entry point ----------------------------------
     xh = torch.empty((B, L_UTT), dtype=torch.float32, pin_memory=True)
@@ -378,16 +564,28 @@ def run_b200(args):
     }
     if not args.no_stream:
         try:
-            line["streaming"] = bench_streaming(G, model, device)
+            line["streaming"] = bench_streaming(G, model, device, hbm_peak, max_search=(world == 1))
         except Exception as e:  # streaming is reported, never allowed to sink the offline number
             line["streaming"] = {"error": f"{type(e).__name__}: {e}"}
+    if not args.no_parity:
+        line["parity"] = parity_of_timed_batch(x_sub, torch.stack(clean_rows), y_sub)
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v, detail = cpu_throughput((1, 4, 16, 64), reps=2, budget_s=45.0)
-        line["cpu_baseline"] = {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"oracle port (torch {torch.__version__} CPU, same ATen ops as the reference), {SECONDS} s utterances, "
-                                          f"best of B in {detail} (1 warm-up + best of 2 each); 1024-utterance batch extrapolated from this sample"}
+        ref = CpuReference()
+        v, detail = cpu_throughput(ref, (1, 4, 16, 64), reps=2, budget_s=45.0)
+        what = "the reference's own GTCRNMicro between torch.stft / torch.istft (baseline/_ref)" if ref.kind == "reference" else "oracle port (same ATen ops as the reference)"
+        line["cpu_baseline"] = {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": ref.kind,
+                                "sample": f"{what}, torch {torch.__version__} CPU, {SECONDS} s utterances, "
+                                          f"best of B in {detail} (1 warm-up + best of 2 each); 1024-utterance batch extrapolated from this sample",
+                                "streaming": cpu_streaming(ref)}
+        if "streaming" in line and "max_realtime_streams" in line["streaming"]:
+            line["streaming"]["vs_host_cpu"] = round(line["streaming"]["max_realtime_streams"]["streams"] / max(1, line["cpu_baseline"]["streaming"]["max_realtime_streams"]), 1)
     emit(line)
+    if "parity" in line and not line["parity"]["ok"]:
+        sys.stderr.write(f"bench: PARITY FAILURE on the timed batch: {line['parity']}\n")
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        sys.exit(3)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
@@ -413,6 +611,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="utterances per GPU per step (BASELINE configs[1]: 1024)")
     ap.add_argument("--no-stream", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch (A/B runs only)")
     ap.add_argument("--sweep-utterances", type=int, default=0,
                     help="BASELINE configs[4]: a fixed job of this many 10 s utterances (65536) sharded over the ranks in contiguous "
                          "blocks (shard.shard_range); sets --steps to the rank's share / --batch and reports scaling 'strong'")

@@ -6,8 +6,8 @@ forward contract and state_dict keys) in front of hand-written CUDA kernels reac
 """
 from .lib import GtcrnB200Error  # noqa: F401
 from .modules import (GTCRNMicro, StreamGTCRNMicro, StreamState, convert_to_stream,  # noqa: F401
-                      load_checkpoint, param_spec, pinned_empty)
+                      load_checkpoint, load_state_dict_npz, param_spec, pinned_empty)
 from .pack import blob_size, pack_state_dict  # noqa: F401
 
 __all__ = ["GTCRNMicro", "StreamGTCRNMicro", "StreamState", "convert_to_stream", "load_checkpoint",
-           "pack_state_dict", "blob_size", "param_spec", "pinned_empty", "GtcrnB200Error"]
+           "load_state_dict_npz", "pack_state_dict", "blob_size", "param_spec", "pinned_empty", "GtcrnB200Error"]

@@ -517,6 +517,12 @@ def pinned_empty(shape, write_combined: bool = False) -> torch.Tensor:
     return t.view(*shape)
 
 
+def load_state_dict_npz(path: str) -> dict:
+    """state_dict saved as .npz (keys = reference state_dict keys; the fixtures under tests/golden) -> dict of tensors."""
+    z = np.load(path)
+    return {k: torch.from_numpy(np.array(z[k])) for k in z.files}
+
+
 def load_checkpoint(path: str, stream: bool = False, map_location="cpu", unsafe: bool = False) -> nn.Module:
     """Build a model from a reference training checkpoint `{"epoch","optimizer","scheduler","model"}`
     (train.py:206-211); also tolerates a bare state_dict, `state_dict`/`model_state_dict` keys and a DDP
