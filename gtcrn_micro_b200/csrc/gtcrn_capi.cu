@@ -12,6 +12,7 @@
 #include "../../include/gtcrn_b200.h"
 #include "gtcrn_kernels.cuh"
 #include "gtcrn_stream.cuh"
+#include "gtcrn_full_host.cuh"
 
 namespace {
 
@@ -38,7 +39,8 @@ constexpr int64_t kMaxChunkFrames = 1024 * 1024;  // activation workspace capaci
 constexpr int kNumAct33 = 9;                      // en1..en4, gtcn1, gtcn2, de0..de2
 const char* const kActNames[kNumAct33] = {"en1", "en2", "en3", "en4", "gtcn1", "gtcn2", "de0", "de1", "de2"};
 
-enum KernelClass { KC_STFT = 0, KC_FRONT, KC_ENC_GT, KC_GTCN, KC_DEC_GT, KC_BACK, KC_ISTFT, KC_STREAM, kNumKernelClasses };
+enum KernelClass { KC_STFT = 0, KC_FRONT, KC_ENC_GT, KC_GTCN, KC_DEC_GT, KC_BACK, KC_ISTFT, KC_STREAM,
+                   KC_FULL_ENC_GT, KC_DP_INTRA, KC_DP_INTER, KC_FULL_DEC_GT, kNumKernelClasses };
 struct ProfEvent { int cls; int64_t frames; cudaEvent_t e0, e1; };
 
 }  // namespace
@@ -47,7 +49,9 @@ struct gtcrnb_handle {
     int device = 0;
     int sm_count = 148;
     float* blob = nullptr;
+    int variant = 0;                              // 0 GTCRN-Micro, 1 original-GTCRN-style (BASELINE configs[3])
     gs::HostParams* hp = nullptr;                 // host copies of the weight chunks passed as kernel parameters
+    gf::HostParams* hpf = nullptr;                // same for variant 1
     bool fuse_fft = true;                         // fuse STFT / iSTFT into the front / back kernels in gtcrnb_enhance
     bool tcn_smem_w = false;                      // GTCN weights from shared memory (LDS.128) instead of the constant bank; with FFMA2 the
                                                   // constant-bank feed wins (B200: 4.73 vs 5.67 ms per 1024 x 10 s), before FFMA2 smem won (6.4 vs 7.3)
@@ -206,9 +210,8 @@ int pick_seg_len(int64_t ctas_per_seg_row, int T, int gran, int warm, int slots)
 
 // Fused wav -> wav mode (wav != nullptr): the STFT runs inside k_front (spectrum parked in h->spec_in for the mask stage)
 // and the iSTFT + overlap-add inside k_back (wav_out must be zeroed by the caller).
-int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t B, int64_t T, float* out,
-              const int64_t os[4], cudaStream_t st, const float* wav = nullptr, int64_t wav_stride = 0, int L = 0,
-              float* wav_out = nullptr, int64_t wav_out_stride = 0) {
+int run_model_full(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t B, int64_t T, float* out,
+                   const int64_t os[4], cudaStream_t st, const float* wav, int64_t wav_stride, int L, float* wav_out, int64_t wav_out_stride) {
     using namespace gk;
     const int Ti = (int)T;
     const int64_t nframes = B * T;
@@ -217,10 +220,46 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
     {
         ProfScope ps(h, KC_FRONT, nframes, st);
         if (fused)
-            k_front<true><<<gfr, FR_THREADS, fr_smem_floats(true) * sizeof(float), st>>>(nullptr, 0, 0, 0, 0, wav, wav_stride, L, h->spec_in,
+            k_front<true, 1><<<gfr, FR_THREADS, fr_smem_floats(true) * sizeof(float), st>>>(nullptr, 0, 0, 0, 0, wav, wav_stride, L, h->spec_in,
+                                                                                            Ti, nframes, h->blob, h->hpf->front, h->en0, h->act[0]);
+        else
+            k_front<false, 1><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, is[0], is[1], is[2], is[3], nullptr, 0, 0, nullptr,
+                                                                                              Ti, nframes, h->blob, h->hpf->front, h->en0, h->act[0]);
+    }
+    static const int kCls[4] = {KC_FULL_ENC_GT, KC_DP_INTRA, KC_DP_INTER, KC_FULL_DEC_GT};
+    h->launches += 1 + gf::run_body(h->blob, *h->hpf, h->act, B, Ti, nullptr, st, [&](int c, int64_t fr) { return ProfScope(h, kCls[c], fr, st); });
+    {
+        ProfScope ps(h, KC_BACK, nframes, st);
+        if (fused) {
+            const int64_t ss[4] = {T * kSpecFrame, 2, kSpecFrame, 1};
+            k_back<true, 1><<<gbk, BK_THREADS, bk_smem_floats(true) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, h->spec_in, ss[0], ss[1], ss[2], ss[3],
+                                                                                           nullptr, 0, 0, 0, 0, wav_out, wav_out_stride, Ti, nframes, h->blob, h->hpf->back);
+        } else {
+            k_back<false, 1><<<gbk, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, spec, is[0], is[1], is[2], is[3],
+                                                                                             out, os[0], os[1], os[2], os[3], nullptr, 0, Ti, nframes, h->blob, h->hpf->back);
+        }
+    }
+    h->launches++;
+    CU(cudaGetLastError());
+    return GTCRNB_OK;
+}
+
+int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t B, int64_t T, float* out,
+              const int64_t os[4], cudaStream_t st, const float* wav = nullptr, int64_t wav_stride = 0, int L = 0,
+              float* wav_out = nullptr, int64_t wav_out_stride = 0) {
+    using namespace gk;
+    if (h->variant == 1) return run_model_full(h, spec, is, B, T, out, os, st, wav, wav_stride, L, wav_out, wav_out_stride);
+    const int Ti = (int)T;
+    const int64_t nframes = B * T;
+    const dim3 gfr((unsigned)((nframes + FR_NF - 1) / FR_NF)), gbk((unsigned)((nframes + BK_NF - 1) / BK_NF));
+    const bool fused = wav != nullptr;
+    {
+        ProfScope ps(h, KC_FRONT, nframes, st);
+        if (fused)
+            k_front<true, 0><<<gfr, FR_THREADS, fr_smem_floats(true) * sizeof(float), st>>>(nullptr, 0, 0, 0, 0, wav, wav_stride, L, h->spec_in,
                                                                                          Ti, nframes, h->blob, h->hp->front, h->en0, h->act[0]);
         else
-            k_front<false><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, is[0], is[1], is[2], is[3], nullptr, 0, 0, nullptr,
+            k_front<false, 0><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, is[0], is[1], is[2], is[3], nullptr, 0, 0, nullptr,
                                                                                            Ti, nframes, h->blob, h->hp->front, h->en0, h->act[0]);
     }
     h->launches++;
@@ -261,10 +300,10 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
         ProfScope ps(h, KC_BACK, nframes, st);
         if (fused) {
             const int64_t ss[4] = {T * kSpecFrame, 2, kSpecFrame, 1};
-            k_back<true><<<gbk, BK_THREADS, bk_smem_floats(true) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, h->spec_in, ss[0], ss[1], ss[2], ss[3],
+            k_back<true, 0><<<gbk, BK_THREADS, bk_smem_floats(true) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, h->spec_in, ss[0], ss[1], ss[2], ss[3],
                                                                                         nullptr, 0, 0, 0, 0, wav_out, wav_out_stride, Ti, nframes, h->blob, h->hp->back);
         } else {
-            k_back<false><<<gbk, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, spec, is[0], is[1], is[2], is[3],
+            k_back<false, 0><<<gbk, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, spec, is[0], is[1], is[2], is[3],
                                                                                           out, os[0], os[1], os[2], os[3], nullptr, 0, Ti, nframes, h->blob, h->hp->back);
         }
     }
@@ -305,17 +344,25 @@ void* gtcrnb_host_alloc_wc(size_t bytes) {
 }
 void gtcrnb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
-int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) {
+size_t gtcrnb_blob_floats_variant(int variant) { return variant == 1 ? (size_t)blobf::kBlobFloats : variant == 0 ? (size_t)blob::kBlobFloats : 0; }
+
+int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) { return gtcrnb_create_variant(blob_host, n_floats, GTCRNB_VARIANT_MICRO, out); }
+
+int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, gtcrnb_handle** out) {
     if (!blob_host || !out) return fail(GTCRNB_E_INVALID, "gtcrnb_create: NULL argument");
-    if (n_floats != (size_t)blob::kBlobFloats) return fail(GTCRNB_E_BLOB, "weight blob has %zu floats, expected %d", n_floats, blob::kBlobFloats);
-    if (blob_host[0] != blob::kVersion || blob_host[1] != (float)blob::kBlobFloats)
-        return fail(GTCRNB_E_BLOB, "weight blob version %.1f / size %.0f does not match library (%.1f / %d)", blob_host[0], blob_host[1], blob::kVersion, blob::kBlobFloats);
+    if (variant != GTCRNB_VARIANT_MICRO && variant != GTCRNB_VARIANT_FULL) return fail(GTCRNB_E_INVALID, "gtcrnb_create: unknown variant %d", variant);
+    const int want_n = variant == 1 ? blobf::kBlobFloats : blob::kBlobFloats;
+    const float want_v = variant == 1 ? blobf::kVersion : blob::kVersion;
+    if (n_floats != (size_t)want_n) return fail(GTCRNB_E_BLOB, "weight blob has %zu floats, expected %d (variant %d)", n_floats, want_n, variant);
+    if (blob_host[0] != want_v || blob_host[1] != (float)want_n)
+        return fail(GTCRNB_E_BLOB, "weight blob version %.1f / size %.0f does not match library (%.1f / %d, variant %d)", blob_host[0], blob_host[1], want_v, want_n, variant);
     int dev = 0;
     CU(cudaGetDevice(&dev));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) return fail(GTCRNB_E_ARCH, "device %s is sm_%d%d; this library contains sm_100a code only", prop.name, prop.major, prop.minor);
     gtcrnb_handle* h = new gtcrnb_handle();
+    h->variant = variant;
     h->device = dev;
     h->sm_count = prop.multiProcessorCount;
     if (cudaMalloc(&h->blob, sizeof(float) * n_floats) != cudaSuccess) { delete h; return fail(GTCRNB_E_NOMEM, "cudaMalloc(blob) failed"); }
@@ -324,9 +371,9 @@ int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) 
     }
     using namespace gk;
     struct { const void* fn; int floats; } attrs[] = {
-        {(const void*)k_front<false>, fr_smem_floats(false)}, {(const void*)k_front<true>, fr_smem_floats(true)},
+        {(const void*)k_front<false, 0>, fr_smem_floats(false)}, {(const void*)k_front<true, 0>, fr_smem_floats(true)},
         {(const void*)k_gtcn<2, false>, wc_smem_floats(2)}, {(const void*)k_gtcn<2, true>, wc_smem_floats(2, true)},
-        {(const void*)k_back<false>, bk_smem_floats(false)}, {(const void*)k_back<true>, bk_smem_floats(true)},
+        {(const void*)k_back<false, 0>, bk_smem_floats(false)}, {(const void*)k_back<true, 0>, bk_smem_floats(true)},
         {(const void*)k_stft, 0},
         {(const void*)k_istft, 0},
     };
@@ -342,6 +389,14 @@ int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out) 
     }
     int e2 = gs::stream_init_attributes();
     if (e2 != 0) { gtcrnb_destroy(h); return fail(GTCRNB_E_CUDA, "stream kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e2)); }
+    if (variant == 1) {
+        const int e3 = gf::init_attributes();
+        if (e3 != 0) { gtcrnb_destroy(h); return fail(GTCRNB_E_CUDA, "variant-1 kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e3)); }
+        h->hpf = new gf::HostParams();
+        h->hpf->load(blob_host);
+        *out = h;
+        return GTCRNB_OK;
+    }
     h->hp = new gs::HostParams();
     h->hp->load(blob_host);
     auto pick = [](const char* env, int dflt) {
@@ -376,6 +431,7 @@ void gtcrnb_destroy(gtcrnb_handle* h) {
     freep(h->parked.en0); freep(h->parked.spec_in); freep(h->parked.spec_out);
     for (auto p : h->parked.act) freep(p);
     delete h->hp;
+    delete h->hpf;
     for (auto p : h->act) freep(p);
     for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
         freep(h->stage_in[i]); freep(h->stage_out[i]);
@@ -649,8 +705,9 @@ int gtcrnb_debug_activation(gtcrnb_handle* h, const char* name, float* out_dev, 
     const float* src = nullptr;
     size_t per_frame = gk::kF2 * 16;
     if (!strcmp(name, "en0")) { src = h->en0; per_frame = gk::kF1 * 16; }
+    static const char* const kActNamesFull[kNumAct33] = {"en1", "en2", "en3", "en4", "dp1", "dp2", "de0", "de1", "de2"};
     for (int i = 0; i < kNumAct33 && !src; ++i)
-        if (!strcmp(name, kActNames[i])) src = h->act[i];
+        if (!strcmp(name, h->variant == 1 ? kActNamesFull[i] : kActNames[i])) src = h->act[i];
     if (!src) return fail(GTCRNB_E_INVALID, "unknown activation '%s'", name);
     const size_t have = per_frame * (size_t)(h->last_B * h->last_T);
     if (n_floats > have) return fail(GTCRNB_E_INVALID, "activation '%s' holds %zu floats, %zu requested", name, have, n_floats);
@@ -700,16 +757,18 @@ int gtcrnb_profile_read(gtcrnb_handle* h, int reset, double* ms_out, int64_t* la
 
 int gtcrnb_profile_num_classes(void) { return kNumKernelClasses; }
 const char* gtcrnb_profile_class_name(int i) {
-    static const char* const names[kNumKernelClasses] = {"stft", "front", "enc_gtconv", "gtcn", "dec_gtconv", "back", "istft", "stream"};
+    static const char* const names[kNumKernelClasses] = {"stft", "front", "enc_gtconv", "gtcn", "dec_gtconv", "back", "istft", "stream",
+                                                         "full_enc_gtconv", "dp_intra", "dp_inter", "full_dec_gtconv"};
     return (i >= 0 && i < kNumKernelClasses) ? names[i] : "";
 }
 
 // ---------------------------------------------------------------- streaming
 size_t gtcrnb_stream_state_bytes(int64_t N) { return N < 0 ? 0 : gs::state_bytes(N); }
+size_t gtcrnb_stream_state_bytes_variant(int variant, int64_t N) { return N < 0 ? 0 : variant == 1 ? gf::state_bytes(N) : variant == 0 ? gs::state_bytes(N) : 0; }
 
 int gtcrnb_stream_reset(gtcrnb_handle* h, void* state_dev, int64_t N, void* stream) {
     if (!h || !state_dev || N < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_reset: bad argument");
-    CU(cudaMemsetAsync(state_dev, 0, gs::state_bytes(N), (cudaStream_t)stream));
+    CU(cudaMemsetAsync(state_dev, 0, h->variant == 1 ? gf::state_bytes(N) : gs::state_bytes(N), (cudaStream_t)stream));
     return GTCRNB_OK;
 }
 
@@ -727,6 +786,8 @@ int stream_step_impl(gtcrnb_handle* h, int kind, void* state, const float* in, f
     int rc = ensure_workspace(h, N);
     if (rc) return rc;
     auto direct = [&](cudaStream_t s) {
+        if (h->variant == 1)
+            return kind ? gf::step_wav(h->blob, *h->hpf, state, stream_ws(h), in, out, N, s) : gf::step_spec(h->blob, *h->hpf, state, stream_ws(h), in, out, N, s);
         return kind ? gs::step_wav(h->blob, *h->hp, state, stream_ws(h), in, out, N, s) : gs::step_spec(h->blob, *h->hp, state, stream_ws(h), in, out, N, s);
     };
     if (!h->stream_graphs || h->profiling || h->ws_cur != 0) {
@@ -798,7 +859,8 @@ int gtcrnb_stream_flush_wav(gtcrnb_handle* h, void* state_dev, const float* tail
     if (N > 2147483647LL) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_flush_wav: too many streams");
     int rc = ensure_workspace(h, N);
     if (rc) return rc;
-    h->launches += gs::flush_wav(h->blob, *h->hp, state_dev, stream_ws(h), tail_dev, (int)tail_len, out_dev, N, (cudaStream_t)stream);
+    if (h->variant == 1) h->launches += gf::flush_wav(h->blob, *h->hpf, state_dev, stream_ws(h), tail_dev, (int)tail_len, out_dev, N, (cudaStream_t)stream);
+    else h->launches += gs::flush_wav(h->blob, *h->hp, state_dev, stream_ws(h), tail_dev, (int)tail_len, out_dev, N, (cudaStream_t)stream);
     CU(cudaGetLastError());
     note_user_work(h, (cudaStream_t)stream);
     return GTCRNB_OK;
@@ -807,6 +869,7 @@ int gtcrnb_stream_flush_wav(gtcrnb_handle* h, void* state_dev, const float* tail
 int gtcrnb_stream_import_caches(gtcrnb_handle* h, void* state_dev, int64_t N, const float* conv_cache_dev, const float* tra_cache_dev,
                                 const float* const tcn_cache_dev[8], void* stream) {
     if (!h || !state_dev || !conv_cache_dev || !tra_cache_dev || !tcn_cache_dev || N < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_import_caches: bad argument");
+    if (h->variant != 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_import_caches: the reference cache layout exists for GTCRN-Micro only");
     if (N == 0) return GTCRNB_OK;
     h->launches += gs::convert_caches(true, state_dev, N, const_cast<float*>(conv_cache_dev), const_cast<float*>(tra_cache_dev),
                                       const_cast<float* const*>(tcn_cache_dev), (cudaStream_t)stream);
@@ -817,6 +880,7 @@ int gtcrnb_stream_import_caches(gtcrnb_handle* h, void* state_dev, int64_t N, co
 int gtcrnb_stream_export_caches(gtcrnb_handle* h, const void* state_dev, int64_t N, float* conv_cache_dev, float* tra_cache_dev,
                                 float* const tcn_cache_dev[8], void* stream) {
     if (!h || !state_dev || !conv_cache_dev || !tra_cache_dev || !tcn_cache_dev || N < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_export_caches: bad argument");
+    if (h->variant != 0) return fail(GTCRNB_E_INVALID, "gtcrnb_stream_export_caches: the reference cache layout exists for GTCRN-Micro only");
     if (N == 0) return GTCRNB_OK;
     h->launches += gs::convert_caches(false, const_cast<void*>(state_dev), N, conv_cache_dev, tra_cache_dev, tcn_cache_dev, (cudaStream_t)stream);
     CU(cudaGetLastError());

@@ -26,6 +26,7 @@
 #include <utility>
 
 #include "blob_layout.h"
+#include "blob_full_layout.h"
 
 namespace gk {
 
@@ -369,13 +370,39 @@ constexpr int FR_FFT_FLOATS = 1540;         // FftTables: tw256 (512) + tw512 (5
 static_assert(sizeof(FftTables) == FR_FFT_FLOATS * 4, "FftTables layout");
 __host__ __device__ constexpr int fr_smem_floats(bool from_wav) { return FR_W_FLOATS + FR_NF * FR_SLOT + (from_wav ? FR_FFT_FLOATS : 0); }
 
+// Model variant of the per-frame front / back kernels.  VAR 0: GTCRN-Micro (SFE-Lite, dense en1 / de3).  VAR 1: original-GTCRN-style
+// (BASELINE configs[3]): unfold SFE -- en0 contracts 9 channels x 5 taps (gtcrn_micro.py:346 `# 3 * 3,  # SFE`) -- and en1 / de3 with
+// groups = 2 (gtcrn_micro.py:361,448 `# groups=2`).  The ERB / SFE tables sit at the same offsets in both blob layouts.
+template <int VAR> struct FrontL;
+template <> struct FrontL<0> {
+    static constexpr int SIZE = blob::FRONT_SIZE, EN0_W = blob::FRONT_EN0_W, EN0_B = blob::FRONT_EN0_B, EN1_W = blob::FRONT_EN1_W,
+                         EN1_B = blob::FRONT_EN1_B, SLOPE = blob::FRONT_SLOPE, OFF = blob::FRONT_OFF, FFT = blob::FFT_OFF;
+};
+template <> struct FrontL<1> {
+    static constexpr int SIZE = blobf::FRONT_SIZE, EN0_W = blobf::FRONT_EN0_W, EN0_B = blobf::FRONT_EN0_B, EN1_W = blobf::FRONT_EN1_W,
+                         EN1_B = blobf::FRONT_EN1_B, SLOPE = blobf::FRONT_SLOPE, OFF = blobf::FRONT_OFF, FFT = blobf::FFT_OFF;
+};
+static_assert(blob::FRONT_EN0_W == blobf::FRONT_EN0_W && blob::FRONT_ERB_W == blobf::FRONT_ERB_W && blob::FRONT_SFE_W == blobf::FRONT_SFE_W &&
+              blob::FFT_OFF == blobf::FFT_OFF && blob::FFT_SIZE == blobf::FFT_SIZE, "front tables share their offsets between the variants");
+template <int VAR> struct BackL;
+template <> struct BackL<0> {
+    static constexpr int SIZE = blob::BACK_SIZE, OFF = blob::BACK_OFF, DE3_W = blob::BACK_DE3_W, DE3_B = blob::BACK_DE3_B, DE4_W = blob::BACK_DE4_W,
+                         DE4_B = blob::BACK_DE4_B, IERB_B0 = blob::BACK_IERB_B0, IERB_W = blob::BACK_IERB_W, SLOPE = blob::BACK_SLOPE;
+};
+template <> struct BackL<1> {
+    static constexpr int SIZE = blobf::BACK_SIZE, OFF = blobf::BACK_OFF, DE3_W = blobf::BACK_DE3_W, DE3_B = blobf::BACK_DE3_B, DE4_W = blobf::BACK_DE4_W,
+                         DE4_B = blobf::BACK_DE4_B, IERB_B0 = blobf::BACK_IERB_B0, IERB_W = blobf::BACK_IERB_W, SLOPE = blobf::BACK_SLOPE;
+};
+
 // en1 for one output-channel half H (compile-time so the weight indices stay warp-uniform): thread = 2 slots x 8 co at one f''
-template <int H, class PB>
+// VAR 1 (groups = 2): half H only sees input channels 8H .. 8H+7 (ci quads 2H, 2H+1), weights [k][ci][co within the group]
+template <int H, int VAR, class PB>
 __device__ __forceinline__ void front_en1(const PB& prm, const float* slots, int r, int64_t fi0, int64_t nframes, float* __restrict__ en1) {
+    using L = FrontL<VAR>;
     const int sp2 = r / kF2, f = r - sp2 * kF2, s0 = 2 * sp2, s1 = s0 + 1;
     float acc0[8], acc1[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc0[c] = acc1[c] = prm.w[blob::FRONT_EN1_B + 8 * H + c];
+    for (int c = 0; c < 8; ++c) acc0[c] = acc1[c] = prm.w[L::EN1_B + 8 * H + c];
     const float4* i0p = reinterpret_cast<const float4*>(slots + s0 * FR_SLOT) + f;
     const float4* i1p = reinterpret_cast<const float4*>(slots + s1 * FR_SLOT) + f;
 #if GTCRNB_EN1_UNROLL
@@ -386,20 +413,21 @@ __device__ __forceinline__ void front_en1(const PB& prm, const float* slots, int
     for (int k = 0; k < 5; ++k) {
         const int po = (k & 1) * 35 + (k >> 1);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = (VAR == 1 ? 2 * H : 0); q < (VAR == 1 ? 2 * H + 2 : 4); ++q) {
             const float4 x0 = i0p[q * 70 + po], x1 = i1p[q * 70 + po];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int c = 0; c < 8; c += 2) {
-                    const float w0 = prm.w[blob::FRONT_EN1_W + (k * 16 + 4 * q + i) * 16 + 8 * H + c];
-                    const float w1 = prm.w[blob::FRONT_EN1_W + (k * 16 + 4 * q + i) * 16 + 8 * H + c + 1];
+                    const int wi = VAR == 1 ? L::EN1_W + (k * 16 + 4 * q + i) * 8 + c : L::EN1_W + (k * 16 + 4 * q + i) * 16 + 8 * H + c;
+                    const float w0 = prm.w[wi];
+                    const float w1 = prm.w[wi + 1];
                     fma_pair(acc0[c], acc0[c + 1], f4get(x0, i), w0, w1);
                     fma_pair(acc1[c], acc1[c + 1], f4get(x1, i), w0, w1);
                 }
         }
     }
-    const float a = prm.w[blob::FRONT_SLOPE + 1];
+    const float a = prm.w[L::SLOPE + 1];
 #pragma unroll
     for (int c = 0; c < 8; c += 2) { prelu_pair(acc0[c], acc0[c + 1], a); prelu_pair(acc1[c], acc1[c + 1], a); }
     if (fi0 + s0 < nframes) {
@@ -418,12 +446,13 @@ __device__ __forceinline__ void front_en1(const PB& prm, const float* slots, int
 // FROM_WAV = true : the STFT is fused in: frames are cut from `wav` [B][L] (reflect padding, sqrt-Hann), transformed in
 //                   shared memory (the FFT ping-pong buffers overlay the slot's own feat / sfe regions) and the spectrum is
 //                   written once to `spec_out` [B][T][257][2] for the mask stage; it is never read back here.
-template <bool FROM_WAV>
+template <bool FROM_WAV, int VAR>
 __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float* __restrict__ spec, int64_t sb, int64_t sf, int64_t st, int64_t sc,
                                                          const float* __restrict__ wav, int64_t wav_stride, int L, float* __restrict__ spec_out,
                                                          int T, int64_t nframes, const float* __restrict__ blobp,
-                                                         const __grid_constant__ ParamBlock<blob::FRONT_SIZE> prm,
+                                                         const __grid_constant__ ParamBlock<FrontL<VAR>::SIZE> prm,
                                                          float* __restrict__ en0, float* __restrict__ en1) {
+    using LY = FrontL<VAR>;
     extern __shared__ float4 smem4[];
     float* W = reinterpret_cast<float*>(smem4);
     float* slots = W + FR_W_FLOATS;            // per slot: [feat | erb | sfe]; a0 overlays feat|erb
@@ -457,7 +486,7 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
         }
         load_fft_tables_async(tb, blobp, tid, FR_THREADS);         // needed by the FFT right after the barrier
         cp_async_commit();
-        copy_f4_async(W, blobp + blob::FRONT_OFF, FR_W_FLOATS, tid, FR_THREADS);   // ERB / SFE tables: needed after the FFT phase
+        copy_f4_async(W, blobp + LY::OFF, FR_W_FLOATS, tid, FR_THREADS);   // ERB / SFE tables: needed after the FFT phase
         cp_async_commit();
         cp_async_wait_group<1>();
         __syncthreads();
@@ -512,7 +541,7 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
                 else { re[i] = p[0]; im[i] = p[sc]; }
             }
         }
-        copy_f4_async(W, blobp + blob::FRONT_OFF, FR_W_FLOATS, tid, FR_THREADS);
+        copy_f4_async(W, blobp + LY::OFF, FR_W_FLOATS, tid, FR_THREADS);
         for (int i = tid; i < FR_NF * 4; i += FR_THREADS) {
             float4* sfe4 = reinterpret_cast<float4*>(slots + (i >> 2) * FR_SLOT + FR_FEAT + FR_ERB);
             const int c = i & 3;                                  // padded bins 0, 1, 131, 132 -> (parity, entry)
@@ -580,22 +609,58 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
         const int sp2 = tid / kF1, f = tid - sp2 * kF1, s0 = 2 * sp2, s1 = s0 + 1;
         float acc0[16], acc1[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = prm.w[blob::FRONT_EN0_B + c];
+        for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = prm.w[LY::EN0_B + c];
         const float4* i0p = reinterpret_cast<const float4*>(slots + s0 * FR_SLOT + FR_FEAT + FR_ERB) + f;
         const float4* i1p = reinterpret_cast<const float4*>(slots + s1 * FR_SLOT + FR_FEAT + FR_ERB) + f;
+        if constexpr (VAR == 0) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const float4 x0 = i0p[(k & 1) * 67 + (k >> 1)], x1 = i1p[(k & 1) * 67 + (k >> 1)];
+            for (int k = 0; k < 5; ++k) {
+                const float4 x0 = i0p[(k & 1) * 67 + (k >> 1)], x1 = i1p[(k & 1) * 67 + (k >> 1)];
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+                for (int i = 0; i < 3; ++i)
 #pragma unroll
-                for (int c = 0; c < 16; c += 2) {
-                    const float w0 = prm.w[blob::FRONT_EN0_W + k * 48 + i * 16 + c], w1 = prm.w[blob::FRONT_EN0_W + k * 48 + i * 16 + c + 1];
-                    fma_pair(acc0[c], acc0[c + 1], f4get(x0, i), w0, w1);
-                    fma_pair(acc1[c], acc1[c + 1], f4get(x1, i), w0, w1);
+                    for (int c = 0; c < 16; c += 2) {
+                        const float w0 = prm.w[LY::EN0_W + k * 48 + i * 16 + c], w1 = prm.w[LY::EN0_W + k * 48 + i * 16 + c + 1];
+                        fma_pair(acc0[c], acc0[c + 1], f4get(x0, i), w0, w1);
+                        fma_pair(acc1[c], acc1[c + 1], f4get(x1, i), w0, w1);
+                    }
+            }
+        } else {
+            // unfold SFE + en0: the conv sees 9 channels (c*3 + k', k' = neighbour bin p-1, p, p+1) at the unfolded positions
+            // p = 2f' + k - 2; positions outside [0,128] are the conv's own zero padding (whole tap dropped), neighbours outside
+            // are the unfold's zero padding (zero columns of the feature row).  Padded bin of (k, k') = 2f' + (k + k') + 1 - 2:
+            // the 7 distinct float4 (j = k + k') are loaded once.
+            float4 in0[7], in1[7];
+            const float4* b0p = i0p - f;
+            const float4* b1p = i1p - f;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const int c = 2 * f + j - 1;                                    // padded bin (= bin + 2) of tap pair k + k' = j
+                const bool ok = c >= 0 && c <= 132;
+                const int e = ok ? (c & 1) * 67 + (c >> 1) : 0;
+                in0[j] = ok ? b0p[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+                in1[j] = ok ? b1p[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int p = 2 * f + k - 2;
+                const bool pv = p >= 0 && p <= 128;
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                    float4 x0 = in0[k + kk], x1 = in1[k + kk];
+                    if (!pv) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int c = 0; c < 16; c += 2) {
+                            const float w0 = prm.w[LY::EN0_W + ((k * 3 + kk) * 3 + i) * 16 + c], w1 = prm.w[LY::EN0_W + ((k * 3 + kk) * 3 + i) * 16 + c + 1];
+                            fma_pair(acc0[c], acc0[c + 1], f4get(x0, i), w0, w1);
+                            fma_pair(acc1[c], acc1[c + 1], f4get(x1, i), w0, w1);
+                        }
                 }
+            }
         }
-        const float a = prm.w[blob::FRONT_SLOPE + 0];
+        const float a = prm.w[LY::SLOPE + 0];
 #pragma unroll
         for (int c = 0; c < 16; c += 2) { prelu_pair(acc0[c], acc0[c + 1], a); prelu_pair(acc1[c], acc1[c + 1], a); }
         float4* o0 = reinterpret_cast<float4*>(slots + s0 * FR_SLOT);
@@ -622,8 +687,8 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
     {
         const int half = tid >= FR_HALF, r = tid - half * FR_HALF;
         if (r < (FR_NF / 2) * kF2) {
-            if (half == 0) front_en1<0>(prm, slots, r, fi0, nframes, en1);
-            else front_en1<1>(prm, slots, r, fi0, nframes, en1);
+            if (half == 0) front_en1<0, VAR>(prm, slots, r, fi0, nframes, en1);
+            else front_en1<1, VAR>(prm, slots, r, fi0, nframes, en1);
         }
     }
 }
@@ -1158,39 +1223,52 @@ constexpr int BK_Y4 = 4 * 67;                    // float4 per slot: [q][g + 1]
 constexpr int BK_M = 130 * 2;                    // floats per slot: [h][2] -- overlays X (dead after de3)
 static_assert(BK_M <= BK_X4 * 4, "mask buffer must fit in the dead input tile");
 constexpr int BK_FFT_FLOATS = FR_FFT_FLOATS + 256;        // FftTables + 1/envelope
-constexpr int BK_W_OFF = blob::BACK_DE4_W;                 // only de4 / inverse-ERB tables go to shared memory (non-uniform indices);
-constexpr int BK_W_FLOATS = blob::BACK_SIZE - BK_W_OFF;    // the de3 weights are a kernel parameter
+constexpr int BK_W_FLOATS = blob::BACK_SIZE - blob::BACK_DE4_W;   // only de4 / inverse-ERB tables go to shared memory (non-uniform indices);
+                                                                  // the de3 weights are a kernel parameter
+static_assert(BK_W_FLOATS == blobf::BACK_SIZE - blobf::BACK_DE4_W, "both variants copy the same number of table floats");
 __host__ __device__ constexpr int bk_smem_floats(bool to_wav) { return BK_W_FLOATS + BK_NF * (BK_X4 * 4 + BK_Y4 * 4) + (to_wav ? BK_FFT_FLOATS : 0); }
 
 // de3 for output bins of one parity (compile-time, so tap set and weight indices are warp-uniform): thread = 2 slots x 16 co.
 // transposed conv in gather form: even g = 2m uses taps k = 0,2,4 on input bins m+1, m, m-1; odd g = 2m+1 taps k = 1,3 on m+1, m.
-template <int ODD, class PB>
+// VAR 1 (groups = 2): input channel quad qd feeds only the 8 outputs of its group (qd / 2), weights [k][ci][co within the group]
+template <int ODD, int VAR, class PB>
 __device__ __forceinline__ void back_de3(const PB& prm, const float4* X, float4* Y3, int sp2, int m, int64_t fi0, int64_t nframes,
                                          const float* __restrict__ en0) {
+    using LY = BackL<VAR>;
     const int g = 2 * m + ODD;
     float acc0[16], acc1[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = prm.w[blob::BACK_DE3_B + c];
+    for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = prm.w[LY::DE3_B + c];
     const float4* x0 = X + (2 * sp2) * BK_X4;
     const float4* x1 = x0 + BK_X4;
 #pragma unroll 1
     for (int j = 0; j < 3 - ODD; ++j) {
         const int colx = m + 2 - j;                            // input bin f = m + 1 - j, stored at col f + 1
-        const int wb = blob::BACK_DE3_W + (2 * j + ODD) * 256;
+        const int wb = LY::DE3_W + (2 * j + ODD) * (VAR == 1 ? 128 : 256);
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
             const float4 i0 = x0[qd * 35 + colx], i1 = x1[qd * 35 + colx];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i) {
+                if constexpr (VAR == 1) {
 #pragma unroll
-                for (int c = 0; c < 16; c += 2) {
-                    const float w0 = prm.w[wb + (4 * qd + i) * 16 + c], w1 = prm.w[wb + (4 * qd + i) * 16 + c + 1];
-                    fma_pair(acc0[c], acc0[c + 1], f4get(i0, i), w0, w1);
-                    fma_pair(acc1[c], acc1[c + 1], f4get(i1, i), w0, w1);
+                    for (int c = 0; c < 8; c += 2) {
+                        const float w0 = prm.w[wb + (4 * qd + i) * 8 + c], w1 = prm.w[wb + (4 * qd + i) * 8 + c + 1];
+                        fma_pair(acc0[8 * (qd >> 1) + c], acc0[8 * (qd >> 1) + c + 1], f4get(i0, i), w0, w1);
+                        fma_pair(acc1[8 * (qd >> 1) + c], acc1[8 * (qd >> 1) + c + 1], f4get(i1, i), w0, w1);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 16; c += 2) {
+                        const float w0 = prm.w[wb + (4 * qd + i) * 16 + c], w1 = prm.w[wb + (4 * qd + i) * 16 + c + 1];
+                        fma_pair(acc0[c], acc0[c + 1], f4get(i0, i), w0, w1);
+                        fma_pair(acc1[c], acc1[c + 1], f4get(i1, i), w0, w1);
+                    }
                 }
+            }
         }
     }
-    const float a = prm.w[blob::BACK_SLOPE + 0];
+    const float a = prm.w[LY::SLOPE + 0];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const int slot = 2 * sp2 + s;
@@ -1213,16 +1291,17 @@ __device__ __forceinline__ void back_de3(const PB& prm, const float4* X, float4*
 //                 on their order (bitwise deterministic).  The caller zeroes wav_out first.
 // de4 (16 -> 2) + tanh for output bins of one parity: thread = 4 slots x 2 co at bin h = 2m + ODD; every weight pair (one LDCU.64)
 // feeds 8 FFMAs.  Same gather form as de3.  Result: mask on the compressed axis, M[slot][h][2].
-template <int ODD, class PB>
+template <int ODD, int VAR, class PB>
 __device__ __forceinline__ void back_de4(const PB& prm, const float4* Y3, float* M, int m_stride, int sg, int m) {
+    using LY = BackL<VAR>;
     const int h = 2 * m + ODD;
     float a0[4], a1[4];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) { a0[s] = prm.w[blob::BACK_DE4_B + 0]; a1[s] = prm.w[blob::BACK_DE4_B + 1]; }
+    for (int s = 0; s < 4; ++s) { a0[s] = prm.w[LY::DE4_B + 0]; a1[s] = prm.w[LY::DE4_B + 1]; }
     const float4* y = Y3 + (4 * sg) * BK_Y4;
 #pragma unroll
     for (int j = 0; j < 3 - ODD; ++j) {
-        const int colx = m + 2 - j, wb = blob::BACK_DE4_W + (2 * j + ODD) * 32;
+        const int colx = m + 2 - j, wb = LY::DE4_W + (2 * j + ODD) * 32;
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
             float4 in[4];
@@ -1241,17 +1320,19 @@ __device__ __forceinline__ void back_de4(const PB& prm, const float4* Y3, float*
         *reinterpret_cast<float2*>(M + (4 * sg + s) * m_stride + 2 * h) = make_float2(tanhf(a0[s]), tanhf(a1[s]));
 }
 
-template <bool TO_WAV>
+template <bool TO_WAV, int VAR>
 __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict__ de2, const float* __restrict__ en1,
                                                         const float* __restrict__ en0, const float* __restrict__ spec,
                                                         int64_t sb, int64_t sf, int64_t st, int64_t sc,
                                                         float* __restrict__ outp, int64_t ob, int64_t of, int64_t ot, int64_t oc,
                                                         float* __restrict__ wav_out, int64_t wav_stride,
                                                         int T, int64_t nframes, const float* __restrict__ blobp,
-                                                        const __grid_constant__ ParamBlock<blob::BACK_SIZE> prm) {
+                                                        const __grid_constant__ ParamBlock<BackL<VAR>::SIZE> prm) {
+    using LY = BackL<VAR>;
+    constexpr int BK_W_OFF = LY::DE4_W;
     extern __shared__ float4 smem4[];
     float* Wsm = reinterpret_cast<float*>(smem4);
-    float* W = Wsm - BK_W_OFF;                       // so that W[blob::BACK_xxx] addresses the copied sub-range
+    float* W = Wsm - BK_W_OFF;                       // so that W[LY::xxx] addresses the copied sub-range
     float4* X = reinterpret_cast<float4*>(Wsm + BK_W_FLOATS);
     float4* const X4all = X;
     float4* Y3 = X + BK_NF * BK_X4;
@@ -1287,7 +1368,7 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(spec + fi0 * kSpecFrame) + tid * 128));
     }
     // tables (de4 / inverse-ERB weights, iSTFT tables) are not needed before de4: asynchronous copies that land during de3
-    copy_f4_async(Wsm, blobp + blob::BACK_OFF + BK_W_OFF, BK_W_FLOATS, tid, BK_THREADS);
+    copy_f4_async(Wsm, blobp + LY::OFF + BK_W_OFF, BK_W_FLOATS, tid, BK_THREADS);
     if (TO_WAV) {
         FftTables& tb0 = *reinterpret_cast<FftTables*>(Wsm + bk_smem_floats(false));
         load_fft_tables_async(tb0, blobp, tid, BK_THREADS);
@@ -1310,25 +1391,25 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
     __syncthreads();
     // ---- b: de3: even output bins on warps 0-4 (132 of 160 lanes), odd bins on warps 5-8 (128 lanes)
     if (tid < 160) {
-        if (tid < (BK_NF / 2) * 33) back_de3<0>(prm, X, Y3, tid / 33, tid % 33, fi0, nframes, en0);
+        if (tid < (BK_NF / 2) * 33) back_de3<0, VAR>(prm, X, Y3, tid / 33, tid % 33, fi0, nframes, en0);
     } else {
         const int r = tid - 160;
-        back_de3<1>(prm, X, Y3, r >> 5, r & 31, fi0, nframes, en0);
+        back_de3<1, VAR>(prm, X, Y3, r >> 5, r & 31, fi0, nframes, en0);
     }
     cp_async_wait_all();                                           // this thread's share of the table copies has landed
     __syncthreads();
     // ---- c: de4 (16 -> 2) + tanh -> mask on the 129 compressed bins: even bins (65) on warps 0-4, odd bins (64) on warps 5-8
     static_assert(BK_NF == 8, "de4 mapping assumes two groups of four slots");
     if (tid < 160) {
-        if (tid < 130) back_de4<0>(prm, Y3, M, M_STRIDE, tid / 65, tid % 65);
+        if (tid < 130) back_de4<0, VAR>(prm, Y3, M, M_STRIDE, tid / 65, tid % 65);
     } else {
         const int r = tid - 160;
-        back_de4<1>(prm, Y3, M, M_STRIDE, r >> 6, r & 63);
+        back_de4<1, VAR>(prm, Y3, M, M_STRIDE, r >> 6, r & 63);
     }
     __syncthreads();
     // ---- d: ERB expand + complex ratio mask (+ e: fused iSTFT).  mask(i) on the 257 spectrum bins from the 129 compressed ones.
-    const int* ib0 = reinterpret_cast<const int*>(W + blob::BACK_IERB_B0);
-    const float* iw = W + blob::BACK_IERB_W;
+    const int* ib0 = reinterpret_cast<const int*>(W + LY::IERB_B0);
+    const float* iw = W + LY::IERB_W;
     auto mask_at = [&](const float* ms, int i, float& m0, float& m1) {
         if (i < 65) {
             m0 = ms[2 * i];

@@ -56,6 +56,13 @@ struct Ws {          // per-hop activation workspace (owned by the handle), all 
 
 inline size_t state_bytes(int64_t N) { return sizeof(float) * ((size_t)kHdrFloats + (size_t)N * kPerStream); }
 
+// where the wav-streaming tails of a stream live (the streaming STFT / iSTFT kernels serve both model variants)
+struct WavLayout { int per_stream, wav_in, ola; };
+constexpr WavLayout kWavLayoutMicro{kPerStream, kWavIn, kOla};
+__device__ __forceinline__ float* wav_base(void* state, int64_t n, const WavLayout& wl) {
+    return reinterpret_cast<float*>(state) + kHdrFloats + n * (int64_t)wl.per_stream;
+}
+
 __device__ __forceinline__ float* stream_base(void* state, int64_t n) {
     return reinterpret_cast<float*>(state) + kHdrFloats + n * (int64_t)kPerStream;
 }
@@ -262,7 +269,7 @@ ks_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_con
 // so the enhanced stream lags the input by two hops (512 samples); every emitted hop equals the offline output.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ks_stft_step(void* state, const float* __restrict__ hop_in, const float* __restrict__ blobp,
-                                                    float* __restrict__ spec, int64_t N) {
+                                                    float* __restrict__ spec, int64_t N, WavLayout wl) {
     using namespace gk;
     __shared__ FftTables tb;
     __shared__ __align__(16) float2 buf[4][2][256];
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(256) ks_stft_step(void* state, const float* __
     __syncthreads();
     float2* A = buf[fr][0];
     float2* Bf = buf[fr][1];
-    float* ring = valid ? stream_base(state, n) + kWavIn : nullptr;
+    float* ring = valid ? wav_base(state, n, wl) + wl.wav_in : nullptr;
     const float* nh = valid ? hop_in + n * 256 : nullptr;
     if (valid && k >= 1) {
         const float* h_prev = ring + ((k - 1) & 1) * 256;      // hop k-1
@@ -319,7 +326,7 @@ __global__ void __launch_bounds__(256) ks_stft_step(void* state, const float* __
 }
 
 __global__ void __launch_bounds__(256) ks_istft_step(void* state, const float* __restrict__ spec, const float* __restrict__ blobp,
-                                                     float* __restrict__ hop_out, int64_t N) {
+                                                     float* __restrict__ hop_out, int64_t N, WavLayout wl) {
     using namespace gk;
     __shared__ FftTables tb;
     __shared__ __align__(16) float2 buf[4][2][256];
@@ -360,7 +367,7 @@ __global__ void __launch_bounds__(256) ks_istft_step(void* state, const float* _
         for (int r = 0; r < 4; ++r) o[j + 64 * r] = 0.f;
         return;
     }
-    float* tail = stream_base(state, n) + kOla;
+    float* tail = wav_base(state, n, wl) + wl.ola;
     // time-domain samples 2m, 2m+1 of the frame = (Re z[m], -Im z[m]) / 256, windowed.  m = j + 64 r: the thread that
     // consumes tail[2m] (r = 0,1) is the same thread that rewrites it from sample m + 128 (r = 2,3) -> no barrier needed.
 #pragma unroll
@@ -384,13 +391,13 @@ __global__ void __launch_bounds__(256) ks_istft_step(void* state, const float* _
 // This kernel builds v [N][256] from the trailing samples and the two hops in the WAV_IN ring; two ordinary step_wav calls
 // with v as the new hop then emit the last two offline hops.
 __global__ void __launch_bounds__(256) ks_reflect_tail(const void* state, const float* __restrict__ tail, int tail_len,
-                                                       float* __restrict__ v, int64_t N) {
+                                                       float* __restrict__ v, int64_t N, WavLayout wl) {
     const Header* hdr = reinterpret_cast<const Header*>(state);
     const long long K = hdr->wav_calls;
     const int64_t n = blockIdx.x;
     const int j = threadIdx.x;
     if (n >= N) return;
-    const float* ring = reinterpret_cast<const float*>(state) + kHdrFloats + n * (int64_t)kPerStream + kWavIn;
+    const float* ring = reinterpret_cast<const float*>(state) + kHdrFloats + n * (int64_t)wl.per_stream + wl.wav_in;
     const float* h1 = ring + ((K - 1) & 1) * 256;              // hop K-1
     const float* h2 = ring + (K & 1) * 256;                    // hop K-2
     float val = 0.f;
@@ -494,7 +501,7 @@ inline int model_step(const float* blobp, const HostParams& hp, void* state, con
     const unsigned gfr = (unsigned)((N + FR_NF - 1) / FR_NF), gbk = (unsigned)((N + BK_NF - 1) / BK_NF);
     // T = 1: strides {b: 514, f: 2, t: 0, c: 1}.  k_front / k_back do not know about `skip`; on the skipped call
     // (first wav hop) they run on a zero spectrum and their outputs are simply never consumed.
-    k_front<false><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, kSpecFrame, 2, 0, 1, nullptr, 0, 0, nullptr, 1, N, blobp, hp.front, ws.en0, ws.act[0]);
+    k_front<false, 0><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, kSpecFrame, 2, 0, 1, nullptr, 0, 0, nullptr, 1, N, blobp, hp.front, ws.en0, ws.act[0]);
     ++launches;
     const unsigned gsg = (unsigned)((N + SG_NS - 1) / SG_NS);
     for (int i = 0; i < 3; ++i) {
@@ -507,7 +514,7 @@ inline int model_step(const float* blobp, const HostParams& hp, void* state, con
         ks_gtconv<true><<<gsg, SG_THREADS, SG_SMEM_FLOATS * sizeof(float), st>>>(ws.act[5 + i], ws.act[3 - i], ws.act[6 + i], hp.dec[i], state, 3 + i, N);
         ++launches;
     }
-    k_back<false><<<gbk, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(ws.act[8], ws.act[0], ws.en0, spec, kSpecFrame, 2, 0, 1,
+    k_back<false, 0><<<gbk, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(ws.act[8], ws.act[0], ws.en0, spec, kSpecFrame, 2, 0, 1,
                                                                                   out, kSpecFrame, 2, 0, 1, nullptr, 0, 1, N, blobp, hp.back);
     ++launches;
     return launches;
@@ -521,9 +528,9 @@ inline int step_spec(const float* blobp, const HostParams& hp, void* state, cons
 
 inline int step_wav(const float* blobp, const HostParams& hp, void* state, const Ws& ws, const float* hop_in, float* hop_out, int64_t N, cudaStream_t st) {
     const unsigned g4 = (unsigned)((N + 3) / 4);
-    ks_stft_step<<<g4, 256, 0, st>>>(state, hop_in, blobp, ws.spec_in, N);
+    ks_stft_step<<<g4, 256, 0, st>>>(state, hop_in, blobp, ws.spec_in, N, kWavLayoutMicro);
     int launches = 1 + model_step(blobp, hp, state, ws, ws.spec_in, ws.spec_out, N, st);
-    ks_istft_step<<<g4, 256, 0, st>>>(state, ws.spec_out, blobp, hop_out, N);
+    ks_istft_step<<<g4, 256, 0, st>>>(state, ws.spec_out, blobp, hop_out, N, kWavLayoutMicro);
     ks_advance<<<1, 1, 0, st>>>(state, 1);
     return launches + 2;
 }
@@ -531,7 +538,7 @@ inline int step_wav(const float* blobp, const HostParams& hp, void* state, const
 // the last two offline hops; out [2][N][256] (out[1] doubles as the buffer of the virtual hop).  Returns the number of launches.
 inline int flush_wav(const float* blobp, const HostParams& hp, void* state, const Ws& ws, const float* tail, int tail_len, float* out, int64_t N, cudaStream_t st) {
     float* v = out + N * 256;
-    ks_reflect_tail<<<(unsigned)N, 256, 0, st>>>(state, tail, tail_len, v, N);
+    ks_reflect_tail<<<(unsigned)N, 256, 0, st>>>(state, tail, tail_len, v, N, kWavLayoutMicro);
     int launches = 1 + step_wav(blobp, hp, state, ws, v, out, N, st);
     launches += step_wav(blobp, hp, state, ws, v, v, N, st);
     return launches;

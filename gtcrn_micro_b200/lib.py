@@ -22,6 +22,7 @@ SYMBOLS = [
     "gtcrnb_host_free", "gtcrnb_last_error", "gtcrnb_profile_enable", "gtcrnb_profile_read",
     "gtcrnb_profile_num_classes", "gtcrnb_profile_class_name", "gtcrnb_pair_metrics", "gtcrnb_host_alloc_wc",
     "gtcrnb_enhance_host_pcm16", "gtcrnb_pcm16_to_f32", "gtcrnb_f32_to_pcm16", "gtcrnb_stream_flush_wav",
+    "gtcrnb_create_variant", "gtcrnb_blob_floats_variant", "gtcrnb_stream_state_bytes_variant",
 ]
 
 
@@ -49,6 +50,9 @@ def load() -> C.CDLL:
             "gtcrnb_abi_version": (C.c_int, []),
             "gtcrnb_blob_floats": (sz, []),
             "gtcrnb_create": (C.c_int, [vp, sz, C.POINTER(vp)]),
+            "gtcrnb_create_variant": (C.c_int, [vp, sz, C.c_int, C.POINTER(vp)]),
+            "gtcrnb_blob_floats_variant": (sz, [C.c_int]),
+            "gtcrnb_stream_state_bytes_variant": (sz, [C.c_int, i64]),
             "gtcrnb_destroy": (None, [vp]),
             "gtcrnb_forward_spec": (C.c_int, [vp, vp, i64p, i64, i64, vp, i64p, vp]),
             "gtcrnb_enhance": (C.c_int, [vp, vp, i64, i64, i64, vp, i64, vp]),

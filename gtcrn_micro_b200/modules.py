@@ -103,9 +103,9 @@ def _init_tensor(shape, kind: str, gen: torch.Generator) -> torch.Tensor:
         return torch.from_numpy(erb_filter_bank())
     if kind == "erbT":
         return torch.from_numpy(np.ascontiguousarray(erb_filter_bank().T))
-    if kind == "bn_w" or kind == "bn_v":
+    if kind in ("bn_w", "bn_v", "ln_w"):
         return torch.ones(shape)
-    if kind == "bn_b" or kind == "bn_m":
+    if kind in ("bn_b", "bn_m", "ln_b"):
         return torch.zeros(shape)
     if kind == "bn_n":
         return torch.zeros((), dtype=torch.long)
@@ -119,13 +119,21 @@ def _init_tensor(shape, kind: str, gen: torch.Generator) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 class _B200Module(nn.Module):
     _stream = False
+    _variant = 0                  # C-ABI model variant (GTCRNB_VARIANT_MICRO / _FULL)
+
+    @classmethod
+    def _param_spec(cls):
+        return param_spec(cls._stream)
+
+    def _pack(self) -> np.ndarray:
+        return _pack.pack_state_dict(self.state_dict())
 
     def __init__(self, n_fft: int = 512, hop_len: int = 256, win_len: int = 512):
         # like the reference constructor (gtcrn_micro.py:486-504) the three arguments are accepted for
         # config compatibility; the architecture is fixed at n_fft 512 / hop 256.
         super().__init__()
         gen = torch.Generator().manual_seed(torch.initial_seed() % (2 ** 31))
-        for key, shape, kind in param_spec(self._stream):
+        for key, shape, kind in self._param_spec():
             _attach(self, key, _init_tensor(shape, kind, gen), kind)
         self._handle = C.c_void_p(None)
         self._handle_key = None
@@ -143,10 +151,10 @@ class _B200Module(nn.Module):
             return self._handle
         L = _lib.load()
         self._release()
-        blob = _pack.pack_state_dict(self.state_dict())
+        blob = self._pack()
         with torch.cuda.device(device):
             h = C.c_void_p(None)
-            _lib.check(L.gtcrnb_create(blob.ctypes.data_as(C.c_void_p), blob.size, C.byref(h)), "gtcrnb_create")
+            _lib.check(L.gtcrnb_create_variant(blob.ctypes.data_as(C.c_void_p), blob.size, self._variant, C.byref(h)), "gtcrnb_create_variant")
         self._handle, self._handle_key = h, key
         return h
 
@@ -344,9 +352,10 @@ class StreamState:
     """Opaque per-batch streaming state living in one device buffer (conv / TRA / TCN ring buffers of N
     streams plus the STFT / overlap-add tails used by `step_wav`)."""
 
-    def __init__(self, n_streams: int, device: torch.device):
+    def __init__(self, n_streams: int, device: torch.device, variant: int = 0):
         self.n = int(n_streams)
-        nbytes = int(_lib.load().gtcrnb_stream_state_bytes(self.n))
+        self.variant = int(variant)
+        nbytes = int(_lib.load().gtcrnb_stream_state_bytes_variant(self.variant, self.n))
         self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
 
     @property
@@ -405,7 +414,7 @@ class StreamGTCRNMicro(_B200Module):
     def new_state(self, n_streams: int, device=None) -> StreamState:
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._ensure_handle(dev)
-        return StreamState(n_streams, dev)
+        return StreamState(n_streams, dev, self._variant)
 
     @torch.no_grad()
     def reset(self, state: StreamState) -> None:

@@ -44,6 +44,17 @@ size_t gtcrnb_blob_floats(void);
 /* Create a model instance on the current CUDA device from a packed weight blob (host pointer).
  * Replaces: GTCRNMicro().load_state_dict(ckpt["model"]).eval()   (infer.py:37-40). */
 int gtcrnb_create(const float* blob_host, size_t n_floats, gtcrnb_handle** out);
+/* Same with an explicit model variant (SURVEY 8(b) proposal):
+ *   GTCRNB_VARIANT_MICRO  the reference's GTCRNMicro (SFE-Lite, TRALite, GTCN) -- what gtcrnb_create builds;
+ *   GTCRNB_VARIANT_FULL   the original-GTCRN-style architecture of BASELINE configs[3] (unfold SFE, groups = 2, GTConv dilations
+ *                         1/2/5, GRU-based TRA, DPGRNN), which the reference only keeps as commented-out lines
+ *                         (gtcrn_micro/models/gtcrn_micro.py:187,199,346,361,381,391,417-418,429,448,494): parity UNPINNED, checked
+ *                         against the builder-written oracle/gtcrn_full_oracle.py; blob layout gtcrn_micro_b200/pack_full.py.
+ * Every other entry point takes either kind of handle; gtcrnb_stream_import/export_caches are Micro-only. */
+#define GTCRNB_VARIANT_MICRO 0
+#define GTCRNB_VARIANT_FULL 1
+int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, gtcrnb_handle** out);
+size_t gtcrnb_blob_floats_variant(int variant);
 void gtcrnb_destroy(gtcrnb_handle* h);
 
 /* Drop-in for GTCRNMicro.forward (gtcrn_micro.py:506-532): spec [B,257,T,2] -> enhanced spec.
@@ -79,7 +90,8 @@ int gtcrnb_istft(gtcrnb_handle* h, const float* spec_dev, int64_t B, int64_t T, 
 /* ---- streaming (StreamGTCRNMicro.forward, gtcrn_micro_stream.py:541-574) ------------------------
  * The state of N concurrent streams (conv / TRA / TCN caches, plus STFT/OLA tails for the wav
  * entry point) lives in one device buffer owned by the caller, `gtcrnb_stream_state_bytes(N)` big. */
-size_t gtcrnb_stream_state_bytes(int64_t N);
+size_t gtcrnb_stream_state_bytes(int64_t N);                       /* GTCRNB_VARIANT_MICRO */
+size_t gtcrnb_stream_state_bytes_variant(int variant, int64_t N);
 int gtcrnb_stream_reset(gtcrnb_handle* h, void* state_dev, int64_t N, void* stream);
 /* One 16 ms hop for N streams on spectra: spec_frame [N][257][2] -> out [N][257][2] (contiguous). */
 int gtcrnb_stream_step_spec(gtcrnb_handle* h, void* state_dev, const float* spec_dev, float* out_dev,

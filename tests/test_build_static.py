@@ -18,8 +18,11 @@ import gtcrn_micro_b200.build as B
 
 CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 # kernels launched with the default tuning (gtcrn_capi.cu): offline + streaming
-HOT = ["k_frontILb0", "k_frontILb1", "k_backILb0", "k_backILb1", "k_gtconvILb0ELi2ELi4ELb0", "k_gtconvILb1ELi4ELi7ELb0",
+HOT = ["k_frontILb0ELi0E", "k_frontILb1ELi0E", "k_backILb0ELi0E", "k_backILb1ELi0E", "k_gtconvILb0ELi2ELi4ELb0", "k_gtconvILb1ELi4ELi7ELb0",
        "k_gtcnILi2ELb0", "ks_gtconvILb0", "ks_gtconvILb1", "ks_gtcn"]
+# kernels of the original-GTCRN-style variant (BASELINE configs[3]): same weight-feed property, spills tolerated up to a small frame
+HOT_FULL = ["k_frontILb0ELi1E", "k_frontILb1ELi1E", "k_backILb0ELi1E", "k_backILb1ELi1E", "kf_gtconvILb0ELi2ELi4E", "kf_gtconvILb1ELi2ELi4E",
+            "kf_dp_intra", "kf_dp_inter"]
 
 
 @pytest.fixture(scope="module")
@@ -44,7 +47,7 @@ def _find(per, key):
     return per[hits[0]]
 
 
-@pytest.mark.parametrize("key", HOT)
+@pytest.mark.parametrize("key", HOT + HOT_FULL)
 def test_weights_use_the_uniform_datapath(sass, key):
     body = _find(sass, key)
     r_indexed = sum(1 for l in body if re.search(r"c\[0x0\]\[R\d", l))
