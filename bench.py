@@ -53,6 +53,14 @@ FP32_PEAK_TFLOPS = 73.4                   # measured on this pool's B200: tools/
 DEC_GT_DRAM_BYTES_PER_FRAME = 8555        # ncu --set full, dram__bytes_read+write of one k_gtconv<DEC> launch / frames (profiles/ncu_r1_v13_summary.txt)
 DEC_GT_ALG_BYTES_PER_FRAME = 3 * 33 * 16 * 4   # read x + skip, write out: 6,336 B
 WEIGHTS = os.path.join(ROOT, "tests", "golden", "weights_dns3.npz")
+# BASELINE configs[3], `--variant full`: the original-GTCRN-style architecture (parity unpinned, oracle/gtcrn_full_oracle.py).
+# conv / linear / GRU MACs per frame of its own ops: ERB 61,440 + en0 46,800 + en1 21,120 + 6 GTConv x 23,456 (1x1 24->16, dw 3x3,
+# 1x1 16->8, TRA GRU 8->16 + fc) + 2 DPGRNN x 61,248 (intra 4 chains x 33 x 144 + fc, inter 66 chains x 384 + fc) + de3 21,120 +
+# de4 10,400 + ERB^-1 24,576 + mask 1,028
+FULL_MAC_PER_FRAME = 449_716
+FULL_CLASS_MAC = {"front": 61_440 + 46_800 + 21_120, "full_enc_gtconv": 23_456, "full_dec_gtconv": 23_456, "dp_intra": 19_008 + 8_448,
+                  "dp_inter": 25_344 + 8_448, "back": 21_120 + 10_400 + 24_576 + 1_028}
+FULL_SEED = 20261017
 
 
 def measured_peaks():
@@ -163,12 +171,20 @@ class CpuReference:
     (oracle/install_reference.sh) driven exactly like infer.py:60-76 and gtcrn_micro_stream.py:618-636; kind "port": the
     oracle restatement (same ATen ops), used only when baseline/_ref is missing."""
 
-    def __init__(self):
+    def __init__(self, variant: str = "micro", weights=None):
         import gtcrn_oracle as O
         self.O = O
-        self.W = O.load_weights_npz(WEIGHTS)
+        self.variant = variant
         self.kind = "port"
         self.model = self.smodel = None
+        if variant == "full":
+            # no reference implementation of this variant exists (only commented-out lines in gtcrn_micro.py): the CPU arm is the
+            # builder-written oracle (parity unpinned)
+            import gtcrn_full_oracle as FO
+            self.FO = FO
+            self.W = weights if weights is not None else full_variant_weights()
+            return
+        self.W = O.load_weights_npz(WEIGHTS)
         if os.path.isdir(os.path.join(REF_DIR, "gtcrn_micro")):
             try:
                 import types
@@ -190,6 +206,8 @@ class CpuReference:
                 self.model = self.smodel = None
 
     def enhance(self, x: torch.Tensor) -> torch.Tensor:
+        if self.variant == "full":
+            return self.FO.enhance(self.W, x)
         if self.model is None:
             return self.O.enhance(self.W, x)
         with torch.inference_mode():                                               # infer.py:60-76, batched
@@ -203,7 +221,10 @@ class CpuReference:
         g = torch.Generator().manual_seed(B)
         frames = [torch.randn(B, 257, 1, 2, generator=g) for _ in range(4)]
         with torch.inference_mode():
-            if self.smodel is None:
+            if self.variant == "full":
+                stf = self.FO.StreamState(B)
+                step = lambda f: self.FO.forward_spec(self.W, f, stf)
+            elif self.smodel is None:
                 st = self.O.StreamState(B)
                 step = lambda f: self.O.forward_spec(self.W, f, st)
             else:
@@ -219,6 +240,31 @@ class CpuReference:
             for i in range(hops):
                 step(frames[i % 4])
             return (time.perf_counter() - t0) / hops
+
+
+def full_variant_weights():
+    """Seeded random weights of the configs[3] model as a state_dict (no checkpoint exists).  Built from the PACKAGE's own
+    module (gtcrn_micro_b200.GTCRN) so that the timed arm never touches oracle/; BN statistics, PReLU slopes and LayerNorm
+    affine terms are randomised too so that nothing folds away."""
+    import gtcrn_micro_b200 as G
+    torch.manual_seed(FULL_SEED)
+    m = G.GTCRN()
+    g = torch.Generator().manual_seed(FULL_SEED)
+    sd = m.state_dict()
+    for k, v in sd.items():
+        if k.startswith("erb.") or not v.is_floating_point():
+            continue
+        if k.endswith("running_var"):
+            sd[k] = 0.3 + 1.5 * torch.rand(v.shape, generator=g)
+        elif k.endswith("running_mean") or (".bn" in k or "_bn" in k or "_ln" in k) and k.endswith("bias"):
+            sd[k] = 0.3 * torch.randn(v.shape, generator=g)
+        elif (".bn" in k or "_bn" in k or "_ln" in k) and k.endswith("weight"):
+            sd[k] = 0.6 + 0.8 * torch.rand(v.shape, generator=g)
+        elif k.endswith("act.weight"):
+            sd[k] = 0.05 + 0.5 * torch.rand(v.shape, generator=g)
+        elif v.dim() > 1:
+            sd[k] = v * 1.7
+    return {k: v.clone() for k, v in sd.items()}
 
 
 def cpu_streaming(ref: "CpuReference", budget_s: float = 20.0) -> dict:
@@ -261,7 +307,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ref = CpuReference()
+    ref = CpuReference(args.variant)
     O = ref.O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -282,13 +328,18 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = best_B * SECONDS * args.steps / dt
     what = "the reference's own GTCRNMicro between torch.stft / torch.istft (baseline/_ref)" if ref.kind == "reference" else "oracle port of the reference"
+    if args.variant == "full":
+        what = "builder-written oracle of the original-GTCRN-style variant (PARITY UNPINNED: the reference has no implementation of it)"
     sample = (f"{what}: {best_B} x {SECONDS} s utterances per step (bounded sample of the 1024-utterance batch), "
               f"torch {torch.__version__} CPU, {cores} threads")
     emit({
         "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"GTCRN-Micro offline batched inference, 1024 x {SECONDS} s synthetic 16 kHz utterances per GPU (configs[1]); CPU arm times a bounded sample"},
+        "config": {"workload": (f"GTCRN-Micro offline batched inference, 1024 x {SECONDS} s synthetic 16 kHz utterances per GPU (configs[1]); CPU arm times a bounded sample"
+                                if args.variant == "micro" else
+                                f"original-GTCRN-style variant (configs[3], parity unpinned), 1024 x {SECONDS} s synthetic utterances per GPU; CPU arm times a bounded sample"),
+                   "variant": args.variant},
         "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": ref.kind, "sample": sample,
                          "streaming": cpu_streaming(ref)},
         "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -359,8 +410,9 @@ def bench_streaming(G, model, device, hbm_peak, n_list=(4096, 16384), hops=625, 
     largest stream count whose WORST hop still meets the deadline (doubling + bisection, confirmed over `hops` hops)."""
     res = {"deadline_ms": 16.0, "hops": hops, "io": "wav in / wav out, pinned host buffers, H2D + D2H of N x 256 samples inside every hop",
            "latency_contract": "output lags input by 512 samples (32 ms); gtcrnb_stream_flush_wav emits the last two hops"}
-    smodel = G.StreamGTCRNMicro()
+    smodel = G.StreamGTCRN() if isinstance(model, G.GTCRN) else G.StreamGTCRNMicro()
     G.convert_to_stream(smodel, model)
+    per_stream_floats = 18816 if isinstance(model, G.GTCRN) else 38880
     for N in n_list:
         ms, ok = _stream_wav_hops(smodel, N, device, hops)
         r = _hop_stats(ms)
@@ -379,7 +431,7 @@ def bench_streaming(G, model, device, hbm_peak, n_list=(4096, 16384), hops=625, 
             torch.cuda.empty_cache()
             return max(ms) if ok else float("inf")
         free = torch.cuda.mem_get_info(device)[0]
-        cap = int(free * 0.7 // (38880 * 4 + 27 * 1024 + 4096))          # state + per-hop workspace per stream
+        cap = int(free * 0.7 // (per_stream_floats * 4 + 27 * 1024 + 4096))          # state + per-hop workspace per stream
         lo, hi = max(n_list), None
         n = lo * 2
         while hi is None and n <= cap:
@@ -410,17 +462,22 @@ def bench_streaming(G, model, device, hbm_peak, n_list=(4096, 16384), hops=625, 
 PARITY_IDX = [0, 1, 63, 64, 127, 128, 255, 256, 511, 512, 700, 767, 768, 900, 1022, 1023]
 
 
-def parity_of_timed_batch(x_sub: torch.Tensor, clean_sub: torch.Tensor, y_sub: torch.Tensor) -> dict:
+def parity_of_timed_batch(x_sub: torch.Tensor, clean_sub: torch.Tensor, y_sub: torch.Tensor, variant: str = "micro", weights=None) -> dict:
     """CHECKER leg (the only place the B200 arm touches oracle/): the oracle's CPU restatement of the reference run on a fixed
     16-utterance subset of the batch that was just timed, compared with the timed run's own output rows."""
     import gtcrn_oracle as O
-    W = O.load_weights_npz(WEIGHTS)
-    ref = O.enhance(W, x_sub)
+    if variant == "full":
+        import gtcrn_full_oracle as FO
+        ref = FO.enhance(weights, x_sub)
+    else:
+        W = O.load_weights_npz(WEIGHTS)
+        ref = O.enhance(W, x_sub)
     n = ref.shape[1]
     err = float((y_sub - ref).abs().max())
     d = max(abs(O.si_snr(clean_sub[i, :n].numpy(), y_sub[i].numpy()) - O.si_snr(clean_sub[i, :n].numpy(), ref[i].numpy())) for i in range(ref.shape[0]))
     return {"max_abs": err, "si_snr_delta_db": round(d, 6), "n": int(ref.shape[0]), "tolerance": {"max_abs": 1e-4, "si_snr_delta_db": 0.01},
-            "against": "oracle/gtcrn_oracle.py on the same 16 utterances of the timed batch", "ok": bool(err <= 1e-4 and d <= 0.01)}
+            "against": ("oracle/gtcrn_oracle.py" if variant == "micro" else "oracle/gtcrn_full_oracle.py (PARITY UNPINNED: builder-written, no reference implementation)")
+                       + " on the same 16 utterances of the timed batch", "ok": bool(err <= 1e-4 and d <= 0.01)}
 
 
 def run_b200(args):
@@ -439,8 +496,14 @@ def run_b200(args):
         build.build()
     if world > 1:
         dist.barrier()
-    model = G.GTCRNMicro()
-    model.load_state_dict(G.load_state_dict_npz(WEIGHTS))
+    full = args.variant == "full"
+    if full:
+        full_sd = full_variant_weights()
+        model = G.GTCRN()
+        model.load_state_dict(full_sd)
+    else:
+        model = G.GTCRNMicro()
+        model.load_state_dict(G.load_state_dict_npz(WEIGHTS))
 
     B = args.batch
     pidx = [i for i in PARITY_IDX if i < B]
@@ -516,40 +579,63 @@ def run_b200(args):
     e2e_value = audio_s / (e2e_ms * 1e-3)
     peaks = measured_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    # roofline of the dominant kernel (decoder GTConvBlock: full 16->16 3x3 conv + 1x1s + TRALite), live CUDA-event timing
-    dom = max(prof, key=lambda k: prof[k]["ms"])
-    dk = prof["dec_gtconv"]
-    dec_tflops = (2.0 * DEC_GT_MAC_PER_FRAME * dk["frames"]) / (dk["ms"] * 1e-3) / 1e12 if dk["ms"] > 0 else 0.0
+    mac_per_frame = FULL_MAC_PER_FRAME if full else MAC_PER_FRAME
     step_kernel_ms = sum(v["ms"] for v in prof.values())
-    roofline = {
-        "kernel": "k_gtconv<DEC> (decoder GTConvBlock, 3 launches per chunk)", "bound": "fp32_fma",
-        "achieved": round(dec_tflops, 2), "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": round(dec_tflops / FP32_PEAK_TFLOPS, 4),
-        "peak_source": "measured FFMA micro-benchmark on this pool's B200 (tools/microbench/ffma_feed.cu, profiles/ffma_feed_r1.txt); "
-                       "MEASURED_PEAKS.json carries HBM and bf16-tensor peaks only and this path is FP32-FMA bound (SURVEY 8d)",
-        "traffic": DEC_GT_DRAM_BYTES_PER_FRAME * (dk["frames"] // max(1, dk["launches"])),
-        "traffic_note": "DRAM bytes per launch from ncu (8,555 B/frame, profiles/ncu_r1_v13_summary.txt) vs 6,336 algorithmic B/frame: "
-                        "the untouched channel half is re-read in the store phase instead of being held in 32 registers",
-        "algorithmic_bytes_per_launch": DEC_GT_ALG_BYTES_PER_FRAME * (dk["frames"] // max(1, dk["launches"])),
-        # the same kernel against the HBM roof (it is not the binding one: arithmetic intensity 84,582 MAC / 6,336 B = 26.7 flop/B)
-        "hbm_view": {"bound": "hbm", "achieved": round(DEC_GT_ALG_BYTES_PER_FRAME * dk["frames"] / (dk["ms"] * 1e-3) / 1e9, 1) if dk["ms"] > 0 else 0.0,
-                     "peak": hbm_peak, "unit": "GB/s",
-                     "frac": round(DEC_GT_ALG_BYTES_PER_FRAME * dk["frames"] / (dk["ms"] * 1e-3) / 1e9 / hbm_peak, 4) if dk["ms"] > 0 else 0.0},
-        "ms_per_launch": round(dk["ms"] / max(1, dk["launches"]), 4), "launches": dk["launches"],
-        "share_of_step": round(dk["ms"] / step_kernel_ms, 4) if step_kernel_ms else None,
-        "dominant_class_by_time": dom,
-        "whole_path": {"achieved_tflops": round(2.0 * MAC_PER_FRAME * FRAMES_PER_UTT * world * B * args.steps / (ms_total * 1e-3) / 1e12 / world, 2),
-                       "frac_fp32": round(2.0 * MAC_PER_FRAME * FRAMES_PER_UTT * B * args.steps / (ms_total * 1e-3) / 1e12 / FP32_PEAK_TFLOPS, 4),
-                       "achieved_hbm_gbs_algorithmic": round(8.0 * L_UTT * B * args.steps / (ms_total * 1e-3) / 1e9, 1),
-                       "frac_hbm": round(8.0 * L_UTT * B * args.steps / (ms_total * 1e-3) / 1e9 / hbm_peak, 4),
-                       "hbm_peak_gbs": hbm_peak, "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
-        "per_class_ms": {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]},
-    }
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    whole = {"achieved_tflops": round(2.0 * mac_per_frame * FRAMES_PER_UTT * B * args.steps / (ms_total * 1e-3) / 1e12, 2),
+             "frac_fp32": round(2.0 * mac_per_frame * FRAMES_PER_UTT * B * args.steps / (ms_total * 1e-3) / 1e12 / FP32_PEAK_TFLOPS, 4),
+             "mac_per_frame": mac_per_frame,
+             "achieved_hbm_gbs_algorithmic": round(8.0 * L_UTT * B * args.steps / (ms_total * 1e-3) / 1e9, 1),
+             "frac_hbm": round(8.0 * L_UTT * B * args.steps / (ms_total * 1e-3) / 1e9 / hbm_peak, 4),
+             "hbm_peak_gbs": hbm_peak, "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}
+    peak_src = ("measured FFMA micro-benchmark on this pool's B200 (tools/microbench/ffma_feed.cu, profiles/ffma_feed_r1.txt); "
+                "MEASURED_PEAKS.json carries HBM and bf16-tensor peaks only and this path is FP32-FMA bound (SURVEY 8d)")
+    if full:
+        # dominant kernel class of the variant, against the FP32 roof (all its contractions run on the FMA pipe) and the HBM roof
+        dk = prof[dom]
+        cls_mac = FULL_CLASS_MAC.get(dom, 0)
+        tfl = (2.0 * cls_mac * dk["frames"]) / (dk["ms"] * 1e-3) / 1e12 if dk["ms"] > 0 else 0.0
+        alg_bytes = (3 if dom == "full_dec_gtconv" else 2) * 33 * 16 * 4
+        roofline = {"kernel": f"{dom} ({dk['launches'] // max(1, args.steps)} launches per step)", "bound": "fp32_fma", "achieved": round(tfl, 2), "peak": FP32_PEAK_TFLOPS,
+                    "unit": "TFLOP/s", "frac": round(tfl / FP32_PEAK_TFLOPS, 4), "peak_source": peak_src, "traffic": None,
+                    "algorithmic_bytes_per_launch": alg_bytes * (dk["frames"] // max(1, dk["launches"])),
+                    "hbm_view": {"bound": "hbm", "achieved": round(alg_bytes * dk["frames"] / (dk["ms"] * 1e-3) / 1e9, 1) if dk["ms"] > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": round(alg_bytes * dk["frames"] / (dk["ms"] * 1e-3) / 1e9 / hbm_peak, 4) if dk["ms"] > 0 else 0.0},
+                    "ms_per_launch": round(dk["ms"] / max(1, dk["launches"]), 4), "launches": dk["launches"],
+                    "share_of_step": round(dk["ms"] / step_kernel_ms, 4) if step_kernel_ms else None, "dominant_class_by_time": dom,
+                    "whole_path": whole, "per_class_ms": {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]},
+                    "per_class_tflops": {k: round(2.0 * FULL_CLASS_MAC[k] * v["frames"] / (v["ms"] * 1e-3) / 1e12, 2) for k, v in prof.items() if v["launches"] and k in FULL_CLASS_MAC}}
+    else:
+        # roofline of the dominant kernel (decoder GTConvBlock: full 16->16 3x3 conv + 1x1s + TRALite), live CUDA-event timing
+        dk = prof["dec_gtconv"]
+        dec_tflops = (2.0 * DEC_GT_MAC_PER_FRAME * dk["frames"]) / (dk["ms"] * 1e-3) / 1e12 if dk["ms"] > 0 else 0.0
+        roofline = {
+            "kernel": "k_gtconv<DEC> (decoder GTConvBlock, 3 launches per chunk)", "bound": "fp32_fma",
+            "achieved": round(dec_tflops, 2), "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": round(dec_tflops / FP32_PEAK_TFLOPS, 4),
+            "peak_source": peak_src,
+            "traffic": DEC_GT_DRAM_BYTES_PER_FRAME * (dk["frames"] // max(1, dk["launches"])),
+            "traffic_note": "DRAM bytes per launch from ncu (8,555 B/frame, profiles/ncu_r1_v13_summary.txt) vs 6,336 algorithmic B/frame: "
+                            "the untouched channel half is re-read in the store phase instead of being held in 32 registers",
+            "algorithmic_bytes_per_launch": DEC_GT_ALG_BYTES_PER_FRAME * (dk["frames"] // max(1, dk["launches"])),
+            # the same kernel against the HBM roof (it is not the binding one: arithmetic intensity 84,582 MAC / 6,336 B = 26.7 flop/B)
+            "hbm_view": {"bound": "hbm", "achieved": round(DEC_GT_ALG_BYTES_PER_FRAME * dk["frames"] / (dk["ms"] * 1e-3) / 1e9, 1) if dk["ms"] > 0 else 0.0,
+                         "peak": hbm_peak, "unit": "GB/s",
+                         "frac": round(DEC_GT_ALG_BYTES_PER_FRAME * dk["frames"] / (dk["ms"] * 1e-3) / 1e9 / hbm_peak, 4) if dk["ms"] > 0 else 0.0},
+            "ms_per_launch": round(dk["ms"] / max(1, dk["launches"]), 4), "launches": dk["launches"],
+            "share_of_step": round(dk["ms"] / step_kernel_ms, 4) if step_kernel_ms else None,
+            "dominant_class_by_time": dom,
+            "whole_path": whole,
+            "per_class_ms": {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]},
+        }
+    wl = (f"GTCRN-Micro offline batched inference, {B} x {SECONDS} s synthetic 16 kHz utterances per GPU (BASELINE configs[1]), STFT+model+iSTFT, shipped DNS3 checkpoint weights"
+          if not full else
+          f"original-GTCRN-style variant (BASELINE configs[3]: unfold SFE, groups=2, GTConv dilations 1/2/5, GRU-TRA, DPGRNN; PARITY UNPINNED, seeded random weights), "
+          f"{B} x {SECONDS} s synthetic 16 kHz utterances per GPU, STFT+model+iSTFT")
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"GTCRN-Micro offline batched inference, {B} x {SECONDS} s synthetic 16 kHz utterances per GPU (BASELINE configs[1]), "
-                               f"STFT+model+iSTFT, shipped DNS3 checkpoint weights",
+        "config": {"workload": wl, "variant": args.variant,
                    "batch_per_gpu": B, "samples_per_utt": L_UTT, "frames_per_utt": FRAMES_PER_UTT,
                    "cache": f"inputs {B * L_UTT * 4 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                    "parallelism": f"{world} independent shard(s), no collective"},
@@ -568,12 +654,14 @@ def run_b200(args):
         except Exception as e:  # streaming is reported, never allowed to sink the offline number
             line["streaming"] = {"error": f"{type(e).__name__}: {e}"}
     if not args.no_parity:
-        line["parity"] = parity_of_timed_batch(x_sub, torch.stack(clean_rows), y_sub)
+        line["parity"] = parity_of_timed_batch(x_sub, torch.stack(clean_rows), y_sub, args.variant, full_sd if full else None)
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        ref = CpuReference()
+        ref = CpuReference(args.variant, full_sd if full else None)
         v, detail = cpu_throughput(ref, (1, 4, 16, 64), reps=2, budget_s=45.0)
         what = "the reference's own GTCRNMicro between torch.stft / torch.istft (baseline/_ref)" if ref.kind == "reference" else "oracle port (same ATen ops as the reference)"
+        if full:
+            what = "builder-written oracle of the original-GTCRN-style variant (PARITY UNPINNED: no reference implementation exists)"
         line["cpu_baseline"] = {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": ref.kind,
                                 "sample": f"{what}, torch {torch.__version__} CPU, {SECONDS} s utterances, "
                                           f"best of B in {detail} (1 warm-up + best of 2 each); 1024-utterance batch extrapolated from this sample",
@@ -611,6 +699,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="utterances per GPU per step (BASELINE configs[1]: 1024)")
     ap.add_argument("--no-stream", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--variant", default="micro", choices=["micro", "full"],
+                    help="micro: the reference's GTCRNMicro (BASELINE configs[1], the headline); full: the original-GTCRN-style architecture of configs[3] (parity unpinned)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch (A/B runs only)")
     ap.add_argument("--sweep-utterances", type=int, default=0,
                     help="BASELINE configs[4]: a fixed job of this many 10 s utterances (65536) sharded over the ranks in contiguous "
