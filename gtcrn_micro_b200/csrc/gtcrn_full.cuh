@@ -27,7 +27,14 @@ using namespace gk;
 
 constexpr int kMaxDil = 5;
 
-__device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
+// Gate non-linearities on the SFU: ex2.approx + rcp.approx (MUFU.EX2 / MUFU.RCP, ~2^-22 relative error each), 4-5 instructions
+// instead of ~20 (expf + IEEE division) and ~30 (tanhf) -- the recurrent kernels evaluate 40 of them per GRU step and were
+// issue-bound on exactly that (ncu r2_full_v1: 1,280 warp instructions per inter-GRU step).  The same functions are used by the
+// offline and the streaming launches, so the two stay bit-identical; the accuracy cost against the fp32 oracle is ~1e-6.
+__device__ __forceinline__ float ex2_approx(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float rcp_approx(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float sigm(float v) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v)); }
+__device__ __forceinline__ float tanh_(float v) { return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * v)), 1.0f); }
 
 // streaming state of the variant: header (same struct as the Micro stream state) + per stream
 //   GT ring   6 blocks, 2 d_i rows each (d = 1,2,5,5,2,1 -> 32 rows) x [33][16]   point-conv-1 outputs, slot = frame mod 2d
@@ -58,6 +65,7 @@ __host__ __device__ constexpr int gtf_smem_floats(int PS, int G) {
     const int NT = G * PS;
     return (NT + 2 * kMaxDil) * GT_ROW4 * 4        // ring of point-conv-1 rows
            + NT * 2 * 35 * 4                       // X1: the processed half of the input (8 ch) with zero pad columns, for the unfold
+           + NT * 2 * kF2 * 4                      // X2: the untouched half
            + NT * kF2 * 8                          // q^2
            + NT * 8 + NT * 48 + NT * 8             // energies, GRU input projections, gates
            + GTF_GRU_FLOATS;
@@ -72,7 +80,8 @@ kf_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* 
     extern __shared__ float4 smem4[];
     float4* Pb = smem4;
     float4* X1 = Pb + (NT + 2 * kMaxDil) * GT_ROW4;                    // [slot][half][35]
-    float* E2 = reinterpret_cast<float*>(X1 + NT * 2 * 35);            // [slot][33][8]
+    float4* X2 = X1 + NT * 2 * 35;                                     // [slot][half][33]: the untouched half, private to its (slot, bin) thread
+    float* E2 = reinterpret_cast<float*>(X2 + NT * 2 * kF2);           // [slot][33][8]
     float* Ev = E2 + NT * kF2 * 8;                                     // [slot][8]
     float* Gi = Ev + NT * 8;                                           // [slot][48]
     float* Gt = Gi + NT * 48;                                          // [slot][8]
@@ -120,7 +129,6 @@ kf_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* 
     int rb = 2 * d;                                                   // ring row of the tile's first frame
     for (int t0 = 0; t0 < T; t0 += NT) {
         // ---- phase 0: load x (+ skip); processed half -> X1 (for the 3-bin unfold), untouched half stays in registers
-        float4 x2[PS][2];
         if (act) {
 #pragma unroll
             for (int s = 0; s < PS; ++s) {
@@ -138,7 +146,8 @@ kf_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* 
                 }
                 X1[((g * PS + s) * 2 + 0) * 35 + f + 1] = v0;
                 X1[((g * PS + s) * 2 + 1) * 35 + f + 1] = v1;
-                x2[s][0] = v2; x2[s][1] = v3;
+                X2[(g * PS + s) * 2 * kF2 + f] = v2;                   // untouched half parked in shared memory until the store phase
+                X2[((g * PS + s) * 2 + 1) * kF2 + f] = v3;
             }
         }
         __syncthreads();
@@ -237,34 +246,44 @@ kf_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* 
             __syncwarp();
             const int j = lane & 15;
             const int nvalid = min(NT, T - t0);
+            const float4* wr = reinterpret_cast<const float4*>(Whh + j * blobf::kWhhStride);
+            const float4* wz = reinterpret_cast<const float4*>(Whh + (16 + j) * blobf::kWhhStride);
+            const float4* wn = reinterpret_cast<const float4*>(Whh + (32 + j) * blobf::kWhhStride);
             for (int slot = 0; slot < nvalid; ++slot) {
-                float gr = Bhh[j], gz = Bhh[16 + j], gn = Bhh[32 + j];
-                const float4* wr = reinterpret_cast<const float4*>(Whh + j * blobf::kWhhStride);
-                const float4* wz = reinterpret_cast<const float4*>(Whh + (16 + j) * blobf::kWhhStride);
-                const float4* wn = reinterpret_cast<const float4*>(Whh + (32 + j) * blobf::kWhhStride);
+                // three 16-term dot products as 4 partial sums each (dependency depth 4 + 2 instead of 16): this loop is the serial
+                // spine of the block -- every other warp of the CTA waits for it
+                float pr[4], pz[4], pn[4];
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
                     const float4 a = wr[k4], bq = wz[k4], c = wn[k4];
-                    gr = fmaf(a.x, hall[4 * k4], gr); gr = fmaf(a.y, hall[4 * k4 + 1], gr); gr = fmaf(a.z, hall[4 * k4 + 2], gr); gr = fmaf(a.w, hall[4 * k4 + 3], gr);
-                    gz = fmaf(bq.x, hall[4 * k4], gz); gz = fmaf(bq.y, hall[4 * k4 + 1], gz); gz = fmaf(bq.z, hall[4 * k4 + 2], gz); gz = fmaf(bq.w, hall[4 * k4 + 3], gz);
-                    gn = fmaf(c.x, hall[4 * k4], gn); gn = fmaf(c.y, hall[4 * k4 + 1], gn); gn = fmaf(c.z, hall[4 * k4 + 2], gn); gn = fmaf(c.w, hall[4 * k4 + 3], gn);
+                    pr[k4] = fmaf(a.w, hall[4 * k4 + 3], fmaf(a.z, hall[4 * k4 + 2], fmaf(a.y, hall[4 * k4 + 1], a.x * hall[4 * k4])));
+                    pz[k4] = fmaf(bq.w, hall[4 * k4 + 3], fmaf(bq.z, hall[4 * k4 + 2], fmaf(bq.y, hall[4 * k4 + 1], bq.x * hall[4 * k4])));
+                    pn[k4] = fmaf(c.w, hall[4 * k4 + 3], fmaf(c.z, hall[4 * k4 + 2], fmaf(c.y, hall[4 * k4 + 1], c.x * hall[4 * k4])));
                 }
+                const float gr = __fadd_rn(__fadd_rn(__fadd_rn(pr[0], pr[1]), __fadd_rn(pr[2], pr[3])), Bhh[j]);
+                const float gz = __fadd_rn(__fadd_rn(__fadd_rn(pz[0], pz[1]), __fadd_rn(pz[2], pz[3])), Bhh[16 + j]);
+                const float gn = __fadd_rn(__fadd_rn(__fadd_rn(pn[0], pn[1]), __fadd_rn(pn[2], pn[3])), Bhh[32 + j]);
                 const float r = sigm(__fadd_rn(Gi[slot * 48 + j], gr));
                 const float z = sigm(__fadd_rn(Gi[slot * 48 + 16 + j], gz));
-                const float n = tanhf(fmaf(r, gn, Gi[slot * 48 + 32 + j]));
+                const float n = tanh_(fmaf(r, gn, Gi[slot * 48 + 32 + j]));
                 hj = fmaf(z, hj, __fmul_rn(1.0f - z, n));
 #pragma unroll
                 for (int k = 0; k < 16; ++k) hall[k] = __shfl_sync(0xffffffffu, hj, k);
-                if (lane < 8) {
-                    float v = Fcb[lane];
-                    const float4* wf = reinterpret_cast<const float4*>(Fcw + lane * blobf::kWhhStride);
+                if (lane < 16) Gi[slot * 48 + lane] = hj;              // h_t parked in the (consumed) r-gate slots for the Linear below
+            }
+            __syncwarp();
+            // Linear(16 -> 8) + sigmoid for all frames of the tile at once (off the serial spine)
+            for (int i = lane; i < nvalid * 8; i += 32) {
+                const int slot = i >> 3, c = i & 7;
+                float v = Fcb[c];
+                const float4* wf = reinterpret_cast<const float4*>(Fcw + c * blobf::kWhhStride);
+                const float4* hv = reinterpret_cast<const float4*>(Gi + slot * 48);
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const float4 a = wf[k4];
-                        v = fmaf(a.x, hall[4 * k4], v); v = fmaf(a.y, hall[4 * k4 + 1], v); v = fmaf(a.z, hall[4 * k4 + 2], v); v = fmaf(a.w, hall[4 * k4 + 3], v);
-                    }
-                    Gt[slot * 8 + lane] = sigm(v);
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 a = wf[k4], hh = hv[k4];
+                    v = fmaf(a.x, hh.x, v); v = fmaf(a.y, hh.y, v); v = fmaf(a.z, hh.z, v); v = fmaf(a.w, hh.w, v);
                 }
+                Gt[i] = sigm(v);
             }
         }
         __syncthreads();
@@ -275,7 +294,7 @@ kf_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* 
                 const int o = g * PS + s, t = t0 + o;
                 if (t < T) {
                     const float4 g0 = reinterpret_cast<const float4*>(Gt + o * 8)[0], g1 = reinterpret_cast<const float4*>(Gt + o * 8)[1];
-                    const float4 v2 = x2[s][0], v3 = x2[s][1];
+                    const float4 v2 = X2[o * 2 * kF2 + f], v3 = X2[(o * 2 + 1) * kF2 + f];
                     float4* po = reinterpret_cast<float4*>(out + ubase + ((int64_t)t * kF2 + f) * 16);
                     po[0] = make_float4(q[s][0] * g0.x, v2.x, q[s][1] * g0.y, v2.y);
                     po[1] = make_float4(q[s][2] * g0.z, v2.z, q[s][3] * g0.w, v2.w);
@@ -302,23 +321,24 @@ constexpr int DPA_STRIDE = kF2 * 16 + 4;       // 532 floats per frame: lane str
 constexpr int DPA_SMEM_FLOATS = DPA_FR * DPA_STRIDE + 2 * kF2 * 16 + DPA_FR * 2;
 struct DpaParams { float w[blobf::DPA_SIZE]; };
 
-template <int I, int H>   // one GRU step for a chain held by one thread: x[I] inputs, h[H] state; weights at (wih, whh, bih, bhh) of a uniform param struct
+template <int I, int H>   // one GRU step for a chain held by one thread: x[I] inputs, h[H] state; weights [k][3H rows] in a warp-uniform param struct
 __device__ __forceinline__ void gru_thread_step(const float* wih, const float* whh, const float* bih, const float* bhh, const float (&x)[I], float (&h)[H]) {
     float gi[3 * H], gh[3 * H];
 #pragma unroll
     for (int r = 0; r < 3 * H; ++r) { gi[r] = bih[r]; gh[r] = bhh[r]; }
 #pragma unroll
-    for (int r = 0; r < 3 * H; ++r) {
+    for (int k = 0; k < I; ++k)
 #pragma unroll
-        for (int k = 0; k < I; ++k) gi[r] = fmaf(wih[r * I + k], x[k], gi[r]);
+        for (int r = 0; r < 3 * H; r += 2) fma_pair(gi[r], gi[r + 1], x[k], wih[k * 3 * H + r], wih[k * 3 * H + r + 1]);
 #pragma unroll
-        for (int k = 0; k < H; ++k) gh[r] = fmaf(whh[r * H + k], h[k], gh[r]);
-    }
+    for (int k = 0; k < H; ++k)
+#pragma unroll
+        for (int r = 0; r < 3 * H; r += 2) fma_pair(gh[r], gh[r + 1], h[k], whh[k * 3 * H + r], whh[k * 3 * H + r + 1]);
 #pragma unroll
     for (int j = 0; j < H; ++j) {
         const float r = sigm(__fadd_rn(gi[j], gh[j]));
         const float z = sigm(__fadd_rn(gi[H + j], gh[H + j]));
-        const float n = tanhf(fmaf(r, gh[2 * H + j], gi[2 * H + j]));
+        const float n = tanh_(fmaf(r, gh[2 * H + j], gi[2 * H + j]));
         h[j] = fmaf(z, h[j], __fmul_rn(1.0f - z, n));
     }
 }

@@ -79,7 +79,7 @@ constexpr int SG_ROW4 = gk::GT_ROW4;
 constexpr int SG_SMEM_FLOATS = SG_NS * 3 * SG_ROW4 * 4 + SG_NS * kF2 * 8 + SG_NS * 3 * 8 + SG_NS * 8;
 
 template <bool DEC>
-__global__ void __launch_bounds__(SG_THREADS, 2)
+__global__ void __launch_bounds__(SG_THREADS, DEC ? 2 : 3)
 ks_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* __restrict__ out,
           const __grid_constant__ gk::ParamBlock<gk::gt_chunk<DEC>()> prm, void* state, int blk, int64_t N) {
     using namespace gk;
@@ -96,8 +96,13 @@ ks_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* 
 
     const int tid = threadIdx.x;
     const int64_t n0 = (int64_t)blockIdx.x * SG_NS;
-    zero_f4(reinterpret_cast<float*>(Pb), SG_SMEM_FLOATS, tid, SG_THREADS);
-    __syncthreads();
+    // only the pad columns (0 and 34 of every row) and the rows of absent streams must read as zero: everything else is written
+    // before it is read (zeroing all 53 KB per CTA was 5.5 % of the kernel's samples, ncu r2_stream16k_v19)
+    for (int i = tid; i < SG_NS * 3 * 4 * 2; i += SG_THREADS) Pb[(i >> 1) * 35 + (i & 1) * 34] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + SG_NS > N) {
+        zero_f4(reinterpret_cast<float*>(Pb), SG_SMEM_FLOATS, tid, SG_THREADS);
+        __syncthreads();
+    }
 
     const int ls = tid / kF2, f = tid - ls * kF2;
     const int64_t n = n0 + ls;
@@ -197,16 +202,23 @@ ks_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Both GTCNs (8 TCN blocks) for one frame: a pure per-(stream, bin) recurrence.  A thread owns two columns,
-// keeps x in registers through all eight TCNs and touches exactly 2 taps + 1 new row per TCN in the ring.
-// No shared memory at all (weights: kernel parameter / constant bank).  grid ceil(N*33 / 512), 256 threads.
+// Both GTCNs (8 TCN blocks) for one frame: a pure per-(stream, bin) recurrence.  A thread owns two columns (every weight feeds
+// two FFMA2), keeps x in registers through all eight TCNs and touches exactly 2 taps + 1 new row per TCN in the ring.
+// The tap addresses depend only on the frame counter, so the taps of TCN k+1 are requested with cp.async (LDGSTS: global ->
+// shared, no staging registers) before TCN k is computed and read back from a thread-private, lane-interleaved shared-memory
+// slot: the ring reads -- the bulk of a hop's HBM traffic -- overlap the previous TCN's 1,024 FFMA2 per thread.  [The round-1
+// kernel loaded the taps right before use: 61 % of its stall samples sat on the first tap, 1.96 TB/s at 16,384 streams,
+// profiles/ncu_r2_stream16k_v19_lines_ks_gtcn.txt; holding the next taps in registers instead made ptxas fall back to
+// per-thread-indexed LDC for the weights.]  Weights: kernel parameter / constant bank.  grid ceil(N*33 / 256), 128 threads.
 // ------------------------------------------------------------------------------------------------
-constexpr int ST_THREADS = 256;
+constexpr int ST_THREADS = 128;
+constexpr int ST_SMEM_BYTES = 2 * 16 * ST_THREADS * 16;          // 2 stages x 16 float4 per thread
 
-__global__ void __launch_bounds__(ST_THREADS, 2)
+__global__ void __launch_bounds__(ST_THREADS, 3)
 ks_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_constant__ gk::ParamBlock<8 * blob::TCN_SIZE> prm,
         void* state, int64_t N) {
     using namespace gk;
+    extern __shared__ float4 smem4[];                             // [stage][item = (col, tap, quad)][thread]
     const Header* hdr = reinterpret_cast<const Header*>(state);
     if (hdr->skip) return;
     const long long step = hdr->frame_step;
@@ -223,7 +235,28 @@ ks_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_con
         const int64_t n = p / kF2;
         const int f = (int)(p - n * kF2);
         ybase[s] = stream_base(state, n) + kTcnY + f * 16;
-        const float4* px = reinterpret_cast<const float4*>(xin + p * 16);
+    }
+    const unsigned sm0 = (unsigned)__cvta_generic_to_shared(smem4 + tid);
+    auto prefetch = [&](int gk_) {                           // taps of TCN gk_ -> stage gk_ & 1
+        const int g = gk_ >> 2, k = gk_ & 3, d = 1 << k, row0 = g * 30 + (2 << k) - 2;
+        const int slotA = (int)(step & (2 * d - 1)), slotB = (int)((step + d) & (2 * d - 1));
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const float* rA = ybase[s] + (row0 + slotA) * (kF2 * 16);
+            const float* rB = ybase[s] + (row0 + slotB) * (kF2 * 16);
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                const unsigned da = sm0 + (unsigned)((((gk_ & 1) * 16 + s * 8 + qd) * ST_THREADS) * 16);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(rA + 4 * qd) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da + 4u * ST_THREADS * 16u), "l"(rB + 4 * qd) : "memory");
+            }
+        }
+        cp_async_commit();
+    };
+    prefetch(0);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const float4* px = reinterpret_cast<const float4*>(xin + (ok[s] ? pos[s] : pos[0]) * 16);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             const float4 u = px[v];
@@ -234,17 +267,18 @@ ks_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_con
     for (int gk_ = 0; gk_ < 8; ++gk_) {
         const int g = gk_ >> 2, k = gk_ & 3, d = 1 << k, row0 = g * 30 + (2 << k) - 2, wo = gk_ * blob::TCN_SIZE;
         const int slotA = (int)(step & (2 * d - 1));          // frame t-2d, overwritten with frame t
-        const int slotB = (int)((step + d) & (2 * d - 1));    // frame t-d
+        if (gk_ < 7) prefetch(gk_ + 1); else cp_async_commit();
         float y1[2][16];
         tcn_conv1<2>(prm, wo, x, y1);
+        cp_async_wait_group<1>();                             // this TCN's taps have landed (the next one's may still be in flight)
+        const float4* st4 = smem4 + ((gk_ & 1) * 16) * ST_THREADS + tid;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            float4* rA = reinterpret_cast<float4*>(ybase[s] + (row0 + slotA) * (kF2 * 16));
-            const float4* rB = reinterpret_cast<const float4*>(ybase[s] + (row0 + slotB) * (kF2 * 16));
             float4 ta[4], tb[4];
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd) { ta[qd] = rA[qd]; tb[qd] = rB[qd]; }
+            for (int qd = 0; qd < 4; ++qd) { ta[qd] = st4[(s * 8 + qd) * ST_THREADS]; tb[qd] = st4[(s * 8 + 4 + qd) * ST_THREADS]; }
             if (s == 0 || ok[1]) {
+                float4* rA = reinterpret_cast<float4*>(ybase[s] + (row0 + slotA) * (kF2 * 16));
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) rA[qd] = make_float4(y1[s][4 * qd], y1[s][4 * qd + 1], y1[s][4 * qd + 2], y1[s][4 * qd + 3]);
             }
@@ -468,6 +502,10 @@ inline int stream_init_attributes() {
         e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
     }
+    e = cudaFuncSetAttribute(ks_gtcn, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(ks_gtcn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(ks_gtconv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM_FLOATS * (int)sizeof(float));
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(ks_gtconv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM_FLOATS * (int)sizeof(float));
@@ -508,7 +546,7 @@ inline int model_step(const float* blobp, const HostParams& hp, void* state, con
         ks_gtconv<false><<<gsg, SG_THREADS, SG_SMEM_FLOATS * sizeof(float), st>>>(ws.act[i], nullptr, ws.act[i + 1], hp.enc[i], state, i, N);
         ++launches;
     }
-    ks_gtcn<<<(unsigned)((N * kF2 + 2 * ST_THREADS - 1) / (2 * ST_THREADS)), ST_THREADS, 0, st>>>(ws.act[3], ws.act[5], hp.tcn8, state, N);
+    ks_gtcn<<<(unsigned)((N * kF2 + 2 * ST_THREADS - 1) / (2 * ST_THREADS)), ST_THREADS, ST_SMEM_BYTES, st>>>(ws.act[3], ws.act[5], hp.tcn8, state, N);
     ++launches;
     for (int i = 0; i < 3; ++i) {
         ks_gtconv<true><<<gsg, SG_THREADS, SG_SMEM_FLOATS * sizeof(float), st>>>(ws.act[5 + i], ws.act[3 - i], ws.act[6 + i], hp.dec[i], state, 3 + i, N);
