@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgtcrn_b200.so")
 SOURCES = ["gtcrn_capi.cu"]
-DEPS = ["gtcrn_capi.cu", "gtcrn_kernels.cuh", "gtcrn_stream.cuh", "gtcrn_full.cuh", "gtcrn_full_host.cuh", "blob_layout.h", "blob_full_layout.h", os.path.join("..", "..", "include", "gtcrn_b200.h")]
+DEPS = ["gtcrn_capi.cu", "gtcrn_kernels.cuh", "gtcrn_stream.cuh", "gtcrn_full.cuh", "gtcrn_full_host.cuh", "gtcrn_tc.cuh", "tc_util.cuh", "blob_layout.h", "blob_full_layout.h", os.path.join("..", "..", "include", "gtcrn_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

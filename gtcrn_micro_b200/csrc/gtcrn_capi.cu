@@ -12,6 +12,7 @@
 #include "../../include/gtcrn_b200.h"
 #include "gtcrn_kernels.cuh"
 #include "gtcrn_stream.cuh"
+#include "gtcrn_tc.cuh"
 #include "gtcrn_full_host.cuh"
 
 namespace {
@@ -56,6 +57,12 @@ struct gtcrnb_handle {
     bool tcn_smem_w = false;                      // GTCN weights from shared memory (LDS.128) instead of the constant bank; with FFMA2 the
                                                   // constant-bank feed wins (B200: 4.73 vs 5.67 ms per 1024 x 10 s), before FFMA2 smem won (6.4 vs 7.3)
     int tcn_p = 2;                                // frame slots per lane of the GTCN kernel (2..4)
+    // tensor-core (tcgen05, 3xTF32) kernels: bit 0 GTCN pointwise convs, bit 1 decoder GTConv 3x3 (GTCRNB_TC, default both);
+    // 0 selects the FFMA kernels, whose results are bit-identical to the streaming path
+    int tc_mask = 3;
+    int tc_gtcn_nwg = 1;                          // warpgroups per CTA of k_gtcn_tc (GTCRNB_TC_GTCN_NWG: 1, 2 or 4)
+    int occ_tcn_tc = 1;
+    bool tc_stack = true;                         // [W_hi | W_lo] stacked along N: 4 MMAs per conv and 32 accumulator columns instead of 6 and 16
     int gt_enc = 0, gt_dec = 0;                   // index into kGtVariants for the encoder / decoder GTConv kernels
     // activation workspace for one chunk of utterances
     int64_t cap_frames = 0;
@@ -154,6 +161,12 @@ cudaError_t launch_gtconv(const GtVariant& v, dim3 grid, cudaStream_t st, const 
                           const gk::ParamBlock<gk::gt_chunk<DEC>()>& prm, int T, int seg) {
     void* args[] = {(void*)&x, (void*)&skip, (void*)&out, (void*)&prm, (void*)&T, (void*)&seg};
     return cudaLaunchKernel(DEC ? v.dec : v.enc, grid, dim3((unsigned)v.threads), args, (size_t)(DEC ? v.smem_dec : v.smem_enc), st);
+}
+
+const void* tc_gtcn_fn(int nwg, bool stack) {
+    using namespace gk;
+    if (stack) return nwg == 1 ? (const void*)k_gtcn_tc<1, true> : nwg == 2 ? (const void*)k_gtcn_tc<2, true> : (const void*)k_gtcn_tc<4, true>;
+    return nwg == 1 ? (const void*)k_gtcn_tc<1, false> : nwg == 2 ? (const void*)k_gtcn_tc<2, false> : (const void*)k_gtcn_tc<4, false>;
 }
 
 // RAII: brackets a kernel launch with two events when profiling is on
@@ -278,6 +291,21 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
         const int64_t ctas = (ncols + WC_WARPS - 1) / WC_WARPS;
         const int seg = pick_seg_len(ctas, Ti, 32, TC_WARMUP, h->sm_count * h->occ_tcn);
         const dim3 g((unsigned)ctas, (unsigned)((Ti + seg - 1) / seg));
+        if (h->tc_mask & 1) {
+            const int nwg = h->tc_gtcn_nwg;
+            const int64_t ctas_tc = (ncols + 4 * nwg - 1) / (4 * nwg);
+            const int seg_tc = pick_seg_len(ctas_tc, Ti, 32, TC_WARMUP, h->sm_count * h->occ_tcn_tc);
+            const dim3 gt((unsigned)ctas_tc, (unsigned)((Ti + seg_tc - 1) / seg_tc));
+            for (int i = 0; i < 2; ++i) {
+                ProfScope ps(h, KC_GTCN, nframes, st);
+                const size_t sm = tct_smem_floats(nwg) * sizeof(float);
+                const float* xi = h->act[3 + i]; float* xo = h->act[4 + i];
+                int seg_i = seg_tc; int64_t nc = ncols;
+                void* args[] = {(void*)&xi, (void*)&xo, (void*)&h->hp->gtcn[i], (void*)&Ti, (void*)&seg_i, (void*)&nc};
+                cudaLaunchKernel(tc_gtcn_fn(nwg, h->tc_stack), gt, dim3(128 * nwg), args, sm, st);
+                h->launches++;
+            }
+        } else
         for (int i = 0; i < 2; ++i) {
             ProfScope ps(h, KC_GTCN, nframes, st);
             if (h->tcn_smem_w) k_gtcn<2, true><<<g, WC_WARPS * 32, wc_smem_floats(2, true) * sizeof(float), st>>>(h->act[3 + i], h->act[4 + i], h->hp->gtcn[i], Ti, seg, ncols);
@@ -285,7 +313,16 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
             h->launches++;
         }
     }
-    {
+    if (h->tc_mask & 2) {
+        const int rows = (int)((B + GTT_G * GTT_NWG - 1) / (GTT_G * GTT_NWG));
+        const int seg = pick_seg_len(rows, Ti, 1, GT_WARMUP, h->sm_count);
+        const dim3 g((unsigned)((Ti + seg - 1) / seg), (unsigned)rows);
+        for (int i = 0; i < 3; ++i) {
+            ProfScope ps(h, KC_DEC_GT, nframes, st);
+            k_gtconv_dec_tc<<<g, GTT_THREADS, gtt_smem_floats() * sizeof(float), st>>>(h->act[5 + i], h->act[3 - i], h->act[6 + i], h->hp->dec[i], Ti, seg, (int)B);
+            h->launches++;
+        }
+    } else {
         const GtVariant& v = kGtVariants[h->gt_dec];
         const int seg = pick_seg_len(B, Ti, v.ps, GT_WARMUP, h->sm_count * h->occ_gt_dec);
         const dim3 g((unsigned)((Ti + seg - 1) / seg), (unsigned)B);
@@ -376,6 +413,9 @@ int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, 
         {(const void*)k_back<false, 0>, bk_smem_floats(false)}, {(const void*)k_back<true, 0>, bk_smem_floats(true)},
         {(const void*)k_stft, 0},
         {(const void*)k_istft, 0},
+        {tc_gtcn_fn(1, false), tct_smem_floats(1)}, {tc_gtcn_fn(2, false), tct_smem_floats(2)}, {tc_gtcn_fn(4, false), tct_smem_floats(4)},
+        {(const void*)k_gtconv_dec_tc, gtt_smem_floats()},
+        {tc_gtcn_fn(1, true), tct_smem_floats(1)}, {tc_gtcn_fn(2, true), tct_smem_floats(2)}, {tc_gtcn_fn(4, true), tct_smem_floats(4)},
     };
     std::vector<std::pair<const void*, int>> all;
     for (auto& a : attrs) all.push_back({a.fn, a.floats});
@@ -414,6 +454,15 @@ int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, 
     if (const char* e = getenv("GTCRNB_FUSE_FFT")) h->fuse_fft = atoi(e) != 0;
     if (const char* e = getenv("GTCRNB_TCN_SMEMW")) h->tcn_smem_w = atoi(e) != 0;
     if (const char* e = getenv("GTCRNB_STREAM_GRAPH")) h->stream_graphs = atoi(e) != 0;
+    if (const char* e = getenv("GTCRNB_TC")) h->tc_mask = atoi(e);
+    if (const char* e = getenv("GTCRNB_TC_GTCN_NWG")) { const int v = atoi(e); h->tc_gtcn_nwg = v >= 4 ? 4 : v >= 2 ? 2 : 1; }
+    {
+        const int nwg = h->tc_gtcn_nwg;
+        if (const char* e = getenv("GTCRNB_TC_STACK")) h->tc_stack = atoi(e) != 0;
+        const void* fn = tc_gtcn_fn(nwg, h->tc_stack);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn_tc, fn, 128 * nwg, tct_smem_floats(nwg) * sizeof(float));
+        h->occ_tcn_tc = std::max(1, std::min(h->occ_tcn_tc, 8 / nwg));       // 64 TMEM columns per warpgroup, 512 per SM
+    }
     if (h->tcn_smem_w) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn<2, true>, WC_WARPS * 32, wc_smem_floats(2, true) * sizeof(float));
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_tcn, k_gtcn<2, false>, WC_WARPS * 32, wc_smem_floats(2) * sizeof(float));
     h->occ_gt_enc = std::max(1, h->occ_gt_enc); h->occ_gt_dec = std::max(1, h->occ_gt_dec); h->occ_tcn = std::max(1, h->occ_tcn);
