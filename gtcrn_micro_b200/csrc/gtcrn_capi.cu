@@ -62,7 +62,8 @@ struct gtcrnb_handle {
     int tc_mask = 3;
     int tc_gtcn_nwg = 1;                          // warpgroups per CTA of k_gtcn_tc (GTCRNB_TC_GTCN_NWG: 1, 2 or 4)
     int occ_tcn_tc = 1;
-    bool tc_stack = true;                         // [W_hi | W_lo] stacked along N: 4 MMAs per conv and 32 accumulator columns instead of 6 and 16
+    int tc_dec_nwg = 4;                           // warpgroups per CTA of k_gtconv_dec_tc (GTCRNB_TC_DEC_NWG: 1, 2, 4 or 5; 96 TMEM columns each)
+    bool tc_stack = false;                        // [W_hi | W_lo] stacked along N: 4 MMAs per conv and 32 accumulator columns instead of 6 and 16
     int gt_enc = 0, gt_dec = 0;                   // index into kGtVariants for the encoder / decoder GTConv kernels
     // activation workspace for one chunk of utterances
     int64_t cap_frames = 0;
@@ -163,6 +164,10 @@ cudaError_t launch_gtconv(const GtVariant& v, dim3 grid, cudaStream_t st, const 
     return cudaLaunchKernel(DEC ? v.dec : v.enc, grid, dim3((unsigned)v.threads), args, (size_t)(DEC ? v.smem_dec : v.smem_enc), st);
 }
 
+const void* tc_dec_fn(int nwg) {
+    using namespace gk;
+    return nwg == 1 ? (const void*)k_gtconv_dec_tc<1> : nwg == 2 ? (const void*)k_gtconv_dec_tc<2> : nwg == 4 ? (const void*)k_gtconv_dec_tc<4> : (const void*)k_gtconv_dec_tc<5>;
+}
 const void* tc_gtcn_fn(int nwg, bool stack) {
     using namespace gk;
     if (stack) return nwg == 1 ? (const void*)k_gtcn_tc<1, true> : nwg == 2 ? (const void*)k_gtcn_tc<2, true> : (const void*)k_gtcn_tc<4, true>;
@@ -314,12 +319,16 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
         }
     }
     if (h->tc_mask & 2) {
-        const int rows = (int)((B + GTT_G * GTT_NWG - 1) / (GTT_G * GTT_NWG));
-        const int seg = pick_seg_len(rows, Ti, 1, GT_WARMUP, h->sm_count);
+        const int nwg = h->tc_dec_nwg;
+        const int rows = (int)((B + GTT_G * nwg - 1) / (GTT_G * nwg));
+        const int seg = pick_seg_len(rows, Ti, 1, GT_WARMUP, h->sm_count * gtt_min_blocks(nwg));
         const dim3 g((unsigned)((Ti + seg - 1) / seg), (unsigned)rows);
         for (int i = 0; i < 3; ++i) {
             ProfScope ps(h, KC_DEC_GT, nframes, st);
-            k_gtconv_dec_tc<<<g, GTT_THREADS, gtt_smem_floats() * sizeof(float), st>>>(h->act[5 + i], h->act[3 - i], h->act[6 + i], h->hp->dec[i], Ti, seg, (int)B);
+            const float* xi = h->act[5 + i]; const float* sk = h->act[3 - i]; float* xo = h->act[6 + i];
+            int seg_i = seg, Bi = (int)B;
+            void* args[] = {(void*)&xi, (void*)&sk, (void*)&xo, (void*)&h->hp->dec[i], (void*)&Ti, (void*)&seg_i, (void*)&Bi};
+            cudaLaunchKernel(tc_dec_fn(nwg), g, dim3(128 * nwg), args, gtt_smem_floats(nwg) * sizeof(float), st);
             h->launches++;
         }
     } else {
@@ -414,7 +423,7 @@ int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, 
         {(const void*)k_stft, 0},
         {(const void*)k_istft, 0},
         {tc_gtcn_fn(1, false), tct_smem_floats(1)}, {tc_gtcn_fn(2, false), tct_smem_floats(2)}, {tc_gtcn_fn(4, false), tct_smem_floats(4)},
-        {(const void*)k_gtconv_dec_tc, gtt_smem_floats()},
+        {tc_dec_fn(1), gtt_smem_floats(1)}, {tc_dec_fn(2), gtt_smem_floats(2)}, {tc_dec_fn(4), gtt_smem_floats(4)}, {tc_dec_fn(5), gtt_smem_floats(5)},
         {tc_gtcn_fn(1, true), tct_smem_floats(1)}, {tc_gtcn_fn(2, true), tct_smem_floats(2)}, {tc_gtcn_fn(4, true), tct_smem_floats(4)},
     };
     std::vector<std::pair<const void*, int>> all;
@@ -455,6 +464,7 @@ int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, 
     if (const char* e = getenv("GTCRNB_TCN_SMEMW")) h->tcn_smem_w = atoi(e) != 0;
     if (const char* e = getenv("GTCRNB_STREAM_GRAPH")) h->stream_graphs = atoi(e) != 0;
     if (const char* e = getenv("GTCRNB_TC")) h->tc_mask = atoi(e);
+    if (const char* e = getenv("GTCRNB_TC_DEC_NWG")) { const int v = atoi(e); h->tc_dec_nwg = v >= 5 ? 5 : v >= 4 ? 4 : v >= 2 ? 2 : 1; }
     if (const char* e = getenv("GTCRNB_TC_GTCN_NWG")) { const int v = atoi(e); h->tc_gtcn_nwg = v >= 4 ? 4 : v >= 2 ? 2 : 1; }
     {
         const int nwg = h->tc_gtcn_nwg;

@@ -17,6 +17,7 @@
 // MMA adds lo*w_hi: 2 MMAs per K = 8 step instead of 3; the two column blocks are added in registers after tcgen05.ld.
 #pragma once
 #include "gtcrn_kernels.cuh"
+#include <cuda_fp16.h>
 #include "tc_util.cuh"
 
 namespace gk {
@@ -245,69 +246,99 @@ k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_c
 //      D_f[kf*16 + co] = sum_{kt, ci} p[t-2+kt][f][ci] * W[kt][kf][ci][co]                     (K = 3 frames x 16 ci = 48)
 //      m[t][f]         = D_{f-1}[kf=0] + D_f[kf=1] + D_{f+1}[kf=2] + b                          (zero padded in f)
 // The three K blocks are the point-conv outputs p of frames t-2, t-1, t AT THE SAME BIN, i.e. values the same thread produced in
-// its last three steps: they sit in a 3-slot ring of TMEM columns (A_hi / A_lo, 16 columns per slot), every step overwrites the
-// oldest slot with the new frame and pairs each slot's columns with the weight planes of its current kt -- the activations of the
-// 3x3 convolution never touch shared memory.  Only the two outer kf blocks of D are exchanged with the neighbouring bins through
-// shared memory (32 floats per position instead of the 9-tap x 16-channel gather of the FFMA kernel).
-//   TMEM per warpgroup (144 columns): D[0:48], A_hi[48:96] (slot s at 48 + 16 s), A_lo[96:144]; one CTA of 3 warpgroups per SM
-//   shared memory: B = W_hi, W_lo as [kt][4 k-planes][48 rows = kf*16+co][4] (18 KB); per warpgroup the exchange buffer
-//                  X[2][4 quads][100 rows] float4, E2[99][8] (q^2), Ev[3 groups][3 slots][8] TRA energies, Gt[3][8] gates
+// its last three steps: they sit in a 3-slot ring of TMEM columns, every step overwrites the oldest slot with the new frame and
+// pairs each slot's columns with the weight planes of its current kt -- the activations of the 3x3 convolution never touch shared
+// memory.  Only the two outer kf blocks of D are exchanged with the neighbouring bins through shared memory (32 floats per
+// position instead of the 9-tap x 16-channel gather of the FFMA kernel).
+//
+// Operand format: kind::f16 with fp32-class accuracy through an fp16 hi/lo split, x = hi + lo, hi = fp16(x), lo = fp16(x - hi)
+// (11 + 11 mantissa bits, the same as the TF32 split, measured 8.8e-7 abs on K = 48 sums of O(1) values against 5.7e-7 for
+// sequential fp32 FMA: profiles/umma_ts_test_r2.txt).  Against TF32 it halves both the TMEM columns of A (two elements per column:
+// 8 columns of hi pairs + 8 of lo pairs per 16-channel block) and the number of MMAs (K = 16 per instruction): 9 per step.  TMEM
+// is what limits the warpgroups in flight per SM (96 columns each -> 4 or 5 instead of 3), and a CTA's MMAs execute one after the
+// other at ~46 cycles each whatever their shape, so both matter.  The weights are scaled by a power of two (exact) so that the lo
+// parts stay normal fp16 numbers; the scale is undone in the bias FMA.  fp16 saturates at 65,504: the conversion clamps
+// (cvt.rn.satfinite), the point-conv activations it applies to are O(10) for the shipped checkpoint at full-scale input and O(500)
+// for the random test weights; GTCRNB_TC=0 selects the FFMA kernels, which have no such limit.
+//   TMEM per warpgroup (96 columns): D[0:48], A ring [48:96] (slot s: hi pairs at 48 + 16 s, lo pairs at 56 + 16 s)
+//   shared memory: B = W_hi, W_lo fp16 as [kt][2 k-chunks][48 rows = kf*16+co][8 halves] (9 KB); per warpgroup the exchange buffer
+//                  X[2][4 quads][100 rows] float4, E2[99][8] (q^2), Gt[3][8] gates; per CTA the 104 TRALite weights
 // Point conv 1 / 2 (128 MACs each), PReLUs, TRALite and the channel shuffle stay on the CUDA cores (gt_pc1 / gt_pc2 / gt_gate1, the
 // device functions of the FFMA kernel).
-// grid (segments, ceil(B / 9)), 384 threads.
+// grid (segments, ceil(B / (3 NWG))), 128 NWG threads.
 // ================================================================================================
-constexpr int GTT_NWG = 3;
 constexpr int GTT_G = 3;
 constexpr int GTT_ROWS = GTT_G * kF2;                       // 99 active rows per warpgroup
-constexpr int GTT_THREADS = 128 * GTT_NWG;
-constexpr int GTT_B_FLOATS = 2 * 3 * 768;                   // [hi/lo][kt][4][48][4]
-constexpr int GTT_WG_FLOATS = 2 * 4 * 100 * 4 + GTT_ROWS * 8 + GTT_G * 3 * 8 + GTT_G * 8 + 8;   // X, E2, Ev, Gt (+ pad to 16 B)
-__host__ __device__ constexpr int gtt_smem_floats() { return GTT_B_FLOATS + GTT_NWG * GTT_WG_FLOATS; }
-static_assert(GTT_WG_FLOATS % 4 == 0 && GTT_B_FLOATS % 4 == 0, "16-byte aligned regions");
+constexpr int GTT_B_FLOATS = 2 * 3 * 384;                   // [hi/lo][kt][2][48][8 halves] = 9,216 bytes
+constexpr int GTT_GW_FLOATS = 104;                          // TRALite weights: TDW_W[3][8], TDW_B[8], TPW_W[8][8], TPW_B[8]
+constexpr int GTT_WG_FLOATS = 2 * 4 * 100 * 4 + GTT_ROWS * 8 + GTT_G * 8;   // X, E2, Gt
+__host__ __device__ constexpr int gtt_smem_floats(int nwg) { return GTT_B_FLOATS + GTT_GW_FLOATS + nwg * GTT_WG_FLOATS; }
+__host__ __device__ constexpr int gtt_min_blocks(int nwg) { return nwg == 1 ? 4 : nwg == 2 ? 2 : 1; }
+__host__ __device__ constexpr uint32_t gtt_tmem_cols(int nwg) { return nwg == 1 ? 128 : nwg == 2 ? 256 : 512; }
+static_assert(GTT_WG_FLOATS % 4 == 0 && GTT_B_FLOATS % 4 == 0 && GTT_GW_FLOATS % 4 == 0, "16-byte aligned regions");
 
-__global__ void __launch_bounds__(GTT_THREADS, 1)
+template <int NWG>
+__global__ void __launch_bounds__(128 * NWG, gtt_min_blocks(NWG))
 k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, float* __restrict__ out,
                 const __grid_constant__ ParamBlock<gt_chunk<true>()> prm, int T, int seg_len, int B) {
     using O = GtOff<true>;
+    static_assert(NWG == 1 || NWG == 2 || (NWG >= 3 && NWG <= 5), "96 TMEM columns per warpgroup, power-of-two allocations");
+    constexpr int NTHR = 128 * NWG;
     extern __shared__ float4 smem4[];
-    __shared__ __align__(8) uint64_t bars[GTT_NWG];
+    __shared__ __align__(8) uint64_t bars[NWG];
     __shared__ uint32_t tmem_base_s;
+    __shared__ unsigned wmax_bits;
     float* Bw = reinterpret_cast<float*>(smem4);
     const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, tig = tid & 127;
-    float* wgm = Bw + GTT_B_FLOATS + wg * GTT_WG_FLOATS;
+    float* Gw = Bw + GTT_B_FLOATS;                                    // TRALite weights
+    float* wgm = Gw + GTT_GW_FLOATS + wg * GTT_WG_FLOATS;
     float4* X = reinterpret_cast<float4*>(wgm);                       // [2][4][100]
     float* E2 = wgm + 2 * 4 * 100 * 4;                                // [99][8]
-    float* Ev = E2 + GTT_ROWS * 8;                                    // [3][3][8]
-    float* Gt = Ev + GTT_G * 3 * 8;                                   // [3][8]
+    float* Gt = E2 + GTT_ROWS * 8;                                    // [3][8]
 
-    // ---- prologue: weight planes (3xTF32 split, round to nearest), zeroed TRA history, tensor memory
-    for (int i = tid; i < 2304; i += GTT_THREADS) {
-        const int kt = i / 768, r = i - kt * 768, kf = r >> 8, ci = (r >> 4) & 15, co = r & 15;
-        const float w = prm.w[O::MID_W + ((kt * 3 + kf) * 16 + ci) * 16 + co];
-        float hi, lo;
-        tf32_split_rn(w, hi, lo);
-        const int o = kt * 768 + (ci >> 2) * 192 + (kf * 16 + co) * 4 + (ci & 3);
-        Bw[o] = hi;
-        Bw[2304 + o] = lo;
+    // ---- prologue: power-of-two weight scale, fp16 hi/lo weight planes, zeroed TRA history, tensor memory
+    if (tid == 0) wmax_bits = 0u;
+    __syncthreads();
+    {
+        unsigned mx = 0u;
+        for (int i = tid; i < 2304; i += NTHR) mx = max(mx, __float_as_uint(fabsf(prm.w[O::MID_W + i])));
+        atomicMax(&wmax_bits, mx);
     }
-    for (int i = tig; i < GTT_G * 3 * 8; i += 128) Ev[i] = 0.f;
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
-    if (tid < GTT_NWG) tc::mbar_init(&bars[tid], 1);
+    __syncthreads();
+    // |w| < 2^(e+1)  =>  |w| * 2^(13-e) < 2^14: hi parts well inside fp16, lo parts (~2^-11 of that) normal down to |w| ~ 2^-13 max|w|
+    const int wexp = max(14, min(253, (int)(wmax_bits >> 23)));
+    const float wscale = __uint_as_float((unsigned)(127 + 13 + 127 - wexp) << 23);
+    const float winv = __uint_as_float((unsigned)(wexp - 13) << 23);
+    {
+        __half* Bh = reinterpret_cast<__half*>(Bw);
+        for (int i = tid; i < 2304; i += NTHR) {
+            const int kt = i / 768, r = i - kt * 768, kf = r >> 8, ci = (r >> 4) & 15, co = r & 15;
+            const float w = prm.w[O::MID_W + ((kt * 3 + kf) * 16 + ci) * 16 + co] * wscale;
+            const __half hi = __float2half_rn(w);
+            const int o = kt * 768 + (ci >> 3) * 384 + (kf * 16 + co) * 8 + (ci & 7);      // in halves
+            Bh[o] = hi;
+            Bh[2304 + o] = __float2half_rn(w - __half2float(hi));
+        }
+    }
+    for (int i = tid; i < GTT_GW_FLOATS; i += NTHR)
+        Gw[i] = i < 24 ? prm.w[O::TDW_W + i] : i < 32 ? prm.w[O::TDW_B + i - 24] : i < 96 ? prm.w[O::TPW_W + i - 32] : prm.w[O::TPW_B + i - 96];
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, gtt_tmem_cols(NWG));
+    if (tid < NWG) tc::mbar_init(&bars[tid], 1);
     tc::fence_async_smem();
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
-    const uint32_t tm = tmem_base_s + 144 * wg, lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tm = tmem_base_s + 96 * wg, lane_base = (uint32_t)((warp & 3) * 32) << 16;
     {
         // zero history: frames before the start of the utterance (or of the warm-up) contribute nothing
-        float z[8];
+        uint32_t z[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) z[c] = 0.f;
+        for (int c = 0; c < 8; ++c) z[c] = 0u;
 #pragma unroll
-        for (int j = 0; j < 12; ++j) tc::tmem_st8(tm + lane_base + 48 + 8 * j, z);
+        for (int j = 0; j < 6; ++j) tc::tmem_st8u(tm + lane_base + 48 + 8 * j, z);
         tc::tmem_wait_st();
     }
-    const uint64_t bdesc0 = tc::make_desc(tc::smem_u32(Bw), 768, 128);       // LBO = one k-plane (48 rows x 16 B), SBO = 8 rows
+    const uint64_t bdesc0 = tc::make_desc(tc::smem_u32(Bw), 768, 128);       // LBO = one k-chunk plane (48 rows x 16 B), SBO = 8 rows
     const bool issuer = tig == 0;
     const int bar_id = 1 + wg;
     uint64_t* bar = &bars[wg];
@@ -316,7 +347,7 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
     const bool active = tig < GTT_ROWS;
     const int rr = active ? tig : GTT_ROWS - 1;                          // idle lanes shadow the last row (no stores, no smem writes)
     const int g = rr / kF2, f = rr - g * kF2;
-    const int b_raw = blockIdx.y * (GTT_G * GTT_NWG) + wg * GTT_G + g;
+    const int b_raw = blockIdx.y * (GTT_G * NWG) + wg * GTT_G + g;
     const bool store_ok = active && b_raw < B;
     const int b = min(b_raw, B - 1);
     const int s0 = blockIdx.x * seg_len, s1 = min(T, s0 + seg_len);
@@ -330,62 +361,105 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
         const bool is_gate_thread = active && f < 8;
         const unsigned gmask = 0xFFu << ((g * kF2) & 31);                // lanes of (g, c = 0..7): 33 g + c = g + c (mod 32)
 
-        float4 nx[8];                                                     // next frame: x quads 0..3, skip quads 0..3
+        // TRALite energy + gate of one finished frame (its q^2 are in E2): thread (g, c < 8) owns channel c of group g -- its energy
+        // history stays in registers (ea, eb = frames -2, -1), the depthwise temporal conv is one value per thread and the 8 x 8
+        // pointwise conv exchanges them with shuffles among the group's 8 lanes.  Four interleaved partial sums in a fixed order:
+        // deterministic, independent of batch composition and segmentation.
+        float ea = 0.f, eb = 0.f;
+        auto gate_phase = [&]() {
+            if (is_gate_thread) {
+                const int c = f;
+                const float* e2c = E2 + g * kF2 * 8 + c;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) { nx[v] = px[(int64_t)tw0 * FS4 + v]; nx[4 + v] = ps[(int64_t)tw0 * FS4 + v]; }
-        int r = tw0 % 3;                                                  // ring slot of the current frame
-        for (int t = tw0; t < s1; ++t) {
-            float4 cx[4];
+                for (int ff = 0; ff < 32; ff += 4) {
+                    s0 += e2c[ff * 8]; s1 += e2c[(ff + 1) * 8]; s2 += e2c[(ff + 2) * 8]; s3 += e2c[(ff + 3) * 8];
+                }
+                s0 += e2c[32 * 8];
+                const float en = ((s0 + s1) + (s2 + s3)) / 33.0f;
+                float y = Gw[24 + c];
+                y = fmaf(Gw[c], ea, y);
+                y = fmaf(Gw[8 + c], eb, y);
+                y = fmaf(Gw[16 + c], en, y);
+                ea = eb; eb = en;
+                float v = Gw[96 + c];
+                const int lane0 = (g * kF2) & 31;
 #pragma unroll
-            for (int v = 0; v < 4; ++v)
-                cx[v] = make_float4(nx[v].x + nx[4 + v].x, nx[v].y + nx[4 + v].y, nx[v].z + nx[4 + v].z, nx[v].w + nx[4 + v].w);
-            if (t + 1 < s1) {
-#pragma unroll
-                for (int v = 0; v < 4; ++v) { nx[v] = px[(int64_t)(t + 1) * FS4 + v]; nx[4 + v] = ps[(int64_t)(t + 1) * FS4 + v]; }
+                for (int ci = 0; ci < 8; ++ci) v = fmaf(Gw[32 + ci * 8 + c], __shfl_sync(gmask, y, lane0 + ci), v);
+                Gt[g * 8 + c] = 1.0f / (1.0f + expf(-v));
             }
-            // ---- point conv 1 on the first channel half, split, into ring slot r of the A operand
+        };
+        // gate, channel shuffle [q0 g0, x2_0, q1 g1, x2_1, ...], store of frame ts
+        auto store_frame = [&](int ts, const float (&q)[8], const float4& x2a, const float4& x2b) {
+            if (store_ok && ts >= s0) {
+                const float4 g0 = reinterpret_cast<const float4*>(Gt + g * 8)[0];
+                const float4 g1 = reinterpret_cast<const float4*>(Gt + g * 8)[1];
+                float4* o4 = po + (int64_t)ts * FS4;
+                o4[0] = make_float4(q[0] * g0.x, x2a.x, q[1] * g0.y, x2a.y);
+                o4[1] = make_float4(q[2] * g0.z, x2a.z, q[3] * g0.w, x2a.w);
+                o4[2] = make_float4(q[4] * g1.x, x2b.x, q[5] * g1.y, x2b.y);
+                o4[3] = make_float4(q[6] * g1.z, x2b.z, q[7] * g1.w, x2b.w);
+            }
+        };
+
+        // The loop is software-pipelined by one frame: the TRALite gate of frame t-1 is evaluated by its 24 threads while the MMAs
+        // of frame t run, and frame t-1 is stored after the barrier that publishes the gate -- two warpgroup barriers per frame.
+        int r = tw0 % 3;                                                  // ring slot of the current frame
+        float qp[8];                                                      // previous frame: point-conv-2 output and pass-through half
+        float4 x2pa = make_float4(0.f, 0.f, 0.f, 0.f), x2pb = x2pa;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) qp[c] = 0.f;
+        for (int t = tw0; t < s1; ++t) {
+            float4 cx[4];                                                 // x + skip of this frame (the next one is on its way to L2)
+            {
+                float4 a[4], c[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) { a[v] = px[(int64_t)t * FS4 + v]; c[v] = ps[(int64_t)t * FS4 + v]; }
+                if (t + 1 < s1) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(px + (int64_t)(t + 1) * FS4));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + (int64_t)(t + 1) * FS4));
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) cx[v] = make_float4(a[v].x + c[v].x, a[v].y + c[v].y, a[v].z + c[v].z, a[v].w + c[v].w);
+            }
+            // ---- point conv 1 on the first channel half, fp16 hi/lo split, into ring slot r of the A operand
             {
                 const float x1[8] = {cx[0].x, cx[0].y, cx[0].z, cx[0].w, cx[1].x, cx[1].y, cx[1].z, cx[1].w};
                 float p[16];
                 gt_pc1<true>(prm, x1, p);
+                uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float hi[8], lo[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) { hi[c] = tc::tf32_hi(p[8 * h + c]); lo[c] = p[8 * h + c] - hi[c]; }
-                    tc::tmem_st8(tm + lane_base + 48 + 16 * r + 8 * h, hi);
-                    tc::tmem_st8(tm + lane_base + 96 + 16 * r + 8 * h, lo);
+                for (int c = 0; c < 8; ++c) {
+                    hi[c] = tc::pack_f16x2(p[2 * c], p[2 * c + 1]);
+                    lo[c] = tc::pack_f16x2(p[2 * c] - tc::f16lo_to_f32(hi[c]), p[2 * c + 1] - tc::f16hi_to_f32(hi[c]));
                 }
+                tc::tmem_st8u(tm + lane_base + 48 + 16 * r, hi);
+                tc::tmem_st8u(tm + lane_base + 56 + 16 * r, lo);
             }
             tc::tmem_wait_st();
             tc::fence_before();
-            tc::bar_sync(bar_id, 128);
+            tc::bar_sync(bar_id, 128);                                    // A(t) complete; also: E2(t-1) visible to the gate threads
             if (issuer) {
                 tc::fence_after();
-                constexpr uint32_t id48 = tc::make_idesc_tf32(128, 48);
+                constexpr uint32_t id48 = tc::make_idesc_f16(128, 48);
                 uint32_t acc = 0;
 #pragma unroll
-                for (int kt = 0; kt < 3; ++kt) {
+                for (int kt = 0; kt < 3; ++kt) {                          // small terms first
                     int s = r + 1 + kt;                                   // kt = 0 <-> frame t-2 <-> slot r+1, kt = 2 <-> frame t <-> slot r
                     s -= s >= 3 ? 3 : 0;
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint64_t bh = bdesc0 + (uint64_t)((kt * 768 + ks * 384) >> 2);          // (floats * 4 B) >> 4
-                        const uint64_t bl = bh + (uint64_t)(2304 >> 2);
-                        tc::mma_tf32_ts(tm, tm + 96 + 16 * s + 8 * ks, bh, id48, acc); acc = 1;       // small terms first: lo * W_hi
-                        tc::mma_tf32_ts(tm, tm + 48 + 16 * s + 8 * ks, bl, id48, 1);                  // hi * W_lo
-                    }
+                    const uint64_t bh = bdesc0 + (uint64_t)(kt * 96);     // 1,536 bytes per kt >> 4
+                    tc::mma_f16_ts(tm, tm + 56 + 16 * s, bh, id48, acc); acc = 1;             // lo * W_hi
+                    tc::mma_f16_ts(tm, tm + 48 + 16 * s, bh + 288, id48, 1);                  // hi * W_lo (4,608 bytes further)
                 }
 #pragma unroll
                 for (int kt = 0; kt < 3; ++kt) {
                     int s = r + 1 + kt;
                     s -= s >= 3 ? 3 : 0;
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-                        tc::mma_tf32_ts(tm, tm + 48 + 16 * s + 8 * ks, bdesc0 + (uint64_t)((kt * 768 + ks * 384) >> 2), id48, 1);   // hi * W_hi
+                    tc::mma_f16_ts(tm, tm + 48 + 16 * s, bdesc0 + (uint64_t)(kt * 96), id48, 1);   // hi * W_hi
                 }
                 tc::commit(bar);
             }
+            if (t > tw0) gate_phase();                                    // frame t-1, while the tensor core works on frame t
             tc::mbar_wait(bar, parity);
             parity ^= 1;
             tc::fence_after();
@@ -394,10 +468,8 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
             {
                 float d0[16], d2[16];
                 tc::tmem_ld16_nowait(tm + lane_base, d0);
-                tc::tmem_ld16_nowait(tm + lane_base + 16, m);
                 tc::tmem_ld16_nowait(tm + lane_base + 32, d2);
                 tc::tmem_wait_ld(d0);
-                tc::tmem_wait_ld(m);
                 tc::tmem_wait_ld(d2);
                 if (active) {
 #pragma unroll
@@ -407,10 +479,11 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
                     }
                 }
             }
+            tc::tmem_ld16_nowait(tm + lane_base + 16, m);                 // the centre block stays with this thread
+            tc::tmem_wait_ld(m);
             tc::fence_before();                                           // orders the tcgen05.ld above before the next step's MMAs
-            tc::bar_sync(bar_id, 128);
-#pragma unroll
-            for (int c = 0; c < 16; c += 2) add_pair(m[c], m[c + 1], prm.w[O::MID_B + c], prm.w[O::MID_B + c + 1]);
+            tc::bar_sync(bar_id, 128);                                    // exchange buffer and the gate of frame t-1 are visible
+            if (t > tw0) store_frame(t - 1, qp, x2pa, x2pb);
             if (f > 0) {
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
@@ -425,41 +498,27 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
                     add_pair(m[4 * qd], m[4 * qd + 1], u.x, u.y); add_pair(m[4 * qd + 2], m[4 * qd + 3], u.z, u.w);
                 }
             }
-            // ---- PReLU, point conv 2, TRALite energy and gate
-            float q[8];
-            gt_pc2<true>(prm, m, q);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) m[c] = fmaf(m[c], winv, prm.w[O::MID_B + c]);     // undo the weight scale, add the bias
+            // ---- PReLU, point conv 2, q^2 for the TRALite energy of this frame (summed during the next step)
+            gt_pc2<true>(prm, m, qp);
             if (active) {
                 float4* e4 = reinterpret_cast<float4*>(E2 + rr * 8);
-                e4[0] = make_float4(q[0] * q[0], q[1] * q[1], q[2] * q[2], q[3] * q[3]);
-                e4[1] = make_float4(q[4] * q[4], q[5] * q[5], q[6] * q[6], q[7] * q[7]);
+                e4[0] = make_float4(qp[0] * qp[0], qp[1] * qp[1], qp[2] * qp[2], qp[3] * qp[3]);
+                e4[1] = make_float4(qp[4] * qp[4], qp[5] * qp[5], qp[6] * qp[6], qp[7] * qp[7]);
             }
-            tc::bar_sync(bar_id, 128);
-            if (is_gate_thread) {
-                const int c = f;
-                int r1 = r - 1; r1 += r1 < 0 ? 3 : 0;
-                int r2 = r1 - 1; r2 += r2 < 0 ? 3 : 0;
-                float* ev = Ev + g * 24;
-                ev[r * 8 + c] = gt_energy(E2 + g * kF2 * 8 + c);
-                __syncwarp(gmask);
-                Gt[g * 8 + c] = gt_gate1<true>(prm, ev + r2 * 8, ev + r1 * 8, ev + r * 8, c);
-            }
-            tc::bar_sync(bar_id, 128);
-            // ---- gate, channel shuffle [q0 g0, x2_0, q1 g1, x2_1, ...], store
-            if (store_ok && t >= s0) {
-                const float4 g0 = reinterpret_cast<const float4*>(Gt + g * 8)[0];
-                const float4 g1 = reinterpret_cast<const float4*>(Gt + g * 8)[1];
-                float4* o4 = po + (int64_t)t * FS4;
-                o4[0] = make_float4(q[0] * g0.x, cx[2].x, q[1] * g0.y, cx[2].y);
-                o4[1] = make_float4(q[2] * g0.z, cx[2].z, q[3] * g0.w, cx[2].w);
-                o4[2] = make_float4(q[4] * g1.x, cx[3].x, q[5] * g1.y, cx[3].y);
-                o4[3] = make_float4(q[6] * g1.z, cx[3].z, q[7] * g1.w, cx[3].w);
-            }
+            x2pa = cx[2]; x2pb = cx[3];
             r = r == 2 ? 0 : r + 1;
         }
+        // ---- drain: gate and store of the last frame
+        tc::bar_sync(bar_id, 128);
+        gate_phase();
+        tc::bar_sync(bar_id, 128);
+        store_frame(s1 - 1, qp, x2pa, x2pb);
     }
     tc::fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+    if (warp == 0) tc::tmem_dealloc(tmem_base_s, gtt_tmem_cols(NWG));
 }
 
 }  // namespace gk

@@ -31,6 +31,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// instruction descriptor: kind::f16 with fp16 operands (a_format = b_format = 0), D = f32, A and B K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem], fp16 operands: K = 16 per instruction = 8 TMEM columns of A (two elements per 32-bit column)
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -118,6 +128,19 @@ __device__ __forceinline__ void tmem_wait_ld(float (&v)[8]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])
                  :: "memory");
+}
+
+// two fp32 values -> packed fp16x2 (a in the low half, b in the high half), round to nearest, saturating at +-65504
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ float f16lo_to_f32(uint32_t h2) { float r; asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}\n" : "=f"(r) : "r"(h2)); return r; }
+__device__ __forceinline__ float f16hi_to_f32(uint32_t h2) { float r; asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}\n" : "=f"(r) : "r"(h2)); return r; }
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
 // 3xTF32 split: x = hi + lo with hi = x truncated to TF32 (what the tensor core reads of x anyway) and lo = x - hi (exact in

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <vector>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 #include "../../gtcrn_micro_b200/csrc/tc_util.cuh"
 
@@ -222,6 +223,142 @@ __global__ void __launch_bounds__(128 * NWG) k_rt(int iters, int do_mma, long lo
     if (warp == 0) tc::tmem_dealloc(tmem_base, COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// test 4: kind::f16 with the A operand in TMEM as packed fp16 pairs: a 16-channel block is 8 columns of (hi[2c], hi[2c+1]) and
+// 8 columns of (lo[2c], lo[2c+1]), hi = fp16(x), lo = fp16(x - hi) (11 + 11 mantissa bits, like the TF32 split, in half the TMEM
+// columns and half the MMAs: K = 16 per instruction).  B = W_hi / W_lo fp16, K-major planes [k/8][n][8 halves].
+// D[128][N] = sum over KB blocks of 16 channels.
+// ---------------------------------------------------------------------------------------------------------------------------
+template <int KB, int N>
+__global__ void __launch_bounds__(128) k_f16_correct(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ out, float wscale) {
+    __shared__ __align__(128) __half Bhi[KB][2][N][8];
+    __shared__ __align__(128) __half Blo[KB][2][N][8];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    constexpr uint32_t D0 = 16 * KB, COLS = pow2_cols(16 * KB + N);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < KB * 16 * N; i += 128) {
+        const int k = i / N, n = i % N, kb = k >> 4, kk = k & 15;
+        const float v = B[i] * wscale;
+        const __half hi = __float2half_rn(v);
+        Bhi[kb][kk >> 3][n][kk & 7] = hi;
+        Blo[kb][kk >> 3][n][kk & 7] = __float2half_rn(v - __half2float(hi));
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base, COLS);
+    if (tid == 0) tc::mbar_init(&bar, 1);
+    tc::fence_async_smem(); tc::fence_before(); __syncthreads(); tc::fence_after();
+    const uint32_t tb = tmem_base, lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float a = A[tid * 16 * KB + 16 * kb + 2 * c], b = A[tid * 16 * KB + 16 * kb + 2 * c + 1];
+            hi[c] = tc::pack_f16x2(a, b);
+            lo[c] = tc::pack_f16x2(a - tc::f16lo_to_f32(hi[c]), b - tc::f16hi_to_f32(hi[c]));
+        }
+        tc::tmem_st8u(tb + lane_base + 16 * kb, hi);
+        tc::tmem_st8u(tb + lane_base + 16 * kb + 8, lo);
+    }
+    tc::tmem_wait_st(); tc::fence_before(); __syncthreads();
+    if (tid == 0) {
+        tc::fence_after();
+        const uint32_t idesc = tc::make_idesc_f16(128, N);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; ++kb) {
+            const uint64_t bh = tc::make_desc(tc::smem_u32(&Bhi[kb][0][0][0]), N * 16, 128);
+            const uint64_t bl = tc::make_desc(tc::smem_u32(&Blo[kb][0][0][0]), N * 16, 128);
+            tc::mma_f16_ts(tb + D0, tb + 16 * kb + 8, bh, idesc, acc); acc = 1;     // lo * W_hi
+            tc::mma_f16_ts(tb + D0, tb + 16 * kb, bl, idesc, 1);                     // hi * W_lo
+            tc::mma_f16_ts(tb + D0, tb + 16 * kb, bh, idesc, 1);                     // hi * W_hi
+        }
+        tc::commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0); tc::fence_after();
+#pragma unroll
+    for (int c = 0; c < N / 16; ++c) {
+        float v[16];
+        tc::tmem_ld16_nowait(tb + lane_base + D0 + 16 * c, v);
+        tc::tmem_wait_ld(v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) out[tid * N + 16 * c + j] = v[j] / wscale;
+    }
+    tc::fence_before(); __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tb, COLS);
+}
+
+// test 5: MMA cost with NACC independent accumulators (round robin), TS form, N columns each
+template <int N, int NACC>
+__global__ void __launch_bounds__(128) k_time_acc(int nmma, int reps, long long* cycles, float* sink) {
+    extern __shared__ __align__(128) float dsm[];
+    float* B = dsm;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 4 * N * 4; i += 128) B[i] = 0.5f;
+    if (warp == 0) tc::tmem_alloc(&tmem_base, 512);
+    if (tid == 0) tc::mbar_init(&bar, 1);
+    tc::fence_async_smem(); tc::fence_before(); __syncthreads(); tc::fence_after();
+    const uint32_t tb = tmem_base, lane_base = (uint32_t)(warp * 32) << 16;
+    { float one[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) one[j] = 1.0f;
+      tc::tmem_st16(tb + lane_base + 0, one); tc::tmem_st16(tb + lane_base + 16, one); tc::tmem_wait_st(); }
+    tc::fence_before(); __syncthreads(); tc::fence_after();
+    const uint32_t idesc = tc::make_idesc_tf32(128, N), td = tb + 64;
+    const uint64_t db = tc::make_desc(tc::smem_u32(B), N * 16, 128);
+    uint32_t parity = 0; long long best = 1ll << 60;
+    for (int rep = 0; rep < reps; ++rep) {
+        long long t0 = 0;
+        if (tid == 0) {
+            t0 = clock64();
+            for (int i = 0; i < nmma; ++i) tc::mma_tf32_ts(td + N * (i % NACC), tb + 8 * (i & 3), db, idesc, i >= NACC);
+            tc::commit(&bar);
+        }
+        tc::mbar_wait(&bar, parity); parity ^= 1;
+        if (tid == 0) { long long dt = clock64() - t0; if (dt < best) best = dt; }
+    }
+    tc::fence_after();
+    float v[16]; tc::tmem_ld16_nowait(td + lane_base, v); tc::tmem_wait_ld(v);
+    sink[tid] = v[0];
+    if (tid == 0) *cycles = best;
+    tc::fence_before(); __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tb, 512);
+}
+
+template <int KB, int N>
+static void run_f16(float amp) {
+    std::vector<float> A(128 * 16 * KB), B(16 * KB * N), out(128 * N);
+    float *dA, *dB, *dO;
+    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dO, out.size() * 4));
+    for (auto& v : A) v = ((float)rand() / RAND_MAX * 2.f - 1.f) * amp;
+    float wmax = 0;
+    for (auto& v : B) { v = ((float)rand() / RAND_MAX * 2.f - 1.f) * 0.3f; wmax = fmaxf(wmax, fabsf(v)); }
+    const float wscale = exp2f(floorf(log2f(16384.f / wmax)));
+    CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    k_f16_correct<KB, N><<<1, 128>>>(dA, dB, dO, wscale);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out.data(), dO, out.size() * 4, cudaMemcpyDeviceToHost));
+    double es = 0, ef = 0, mx = 0;
+    for (int r = 0; r < 128; ++r) for (int n = 0; n < N; ++n) {
+        double rx = 0; float s = 0.f;
+        for (int k = 0; k < 16 * KB; ++k) { rx += (double)A[r * 16 * KB + k] * B[k * N + n]; s = fmaf(A[r * 16 * KB + k], B[k * N + n], s); }
+        es = fmax(es, fabs(rx - out[r * N + n])); ef = fmax(ef, fabs(rx - (double)s)); mx = fmax(mx, fabs(rx));
+    }
+    printf("test4 f16 hi/lo TS K=%d N=%d |a|<=%g wscale=%g: max err %.3e (rel %.2e, |ref|max %.2f); sequential fp32 FFMA: %.3e\n", 16 * KB, N, amp, wscale, es, es / mx, mx, ef);
+    CK(cudaFree(dA)); CK(cudaFree(dB)); CK(cudaFree(dO));
+}
+
+template <int N, int NACC>
+static void run_time_acc(long long* d_cyc, float* d_sink) {
+    const size_t sm = (4 * N * 4) * 4;
+    long long c[2]; int ns[2] = {24, 120};
+    for (int i = 0; i < 2; ++i) { k_time_acc<N, NACC><<<1, 128, sm>>>(ns[i], 20, d_cyc, d_sink); CK(cudaDeviceSynchronize()); CK(cudaMemcpy(&c[i], d_cyc, 8, cudaMemcpyDeviceToHost)); }
+    printf("test5 TS M128 N=%d K8, %d independent accumulators: 24/120 MMAs = %lld %lld cyc (%.1f per MMA)\n", N, NACC, c[0], c[1], (c[1] - c[0]) / 96.0);
+}
+
 template <int K, int N>
 static void run_correct() {
     std::vector<float> A(128 * K), B(K * N), out(128 * N);
@@ -320,6 +457,10 @@ int main() {
     run_correct<48, 48>();
     long long* d_cyc; float* d_sink;
     CK(cudaMalloc(&d_cyc, 8)); CK(cudaMalloc(&d_sink, 148 * 8 * 1024 * 4));
+    run_f16<1, 16>(1.f); run_f16<3, 48>(1.f); run_f16<3, 48>(100.f); run_f16<3, 48>(0.001f);
+    run_time_acc<16, 1>(d_cyc, d_sink); run_time_acc<16, 2>(d_cyc, d_sink); run_time_acc<16, 3>(d_cyc, d_sink); run_time_acc<16, 6>(d_cyc, d_sink);
+    run_time_acc<48, 1>(d_cyc, d_sink); run_time_acc<48, 2>(d_cyc, d_sink); run_time_acc<48, 3>(d_cyc, d_sink);
+    if (getenv("UMMA_SHORT")) { printf("done\n"); return 0; }
     run_time<16>(d_cyc, d_sink); run_time<48>(d_cyc, d_sink); run_time<64>(d_cyc, d_sink);
     run_time<128>(d_cyc, d_sink); run_time<144>(d_cyc, d_sink); run_time<256>(d_cyc, d_sink);
     const int it = 2000;
