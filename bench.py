@@ -10,7 +10,7 @@ process N such batches with no collective (weak scaling).  One JSON line is prin
   value         device-timed (CUDA events on the launching stream), inputs resident in HBM
   e2e           same metric through `GTCRNMicro.enhance_host` (C ABI gtcrnb_enhance_host): pinned HOST
                 buffers in, pinned HOST buffers out, H2D / D2H inside the timed region
-  roofline      dominant kernel (decoder GTConv 3x3), timed live with CUDA events inside the library
+  roofline      dominant kernel class (by time), timed live with CUDA events inside the library; HBM roof for the tensor-core kernels
   cpu_baseline  the reference's own CPU implementation (baseline/_ref; oracle port if absent) on this box's host
                 cores: offline audio-s/s and, per BASELINE.md section 3, max real-time streams of its frame-by-frame model
   streaming     frame-by-frame path (BASELINE configs[2]): p50/p99/max hop latency over 625 hops for 4,096 / 16,384
@@ -50,8 +50,34 @@ FRAMES_PER_UTT = 1 + L_UTT // 256
 MAC_PER_FRAME = 614_530                   # conv/linear MACs of the reference's own ops
 DEC_GT_MAC_PER_FRAME = 84_582             # one decoder GTConvBlock
 FP32_PEAK_TFLOPS = 73.4                   # measured on this pool's B200: tools/microbench/ffma_feed.cu -> profiles/ffma_feed_r1.txt
-DEC_GT_DRAM_BYTES_PER_FRAME = 8555        # ncu --set full, dram__bytes_read+write of one k_gtconv<DEC> launch / frames (profiles/ncu_r1_v13_summary.txt)
-DEC_GT_ALG_BYTES_PER_FRAME = 3 * 33 * 16 * 4   # read x + skip, write out: 6,336 B
+# Per kernel class of the GTCRN-Micro path: algorithmic MACs and HBM bytes per 16 ms frame,
+# the roof that bounds the FFMA build of the class, and ncu DRAM bytes per frame where a capture exists (profiles/).
+A33 = 33 * 16 * 4                          # one [33][16] fp32 activation frame: 2,112 B
+MICRO_CLASS_INFO = {
+    "front": {"kernel": "k_front<FROM_WAV> (STFT, ERB, SFE-Lite, en0, en1)", "mac": 36_864 + 1_161 + 15_600 + 42_240, "alg_bytes": 1024 + 2056 + 65 * 64 + A33, "bound": "fp32_fma",
+              "why": "FP32 FMA / shared-memory bound (radix-4 FFTs and two strided convs on the CUDA cores)"},
+    "enc_gtconv": {"kernel": "k_gtconv<ENC> (encoder GTConvBlock)", "mac": 13_288, "alg_bytes": 2 * A33, "bound": "hbm",
+                   "why": "13.3 k MAC per 4,224 B: HBM / latency bound", "dram_bytes": 4212, "dram_note": "ncu r1_v13: 2.70 GB per launch of 641,024 frames"},
+    "gtcn": {"kernel": "k_gtcn (4 dilated TCNs, FFMA)", "mac": 73_920, "alg_bytes": 2 * A33, "bound": "fp32_fma",
+             "why": "FFMA build: FMA pipe 66 % busy (ncu r1_v13)", "dram_bytes": 4150, "dram_note": "ncu r1_v13: 2.66 GB per launch"},
+    "dec_gtconv": {"kernel": "k_gtconv<DEC> (decoder GTConvBlock, FFMA)", "mac": 84_582, "alg_bytes": 3 * A33, "bound": "fp32_fma",
+                   "why": "FFMA build: FMA pipe 70 % busy (ncu r1_v13)", "dram_bytes": 8555,
+                   "dram_note": "ncu r1_v13: the untouched channel half is re-read in the store phase"},
+    "back": {"kernel": "k_back<TO_WAV> (de3, de4, ERB expand, mask, iSTFT, overlap-add)", "mac": 42_240 + 10_400 + 24_576, "alg_bytes": A33 + A33 + 65 * 64 + 2056 + 1024, "bound": "fp32_fma",
+             "why": "FP32 FMA / shared-memory bound"},
+}
+# the same classes when they run on the tensor cores (GTCRNB_TC bits, default on): the contraction leaves the FMA pipe, what remains is
+# bounded by HBM (and, inside the SM, by the L1TEX data pipe that carries shared-memory, global and tensor-memory traffic: ncu r2)
+MICRO_TC_INFO = {
+    "dec_gtconv": {"kernel": "k_gtconv_dec_tc (decoder GTConvBlock, 3x3 conv as tcgen05 kind::f16 MMAs on fp16 hi/lo operands in tensor memory)", "bound": "hbm",
+                   "why": "the 2,304-MAC 3x3 contraction runs on the tensor cores (9 MMAs per 99-position tile); the rest is bounded by HBM traffic "
+                          "(6,336 B per frame) and latency: ncu r2 L1TEX data pipe 68 %, DRAM 34 %, tensor pipe < 10 %",
+                   "dram_bytes": 6396, "dram_note": "ncu r2 (profiles/ncu_r2_dec_tc_summary.txt): 2.78 GB read + 1.32 GB written per launch of 641,024 frames = 1.01 x algorithmic"},
+    "gtcn": {"kernel": "k_gtcn_tc (4 dilated TCNs, pointwise convs as tcgen05 kind::tf32 3xTF32 MMAs, A operand in tensor memory)", "bound": "hbm",
+             "why": "the 512 of 560 MACs per position-TCN that are pointwise contractions run on the tensor cores; the kernel is instruction-issue "
+                    "bound (ncu r2: issue 63 %), nearest hardware roof HBM", "dram_bytes": 4155,
+             "dram_note": "ncu r2 (profiles/ncu_r2_gtcn_tc_summary.txt): 1.35 GB read + 1.31 GB written per launch"},
+}
 WEIGHTS = os.path.join(ROOT, "tests", "golden", "weights_dns3.npz")
 # BASELINE configs[3], `--variant full`: the original-GTCRN-style architecture (parity unpinned, oracle/gtcrn_full_oracle.py).
 # conv / linear / GRU MACs per frame of its own ops: ERB 61,440 + en0 46,800 + en1 21,120 + 6 GTConv x 23,456 (1x1 24->16, dw 3x3,
@@ -606,26 +632,44 @@ def run_b200(args):
                     "whole_path": whole, "per_class_ms": {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]},
                     "per_class_tflops": {k: round(2.0 * FULL_CLASS_MAC[k] * v["frames"] / (v["ms"] * 1e-3) / 1e12, 2) for k, v in prof.items() if v["launches"] and k in FULL_CLASS_MAC}}
     else:
-        # roofline of the dominant kernel (decoder GTConvBlock: full 16->16 3x3 conv + 1x1s + TRALite), live CUDA-event timing
-        dk = prof["dec_gtconv"]
-        dec_tflops = (2.0 * DEC_GT_MAC_PER_FRAME * dk["frames"]) / (dk["ms"] * 1e-3) / 1e12 if dk["ms"] > 0 else 0.0
+        # roofline of the dominant kernel class, timed live with CUDA events inside the library (gtcrnb_profile_*)
+        tc_mask = model.tc_mask()
+        dk = prof[dom]
+        ci = dict(MICRO_CLASS_INFO[dom])
+        on_tc = (dom == "dec_gtconv" and tc_mask & 2) or (dom == "gtcn" and tc_mask & 1)
+        if on_tc:
+            ci.update(MICRO_TC_INFO[dom])
+        frames_per_launch = dk["frames"] // max(1, dk["launches"])
+        tfl = (2.0 * ci["mac"] * dk["frames"]) / (dk["ms"] * 1e-3) / 1e12 if dk["ms"] > 0 else 0.0
+        gbs = ci["alg_bytes"] * dk["frames"] / (dk["ms"] * 1e-3) / 1e9 if dk["ms"] > 0 else 0.0
+        fp32_view = {"bound": "fp32_fma", "achieved": round(tfl, 2), "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": round(tfl / FP32_PEAK_TFLOPS, 4),
+                     "peak_source": peak_src}
+        hbm_view = {"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
+        primary = hbm_view if ci["bound"] == "hbm" else fp32_view
         roofline = {
-            "kernel": "k_gtconv<DEC> (decoder GTConvBlock, 3 launches per chunk)", "bound": "fp32_fma",
-            "achieved": round(dec_tflops, 2), "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": round(dec_tflops / FP32_PEAK_TFLOPS, 4),
-            "peak_source": peak_src,
-            "traffic": DEC_GT_DRAM_BYTES_PER_FRAME * (dk["frames"] // max(1, dk["launches"])),
-            "traffic_note": "DRAM bytes per launch from ncu (8,555 B/frame, profiles/ncu_r1_v13_summary.txt) vs 6,336 algorithmic B/frame: "
-                            "the untouched channel half is re-read in the store phase instead of being held in 32 registers",
-            "algorithmic_bytes_per_launch": DEC_GT_ALG_BYTES_PER_FRAME * (dk["frames"] // max(1, dk["launches"])),
-            # the same kernel against the HBM roof (it is not the binding one: arithmetic intensity 84,582 MAC / 6,336 B = 26.7 flop/B)
-            "hbm_view": {"bound": "hbm", "achieved": round(DEC_GT_ALG_BYTES_PER_FRAME * dk["frames"] / (dk["ms"] * 1e-3) / 1e9, 1) if dk["ms"] > 0 else 0.0,
-                         "peak": hbm_peak, "unit": "GB/s",
-                         "frac": round(DEC_GT_ALG_BYTES_PER_FRAME * dk["frames"] / (dk["ms"] * 1e-3) / 1e9 / hbm_peak, 4) if dk["ms"] > 0 else 0.0},
+            "kernel": f"{ci['kernel']} ({dk['launches'] // max(1, args.steps)} launches per step)",
+            "bound": primary["bound"], "achieved": primary["achieved"], "peak": primary["peak"], "unit": primary["unit"], "frac": primary["frac"],
+            "peak_source": primary["peak_source"],
+            "why_this_bound": ci["why"],
+            "traffic": ci["dram_bytes"] * frames_per_launch if ci.get("dram_bytes") else None,
+            "traffic_note": ci.get("dram_note"),
+            "algorithmic_bytes_per_launch": ci["alg_bytes"] * frames_per_launch,
+            "algorithmic_flop_per_launch": 2 * ci["mac"] * frames_per_launch,
+            "other_view": fp32_view if primary is hbm_view else hbm_view,
             "ms_per_launch": round(dk["ms"] / max(1, dk["launches"]), 4), "launches": dk["launches"],
             "share_of_step": round(dk["ms"] / step_kernel_ms, 4) if step_kernel_ms else None,
             "dominant_class_by_time": dom,
+            "tensor_core_layers": {"mask": tc_mask, "gtcn_pointwise": bool(tc_mask & 1), "decoder_3x3": bool(tc_mask & 2),
+                                   "operands": "fp16 hi/lo (decoder), 3xTF32 (GTCN): fp32-class accuracy, A operand in tensor memory"},
             "whole_path": whole,
             "per_class_ms": {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]},
+            "per_class": {k: {"ms": round(v["ms"] / args.steps, 3),
+                              "alg_tflops": round(2.0 * MICRO_CLASS_INFO[k]["mac"] * v["frames"] / (v["ms"] * 1e-3) / 1e12, 2),
+                              "alg_hbm_gbs": round(MICRO_CLASS_INFO[k]["alg_bytes"] * v["frames"] / (v["ms"] * 1e-3) / 1e9, 1),
+                              "frac_fp32": round(2.0 * MICRO_CLASS_INFO[k]["mac"] * v["frames"] / (v["ms"] * 1e-3) / 1e12 / FP32_PEAK_TFLOPS, 4),
+                              "frac_hbm": round(MICRO_CLASS_INFO[k]["alg_bytes"] * v["frames"] / (v["ms"] * 1e-3) / 1e9 / hbm_peak, 4)}
+                          for k, v in prof.items() if v["launches"] and v["ms"] > 0 and k in MICRO_CLASS_INFO},
         }
     wl = (f"GTCRN-Micro offline batched inference, {B} x {SECONDS} s synthetic 16 kHz utterances per GPU (BASELINE configs[1]), STFT+model+iSTFT, shipped DNS3 checkpoint weights"
           if not full else

@@ -377,6 +377,7 @@ int gtcrnb_abi_version(void) { return kAbiVersion; }
 size_t gtcrnb_blob_floats(void) { return (size_t)blob::kBlobFloats; }
 const char* gtcrnb_last_error(void) { return g_err.c_str(); }
 int64_t gtcrnb_launch_count(const gtcrnb_handle* h) { return h ? h->launches : 0; }
+int gtcrnb_tc_mask(const gtcrnb_handle* h) { return (h && h->variant == 0) ? h->tc_mask : 0; }
 
 void* gtcrnb_host_alloc(size_t bytes) {
     void* p = nullptr;

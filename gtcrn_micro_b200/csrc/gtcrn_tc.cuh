@@ -40,7 +40,7 @@ __device__ __forceinline__ void tf32_split_rn(float w, float& hi, float& lo) {
 constexpr int TCT_B_FLOATS = 8 * 512;
 constexpr int TCT_WARP4 = 4 * 32 + 4 * 30;                 // float4 per warp
 __host__ __device__ constexpr int tct_smem_floats(int nwg) { return TCT_B_FLOATS + nwg * 4 * TCT_WARP4 * 4; }
-__host__ __device__ constexpr int tct_min_blocks(int nwg) { return nwg == 1 ? 7 : nwg == 2 ? 4 : 2; }
+__host__ __device__ constexpr int tct_min_blocks(int nwg) { return nwg == 1 ? 6 : nwg == 2 ? 3 : 1; }   // shared memory allows 6 warpgroups per SM
 
 // one pointwise 16 -> 16 convolution of the warpgroup's 128 rows, first half: v (registers) -> A in TMEM, MMAs, completion wait.
 // STACK: 4 MMAs, the accumulator holds hi*w_hi + lo*w_hi in columns 0..15 and hi*w_lo in 16..31 (dependent chain of 4);
@@ -52,7 +52,11 @@ __device__ __forceinline__ void tct_conv16_issue(const float (&v)[16], uint32_t 
     for (int h = 0; h < 2; ++h) {                                  // in halves: 16 instead of 32 staging registers
         float hi[8], lo[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { hi[c] = tc::tf32_hi(v[8 * h + c]); lo[c] = v[8 * h + c] - hi[c]; }
+        for (int c = 0; c < 8; c += 2) {
+            hi[c] = tc::tf32_hi(v[8 * h + c]); hi[c + 1] = tc::tf32_hi(v[8 * h + c + 1]);
+            lo[c] = v[8 * h + c]; lo[c + 1] = v[8 * h + c + 1];
+            add_pair(lo[c], lo[c + 1], -hi[c], -hi[c + 1]);
+        }
         tc::tmem_st8(tm + lane_base + 32 + 8 * h, hi);
         tc::tmem_st8(tm + lane_base + 48 + 8 * h, lo);
     }
@@ -189,13 +193,14 @@ k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_c
                         const float4 ta = lane >= 2 * d ? Y[qd * 32 + lane - 2 * d] : H[qd * 30 + coff + lane];
                         const float4 tb = lane >= d ? Y[qd * 32 + lane - d] : H[qd * 30 + coff + lane + d];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {                    // scalar on purpose (see tcn_dw)
+                        for (int i = 0; i < 4; i += 2) {
                             const int c = 4 * qd + i;
-                            float v = prm.w[wo + blob::TCN_B2 + c];
-                            v = fmaf(prm.w[wo + blob::TCN_W2 + c], f4get(ta, i), v);
-                            v = fmaf(prm.w[wo + blob::TCN_W2 + 16 + c], f4get(tb, i), v);
-                            v = fmaf(prm.w[wo + blob::TCN_W2 + 32 + c], y[c], v);
-                            y[c] = prelu(v, a2);
+                            float v0 = prm.w[wo + blob::TCN_B2 + c], v1 = prm.w[wo + blob::TCN_B2 + c + 1];
+                            fma_pair2(v0, v1, f4get(ta, i), f4get(ta, i + 1), prm.w[wo + blob::TCN_W2 + c], prm.w[wo + blob::TCN_W2 + c + 1]);
+                            fma_pair2(v0, v1, f4get(tb, i), f4get(tb, i + 1), prm.w[wo + blob::TCN_W2 + 16 + c], prm.w[wo + blob::TCN_W2 + 16 + c + 1]);
+                            fma_pair2(v0, v1, y[c], y[c + 1], prm.w[wo + blob::TCN_W2 + 32 + c], prm.w[wo + blob::TCN_W2 + 32 + c + 1]);
+                            prelu_pair(v0, v1, a2);
+                            y[c] = v0; y[c + 1] = v1;
                         }
                     }
                 }

@@ -22,7 +22,7 @@ SYMBOLS = [
     "gtcrnb_host_free", "gtcrnb_last_error", "gtcrnb_profile_enable", "gtcrnb_profile_read",
     "gtcrnb_profile_num_classes", "gtcrnb_profile_class_name", "gtcrnb_pair_metrics", "gtcrnb_host_alloc_wc",
     "gtcrnb_enhance_host_pcm16", "gtcrnb_pcm16_to_f32", "gtcrnb_f32_to_pcm16", "gtcrnb_stream_flush_wav",
-    "gtcrnb_create_variant", "gtcrnb_blob_floats_variant", "gtcrnb_stream_state_bytes_variant",
+    "gtcrnb_create_variant", "gtcrnb_blob_floats_variant", "gtcrnb_stream_state_bytes_variant", "gtcrnb_tc_mask",
 ]
 
 
@@ -71,6 +71,7 @@ def load() -> C.CDLL:
             "gtcrnb_stream_export_caches": (C.c_int, [vp, vp, i64, vp, vp, C.POINTER(vp), vp]),
             "gtcrnb_debug_activation": (C.c_int, [vp, cp, vp, sz, vp]),
             "gtcrnb_launch_count": (i64, [vp]),
+            "gtcrnb_tc_mask": (C.c_int, [vp]),
             "gtcrnb_host_alloc": (vp, [sz]),
             "gtcrnb_host_alloc_wc": (vp, [sz]),
             "gtcrnb_host_free": (None, [vp]),

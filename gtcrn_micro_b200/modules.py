@@ -190,6 +190,10 @@ class _B200Module(nn.Module):
     def launch_count(self) -> int:
         return int(_lib.load().gtcrnb_launch_count(self._handle)) if self._handle.value is not None else 0
 
+    def tc_mask(self) -> int:
+        """Layers running on the tensor cores: bit 0 GTCN pointwise convs, bit 1 decoder GTConv 3x3 (GTCRNB_TC, default 3)."""
+        return int(_lib.load().gtcrnb_tc_mask(self._handle)) if self._handle.value is not None else 0
+
     @staticmethod
     def _check_spec(spec: torch.Tensor, T: Optional[int] = None):
         if spec.dim() != 4 or spec.shape[1] != 257 or spec.shape[3] != 2:

@@ -20,6 +20,8 @@ CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 # kernels launched with the default tuning (gtcrn_capi.cu): offline + streaming
 HOT = ["k_frontILb0ELi0E", "k_frontILb1ELi0E", "k_backILb0ELi0E", "k_backILb1ELi0E", "k_gtconvILb0ELi2ELi4ELb0", "k_gtconvILb1ELi4ELi7ELb0",
        "k_gtcnILi2ELb0", "ks_gtconvILb0", "ks_gtconvILb1", "ks_gtcn"]
+# tensor-core kernels of the default path (gtcrn_tc.cuh): decoder GTConv with 4 warpgroups per CTA, GTCN with one
+HOT_TC = ["k_gtconv_dec_tcILi4E", "k_gtcn_tcILi1ELb0"]
 # kernels of the original-GTCRN-style variant (BASELINE configs[3]): same weight-feed property, spills tolerated up to a small frame
 HOT_FULL = ["k_frontILb0ELi1E", "k_frontILb1ELi1E", "k_backILb0ELi1E", "k_backILb1ELi1E", "kf_gtconvILb0ELi2ELi4E", "kf_gtconvILb1ELi2ELi4E",
             "kf_dp_intra", "kf_dp_inter"]
@@ -52,6 +54,21 @@ def test_weights_use_the_uniform_datapath(sass, key):
     body = _find(sass, key)
     r_indexed = sum(1 for l in body if re.search(r"c\[0x0\]\[R\d", l))
     assert r_indexed <= 16, f"{key}: {r_indexed} per-thread-indexed constant loads (LDC c[0x0][R..]) -- see tools/sass_check.sh"
+
+
+@pytest.mark.parametrize("key", HOT_TC)
+def test_tensor_core_kernels_use_tcgen05_with_operands_in_tensor_memory(sass, key):
+    """The TC kernels must contain the tcgen05 MMA (SASS UTCHMMA), write their A operand with tcgen05.st (STTM) and read the
+    accumulator with tcgen05.ld (LDTM); weights still come through the uniform datapath; no spills."""
+    body = _find(sass, key)
+    n = {op: sum(1 for l in body if re.search(r"\s" + op + r"[.\s]", l)) for op in ("UTCHMMA", "STTM", "LDTM", "UTCBAR")}
+    assert n["UTCHMMA"] >= 6 and n["STTM"] >= 2 and n["LDTM"] >= 2 and n["UTCBAR"] >= 1, (key, n)
+    # A comes from tensor memory: the MMA's second operand is tmem[..], not a shared-memory descriptor
+    mma = [l for l in body if "UTCHMMA" in l]
+    assert all(len(re.findall(r"tmem\[", l)) >= 3 for l in mma), mma[:2]
+    r_indexed = sum(1 for l in body if re.search(r"c\[0x0\]\[R\d", l))
+    assert r_indexed <= 16, (key, r_indexed)
+    assert not any(re.search(r"\s(STL|LDL)[.\s]", l) for l in body), f"{key} spills"
 
 
 @pytest.mark.parametrize("key", HOT)
