@@ -595,6 +595,24 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)        # plumbing only: max over ranks of the device time
     ms_total, e2e_ms, pcm_ms = float(times[0]), float(times[1]), float(times[2])
+    gather_info = None
+    if world > 1:
+        # Host-side gather of the shards (shard.gather_to_rank0; the only cross-rank data movement of the whole path, OUTSIDE the timed
+        # regions): a small job of 5 one-second utterances per rank is sharded in contiguous blocks, every rank enhances its block on
+        # its own GPU, rank 0 gathers the blocks over a gloo group and compares them bitwise with its own run of the whole job.
+        from gtcrn_micro_b200.shard import gather_to_rank0, shard_range
+        n_items = 5 * world - 2                                   # last shard short on purpose
+        job = 0.1 * torch.randn(n_items, 16000, generator=torch.Generator().manual_seed(4242))
+        lo, hi = shard_range(n_items, rank, world)
+        mine = model.enhance(job[lo:hi].to(device)).cpu() if hi > lo else torch.zeros(0, 256 * (16000 // 256))
+        gloo = dist.new_group(backend="gloo")
+        t0 = time.perf_counter()
+        whole = gather_to_rank0(mine, n_items, group=gloo)
+        g_ms = (time.perf_counter() - t0) * 1e3
+        if rank == 0:
+            ref_all = model.enhance(job.to(device)).cpu()
+            gather_info = {"items": n_items, "ranks": world, "backend": "gloo (host side, outside the timed regions)",
+                           "bitwise_equal_to_single_gpu_run": bool(torch.equal(whole, ref_all)), "ms": round(g_ms, 2)}
     if rank != 0:
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
@@ -692,6 +710,8 @@ def run_b200(args):
         "gpu_launches": launches,
         "roofline": roofline,
     }
+    if gather_info is not None:
+        line["host_gather"] = gather_info
     if not args.no_stream:
         try:
             line["streaming"] = bench_streaming(G, model, device, hbm_peak, max_search=(world == 1))

@@ -166,7 +166,8 @@ cudaError_t launch_gtconv(const GtVariant& v, dim3 grid, cudaStream_t st, const 
 
 const void* tc_dec_fn(int nwg) {
     using namespace gk;
-    return nwg == 1 ? (const void*)k_gtconv_dec_tc<1> : nwg == 2 ? (const void*)k_gtconv_dec_tc<2> : nwg == 4 ? (const void*)k_gtconv_dec_tc<4> : (const void*)k_gtconv_dec_tc<5>;
+    return nwg == 1 ? (const void*)k_gtconv_dec_tc<1, false> : nwg == 2 ? (const void*)k_gtconv_dec_tc<2, false>
+         : nwg == 4 ? (const void*)k_gtconv_dec_tc<4, false> : (const void*)k_gtconv_dec_tc<5, false>;
 }
 const void* tc_gtcn_fn(int nwg, bool stack) {
     using namespace gk;
@@ -327,7 +328,8 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
             ProfScope ps(h, KC_DEC_GT, nframes, st);
             const float* xi = h->act[5 + i]; const float* sk = h->act[3 - i]; float* xo = h->act[6 + i];
             int seg_i = seg, Bi = (int)B;
-            void* args[] = {(void*)&xi, (void*)&sk, (void*)&xo, (void*)&h->hp->dec[i], (void*)&Ti, (void*)&seg_i, (void*)&Bi};
+            void* nostate = nullptr; int blk0 = 0; long long n0 = 0;
+            void* args[] = {(void*)&xi, (void*)&sk, (void*)&xo, (void*)&h->hp->dec[i], (void*)&Ti, (void*)&seg_i, (void*)&Bi, (void*)&nostate, (void*)&blk0, (void*)&n0};
             cudaLaunchKernel(tc_dec_fn(nwg), g, dim3(128 * nwg), args, gtt_smem_floats(nwg) * sizeof(float), st);
             h->launches++;
         }
@@ -425,6 +427,7 @@ int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, 
         {(const void*)k_istft, 0},
         {tc_gtcn_fn(1, false), tct_smem_floats(1)}, {tc_gtcn_fn(2, false), tct_smem_floats(2)}, {tc_gtcn_fn(4, false), tct_smem_floats(4)},
         {tc_dec_fn(1), gtt_smem_floats(1)}, {tc_dec_fn(2), gtt_smem_floats(2)}, {tc_dec_fn(4), gtt_smem_floats(4)}, {tc_dec_fn(5), gtt_smem_floats(5)},
+        {(const void*)k_gtconv_dec_tc<4, true>, gtt_smem_floats(4)},
         {tc_gtcn_fn(1, true), tct_smem_floats(1)}, {tc_gtcn_fn(2, true), tct_smem_floats(2)}, {tc_gtcn_fn(4, true), tct_smem_floats(4)},
     };
     std::vector<std::pair<const void*, int>> all;
@@ -465,6 +468,10 @@ int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, 
     if (const char* e = getenv("GTCRNB_TCN_SMEMW")) h->tcn_smem_w = atoi(e) != 0;
     if (const char* e = getenv("GTCRNB_STREAM_GRAPH")) h->stream_graphs = atoi(e) != 0;
     if (const char* e = getenv("GTCRNB_TC")) h->tc_mask = atoi(e);
+    // streaming: the decoder blocks of a hop follow the offline choice (bit 1) unless GTCRNB_TC_STREAM=0
+    h->hp->tc_stream = (h->tc_mask & 2) != 0;
+    if (const char* e = getenv("GTCRNB_TC_STREAM")) h->hp->tc_stream = atoi(e) != 0;
+    h->hp->sm_count = h->sm_count;
     if (const char* e = getenv("GTCRNB_TC_DEC_NWG")) { const int v = atoi(e); h->tc_dec_nwg = v >= 5 ? 5 : v >= 4 ? 4 : v >= 2 ? 2 : 1; }
     if (const char* e = getenv("GTCRNB_TC_GTCN_NWG")) { const int v = atoi(e); h->tc_gtcn_nwg = v >= 4 ? 4 : v >= 2 ? 2 : 1; }
     {

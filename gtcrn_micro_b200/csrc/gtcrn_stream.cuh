@@ -27,6 +27,12 @@
 #include "blob_layout.h"
 #include "gtcrn_kernels.cuh"
 
+namespace gk {
+// defined in gtcrn_tc.cuh: one decoder GTConvBlock of a streaming hop on the tensor cores
+inline cudaError_t launch_dec_tc_stream(const float* x, const float* skip, float* out, const ParamBlock<gt_chunk<true>()>& prm, void* state, int blk,
+                                        int64_t N, int sm_count, cudaStream_t st);
+}
+
 namespace gs {
 
 using gk::kF1;
@@ -520,6 +526,8 @@ struct HostParams {
     gk::ParamBlock<8 * blob::TCN_SIZE> tcn8;
     gk::ParamBlock<blob::FRONT_SIZE> front;
     gk::ParamBlock<blob::BACK_SIZE> back;
+    bool tc_stream = false;                       // decoder blocks of a hop on the tensor cores (k_gtconv_dec_tc<4, true>)
+    int sm_count = 148;
     void load(const float* blob_host) {
         memcpy(front.w, blob_host + blob::FRONT_OFF, sizeof(front.w));
         memcpy(back.w, blob_host + blob::BACK_OFF, sizeof(back.w));
@@ -549,7 +557,8 @@ inline int model_step(const float* blobp, const HostParams& hp, void* state, con
     ks_gtcn<<<(unsigned)((N * kF2 + 2 * ST_THREADS - 1) / (2 * ST_THREADS)), ST_THREADS, ST_SMEM_BYTES, st>>>(ws.act[3], ws.act[5], hp.tcn8, state, N);
     ++launches;
     for (int i = 0; i < 3; ++i) {
-        ks_gtconv<true><<<gsg, SG_THREADS, SG_SMEM_FLOATS * sizeof(float), st>>>(ws.act[5 + i], ws.act[3 - i], ws.act[6 + i], hp.dec[i], state, 3 + i, N);
+        if (hp.tc_stream) gk::launch_dec_tc_stream(ws.act[5 + i], ws.act[3 - i], ws.act[6 + i], hp.dec[i], state, 3 + i, N, hp.sm_count, st);
+        else ks_gtconv<true><<<gsg, SG_THREADS, SG_SMEM_FLOATS * sizeof(float), st>>>(ws.act[5 + i], ws.act[3 - i], ws.act[6 + i], hp.dec[i], state, 3 + i, N);
         ++launches;
     }
     k_back<false, 0><<<gbk, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(ws.act[8], ws.act[0], ws.en0, spec, kSpecFrame, 2, 0, 1,

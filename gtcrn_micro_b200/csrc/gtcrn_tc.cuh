@@ -16,7 +16,9 @@
 // side along N, so one MMA with A_hi yields hi*w_hi and hi*w_lo in two column blocks of the accumulator and a second, narrower
 // MMA adds lo*w_hi: 2 MMAs per K = 8 step instead of 3; the two column blocks are added in registers after tcgen05.ld.
 #pragma once
+#include <algorithm>
 #include "gtcrn_kernels.cuh"
+#include "gtcrn_stream.cuh"
 #include <cuda_fp16.h>
 #include "tc_util.cuh"
 
@@ -282,13 +284,26 @@ __host__ __device__ constexpr int gtt_min_blocks(int nwg) { return nwg == 1 ? 4 
 __host__ __device__ constexpr uint32_t gtt_tmem_cols(int nwg) { return nwg == 1 ? 128 : nwg == 2 ? 256 : 512; }
 static_assert(GTT_WG_FLOATS % 4 == 0 && GTT_B_FLOATS % 4 == 0 && GTT_GW_FLOATS % 4 == 0, "16-byte aligned regions");
 
-template <int NWG>
+// STREAM = false: offline, grid (segments, ceil(B / (3 NWG))), every group walks its utterance segment one frame per step.
+// STREAM = true:  one 16 ms hop of N streams (StreamGTConvBlock, gtcrn_micro_stream.py:182-262): a persistent grid, every warpgroup
+//                 loops over tiles of 3 streams; the two older K blocks come from the stream's point-conv ring in HBM and the TRALite
+//                 energy history from its energy ring (gtcrn_stream.cuh state layout) instead of TMEM / registers.  Same operand
+//                 split, MMA order and epilogue as the offline kernel, so the decoder blocks of the streaming path are bit-identical
+//                 to the offline tensor-core build.
+template <int NWG, bool STREAM>
 __global__ void __launch_bounds__(128 * NWG, gtt_min_blocks(NWG))
 k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, float* __restrict__ out,
-                const __grid_constant__ ParamBlock<gt_chunk<true>()> prm, int T, int seg_len, int B) {
+                const __grid_constant__ ParamBlock<gt_chunk<true>()> prm, int T, int seg_len, int B, void* state, int blk, long long N) {
     using O = GtOff<true>;
     static_assert(NWG == 1 || NWG == 2 || (NWG >= 3 && NWG <= 5), "96 TMEM columns per warpgroup, power-of-two allocations");
     constexpr int NTHR = 128 * NWG;
+    int slot_old = 0, slot_mid = 1;
+    if (STREAM) {
+        const gs::Header* hdr = reinterpret_cast<const gs::Header*>(state);
+        if (hdr->skip) return;                                        // first wav hop: nothing to enhance yet (whole grid returns)
+        slot_old = (int)(hdr->frame_step & 1);                        // ring slot of frame t-2, overwritten with frame t
+        slot_mid = slot_old ^ 1;
+    }
     extern __shared__ float4 smem4[];
     __shared__ __align__(8) uint64_t bars[NWG];
     __shared__ uint32_t tmem_base_s;
@@ -301,7 +316,7 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
     float* E2 = wgm + 2 * 4 * 100 * 4;                                // [99][8]
     float* Gt = E2 + GTT_ROWS * 8;                                    // [3][8]
 
-    // ---- prologue: power-of-two weight scale, fp16 hi/lo weight planes, zeroed TRA history, tensor memory
+    // ---- prologue: power-of-two weight scale, fp16 hi/lo weight planes, TRALite weights, tensor memory
     if (tid == 0) wmax_bits = 0u;
     __syncthreads();
     {
@@ -334,7 +349,7 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
     __syncthreads();
     tc::fence_after();
     const uint32_t tm = tmem_base_s + 96 * wg, lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    {
+    if (!STREAM) {
         // zero history: frames before the start of the utterance (or of the warm-up) contribute nothing
         uint32_t z[8];
 #pragma unroll
@@ -352,178 +367,262 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
     const bool active = tig < GTT_ROWS;
     const int rr = active ? tig : GTT_ROWS - 1;                          // idle lanes shadow the last row (no stores, no smem writes)
     const int g = rr / kF2, f = rr - g * kF2;
-    const int b_raw = blockIdx.y * (GTT_G * NWG) + wg * GTT_G + g;
-    const bool store_ok = active && b_raw < B;
-    const int b = min(b_raw, B - 1);
-    const int s0 = blockIdx.x * seg_len, s1 = min(T, s0 + seg_len);
-    if (s0 < s1) {
-        const int tw0 = max(0, s0 - GT_WARMUP);
-        const int64_t ubase = (int64_t)b * T * kF2 * 16 + f * 16;
-        const float4* px = reinterpret_cast<const float4*>(xin + ubase);
-        const float4* ps = reinterpret_cast<const float4*>(skip + ubase);
-        float4* po = reinterpret_cast<float4*>(out + ubase);
-        constexpr int FS4 = kF2 * 4;                                     // float4 per frame
-        const bool is_gate_thread = active && f < 8;
-        const unsigned gmask = 0xFFu << ((g * kF2) & 31);                // lanes of (g, c = 0..7): 33 g + c = g + c (mod 32)
+    const bool is_gate_thread = active && f < 8;
+    const unsigned gmask = 0xFFu << ((g * kF2) & 31);                    // lanes of (g, c = 0..7): 33 g + c = g + c (mod 32)
+    constexpr int FS4 = kF2 * 4;                                         // float4 per frame
 
-        // TRALite energy + gate of one finished frame (its q^2 are in E2): thread (g, c < 8) owns channel c of group g -- its energy
-        // history stays in registers (ea, eb = frames -2, -1), the depthwise temporal conv is one value per thread and the 8 x 8
-        // pointwise conv exchanges them with shuffles among the group's 8 lanes.  Four interleaved partial sums in a fixed order:
-        // deterministic, independent of batch composition and segmentation.
-        float ea = 0.f, eb = 0.f;
-        auto gate_phase = [&]() {
-            if (is_gate_thread) {
-                const int c = f;
-                const float* e2c = E2 + g * kF2 * 8 + c;
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    // fp16 hi/lo split of a 16-channel row into ring slot `slot` of the A operand (8 columns of hi pairs, 8 of lo pairs)
+    auto store_slot = [&](int slot, const float (&p)[16]) {
+        uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int ff = 0; ff < 32; ff += 4) {
-                    s0 += e2c[ff * 8]; s1 += e2c[(ff + 1) * 8]; s2 += e2c[(ff + 2) * 8]; s3 += e2c[(ff + 3) * 8];
+        for (int c = 0; c < 8; ++c) {
+            hi[c] = tc::pack_f16x2(p[2 * c], p[2 * c + 1]);
+            lo[c] = tc::pack_f16x2(p[2 * c] - tc::f16lo_to_f32(hi[c]), p[2 * c + 1] - tc::f16hi_to_f32(hi[c]));
+        }
+        tc::tmem_st8u(tm + lane_base + 48 + 16 * slot, hi);
+        tc::tmem_st8u(tm + lane_base + 56 + 16 * slot, lo);
+    };
+    // the 9 MMAs of one frame; r = ring slot of the newest frame: kt = 0 <-> frame t-2 <-> slot r+1, kt = 2 <-> frame t <-> slot r
+    auto issue_mmas = [&](int r) {
+        tc::fence_after();
+        constexpr uint32_t id48 = tc::make_idesc_f16(128, 48);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {                              // small terms first
+            int s = r + 1 + kt;
+            s -= s >= 3 ? 3 : 0;
+            const uint64_t bh = bdesc0 + (uint64_t)(kt * 96);         // 1,536 bytes per kt >> 4
+            tc::mma_f16_ts(tm, tm + 56 + 16 * s, bh, id48, acc); acc = 1;             // lo * W_hi
+            tc::mma_f16_ts(tm, tm + 48 + 16 * s, bh + 288, id48, 1);                  // hi * W_lo (4,608 bytes further)
+        }
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+            int s = r + 1 + kt;
+            s -= s >= 3 ? 3 : 0;
+            tc::mma_f16_ts(tm, tm + 48 + 16 * s, bdesc0 + (uint64_t)(kt * 96), id48, 1);   // hi * W_hi
+        }
+        tc::commit(bar);
+    };
+    // accumulator row back (kf = 0 / kf = 2 blocks to the neighbouring bins through shared memory), first half: up to the barrier
+    auto fetch_and_exchange = [&](float (&m)[16]) {
+        {
+            float d0[16], d2[16];
+            tc::tmem_ld16_nowait(tm + lane_base, d0);
+            tc::tmem_ld16_nowait(tm + lane_base + 32, d2);
+            tc::tmem_wait_ld(d0);
+            tc::tmem_wait_ld(d2);
+            if (active) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    X[qd * 100 + rr] = make_float4(d0[4 * qd], d0[4 * qd + 1], d0[4 * qd + 2], d0[4 * qd + 3]);
+                    X[400 + qd * 100 + rr] = make_float4(d2[4 * qd], d2[4 * qd + 1], d2[4 * qd + 2], d2[4 * qd + 3]);
                 }
-                s0 += e2c[32 * 8];
-                const float en = ((s0 + s1) + (s2 + s3)) / 33.0f;
-                float y = Gw[24 + c];
-                y = fmaf(Gw[c], ea, y);
-                y = fmaf(Gw[8 + c], eb, y);
-                y = fmaf(Gw[16 + c], en, y);
-                ea = eb; eb = en;
-                float v = Gw[96 + c];
-                const int lane0 = (g * kF2) & 31;
+            }
+        }
+        tc::tmem_ld16_nowait(tm + lane_base + 16, m);                 // the centre block stays with this thread
+        tc::tmem_wait_ld(m);
+        tc::fence_before();                                           // orders the tcgen05.ld above before the next step's MMAs
+    };
+    // second half: neighbours' blocks, weight scale + bias, PReLU, point conv 2, q^2 for the TRALite energy
+    auto epilogue = [&](float (&m)[16], float (&q)[8]) {
+        if (f > 0) {
 #pragma unroll
-                for (int ci = 0; ci < 8; ++ci) v = fmaf(Gw[32 + ci * 8 + c], __shfl_sync(gmask, y, lane0 + ci), v);
-                Gt[g * 8 + c] = 1.0f / (1.0f + expf(-v));
+            for (int qd = 0; qd < 4; ++qd) {
+                const float4 u = X[qd * 100 + rr - 1];
+                add_pair(m[4 * qd], m[4 * qd + 1], u.x, u.y); add_pair(m[4 * qd + 2], m[4 * qd + 3], u.z, u.w);
             }
-        };
-        // gate, channel shuffle [q0 g0, x2_0, q1 g1, x2_1, ...], store of frame ts
-        auto store_frame = [&](int ts, const float (&q)[8], const float4& x2a, const float4& x2b) {
-            if (store_ok && ts >= s0) {
-                const float4 g0 = reinterpret_cast<const float4*>(Gt + g * 8)[0];
-                const float4 g1 = reinterpret_cast<const float4*>(Gt + g * 8)[1];
-                float4* o4 = po + (int64_t)ts * FS4;
-                o4[0] = make_float4(q[0] * g0.x, x2a.x, q[1] * g0.y, x2a.y);
-                o4[1] = make_float4(q[2] * g0.z, x2a.z, q[3] * g0.w, x2a.w);
-                o4[2] = make_float4(q[4] * g1.x, x2b.x, q[5] * g1.y, x2b.y);
-                o4[3] = make_float4(q[6] * g1.z, x2b.z, q[7] * g1.w, x2b.w);
+        }
+        if (f < kF2 - 1) {
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                const float4 u = X[400 + qd * 100 + rr + 1];
+                add_pair(m[4 * qd], m[4 * qd + 1], u.x, u.y); add_pair(m[4 * qd + 2], m[4 * qd + 3], u.z, u.w);
             }
-        };
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) m[c] = fmaf(m[c], winv, prm.w[O::MID_B + c]);     // undo the weight scale, add the bias
+        gt_pc2<true>(prm, m, q);
+        if (active) {
+            float4* e4 = reinterpret_cast<float4*>(E2 + rr * 8);
+            e4[0] = make_float4(q[0] * q[0], q[1] * q[1], q[2] * q[2], q[3] * q[3]);
+            e4[1] = make_float4(q[4] * q[4], q[5] * q[5], q[6] * q[6], q[7] * q[7]);
+        }
+    };
+    // TRALite energy + gate of one finished frame (its q^2 are in E2): thread (g, c < 8) owns channel c of group g -- its energy
+    // history (ea, eb = frames -2, -1) is in registers, the depthwise temporal conv is one value per thread and the 8 x 8
+    // pointwise conv exchanges them with shuffles among the group's 8 lanes.  Four interleaved partial sums in a fixed order:
+    // deterministic, independent of batch composition and segmentation.  Returns with eb = the new energy.
+    float ea = 0.f, eb = 0.f;
+    auto gate_phase = [&]() {
+        if (is_gate_thread) {
+            const int c = f;
+            const float* e2c = E2 + g * kF2 * 8 + c;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int ff = 0; ff < 32; ff += 4) {
+                s0 += e2c[ff * 8]; s1 += e2c[(ff + 1) * 8]; s2 += e2c[(ff + 2) * 8]; s3 += e2c[(ff + 3) * 8];
+            }
+            s0 += e2c[32 * 8];
+            const float en = ((s0 + s1) + (s2 + s3)) / 33.0f;
+            float y = Gw[24 + c];
+            y = fmaf(Gw[c], ea, y);
+            y = fmaf(Gw[8 + c], eb, y);
+            y = fmaf(Gw[16 + c], en, y);
+            ea = eb; eb = en;
+            float v = Gw[96 + c];
+            const int lane0 = (g * kF2) & 31;
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) v = fmaf(Gw[32 + ci * 8 + c], __shfl_sync(gmask, y, lane0 + ci), v);
+            Gt[g * 8 + c] = 1.0f / (1.0f + expf(-v));
+        }
+    };
+    // gate, channel shuffle [q0 g0, x2_0, q1 g1, x2_1, ...], store
+    auto store_row = [&](float4* o4, const float (&q)[8], const float4& x2a, const float4& x2b) {
+        const float4 g0 = reinterpret_cast<const float4*>(Gt + g * 8)[0];
+        const float4 g1 = reinterpret_cast<const float4*>(Gt + g * 8)[1];
+        o4[0] = make_float4(q[0] * g0.x, x2a.x, q[1] * g0.y, x2a.y);
+        o4[1] = make_float4(q[2] * g0.z, x2a.z, q[3] * g0.w, x2a.w);
+        o4[2] = make_float4(q[4] * g1.x, x2b.x, q[5] * g1.y, x2b.y);
+        o4[3] = make_float4(q[6] * g1.z, x2b.z, q[7] * g1.w, x2b.w);
+    };
 
-        // The loop is software-pipelined by one frame: the TRALite gate of frame t-1 is evaluated by its 24 threads while the MMAs
-        // of frame t run, and frame t-1 is stored after the barrier that publishes the gate -- two warpgroup barriers per frame.
-        int r = tw0 % 3;                                                  // ring slot of the current frame
-        float qp[8];                                                      // previous frame: point-conv-2 output and pass-through half
-        float4 x2pa = make_float4(0.f, 0.f, 0.f, 0.f), x2pb = x2pa;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) qp[c] = 0.f;
-        for (int t = tw0; t < s1; ++t) {
-            float4 cx[4];                                                 // x + skip of this frame (the next one is on its way to L2)
+    if (STREAM) {
+        const long long ntiles = (N + GTT_G - 1) / GTT_G;
+        for (long long tile = (long long)blockIdx.x * NWG + wg; tile < ntiles; tile += (long long)gridDim.x * NWG) {
+            const long long n_raw = tile * GTT_G + g;
+            const bool valid = active && n_raw < N;
+            const long long n = min(n_raw, N - 1);
+            float* sb = gs::stream_base(state, n);
+            float* ring = sb + gs::kGtP + blk * (2 * kF2 * 16) + f * 16;
+            float4 cx[4];
             {
-                float4 a[4], c[4];
+                const float4* px = reinterpret_cast<const float4*>(xin + (n * kF2 + f) * 16);
+                const float4* ps = reinterpret_cast<const float4*>(skip + (n * kF2 + f) * 16);
+                const float4* h2 = reinterpret_cast<const float4*>(ring + slot_old * (kF2 * 16));
+                const float4* h1 = reinterpret_cast<const float4*>(ring + slot_mid * (kF2 * 16));
+                float4 a[4], c[4], u2[4], u1[4];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) { a[v] = px[(int64_t)t * FS4 + v]; c[v] = ps[(int64_t)t * FS4 + v]; }
-                if (t + 1 < s1) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(px + (int64_t)(t + 1) * FS4));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + (int64_t)(t + 1) * FS4));
+                for (int v = 0; v < 4; ++v) { a[v] = px[v]; c[v] = ps[v]; u2[v] = h2[v]; u1[v] = h1[v]; }
+                if (is_gate_thread) {
+                    ea = sb[gs::kTraE + blk * 16 + slot_old * 8 + f];
+                    eb = sb[gs::kTraE + blk * 16 + slot_mid * 8 + f];
                 }
 #pragma unroll
                 for (int v = 0; v < 4; ++v) cx[v] = make_float4(a[v].x + c[v].x, a[v].y + c[v].y, a[v].z + c[v].z, a[v].w + c[v].w);
+                {
+                    const float p2[16] = {u2[0].x, u2[0].y, u2[0].z, u2[0].w, u2[1].x, u2[1].y, u2[1].z, u2[1].w,
+                                          u2[2].x, u2[2].y, u2[2].z, u2[2].w, u2[3].x, u2[3].y, u2[3].z, u2[3].w};
+                    store_slot(0, p2);
+                }
+                {
+                    const float p1[16] = {u1[0].x, u1[0].y, u1[0].z, u1[0].w, u1[1].x, u1[1].y, u1[1].z, u1[1].w,
+                                          u1[2].x, u1[2].y, u1[2].z, u1[2].w, u1[3].x, u1[3].y, u1[3].z, u1[3].w};
+                    store_slot(1, p1);
+                }
             }
-            // ---- point conv 1 on the first channel half, fp16 hi/lo split, into ring slot r of the A operand
             {
                 const float x1[8] = {cx[0].x, cx[0].y, cx[0].z, cx[0].w, cx[1].x, cx[1].y, cx[1].z, cx[1].w};
                 float p[16];
                 gt_pc1<true>(prm, x1, p);
-                uint32_t hi[8], lo[8];
+                store_slot(2, p);
+                if (valid) {                                              // the new frame replaces frame t-2 in the stream's ring
+                    float4* newest = reinterpret_cast<float4*>(ring + slot_old * (kF2 * 16));
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    hi[c] = tc::pack_f16x2(p[2 * c], p[2 * c + 1]);
-                    lo[c] = tc::pack_f16x2(p[2 * c] - tc::f16lo_to_f32(hi[c]), p[2 * c + 1] - tc::f16hi_to_f32(hi[c]));
+                    for (int qd = 0; qd < 4; ++qd) newest[qd] = make_float4(p[4 * qd], p[4 * qd + 1], p[4 * qd + 2], p[4 * qd + 3]);
                 }
-                tc::tmem_st8u(tm + lane_base + 48 + 16 * r, hi);
-                tc::tmem_st8u(tm + lane_base + 56 + 16 * r, lo);
             }
             tc::tmem_wait_st();
             tc::fence_before();
-            tc::bar_sync(bar_id, 128);                                    // A(t) complete; also: E2(t-1) visible to the gate threads
-            if (issuer) {
-                tc::fence_after();
-                constexpr uint32_t id48 = tc::make_idesc_f16(128, 48);
-                uint32_t acc = 0;
-#pragma unroll
-                for (int kt = 0; kt < 3; ++kt) {                          // small terms first
-                    int s = r + 1 + kt;                                   // kt = 0 <-> frame t-2 <-> slot r+1, kt = 2 <-> frame t <-> slot r
-                    s -= s >= 3 ? 3 : 0;
-                    const uint64_t bh = bdesc0 + (uint64_t)(kt * 96);     // 1,536 bytes per kt >> 4
-                    tc::mma_f16_ts(tm, tm + 56 + 16 * s, bh, id48, acc); acc = 1;             // lo * W_hi
-                    tc::mma_f16_ts(tm, tm + 48 + 16 * s, bh + 288, id48, 1);                  // hi * W_lo (4,608 bytes further)
-                }
-#pragma unroll
-                for (int kt = 0; kt < 3; ++kt) {
-                    int s = r + 1 + kt;
-                    s -= s >= 3 ? 3 : 0;
-                    tc::mma_f16_ts(tm, tm + 48 + 16 * s, bdesc0 + (uint64_t)(kt * 96), id48, 1);   // hi * W_hi
-                }
-                tc::commit(bar);
-            }
-            if (t > tw0) gate_phase();                                    // frame t-1, while the tensor core works on frame t
+            tc::bar_sync(bar_id, 128);
+            if (issuer) issue_mmas(2);                                    // fixed slots: kt = slot
             tc::mbar_wait(bar, parity);
             parity ^= 1;
             tc::fence_after();
-            // ---- accumulator row back: kf = 0 and kf = 2 blocks go to the neighbouring bins through shared memory
-            float m[16];
-            {
-                float d0[16], d2[16];
-                tc::tmem_ld16_nowait(tm + lane_base, d0);
-                tc::tmem_ld16_nowait(tm + lane_base + 32, d2);
-                tc::tmem_wait_ld(d0);
-                tc::tmem_wait_ld(d2);
-                if (active) {
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        X[qd * 100 + rr] = make_float4(d0[4 * qd], d0[4 * qd + 1], d0[4 * qd + 2], d0[4 * qd + 3]);
-                        X[400 + qd * 100 + rr] = make_float4(d2[4 * qd], d2[4 * qd + 1], d2[4 * qd + 2], d2[4 * qd + 3]);
-                    }
-                }
-            }
-            tc::tmem_ld16_nowait(tm + lane_base + 16, m);                 // the centre block stays with this thread
-            tc::tmem_wait_ld(m);
-            tc::fence_before();                                           // orders the tcgen05.ld above before the next step's MMAs
-            tc::bar_sync(bar_id, 128);                                    // exchange buffer and the gate of frame t-1 are visible
-            if (t > tw0) store_frame(t - 1, qp, x2pa, x2pb);
-            if (f > 0) {
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    const float4 u = X[qd * 100 + rr - 1];
-                    add_pair(m[4 * qd], m[4 * qd + 1], u.x, u.y); add_pair(m[4 * qd + 2], m[4 * qd + 3], u.z, u.w);
-                }
-            }
-            if (f < kF2 - 1) {
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    const float4 u = X[400 + qd * 100 + rr + 1];
-                    add_pair(m[4 * qd], m[4 * qd + 1], u.x, u.y); add_pair(m[4 * qd + 2], m[4 * qd + 3], u.z, u.w);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 16; ++c) m[c] = fmaf(m[c], winv, prm.w[O::MID_B + c]);     // undo the weight scale, add the bias
-            // ---- PReLU, point conv 2, q^2 for the TRALite energy of this frame (summed during the next step)
-            gt_pc2<true>(prm, m, qp);
-            if (active) {
-                float4* e4 = reinterpret_cast<float4*>(E2 + rr * 8);
-                e4[0] = make_float4(qp[0] * qp[0], qp[1] * qp[1], qp[2] * qp[2], qp[3] * qp[3]);
-                e4[1] = make_float4(qp[4] * qp[4], qp[5] * qp[5], qp[6] * qp[6], qp[7] * qp[7]);
-            }
-            x2pa = cx[2]; x2pb = cx[3];
-            r = r == 2 ? 0 : r + 1;
+            float m[16], q[8];
+            fetch_and_exchange(m);
+            tc::bar_sync(bar_id, 128);
+            epilogue(m, q);
+            tc::bar_sync(bar_id, 128);
+            gate_phase();
+            if (is_gate_thread && valid) sb[gs::kTraE + blk * 16 + slot_old * 8 + f] = eb;
+            tc::bar_sync(bar_id, 128);
+            if (valid) store_row(reinterpret_cast<float4*>(out + (n * kF2 + f) * 16), q, cx[2], cx[3]);
         }
-        // ---- drain: gate and store of the last frame
-        tc::bar_sync(bar_id, 128);
-        gate_phase();
-        tc::bar_sync(bar_id, 128);
-        store_frame(s1 - 1, qp, x2pa, x2pb);
+    } else {
+        const int b_raw = blockIdx.y * (GTT_G * NWG) + wg * GTT_G + g;
+        const bool store_ok = active && b_raw < B;
+        const int b = min(b_raw, B - 1);
+        const int s0 = blockIdx.x * seg_len, s1 = min(T, s0 + seg_len);
+        if (s0 < s1) {
+            const int tw0 = max(0, s0 - GT_WARMUP);
+            const int64_t ubase = (int64_t)b * T * kF2 * 16 + f * 16;
+            const float4* px = reinterpret_cast<const float4*>(xin + ubase);
+            const float4* ps = reinterpret_cast<const float4*>(skip + ubase);
+            float4* po = reinterpret_cast<float4*>(out + ubase);
+            // The loop is software-pipelined by one frame: the TRALite gate of frame t-1 is evaluated by its 24 threads while the
+            // MMAs of frame t run, and frame t-1 is stored after the barrier that publishes the gate -- two warpgroup barriers per frame.
+            int r = tw0 % 3;                                              // ring slot of the current frame
+            float qp[8];                                                  // previous frame: point-conv-2 output and pass-through half
+            float4 x2pa = make_float4(0.f, 0.f, 0.f, 0.f), x2pb = x2pa;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) qp[c] = 0.f;
+            for (int t = tw0; t < s1; ++t) {
+                float4 cx[4];                                             // x + skip of this frame (the next one is on its way to L2)
+                {
+                    float4 a[4], c[4];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) { a[v] = px[(int64_t)t * FS4 + v]; c[v] = ps[(int64_t)t * FS4 + v]; }
+                    if (t + 1 < s1) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(px + (int64_t)(t + 1) * FS4));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + (int64_t)(t + 1) * FS4));
+                    }
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) cx[v] = make_float4(a[v].x + c[v].x, a[v].y + c[v].y, a[v].z + c[v].z, a[v].w + c[v].w);
+                }
+                // ---- point conv 1 on the first channel half, fp16 hi/lo split, into ring slot r of the A operand
+                {
+                    const float x1[8] = {cx[0].x, cx[0].y, cx[0].z, cx[0].w, cx[1].x, cx[1].y, cx[1].z, cx[1].w};
+                    float p[16];
+                    gt_pc1<true>(prm, x1, p);
+                    store_slot(r, p);
+                }
+                tc::tmem_wait_st();
+                tc::fence_before();
+                tc::bar_sync(bar_id, 128);                                // A(t) complete; also: E2(t-1) visible to the gate threads
+                if (issuer) issue_mmas(r);
+                if (t > tw0) gate_phase();                                // frame t-1, while the tensor core works on frame t
+                tc::mbar_wait(bar, parity);
+                parity ^= 1;
+                tc::fence_after();
+                float m[16];
+                fetch_and_exchange(m);
+                tc::bar_sync(bar_id, 128);                                // exchange buffer and the gate of frame t-1 are visible
+                if (t > tw0 && store_ok && t - 1 >= s0) store_row(po + (int64_t)(t - 1) * FS4, qp, x2pa, x2pb);
+                epilogue(m, qp);
+                x2pa = cx[2]; x2pb = cx[3];
+                r = r == 2 ? 0 : r + 1;
+            }
+            // ---- drain: gate and store of the last frame
+            tc::bar_sync(bar_id, 128);
+            gate_phase();
+            tc::bar_sync(bar_id, 128);
+            if (store_ok) store_row(po + (int64_t)(s1 - 1) * FS4, qp, x2pa, x2pb);
+        }
     }
     tc::fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base_s, gtt_tmem_cols(NWG));
+}
+
+// one decoder block of a streaming hop on the tensor cores: persistent grid of one CTA per SM (or fewer for small N)
+inline cudaError_t launch_dec_tc_stream(const float* x, const float* skip, float* out, const ParamBlock<gt_chunk<true>()>& prm, void* state, int blk,
+                                        int64_t N, int sm_count, cudaStream_t st) {
+    constexpr int NWG = 4;
+    const long long ntiles = (N + GTT_G - 1) / GTT_G;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((ntiles + NWG - 1) / NWG, sm_count));
+    int T = 1, seg = 1, B = 0; long long n = N;
+    void* args[] = {(void*)&x, (void*)&skip, (void*)&out, (void*)&prm, (void*)&T, (void*)&seg, (void*)&B, (void*)&state, (void*)&blk, (void*)&n};
+    return cudaLaunchKernel((const void*)k_gtconv_dec_tc<NWG, true>, dim3(grid), dim3(128 * NWG), args, gtt_smem_floats(NWG) * sizeof(float), st);
 }
 
 }  // namespace gk

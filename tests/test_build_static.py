@@ -21,7 +21,7 @@ CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 HOT = ["k_frontILb0ELi0E", "k_frontILb1ELi0E", "k_backILb0ELi0E", "k_backILb1ELi0E", "k_gtconvILb0ELi2ELi4ELb0", "k_gtconvILb1ELi4ELi7ELb0",
        "k_gtcnILi2ELb0", "ks_gtconvILb0", "ks_gtconvILb1", "ks_gtcn"]
 # tensor-core kernels of the default path (gtcrn_tc.cuh): decoder GTConv with 4 warpgroups per CTA, GTCN with one
-HOT_TC = ["k_gtconv_dec_tcILi4E", "k_gtcn_tcILi1ELb0"]
+HOT_TC = ["k_gtconv_dec_tcILi4ELb0", "k_gtconv_dec_tcILi4ELb1", "k_gtcn_tcILi1ELb0"]
 # kernels of the original-GTCRN-style variant (BASELINE configs[3]): same weight-feed property, spills tolerated up to a small frame
 HOT_FULL = ["k_frontILb0ELi1E", "k_frontILb1ELi1E", "k_backILb0ELi1E", "k_backILb1ELi1E", "kf_gtconvILb0ELi2ELi4E", "kf_gtconvILb1ELi2ELi4E",
             "kf_dp_intra", "kf_dp_inter"]
