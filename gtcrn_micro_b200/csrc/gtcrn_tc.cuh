@@ -494,6 +494,15 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
             const long long n = min(n_raw, N - 1);
             float* sb = gs::stream_base(state, n);
             float* ring = sb + gs::kGtP + blk * (2 * kF2 * 16) + f * 16;
+            {
+                // the operands of this warpgroup's next tile start their trip from HBM now (a tile is ~7 us of dependent work)
+                const long long nn = min((tile + (long long)gridDim.x * NWG) * GTT_G + g, N - 1);
+                const float* rn = gs::stream_base(state, nn) + gs::kGtP + blk * (2 * kF2 * 16) + f * 16;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(xin + (nn * kF2 + f) * 16));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(skip + (nn * kF2 + f) * 16));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rn));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rn + kF2 * 16));
+            }
             float4 cx[4];
             {
                 const float4* px = reinterpret_cast<const float4*>(xin + (n * kF2 + f) * 16);

@@ -25,6 +25,6 @@ torch.cuda.synchronize()
 PY
 # hop = 10 launches (spec) / 12 (wav): skip 6 warm hops, capture one whole hop
 PER=10; [ "$KIND" = wav ] && PER=12
-GTCRNB_STREAM_GRAPH=0 timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:k_front|ks_|k_back" -s $((6 * PER)) -c $PER -f \
+GTCRNB_STREAM_GRAPH=0 timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:k_front|ks_|k_back|k_gtconv_dec_tc" -s $((6 * PER)) -c $PER -f \
     -o gpurun_out/prof_$TAG python gpurun_out/stream_hops.py $N $KIND 8 > gpurun_out/ncu_$TAG.log 2>&1
 echo "ncu rc=$?"; tail -2 gpurun_out/ncu_$TAG.log
