@@ -7,15 +7,15 @@ sys.path.insert(0, 'oracle'); sys.path.insert(0, '.')
 import gtcrn_oracle as O, gtcrn_micro_b200 as G
 W = O.load_weights_npz('tests/golden/weights_dns3.npz')
 m = G.GTCRNMicro(); m.load_state_dict(W)
-x = O.synth_batch(3, 256 * 70 + 9, seed=1).cuda()
+x = O.synth_batch(14, 256 * 70 + 9, seed=1).cuda()          # 14 utterances: ragged tensor-core tiles (12 per CTA, 4 columns per warpgroup)
 y = m.enhance(x); s = m.stft(x); z = m.istft(m(s)); torch.cuda.synchronize()
 sm = G.StreamGTCRNMicro(); G.convert_to_stream(sm, m)
-st = sm.new_state(5, 'cuda:0')
+st = sm.new_state(5, 'cuda:0')                                # 5 streams: one full and one ragged 3-stream tile of the TC decoder
 for k in range(6):
     o = sm.step_wav(x[:1, 256 * k:256 * (k + 1)].repeat(5, 1).contiguous(), st)
 pm = m.pair_metrics(x[:, :y.shape[1]].contiguous(), y)
 yh = m.enhance_host(x.cpu().pin_memory())
-torch.cuda.synchronize(); print('ok', y.shape, float((y - z).abs().max()), bool(torch.equal(yh, y.cpu())), pm.shape)
+torch.cuda.synchronize(); print('ok', y.shape, float((y - z).abs().max()), bool(torch.equal(yh, y.cpu())), pm.shape, 'tc mask', m.tc_mask())
 PY
 for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python gpurun_out/san_case.py > gpurun_out/sanitize_$tool.log 2>&1
