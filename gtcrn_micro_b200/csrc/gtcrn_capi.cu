@@ -72,20 +72,23 @@ struct gtcrnb_handle {
     float* spec_in = nullptr;
     float* spec_out = nullptr;
     // host pipeline staging
-    static constexpr int kStage = 3;                 // staging buffers in flight per direction (workspaces / compute streams: 2)
+    static constexpr int kStage = 3;                 // utterance groups in flight: staging buffers per direction and activation workspaces
     float* stage_in[kStage] = {};
     float* stage_out[kStage] = {};
     size_t stage_in_floats = 0, stage_out_floats = 0;
     int16_t* pcm_in[kStage] = {};                    // PCM16 wire buffers of gtcrnb_enhance_host_pcm16
     int16_t* pcm_out[kStage] = {};
     size_t pcm_in_elems = 0, pcm_out_elems = 0;
-    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_comp2 = nullptr, s_d2h = nullptr;
-    // second activation workspace for the host pipeline: consecutive chunks run on two compute streams so that the tail of one
-    // chunk's kernels overlaps the head of the next (the fields above are the currently selected workspace)
+    // host pipeline streams: copies, per-copy-chunk front / back kernels, per-group walking kernels (see host_pipeline)
+    cudaStream_t s_h2d = nullptr, s_front = nullptr, s_body = nullptr, s_body2 = nullptr, s_back = nullptr, s_d2h = nullptr;
+    // activation workspaces: set 0 serves the caller-stream entry points, the host pipeline rotates through all kNumWs (one per
+    // utterance group in flight).  The fields above are the currently selected set; sets[ws_cur] is stale while it is selected.
     struct WsSet { int64_t cap_frames = 0; float* en0 = nullptr; float* act[kNumAct33] = {}; float* spec_in = nullptr; float* spec_out = nullptr; };
-    WsSet parked;                                 // the workspace that is NOT currently selected
+    static constexpr int kNumWs = kStage;
+    WsSet sets[kNumWs];
     int ws_cur = 0;
-    cudaEvent_t ev_h2d[kStage] = {}, ev_comp[kStage] = {}, ev_d2h[kStage] = {};
+    cudaEvent_t ev_fronts[kStage] = {}, ev_body[kStage] = {}, ev_backs[kStage] = {}, ev_d2h[kStage] = {};
+    std::vector<cudaEvent_t> ev_pool;             // per-copy-chunk events of the host pipeline (grown on demand, reused across calls)
     // Ordering between the caller's stream and the host pipeline's internal streams: both use the handle's activation workspace.
     // Every entry point that launches on a caller stream records ev_user there; the host pipeline makes its compute streams wait
     // on it before touching the workspace (the pipeline itself is synchronous, so nothing is needed in the other direction).
@@ -200,12 +203,12 @@ void note_user_work(gtcrnb_handle* h, cudaStream_t st) {
 
 void select_workspace(gtcrnb_handle* h, int idx) {
     if (h->ws_cur == idx) return;
-    gtcrnb_handle::WsSet tmp;
-    tmp.cap_frames = h->cap_frames; tmp.en0 = h->en0; tmp.spec_in = h->spec_in; tmp.spec_out = h->spec_out;
-    for (int i = 0; i < kNumAct33; ++i) tmp.act[i] = h->act[i];
-    h->cap_frames = h->parked.cap_frames; h->en0 = h->parked.en0; h->spec_in = h->parked.spec_in; h->spec_out = h->parked.spec_out;
-    for (int i = 0; i < kNumAct33; ++i) h->act[i] = h->parked.act[i];
-    h->parked = tmp;
+    gtcrnb_handle::WsSet& cur = h->sets[h->ws_cur];
+    cur.cap_frames = h->cap_frames; cur.en0 = h->en0; cur.spec_in = h->spec_in; cur.spec_out = h->spec_out;
+    for (int i = 0; i < kNumAct33; ++i) cur.act[i] = h->act[i];
+    const gtcrnb_handle::WsSet& nxt = h->sets[idx];
+    h->cap_frames = nxt.cap_frames; h->en0 = nxt.en0; h->spec_in = nxt.spec_in; h->spec_out = nxt.spec_out;
+    for (int i = 0; i < kNumAct33; ++i) h->act[i] = nxt.act[i];
     h->ws_cur = idx;
 }
 
@@ -227,61 +230,56 @@ int pick_seg_len(int64_t ctas_per_seg_row, int T, int gran, int warm, int slots)
     return best_len;
 }
 
-// Fused wav -> wav mode (wav != nullptr): the STFT runs inside k_front (spectrum parked in h->spec_in for the mask stage)
-// and the iSTFT + overlap-add inside k_back (wav_out must be zeroed by the caller).
-int run_model_full(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t B, int64_t T, float* out,
-                   const int64_t os[4], cudaStream_t st, const float* wav, int64_t wav_stride, int L, float* wav_out, int64_t wav_out_stride) {
+// Phases of the model, so that the host pipeline can run the per-frame ends (front: STFT .. en1, back: de3 .. iSTFT) on small
+// copy chunks -- utterances [u0, u0 + nu) of the workspace -- and the walking kernels in between on whole utterance groups.
+enum { PH_FRONT = 1, PH_BODY = 2, PH_BACK = 4, PH_ALL = 7 };
+
+template <int VAR, class HP>
+void launch_front(gtcrnb_handle* h, const HP& hp, const float* spec, const int64_t is[4], int64_t T, int64_t u0, int64_t nu, cudaStream_t st,
+                  const float* wav, int64_t wav_stride, int L) {
     using namespace gk;
-    const int Ti = (int)T;
-    const int64_t nframes = B * T;
-    const dim3 gfr((unsigned)((nframes + FR_NF - 1) / FR_NF)), gbk((unsigned)((nframes + BK_NF - 1) / BK_NF));
-    const bool fused = wav != nullptr;
-    {
-        ProfScope ps(h, KC_FRONT, nframes, st);
-        if (fused)
-            k_front<true, 1><<<gfr, FR_THREADS, fr_smem_floats(true) * sizeof(float), st>>>(nullptr, 0, 0, 0, 0, wav, wav_stride, L, h->spec_in,
-                                                                                            Ti, nframes, h->blob, h->hpf->front, h->en0, h->act[0]);
-        else
-            k_front<false, 1><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, is[0], is[1], is[2], is[3], nullptr, 0, 0, nullptr,
-                                                                                              Ti, nframes, h->blob, h->hpf->front, h->en0, h->act[0]);
-    }
-    static const int kCls[4] = {KC_FULL_ENC_GT, KC_DP_INTRA, KC_DP_INTER, KC_FULL_DEC_GT};
-    h->launches += 1 + gf::run_body(h->blob, *h->hpf, h->act, B, Ti, nullptr, st, [&](int c, int64_t fr) { return ProfScope(h, kCls[c], fr, st); });
-    {
-        ProfScope ps(h, KC_BACK, nframes, st);
-        if (fused) {
-            const int64_t ss[4] = {T * kSpecFrame, 2, kSpecFrame, 1};
-            k_back<true, 1><<<gbk, BK_THREADS, bk_smem_floats(true) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, h->spec_in, ss[0], ss[1], ss[2], ss[3],
-                                                                                           nullptr, 0, 0, 0, 0, wav_out, wav_out_stride, Ti, nframes, h->blob, h->hpf->back);
-        } else {
-            k_back<false, 1><<<gbk, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, spec, is[0], is[1], is[2], is[3],
-                                                                                             out, os[0], os[1], os[2], os[3], nullptr, 0, Ti, nframes, h->blob, h->hpf->back);
-        }
-    }
+    const int64_t nframes = nu * T, f0 = u0 * T;
+    const dim3 gfr((unsigned)((nframes + FR_NF - 1) / FR_NF));
+    ProfScope ps(h, KC_FRONT, nframes, st);
+    if (wav)
+        k_front<true, VAR><<<gfr, FR_THREADS, fr_smem_floats(true) * sizeof(float), st>>>(nullptr, 0, 0, 0, 0, wav + u0 * wav_stride, wav_stride, L,
+                                                                                           h->spec_in + f0 * kSpecFrame, (int)T, nframes, h->blob, hp.front,
+                                                                                           h->en0 + f0 * kF1 * 16, h->act[0] + f0 * kF2 * 16);
+    else
+        k_front<false, VAR><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec + u0 * is[0], is[0], is[1], is[2], is[3], nullptr, 0, 0, nullptr,
+                                                                                             (int)T, nframes, h->blob, hp.front,
+                                                                                             h->en0 + f0 * kF1 * 16, h->act[0] + f0 * kF2 * 16);
     h->launches++;
-    CU(cudaGetLastError());
-    return GTCRNB_OK;
 }
 
-int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t B, int64_t T, float* out,
-              const int64_t os[4], cudaStream_t st, const float* wav = nullptr, int64_t wav_stride = 0, int L = 0,
-              float* wav_out = nullptr, int64_t wav_out_stride = 0) {
+template <int VAR, class HP>
+void launch_back(gtcrnb_handle* h, const HP& hp, const float* spec, const int64_t is[4], int64_t T, int64_t u0, int64_t nu, float* out, const int64_t os[4],
+                 cudaStream_t st, bool fused, float* wav_out, int64_t wav_out_stride) {
     using namespace gk;
-    if (h->variant == 1) return run_model_full(h, spec, is, B, T, out, os, st, wav, wav_stride, L, wav_out, wav_out_stride);
-    const int Ti = (int)T;
-    const int64_t nframes = B * T;
-    const dim3 gfr((unsigned)((nframes + FR_NF - 1) / FR_NF)), gbk((unsigned)((nframes + BK_NF - 1) / BK_NF));
-    const bool fused = wav != nullptr;
-    {
-        ProfScope ps(h, KC_FRONT, nframes, st);
-        if (fused)
-            k_front<true, 0><<<gfr, FR_THREADS, fr_smem_floats(true) * sizeof(float), st>>>(nullptr, 0, 0, 0, 0, wav, wav_stride, L, h->spec_in,
-                                                                                         Ti, nframes, h->blob, h->hp->front, h->en0, h->act[0]);
-        else
-            k_front<false, 0><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, is[0], is[1], is[2], is[3], nullptr, 0, 0, nullptr,
-                                                                                           Ti, nframes, h->blob, h->hp->front, h->en0, h->act[0]);
+    const int64_t nframes = nu * T, f0 = u0 * T;
+    const dim3 gbk((unsigned)((nframes + BK_NF - 1) / BK_NF));
+    ProfScope ps(h, KC_BACK, nframes, st);
+    const float* de2 = h->act[8] + f0 * kF2 * 16;
+    const float* en1 = h->act[0] + f0 * kF2 * 16;
+    const float* en0 = h->en0 + f0 * kF1 * 16;
+    if (fused) {
+        const int64_t ss[4] = {T * kSpecFrame, 2, kSpecFrame, 1};
+        k_back<true, VAR><<<gbk, BK_THREADS, bk_smem_floats(true) * sizeof(float), st>>>(de2, en1, en0, h->spec_in + f0 * kSpecFrame, ss[0], ss[1], ss[2], ss[3],
+                                                                                          nullptr, 0, 0, 0, 0, wav_out + u0 * wav_out_stride, wav_out_stride,
+                                                                                          (int)T, nframes, h->blob, hp.back);
+    } else {
+        k_back<false, VAR><<<gbk, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(de2, en1, en0, spec + u0 * is[0], is[0], is[1], is[2], is[3],
+                                                                                            out + u0 * os[0], os[0], os[1], os[2], os[3], nullptr, 0,
+                                                                                            (int)T, nframes, h->blob, hp.back);
     }
     h->launches++;
+}
+
+// the walking kernels of GTCRN-Micro on B whole utterances: 3 encoder GTConv blocks, 2 GTCNs, 3 decoder GTConv blocks
+void launch_body_micro(gtcrnb_handle* h, int64_t B, int64_t T, cudaStream_t st) {
+    using namespace gk;
+    const int Ti = (int)T;
+    const int64_t nframes = B * T;
     {
         const GtVariant& v = kGtVariants[h->gt_enc];
         const int seg = pick_seg_len(B, Ti, v.ps, GT_WARMUP, h->sm_count * h->occ_gt_enc);
@@ -306,8 +304,8 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
                 ProfScope ps(h, KC_GTCN, nframes, st);
                 const size_t sm = tct_smem_floats(nwg) * sizeof(float);
                 const float* xi = h->act[3 + i]; float* xo = h->act[4 + i];
-                int seg_i = seg_tc; int64_t nc = ncols;
-                void* args[] = {(void*)&xi, (void*)&xo, (void*)&h->hp->gtcn[i], (void*)&Ti, (void*)&seg_i, (void*)&nc};
+                int seg_i = seg_tc; int64_t nc = ncols; int Tl = Ti;
+                void* args[] = {(void*)&xi, (void*)&xo, (void*)&h->hp->gtcn[i], (void*)&Tl, (void*)&seg_i, (void*)&nc};
                 cudaLaunchKernel(tc_gtcn_fn(nwg, h->tc_stack), gt, dim3(128 * nwg), args, sm, st);
                 h->launches++;
             }
@@ -327,9 +325,9 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
         for (int i = 0; i < 3; ++i) {
             ProfScope ps(h, KC_DEC_GT, nframes, st);
             const float* xi = h->act[5 + i]; const float* sk = h->act[3 - i]; float* xo = h->act[6 + i];
-            int seg_i = seg, Bi = (int)B;
+            int seg_i = seg, Bi = (int)B, Tl = Ti;
             void* nostate = nullptr; int blk0 = 0; long long n0 = 0;
-            void* args[] = {(void*)&xi, (void*)&sk, (void*)&xo, (void*)&h->hp->dec[i], (void*)&Ti, (void*)&seg_i, (void*)&Bi, (void*)&nostate, (void*)&blk0, (void*)&n0};
+            void* args[] = {(void*)&xi, (void*)&sk, (void*)&xo, (void*)&h->hp->dec[i], (void*)&Tl, (void*)&seg_i, (void*)&Bi, (void*)&nostate, (void*)&blk0, (void*)&n0};
             cudaLaunchKernel(tc_dec_fn(nwg), g, dim3(128 * nwg), args, gtt_smem_floats(nwg) * sizeof(float), st);
             h->launches++;
         }
@@ -344,18 +342,31 @@ int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t 
             h->launches++;
         }
     }
-    {
-        ProfScope ps(h, KC_BACK, nframes, st);
-        if (fused) {
-            const int64_t ss[4] = {T * kSpecFrame, 2, kSpecFrame, 1};
-            k_back<true, 0><<<gbk, BK_THREADS, bk_smem_floats(true) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, h->spec_in, ss[0], ss[1], ss[2], ss[3],
-                                                                                        nullptr, 0, 0, 0, 0, wav_out, wav_out_stride, Ti, nframes, h->blob, h->hp->back);
-        } else {
-            k_back<false, 0><<<gbk, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(h->act[8], h->act[0], h->en0, spec, is[0], is[1], is[2], is[3],
-                                                                                          out, os[0], os[1], os[2], os[3], nullptr, 0, Ti, nframes, h->blob, h->hp->back);
-        }
+}
+
+// Fused wav -> wav mode (wav != nullptr): the STFT runs inside k_front (spectrum parked in h->spec_in for the mask stage)
+// and the iSTFT + overlap-add inside k_back (wav_out must be zeroed by the caller).  `phases` / [u0, u0 + nu) select a part of the
+// model (host pipeline); the body always covers the B utterances of the workspace.
+int run_model(gtcrnb_handle* h, const float* spec, const int64_t is[4], int64_t B, int64_t T, float* out,
+              const int64_t os[4], cudaStream_t st, const float* wav = nullptr, int64_t wav_stride = 0, int L = 0,
+              float* wav_out = nullptr, int64_t wav_out_stride = 0, int phases = PH_ALL, int64_t u0 = 0, int64_t nu = -1) {
+    if (nu < 0) nu = B - u0;
+    const bool fused = wav != nullptr || wav_out != nullptr;
+    if (phases & PH_FRONT) {
+        if (h->variant == 1) launch_front<1>(h, *h->hpf, spec, is, T, u0, nu, st, wav, wav_stride, L);
+        else launch_front<0>(h, *h->hp, spec, is, T, u0, nu, st, wav, wav_stride, L);
     }
-    h->launches++;
+    if (phases & PH_BODY) {
+        if (h->variant == 1) {
+            static const int kCls[4] = {KC_FULL_ENC_GT, KC_DP_INTRA, KC_DP_INTER, KC_FULL_DEC_GT};
+            h->launches += gf::run_body(h->blob, *h->hpf, h->act, B, (int)T, nullptr, st, [&](int c, int64_t fr) { return ProfScope(h, kCls[c], fr, st); });
+        } else
+            launch_body_micro(h, B, T, st);
+    }
+    if (phases & PH_BACK) {
+        if (h->variant == 1) launch_back<1>(h, *h->hpf, spec, is, T, u0, nu, out, os, st, fused, wav_out, wav_out_stride);
+        else launch_back<0>(h, *h->hp, spec, is, T, u0, nu, out, os, st, fused, wav_out, wav_out_stride);
+    }
     CU(cudaGetLastError());
     return GTCRNB_OK;
 }
@@ -494,24 +505,23 @@ void gtcrnb_destroy(gtcrnb_handle* h) {
     drop_step_graphs(h);
     if (h->s_cap) cudaStreamDestroy(h->s_cap);
     auto freep = [](float* p) { if (p) cudaFree(p); };
+    select_workspace(h, 0);
     freep(h->blob); freep(h->en0); freep(h->spec_in); freep(h->spec_out);
-    freep(h->parked.en0); freep(h->parked.spec_in); freep(h->parked.spec_out);
-    for (auto p : h->parked.act) freep(p);
+    for (auto p : h->act) freep(p);
+    for (int w = 1; w < gtcrnb_handle::kNumWs; ++w) {
+        freep(h->sets[w].en0); freep(h->sets[w].spec_in); freep(h->sets[w].spec_out);
+        for (auto p : h->sets[w].act) freep(p);
+    }
     delete h->hp;
     delete h->hpf;
-    for (auto p : h->act) freep(p);
     for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
         freep(h->stage_in[i]); freep(h->stage_out[i]);
         if (h->pcm_in[i]) cudaFree(h->pcm_in[i]);
         if (h->pcm_out[i]) cudaFree(h->pcm_out[i]);
-        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
-        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
-        if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+        for (cudaEvent_t e : {h->ev_fronts[i], h->ev_body[i], h->ev_backs[i], h->ev_d2h[i]}) if (e) cudaEventDestroy(e);
     }
-    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
-    if (h->s_comp) cudaStreamDestroy(h->s_comp);
-    if (h->s_comp2) cudaStreamDestroy(h->s_comp2);
-    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    for (cudaStream_t st : {h->s_h2d, h->s_front, h->s_body, h->s_body2, h->s_back, h->s_d2h}) if (st) cudaStreamDestroy(st);
     if (h->ev_user) cudaEventDestroy(h->ev_user);
     delete h;
 }
@@ -606,37 +616,73 @@ int gtcrnb_enhance(gtcrnb_handle* h, const float* wav_dev, int64_t B, int64_t L,
 namespace {
 // H2D / compute / D2H pipeline behind gtcrnb_enhance_host (float32 samples) and gtcrnb_enhance_host_pcm16 (PCM16 samples on the
 // wire, converted on the device: x / 32768 in, floor(y * 32768) clamped out -- half the PCIe bytes of the float contract).
+//
+// Two granularities (round 2).  The per-frame ends of the model (front: STFT .. en1; back: de3 .. mask, iSTFT) are frame-parallel
+// and run efficiently on a few utterances, while the walking kernels in between want hundreds of utterances per launch (one CTA
+// or warp per utterance column; small batches are split into time segments that each pay a warm-up: 192 utterances per launch
+// cost 10 % more per utterance than 1024, 48 cost 35 % more, profiles/batch_eff_r2.txt).  So the batch is cut into GROUPS
+// (sized by the schedule below, one activation workspace + staging pair each, kStage in flight) and every group into COPY CHUNKS:
+//   s_h2d   : H2D of copy chunk c                          s_front : front(c) as soon as its copy has landed
+//   s_body  : walking kernels of the whole group once its last front is done
+//   s_back  : back(c) per copy chunk                        s_d2h   : D2H of copy chunk c as soon as back(c) is done
+// The first H2D and the last D2H cannot overlap with anything, so groups ramp up from g1 and down to glast utterances.
+struct HostSchedule { int64_t copy; std::vector<int64_t> groups; int64_t gmax; };
+HostSchedule host_schedule(int64_t B, int64_t L) {
+    auto envi = [](const char* name, int dflt, int lo, int hi) { const char* e = getenv(name); return e ? std::max(lo, std::min(hi, atoi(e))) : dflt; };
+    auto units = [&](int64_t u) { return std::max<int64_t>(1, (u * 160000) / L); };        // knobs are in 10-second-utterance equivalents
+    HostSchedule s;
+    s.copy = units(envi("GTCRNB_HOST_COPY", 24, 1, 4096));
+    const int64_t gmax = std::min<int64_t>({B, units(envi("GTCRNB_HOST_CHUNK", 384, 1, 65535)), std::max<int64_t>(1, kMaxChunkFrames / (1 + L / gk::kHop))});
+    const int64_t g1 = std::min(gmax, units(envi("GTCRNB_HOST_G1", 48, 1, 65535))), gl = std::min(gmax, units(envi("GTCRNB_HOST_GLAST", 24, 1, 65535)));
+    const double up = envi("GTCRNB_HOST_GROWTH", 200, 101, 1000) / 100.0, down = envi("GTCRNB_HOST_DECAY", 160, 101, 1000) / 100.0;
+    std::vector<int64_t> head, tail;
+    int64_t used = 0;
+    double a = (double)g1, b = (double)gl;
+    // grow both ramps alternately while one more pair still leaves a full group for the middle
+    for (bool more = envi("GTCRNB_HOST_RAMP", 1, 0, 1) != 0; more;) {
+        more = false;
+        if ((int64_t)a < gmax && used + (int64_t)a + gmax <= B) { head.push_back((int64_t)a); used += (int64_t)a; a *= up; more = true; }
+        if ((int64_t)b < gmax && used + (int64_t)b + gmax <= B) { tail.push_back((int64_t)b); used += (int64_t)b; b *= down; more = true; }
+    }
+    s.groups = head;
+    const int64_t left = B - used, nmid = (left + gmax - 1) / gmax;                       // the middle in equal groups of at most gmax
+    for (int64_t i = 0; i < nmid; ++i) s.groups.push_back(left / nmid + (i < left % nmid ? 1 : 0));
+    for (auto it = tail.rbegin(); it != tail.rend(); ++it) s.groups.push_back(*it);
+    s.gmax = 0;
+    for (int64_t g : s.groups) s.gmax = std::max(s.gmax, g);
+    return s;
+}
+
 int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, void* out_host, bool pcm) {
-    if (L <= 256 || B < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_enhance_host: need L > 256");
+    if (L <= 256 || L > (int64_t)1 << 30 || B < 0) return fail(GTCRNB_E_INVALID, "gtcrnb_enhance_host: need 256 < L < 2^30");
     if (h && B == 0) return GTCRNB_OK;                            // empty batch: torch hands out NULL data pointers
     if (!h || !wav_host || !out_host) return fail(GTCRNB_E_INVALID, "gtcrnb_enhance_host: NULL argument");
+    constexpr int kStage = gtcrnb_handle::kStage;
     const int64_t T = 1 + L / gk::kHop, Lout = gk::kHop * (T - 1);
     if (!h->s_h2d) {
+        // the per-chunk front / back kernels feed the copy engines and the next group: they go ahead of the walking kernels
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const bool prio = getenv("GTCRNB_HOST_PRIO") ? atoi(getenv("GTCRNB_HOST_PRIO")) != 0 : true;
         CU(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&h->s_comp2, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithPriority(&h->s_front, cudaStreamNonBlocking, prio ? hi : lo));
+        CU(cudaStreamCreateWithPriority(&h->s_body, cudaStreamNonBlocking, lo));
+        CU(cudaStreamCreateWithPriority(&h->s_body2, cudaStreamNonBlocking, lo));
+        CU(cudaStreamCreateWithPriority(&h->s_back, cudaStreamNonBlocking, prio ? hi : lo));
         CU(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
-            CU(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
-        }
+        for (int i = 0; i < kStage; ++i)
+            for (cudaEvent_t* e : {&h->ev_fronts[i], &h->ev_body[i], &h->ev_backs[i], &h->ev_d2h[i]}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
-    // three engines (H2D copy, SMs, D2H copy) run overlapped over chunks; three staging buffers per direction decouple the copies
-    // from the two compute streams / workspaces (measured on B200, 1024 x 10 s: 2 buffers 326k, 3 buffers 346k audio-s/s)
-    // chunk size trades pipeline fill/drain (first H2D and last D2H are exposed) against per-chunk kernel efficiency
-    int64_t chunk_units = 192;                                     // in 10-second-utterance equivalents
-    if (const char* e = getenv("GTCRNB_HOST_CHUNK")) chunk_units = std::max(1, atoi(e));
-    const int64_t Bc = std::max<int64_t>(1, std::min<int64_t>(B, (chunk_units * 160000) / L));
-    const size_t need_in = (size_t)Bc * L, need_out = (size_t)Bc * Lout;
+    const HostSchedule sch = host_schedule(B, L);
+    const size_t need_in = (size_t)sch.gmax * L, need_out = (size_t)sch.gmax * Lout;
     if (need_in > h->stage_in_floats || need_out > h->stage_out_floats) {
-        for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
+        for (int i = 0; i < kStage; ++i) {
             if (h->stage_in[i]) cudaFree(h->stage_in[i]);
             if (h->stage_out[i]) cudaFree(h->stage_out[i]);
             h->stage_in[i] = h->stage_out[i] = nullptr;
         }
         h->stage_in_floats = h->stage_out_floats = 0;
-        for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
+        for (int i = 0; i < kStage; ++i) {
             if (cudaMalloc(&h->stage_in[i], need_in * sizeof(float)) != cudaSuccess ||
                 cudaMalloc(&h->stage_out[i], need_out * sizeof(float)) != cudaSuccess) {
                 cudaGetLastError();
@@ -646,13 +692,13 @@ int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, 
         h->stage_in_floats = need_in; h->stage_out_floats = need_out;
     }
     if (pcm && (need_in > h->pcm_in_elems || need_out > h->pcm_out_elems)) {
-        for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
+        for (int i = 0; i < kStage; ++i) {
             if (h->pcm_in[i]) cudaFree(h->pcm_in[i]);
             if (h->pcm_out[i]) cudaFree(h->pcm_out[i]);
             h->pcm_in[i] = h->pcm_out[i] = nullptr;
         }
         h->pcm_in_elems = h->pcm_out_elems = 0;
-        for (int i = 0; i < gtcrnb_handle::kStage; ++i) {
+        for (int i = 0; i < kStage; ++i) {
             if (cudaMalloc(&h->pcm_in[i], need_in * sizeof(int16_t)) != cudaSuccess ||
                 cudaMalloc(&h->pcm_out[i], need_out * sizeof(int16_t)) != cudaSuccess) {
                 cudaGetLastError();
@@ -661,80 +707,129 @@ int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, 
         }
         h->pcm_in_elems = need_in; h->pcm_out_elems = need_out;
     }
-    const size_t esz = pcm ? sizeof(int16_t) : sizeof(float);
-    // Chunk schedule: the first H2D and the last D2H cannot overlap with anything, so the pipeline ramps up and down through
-    // chunks of Bc/2^ramp .. Bc/2 (the two compute streams hide the small chunks' partial waves behind their neighbours).
-    int ramp = 4;
-    if (const char* e = getenv("GTCRNB_HOST_RAMP")) ramp = std::max(0, std::min(4, atoi(e)));
-    std::vector<int64_t> sizes;
-    {
-        std::vector<int64_t> head;
-        int64_t used = 0;
-        for (int r = ramp; r >= 1; --r) {
-            const int64_t n = Bc >> r;
-            if (n < 1 || used + 2 * n + Bc > B) continue;              // keep at least one full chunk in the middle
-            head.push_back(n); used += 2 * n;
-        }
-        sizes = head;
-        for (int64_t left = B - used; left > 0;) { const int64_t n = std::min(Bc, left); sizes.push_back(n); left -= n; }
-        for (auto it = head.rbegin(); it != head.rend(); ++it) sizes.push_back(*it);
+    // every group slot owns an activation workspace; (re)allocation synchronises the device, so do it before anything is queued
+    for (int w = 0; w < std::min<int>(kStage, (int)sch.groups.size()); ++w) {
+        select_workspace(h, w);
+        const int rc = ensure_workspace(h, sch.gmax * T);
+        if (rc) { select_workspace(h, 0); return rc; }
     }
-    // GTCRNB_HOST_TRACE=1: per-chunk engine timeline on stderr (diagnostic; adds timing events, not for benchmarking)
-    if (h->user_pending) {                                        // work queued on a caller stream still owns the workspaces
-        CU(cudaStreamWaitEvent(h->s_comp, h->ev_user, 0));
-        CU(cudaStreamWaitEvent(h->s_comp2, h->ev_user, 0));
+    const size_t esz = pcm ? sizeof(int16_t) : sizeof(float);
+    // the fused STFT / iSTFT kernels are the pipeline's front / back; with GTCRNB_FUSE_FFT=0 a group is one copy chunk through gtcrnb_enhance
+    const bool split = h->fuse_fft;
+    if (h->user_pending) {                                        // work queued on a caller stream still owns workspace 0
+        CU(cudaStreamWaitEvent(h->s_front, h->ev_user, 0));
+        CU(cudaStreamWaitEvent(h->s_body, h->ev_user, 0));
+        CU(cudaStreamWaitEvent(h->s_body2, h->ev_user, 0));
         h->user_pending = false;
     }
-    struct PipelineFlag { gtcrnb_handle* h; PipelineFlag(gtcrnb_handle* h_) : h(h_) { h->in_pipeline = true; } ~PipelineFlag() { h->in_pipeline = false; } } pflag(h);
+    struct PipelineFlag { gtcrnb_handle* h; PipelineFlag(gtcrnb_handle* h_) : h(h_) { h->in_pipeline = true; } ~PipelineFlag() { h->in_pipeline = false; select_workspace(h, 0); } } pflag(h);
+    // GTCRNB_HOST_TRACE=1: per-chunk engine timeline on stderr (diagnostic; adds timing events, not for benchmarking)
     const bool trace = getenv("GTCRNB_HOST_TRACE") != nullptr;
-    std::vector<cudaEvent_t> tev;
-    auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+    struct TraceRow { int group; int64_t utts; int kind; cudaEvent_t e0, e1; };    // kind 0 h2d, 1 front, 2 body, 3 back, 4 d2h
+    std::vector<TraceRow> rows;
+    auto tbegin = [&](int g, int64_t n, int kind, cudaStream_t st) { if (trace) { TraceRow r{g, n, kind, nullptr, nullptr}; cudaEventCreate(&r.e0); cudaEventCreate(&r.e1); cudaEventRecord(r.e0, st); rows.push_back(r); } };
+    auto tend = [&](cudaStream_t st) { if (trace) cudaEventRecord(rows.back().e1, st); };
+    size_t pool_next = 0;
+    auto pool_event = [&]() -> cudaEvent_t {
+        if (pool_next == h->ev_pool.size()) { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); h->ev_pool.push_back(e); }
+        return h->ev_pool[pool_next++];
+    };
     int64_t b0 = 0;
-    for (size_t c = 0; c < sizes.size(); b0 += sizes[c], ++c) {
-        const int i = (int)(c % gtcrnb_handle::kStage), ws = (int)(c & 1);   // staging slot, workspace / compute stream
-        const int64_t nb = sizes[c];
-        if (c >= (size_t)gtcrnb_handle::kStage) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[i], 0));      // input buffer i consumed
-        mark(h->s_h2d);
-        CU(cudaMemcpyAsync(pcm ? (void*)h->pcm_in[i] : (void*)h->stage_in[i], (const char*)wav_host + b0 * L * esz, esz * nb * L,
-                           cudaMemcpyHostToDevice, h->s_h2d));
-        mark(h->s_h2d);
-        CU(cudaEventRecord(h->ev_h2d[i], h->s_h2d));
-        cudaStream_t sc = ws ? h->s_comp2 : h->s_comp;                         // chunk parity -> compute stream + workspace
-        select_workspace(h, ws);
-        CU(cudaStreamWaitEvent(sc, h->ev_h2d[i], 0));
-        if (c >= (size_t)gtcrnb_handle::kStage) CU(cudaStreamWaitEvent(sc, h->ev_d2h[i], 0));             // output buffer i drained
-        mark(sc);
-        if (pcm) {
-            gk::k_pcm16_to_f32<<<h->sm_count * 8, 256, 0, sc>>>(h->pcm_in[i], h->stage_in[i], nb * L);
-            h->launches++;
+    const int64_t is[4] = {T * gk::kSpecFrame, 2, gk::kSpecFrame, 1};
+    // (measured: no gain from a second walking-kernel stream -- every walking kernel is sized to fill the SMs in one wave; kept as a knob)
+    const bool two_body = getenv("GTCRNB_HOST_BODY2") ? atoi(getenv("GTCRNB_HOST_BODY2")) != 0 : false;
+    for (size_t g = 0; g < sch.groups.size(); b0 += sch.groups[g], ++g) {
+        const int slot = (int)(g % kStage);
+        const int64_t ng = sch.groups[g];
+        const int64_t cc = split ? sch.copy : ng;
+        const bool reuse = g >= (size_t)kStage;
+        select_workspace(h, slot);
+        float* in_f = h->stage_in[slot];
+        float* out_f = h->stage_out[slot];
+        // ---- copies in, fronts
+        if (reuse) {
+            CU(cudaStreamWaitEvent(h->s_h2d, split ? h->ev_fronts[slot] : h->ev_body[slot], 0));   // input staging of group g - kStage consumed
+            CU(cudaStreamWaitEvent(h->s_front, h->ev_backs[slot], 0));     // its workspace released by its backs
         }
-        int rc = gtcrnb_enhance(h, h->stage_in[i], nb, L, L, h->stage_out[i], Lout, sc);
-        if (rc) { select_workspace(h, 0); return rc; }
-        if (pcm) {
-            gk::k_f32_to_pcm16<<<h->sm_count * 8, 256, 0, sc>>>(h->stage_out[i], h->pcm_out[i], nb * Lout);
-            h->launches++;
+        for (int64_t u0 = 0; u0 < ng; u0 += cc) {
+            const int64_t nu = std::min(cc, ng - u0);
+            tbegin((int)g, nu, 0, h->s_h2d);
+            CU(cudaMemcpyAsync(pcm ? (void*)(h->pcm_in[slot] + u0 * L) : (void*)(in_f + u0 * L), (const char*)wav_host + (b0 + u0) * L * esz, esz * nu * L,
+                               cudaMemcpyHostToDevice, h->s_h2d));
+            tend(h->s_h2d);
+            cudaEvent_t e = pool_event();
+            CU(cudaEventRecord(e, h->s_h2d));
+            CU(cudaStreamWaitEvent(h->s_front, e, 0));
+            tbegin((int)g, nu, 1, h->s_front);
+            if (pcm) {
+                gk::k_pcm16_to_f32<<<h->sm_count * 8, 256, 0, h->s_front>>>(h->pcm_in[slot] + u0 * L, in_f + u0 * L, nu * L);
+                h->launches++;
+            }
+            if (split) {
+                const int rc = run_model(h, nullptr, is, ng, T, nullptr, is, h->s_front, in_f, L, (int)L, nullptr, 0, PH_FRONT, u0, nu);
+                if (rc) return rc;
+            }
+            tend(h->s_front);
         }
-        mark(sc);
-        CU(cudaEventRecord(h->ev_comp[i], sc));
-        CU(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[i], 0));
-        mark(h->s_d2h);
-        CU(cudaMemcpyAsync((char*)out_host + b0 * Lout * esz, pcm ? (const void*)h->pcm_out[i] : (const void*)h->stage_out[i], esz * nb * Lout,
-                           cudaMemcpyDeviceToHost, h->s_d2h));
-        mark(h->s_d2h);
-        CU(cudaEventRecord(h->ev_d2h[i], h->s_d2h));
+        CU(cudaEventRecord(h->ev_fronts[slot], h->s_front));
+        // ---- walking kernels of the group (two streams by group parity: the partial waves of one group's kernels fill with the next group's)
+        cudaStream_t sb = (two_body && (g & 1)) ? h->s_body2 : h->s_body;
+        CU(cudaStreamWaitEvent(sb, h->ev_fronts[slot], 0));
+        tbegin((int)g, ng, 2, sb);
+        if (split) {
+            const int rc = run_model(h, nullptr, is, ng, T, nullptr, is, sb, nullptr, 0, 0, nullptr, 0, PH_BODY);
+            if (rc) return rc;
+        } else {
+            if (reuse) CU(cudaStreamWaitEvent(sb, h->ev_d2h[slot], 0));
+            const int rc = gtcrnb_enhance(h, in_f, ng, L, L, out_f, Lout, sb);
+            if (rc) return rc;
+        }
+        tend(sb);
+        CU(cudaEventRecord(h->ev_body[slot], sb));
+        // ---- backs, copies out
+        CU(cudaStreamWaitEvent(h->s_back, h->ev_body[slot], 0));
+        if (reuse) CU(cudaStreamWaitEvent(h->s_back, h->ev_d2h[slot], 0));  // output staging of group g - kStage drained
+        for (int64_t u0 = 0; u0 < ng; u0 += cc) {
+            const int64_t nu = std::min(cc, ng - u0);
+            tbegin((int)g, nu, 3, h->s_back);
+            if (split) {
+                CU(cudaMemsetAsync(out_f + u0 * Lout, 0, sizeof(float) * nu * Lout, h->s_back));   // the fused iSTFT overlap-adds onto zeros
+                const int rc = run_model(h, nullptr, is, ng, T, nullptr, is, h->s_back, nullptr, 0, (int)L, out_f, Lout, PH_BACK, u0, nu);
+                if (rc) return rc;
+            }
+            if (pcm) {
+                gk::k_f32_to_pcm16<<<h->sm_count * 8, 256, 0, h->s_back>>>(out_f + u0 * Lout, h->pcm_out[slot] + u0 * Lout, nu * Lout);
+                h->launches++;
+            }
+            tend(h->s_back);
+            cudaEvent_t e = pool_event();
+            CU(cudaEventRecord(e, h->s_back));
+            CU(cudaStreamWaitEvent(h->s_d2h, e, 0));
+            tbegin((int)g, nu, 4, h->s_d2h);
+            CU(cudaMemcpyAsync((char*)out_host + (b0 + u0) * Lout * esz, pcm ? (const void*)(h->pcm_out[slot] + u0 * Lout) : (const void*)(out_f + u0 * Lout),
+                               esz * nu * Lout, cudaMemcpyDeviceToHost, h->s_d2h));
+            tend(h->s_d2h);
+        }
+        CU(cudaEventRecord(h->ev_backs[slot], h->s_back));
+        CU(cudaEventRecord(h->ev_d2h[slot], h->s_d2h));
     }
-    select_workspace(h, 0);
     CU(cudaStreamSynchronize(h->s_d2h));
-    CU(cudaStreamSynchronize(h->s_comp));
-    CU(cudaStreamSynchronize(h->s_comp2));
+    CU(cudaStreamSynchronize(h->s_back));
+    CU(cudaStreamSynchronize(h->s_body));
+    CU(cudaStreamSynchronize(h->s_body2));
+    CU(cudaStreamSynchronize(h->s_front));
+    CU(cudaStreamSynchronize(h->s_h2d));
     if (trace) {
-        fprintf(stderr, "chunk  utts   h2d[start,end]      compute[start,end]   d2h[start,end]  (ms from first H2D)\n");
-        for (size_t c = 0; c < sizes.size(); ++c) {
-            float t[6];
-            for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], tev[0], tev[6 * c + k]);
-            fprintf(stderr, "%5zu %5lld   %7.3f %7.3f     %7.3f %7.3f      %7.3f %7.3f\n", c, (long long)sizes[c], t[0], t[1], t[2], t[3], t[4], t[5]);
+        static const char* const kKind[5] = {"h2d", "front", "body", "back", "d2h"};
+        fprintf(stderr, "groups:");
+        for (int64_t g : sch.groups) fprintf(stderr, " %lld", (long long)g);
+        fprintf(stderr, "  copy chunk %lld\ngroup  utts  engine   start     end   (ms from the first H2D)\n", (long long)sch.copy);
+        for (const auto& r : rows) {
+            float t0 = 0.f, t1 = 0.f;
+            cudaEventElapsedTime(&t0, rows[0].e0, r.e0); cudaEventElapsedTime(&t1, rows[0].e0, r.e1);
+            fprintf(stderr, "%5d %5lld  %-6s %7.3f %7.3f\n", r.group, (long long)r.utts, kKind[r.kind], t0, t1);
         }
-        for (auto e : tev) cudaEventDestroy(e);
+        for (const auto& r : rows) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     }
     return GTCRNB_OK;
 }

@@ -71,6 +71,15 @@ def test_unpinned_full_enhance_waveform_and_sisnr(full):
     assert torch.equal(m.enhance_host(noisy.pin_memory()), got)
 
 
+def test_unpinned_full_host_pipeline_groups(full, monkeypatch):
+    # several utterance groups and copy chunks (front / back per chunk, persistent GTConv / DPGRNN kernels per group): bitwise equal
+    for k, v in {"CHUNK": "2", "G1": "1", "GLAST": "1", "COPY": "1"}.items():
+        monkeypatch.setenv("GTCRNB_HOST_" + k, v)
+    W, m, _ = full
+    noisy = O.synth_batch(29, 16000 * 3 + 77, seed=9)
+    assert torch.equal(m.enhance_host(noisy.pin_memory()), m.enhance(noisy.to(DEV)).cpu())
+
+
 def test_unpinned_full_batch_invariance_and_causality_bitwise(full):
     W, m, _ = full
     x = O.synth_batch(9, 256 * 50, seed=2).to(DEV)

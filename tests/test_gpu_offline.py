@@ -179,18 +179,32 @@ def test_strided_inputs_and_empty(oracle, weights_dns3, b200_lib):
         m.enhance(torch.zeros(2, 256, device=DEV))                    # reflect padding needs L > 256 (torch.stft raises too)
 
 
-@pytest.mark.parametrize("chunk,ramp", [(None, None), ("1", "0"), ("2", "2"), ("4", "3")])
-def test_enhance_host_matches_device(oracle, weights_dns3, b200_lib, monkeypatch, chunk, ramp):
-    # the pipelined host path (ramped chunk schedule over two workspaces) must equal one device call, whatever the chunking
-    if chunk is not None:
-        monkeypatch.setenv("GTCRNB_HOST_CHUNK", chunk)                # in 10 s units: 1 -> 3 utterances of 3 s per chunk
-        monkeypatch.setenv("GTCRNB_HOST_RAMP", ramp)
+@pytest.mark.parametrize("knobs", [{}, {"CHUNK": "1", "RAMP": "0", "COPY": "1"}, {"CHUNK": "2", "G1": "1", "GLAST": "1", "COPY": "1"},
+                                   {"CHUNK": "4", "G1": "1", "GLAST": "2", "COPY": "2", "GROWTH": "150", "DECAY": "150"},
+                                   {"CHUNK": "8", "G1": "2", "GLAST": "1", "COPY": "1", "PRIO": "0"}])
+def test_enhance_host_matches_device(oracle, weights_dns3, b200_lib, monkeypatch, knobs):
+    # the pipelined host path (utterance groups rotating over three workspaces, front / back kernels per copy chunk on their own
+    # streams) must equal one device call bit for bit, whatever the schedule.  Knobs are in 10 s units: 1 -> 3 utterances of 3 s.
+    for k, v in knobs.items():
+        monkeypatch.setenv("GTCRNB_HOST_" + k, v)
     m = make_model(weights_dns3, b200_lib)
     x = oracle.synth_batch(70, 16000 * 3 + 5, seed=21)
     xp = x.pin_memory()
     out_h = m.enhance_host(xp)
     out_d = m.enhance(x.to(DEV)).cpu()
     assert torch.equal(out_h, out_d)
+    assert torch.equal(m.enhance_host(xp[:1]), out_d[:1])              # a single utterance: one group, one copy chunk
+    assert torch.equal(m.enhance_host(xp), out_d)                      # and again on the warm pipeline (event / buffer reuse)
+
+
+def test_enhance_host_unfused_fft(oracle, weights_dns3, b200_lib, monkeypatch):
+    # GTCRNB_FUSE_FFT=0: groups go through the separate STFT / iSTFT kernels as single copy chunks
+    monkeypatch.setenv("GTCRNB_FUSE_FFT", "0")
+    monkeypatch.setenv("GTCRNB_HOST_CHUNK", "2")
+    monkeypatch.setenv("GTCRNB_HOST_G1", "1")
+    m = make_model(weights_dns3, b200_lib)
+    x = oracle.synth_batch(23, 16000 * 3 + 5, seed=22)
+    assert torch.equal(m.enhance_host(x.pin_memory()), m.enhance(x.to(DEV)).cpu())
 
 
 def test_full_size_properties(oracle, weights_dns3, b200_lib):
@@ -214,6 +228,9 @@ def test_full_size_properties(oracle, weights_dns3, b200_lib):
 
 @pytest.mark.parametrize("chunk", [None, "1"])
 def test_enhance_host_pcm16_matches_float_path(oracle, weights_dns3, pairs, b200_lib, monkeypatch, chunk):
+    if chunk is not None:
+        monkeypatch.setenv("GTCRNB_HOST_COPY", "1")
+        monkeypatch.setenv("GTCRNB_HOST_G1", "1")
     # PCM16 on the wire: decode x/32768 and floor(y*32768) encode on the device must equal doing both on the host around the
     # float path, bit for bit; and it reproduces the reference's shipped enhanced example
     if chunk is not None:
