@@ -384,19 +384,18 @@ def _hop_stats(ms):
     return {"hop_ms_p50": round(ms[len(ms) // 2], 4), "hop_ms_p99": round(ms[min(len(ms) - 1, int(0.99 * len(ms)))], 4), "hop_ms_max": round(ms[-1], 4)}
 
 
-def _stream_wav_hops(smodel, N, device, hops, warm=10):
+def _stream_wav_hops(smodel, N, device, hops, warm=10, groups=None):
     """`hops` real-time hops for N streams, wav in / wav out through PINNED HOST buffers: per hop H2D of [N,256] new samples,
-    gtcrnb_stream_step_wav, D2H of [N,256] enhanced samples, all inside the hop's CUDA-event bracket."""
-    st = smodel.new_state(N, device)
+    gtcrnb_stream_step_wav, D2H of [N,256] enhanced samples, all inside the hop's CUDA-event bracket.  The call is the package's
+    StreamPool.step_wav_host: above 32,768 streams it splits them into groups whose copies overlap the other groups' kernels."""
+    from gtcrn_micro_b200 import StreamPool
+    pool = StreamPool(smodel, N, device, groups=groups)
     g = torch.Generator().manual_seed(N)
     hin = [torch.empty(N, 256, pin_memory=True).copy_(0.1 * torch.randn(N, 256, generator=g)) for _ in range(4)]
     hout = torch.empty(N, 256, pin_memory=True)
-    din, dout = torch.empty(N, 256, device=device), torch.empty(N, 256, device=device)
 
     def hop(i):
-        din.copy_(hin[i % 4], non_blocking=True)
-        smodel.step_wav(din, st, dout)
-        hout.copy_(dout, non_blocking=True)
+        pool.step_wav_host(hin[i % 4], hout)
     for i in range(warm):
         hop(i)
     torch.cuda.synchronize(device)
@@ -407,7 +406,8 @@ def _stream_wav_hops(smodel, N, device, hops, warm=10):
         evs[i][1].record()
     torch.cuda.synchronize(device)
     ok = bool(torch.isfinite(hout).all())
-    del st
+    _stream_wav_hops.last_groups = len(pool.sizes)
+    del pool
     return [a.elapsed_time(b) for a, b in evs], ok
 
 
@@ -434,7 +434,7 @@ def bench_streaming(G, model, device, hbm_peak, n_list=(4096, 16384), hops=625, 
     """BASELINE configs[2]: per-hop latency (p50 / p99 / max over >= 625 hops) of the frame-by-frame path against the 16 ms
     deadline, wav-in / wav-out with the host<->device copies inside every hop, plus the device-resident kernel view and the
     largest stream count whose WORST hop still meets the deadline (doubling + bisection, confirmed over `hops` hops)."""
-    res = {"deadline_ms": 16.0, "hops": hops, "io": "wav in / wav out, pinned host buffers, H2D + D2H of N x 256 samples inside every hop",
+    res = {"deadline_ms": 16.0, "hops": hops, "io": "wav in / wav out, pinned host buffers, H2D + D2H of N x 256 samples inside every hop (StreamPool.step_wav_host)",
            "latency_contract": "output lags input by 512 samples (32 ms); gtcrnb_stream_flush_wav emits the last two hops"}
     smodel = G.StreamGTCRN() if isinstance(model, G.GTCRN) else G.StreamGTCRNMicro()
     G.convert_to_stream(smodel, model)
@@ -479,6 +479,7 @@ def bench_streaming(G, model, device, hbm_peak, n_list=(4096, 16384), hops=625, 
             ms, ok = _stream_wav_hops(smodel, lo, device, hops)
         r = _hop_stats(ms)
         r["streams"] = lo
+        r["stream_groups"] = getattr(_stream_wav_hops, "last_groups", 1)
         r["memory_cap_streams"] = cap
         res["max_realtime_streams"] = r
         torch.cuda.empty_cache()

@@ -59,7 +59,8 @@ struct gtcrnb_handle {
     int tcn_p = 2;                                // frame slots per lane of the GTCN kernel (2..4)
     // tensor-core (tcgen05, 3xTF32) kernels: bit 0 GTCN pointwise convs, bit 1 decoder GTConv 3x3 (GTCRNB_TC, default both);
     // 0 selects the FFMA kernels, whose results are bit-identical to the streaming path
-    int tc_mask = 3;
+    int tc_mask = 7;                              // bit 2: en1 (k_front) and de3 (k_back) as tcgen05 MMAs (round 2)
+    uint32_t* tcw = nullptr;                      // their fp16 hi / lo weight matrices (k_prep_ends_tc)
     int tc_gtcn_nwg = 1;                          // warpgroups per CTA of k_gtcn_tc (GTCRNB_TC_GTCN_NWG: 1, 2 or 4)
     int occ_tcn_tc = 1;
     int tc_dec_nwg = 4;                           // warpgroups per CTA of k_gtconv_dec_tc (GTCRNB_TC_DEC_NWG: 1, 2, 4 or 5; 96 TMEM columns each)
@@ -105,7 +106,7 @@ struct gtcrnb_handle {
     // at small stream counts): instantiated the second consecutive time the same (state, in, out, N) is stepped, replayed after
     struct StepGraph { int kind; const void* state; const void* in; const void* out; int64_t n; cudaGraphExec_t exec; int launches; uint64_t used; };
     std::vector<StepGraph> step_graphs;
-    StepGraph last_step{-1, nullptr, nullptr, nullptr, 0, nullptr, 0, 0};
+    std::vector<StepGraph> seen_steps;               // recent hops that ran uncaptured (keys only)
     cudaStream_t s_cap = nullptr;
     uint64_t step_tick = 0;
     bool stream_graphs = true;                       // GTCRNB_STREAM_GRAPH=0 disables
@@ -120,7 +121,7 @@ namespace {
 void drop_step_graphs(gtcrnb_handle* h) {
     for (auto& g : h->step_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     h->step_graphs.clear();
-    h->last_step.kind = -1;
+    h->seen_steps.clear();
 }
 
 int ensure_workspace(gtcrnb_handle* h, int64_t frames) {
@@ -241,14 +242,26 @@ void launch_front(gtcrnb_handle* h, const HP& hp, const float* spec, const int64
     const int64_t nframes = nu * T, f0 = u0 * T;
     const dim3 gfr((unsigned)((nframes + FR_NF - 1) / FR_NF));
     ProfScope ps(h, KC_FRONT, nframes, st);
+    float* en0 = h->en0 + f0 * kF1 * 16;
+    float* en1 = h->act[0] + f0 * kF2 * 16;
+    if constexpr (VAR == 0) {
+        if (h->tc_mask & 4) {
+            if (wav)
+                k_front<true, 0, true><<<gfr, FR_THREADS, fr_smem_floats(true, true) * sizeof(float), st>>>(nullptr, 0, 0, 0, 0, wav + u0 * wav_stride, wav_stride, L,
+                                                                                                            h->spec_in + f0 * kSpecFrame, (int)T, nframes, h->blob, hp.front, en0, en1, h->tcw);
+            else
+                k_front<false, 0, true><<<gfr, FR_THREADS, fr_smem_floats(false, true) * sizeof(float), st>>>(spec + u0 * is[0], is[0], is[1], is[2], is[3], nullptr, 0, 0, nullptr,
+                                                                                                              (int)T, nframes, h->blob, hp.front, en0, en1, h->tcw);
+            h->launches++;
+            return;
+        }
+    }
     if (wav)
         k_front<true, VAR><<<gfr, FR_THREADS, fr_smem_floats(true) * sizeof(float), st>>>(nullptr, 0, 0, 0, 0, wav + u0 * wav_stride, wav_stride, L,
-                                                                                           h->spec_in + f0 * kSpecFrame, (int)T, nframes, h->blob, hp.front,
-                                                                                           h->en0 + f0 * kF1 * 16, h->act[0] + f0 * kF2 * 16);
+                                                                                           h->spec_in + f0 * kSpecFrame, (int)T, nframes, h->blob, hp.front, en0, en1);
     else
         k_front<false, VAR><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec + u0 * is[0], is[0], is[1], is[2], is[3], nullptr, 0, 0, nullptr,
-                                                                                             (int)T, nframes, h->blob, hp.front,
-                                                                                             h->en0 + f0 * kF1 * 16, h->act[0] + f0 * kF2 * 16);
+                                                                                             (int)T, nframes, h->blob, hp.front, en0, en1);
     h->launches++;
 }
 
@@ -432,6 +445,7 @@ int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, 
     using namespace gk;
     struct { const void* fn; int floats; } attrs[] = {
         {(const void*)k_front<false, 0>, fr_smem_floats(false)}, {(const void*)k_front<true, 0>, fr_smem_floats(true)},
+        {(const void*)k_front<false, 0, true>, fr_smem_floats(false, true)}, {(const void*)k_front<true, 0, true>, fr_smem_floats(true, true)},
         {(const void*)k_gtcn<2, false>, wc_smem_floats(2)}, {(const void*)k_gtcn<2, true>, wc_smem_floats(2, true)},
         {(const void*)k_back<false, 0>, bk_smem_floats(false)}, {(const void*)k_back<true, 0>, bk_smem_floats(true)},
         {(const void*)k_stft, 0},
@@ -479,6 +493,13 @@ int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, 
     if (const char* e = getenv("GTCRNB_TCN_SMEMW")) h->tcn_smem_w = atoi(e) != 0;
     if (const char* e = getenv("GTCRNB_STREAM_GRAPH")) h->stream_graphs = atoi(e) != 0;
     if (const char* e = getenv("GTCRNB_TC")) h->tc_mask = atoi(e);
+    if (h->tc_mask & 4) {
+        if (cudaMalloc(&h->tcw, sizeof(uint32_t) * gk::TCW_WORDS) != cudaSuccess) { cudaGetLastError(); gtcrnb_destroy(h); return fail(GTCRNB_E_NOMEM, "cudaMalloc(tcw) failed"); }
+        gk::k_prep_ends_tc<<<1, 256>>>(h->blob, h->tcw);
+        if (cudaDeviceSynchronize() != cudaSuccess) { gtcrnb_destroy(h); return fail(GTCRNB_E_CUDA, "k_prep_ends_tc failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    }
+    h->hp->tc_ends = (h->tc_mask & 4) != 0;
+    h->hp->tcw = h->tcw;
     // streaming: the decoder blocks of a hop follow the offline choice (bit 1) unless GTCRNB_TC_STREAM=0
     h->hp->tc_stream = (h->tc_mask & 2) != 0;
     if (const char* e = getenv("GTCRNB_TC_STREAM")) h->hp->tc_stream = atoi(e) != 0;
@@ -507,6 +528,7 @@ void gtcrnb_destroy(gtcrnb_handle* h) {
     auto freep = [](float* p) { if (p) cudaFree(p); };
     select_workspace(h, 0);
     freep(h->blob); freep(h->en0); freep(h->spec_in); freep(h->spec_out);
+    if (h->tcw) cudaFree(h->tcw);
     for (auto p : h->act) freep(p);
     for (int w = 1; w < gtcrnb_handle::kNumWs; ++w) {
         freep(h->sets[w].en0); freep(h->sets[w].spec_in); freep(h->sets[w].spec_out);
@@ -965,10 +987,14 @@ int stream_step_impl(gtcrnb_handle* h, int kind, void* state, const float* in, f
             h->launches += g.launches;
             return GTCRNB_OK;
         }
-    auto& l = h->last_step;
-    const bool repeat = l.kind == kind && l.state == state && l.in == in && l.out == out && l.n == N;
-    l.kind = kind; l.state = state; l.in = in; l.out = out; l.n = N;
-    if (!repeat) {                                    // pointers that change every hop never pay for a capture
+    // a hop is captured the second time its (state, in, out, N) shows up among the last few distinct ones: a caller that rotates over
+    // several stream groups (StreamPool) gets one graph per group, pointers that change every hop never pay for a capture
+    bool repeat = false;
+    for (auto& l : h->seen_steps)
+        if (l.kind == kind && l.state == state && l.in == in && l.out == out && l.n == N) { repeat = true; break; }
+    if (!repeat) {
+        if (h->seen_steps.size() >= 16) h->seen_steps.erase(h->seen_steps.begin());
+        h->seen_steps.push_back({kind, state, in, out, N, nullptr, 0, 0});
         h->launches += direct(st);
         CU(cudaGetLastError());
         return GTCRNB_OK;
@@ -988,7 +1014,7 @@ int stream_step_impl(gtcrnb_handle* h, int kind, void* state, const float* in, f
         CU(cudaGetLastError());
         return GTCRNB_OK;
     }
-    if (h->step_graphs.size() >= 8) {                 // small LRU
+    if (h->step_graphs.size() >= 16) {                // small LRU
         size_t victim = 0;
         for (size_t i = 1; i < h->step_graphs.size(); ++i) if (h->step_graphs[i].used < h->step_graphs[victim].used) victim = i;
         cudaGraphExecDestroy(h->step_graphs[victim].exec);

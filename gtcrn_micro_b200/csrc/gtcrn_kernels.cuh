@@ -25,8 +25,11 @@
 #include <stdint.h>
 #include <utility>
 
+#include <cuda_fp16.h>
+
 #include "blob_layout.h"
 #include "blob_full_layout.h"
+#include "tc_util.cuh"
 
 namespace gk {
 
@@ -342,6 +345,84 @@ __global__ void __launch_bounds__(256) k_istft(const float* __restrict__ spec, i
 }
 
 // ================================================================================================
+// Tensor-core ends (round 2): en1 in k_front and de3 in k_back -- the two 16 -> 16, 5-tap strided (transposed) convolutions, 70 % of
+// those kernels' MACs -- as tcgen05 kind::f16 MMAs with BOTH operands in shared memory.  A frame's activations already sit in
+// shared memory as K-major planes [ci chunk][row = slot * 35 + padded bin][8 halves]: rows are 16 bytes apart, so an M = 128 tile
+// is 128 consecutive rows and a convolution tap is the same plane read through a descriptor whose start address is shifted by
+// whole rows (the stride-2 en1 reads parity-split planes).  Rows that straddle a frame's 33 outputs (pad bins, the tail of the
+// third tile) produce accumulator rows nobody reads; a tcgen05 accumulator row depends only on its own row of A.
+// Operand format: x = 256 hi' + lo with hi' = fp16(x / 256) and lo = fp16(x - 256 hi') (exact residual, 22 mantissa bits in all;
+// the offset of 2^8 between the two halves moves fp16's ceiling to |x| = 1.6e7, far above anything 30 x full-scale audio produces
+// -- the conversions saturate instead of overflowing).  Weights: W s split as fp16 hi / lo with a power-of-two s that keeps the
+// lo parts normal; the hi' operand meets 256 W s, the lo operand W s, so one accumulator receives s * sum(x W) and the epilogue
+// multiplies by 1 / s (exact) while adding the bias.  Three MMAs per tap and 16 input channels: hi' [W_hi | W_lo] stacked along N
+// (k_front) or separately (k_back, where N already carries the even | odd output bins), lo W_hi.
+// The weight matrices are identical for every CTA: k_prep_ends_tc builds them once per handle in the exact shared-memory layout
+// (no-swizzle K-major, [k chunk][n][8 halves]) and the kernels copy them with cp.async.
+// ================================================================================================
+constexpr int TCW_EN1_WORDS = 5 * 384 + 4;      // 5 taps x ([2][32][8] + [2][16][8] halves) + {1 / s, 0, 0, 0}
+constexpr int TCW_DE3_WORDS = 3 * 768 + 4;      // 3 taps x 3 x [2][32][8] halves + {1 / s, 0, 0, 0}
+constexpr int TCW_WORDS = TCW_EN1_WORDS + TCW_DE3_WORDS;
+constexpr int TCE_ROWS = 8 * 35;                // rows of an activation plane: 8 frame slots x 35 padded bins
+
+__device__ __forceinline__ void split_f16_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    hi = tc::pack_f16x2(x0 * (1.0f / 256.0f), x1 * (1.0f / 256.0f));
+    lo = tc::pack_f16x2(fmaf(tc::f16lo_to_f32(hi), -256.0f, x0), fmaf(tc::f16hi_to_f32(hi), -256.0f, x1));
+}
+// 16 channels of one position -> two uint4 of hi' halves (ci 0..7, 8..15) and two of lo halves
+__device__ __forceinline__ void split_f16_row(const float (&v)[16], uint4 (&hi)[2], uint4 (&lo)[2]) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) split_f16_pair(v[2 * c], v[2 * c + 1], h[c], l[c]);
+    hi[0] = make_uint4(h[0], h[1], h[2], h[3]); hi[1] = make_uint4(h[4], h[5], h[6], h[7]);
+    lo[0] = make_uint4(l[0], l[1], l[2], l[3]); lo[1] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+
+// one CTA, run once per handle: fp16 hi / lo weight matrices of en1 (blob FRONT_EN1_W [k][ci][co]) and de3 (BACK_DE3_W [k][ci][co])
+__global__ void __launch_bounds__(256) k_prep_ends_tc(const float* __restrict__ blobp, uint32_t* __restrict__ tcw) {
+    __shared__ unsigned mx[2];
+    const int tid = threadIdx.x;
+    if (tid < 2) mx[tid] = 0u;
+    for (int i = tid; i < TCW_WORDS; i += 256) tcw[i] = 0u;
+    __syncthreads();
+    const float* w1 = blobp + blob::FRONT_OFF + blob::FRONT_EN1_W;
+    const float* w3 = blobp + blob::BACK_OFF + blob::BACK_DE3_W;
+    unsigned m1 = 0u, m3 = 0u;
+    for (int i = tid; i < 1280; i += 256) { m1 = max(m1, __float_as_uint(fabsf(w1[i]))); m3 = max(m3, __float_as_uint(fabsf(w3[i]))); }
+    atomicMax(&mx[0], m1); atomicMax(&mx[1], m3);
+    __syncthreads();
+    __half* hw = reinterpret_cast<__half*>(tcw);
+#pragma unroll
+    for (int layer = 0; layer < 2; ++layer) {
+        // |w| < 2^(e+1): 256 w s < 2^14 with s = 2^(5-e); the lo parts (2^-11 of that) stay normal down to |w| ~ 2^-13 max|w|
+        const int wexp = max(14, min(253, (int)(mx[layer] >> 23)));
+        const float sa = __uint_as_float((unsigned)(267 - wexp) << 23), sb = __uint_as_float((unsigned)(259 - wexp) << 23);
+        const float winv = __uint_as_float((unsigned)(wexp - 5) << 23);
+        for (int i = tid; i < 1280; i += 256) {
+            const int k = i >> 8, ci = (i >> 4) & 15, co = i & 15, jc = ci >> 3, cl = ci & 7;
+            const float w = layer == 0 ? w1[i] : w3[i];
+            const float wa = w * sa;
+            const __half ah = __float2half_rn(wa), al = __float2half_rn(wa - __half2float(ah)), bh = __float2half_rn(w * sb);
+            if (layer == 0) {
+                __half* t = hw + k * 768;                                   // [W_hi | W_lo] stacked: n = co, 16 + co
+                t[jc * 256 + co * 8 + cl] = ah;
+                t[jc * 256 + (16 + co) * 8 + cl] = al;
+                t[512 + jc * 128 + co * 8 + cl] = bh;
+            } else {
+                // transposed conv in gather form: tap pair j = k / 2 reads input bin m + 1 - j; even output bins use tap 2j,
+                // odd ones tap 2j + 1 (none for j = 2): n = (k & 1) * 16 + co
+                __half* t = hw + 2 * TCW_EN1_WORDS + (k >> 1) * 1536;
+                const int n = (k & 1) * 16 + co;
+                t[jc * 256 + n * 8 + cl] = ah;
+                t[512 + jc * 256 + n * 8 + cl] = al;
+                t[1024 + jc * 256 + n * 8 + cl] = bh;
+            }
+        }
+        if (tid == 0) reinterpret_cast<float*>(tcw)[layer == 0 ? TCW_EN1_WORDS - 4 : TCW_WORDS - 4] = winv;
+    }
+}
+
+// ================================================================================================
 // FRONT: spec -> |.|,re,im -> ERB compress -> SFE-Lite -> en0 (3->16, k5 s2) -> en1 (16->16, k5 s2)
 // reference: gtcrn_micro.py:512-518 (features, erb.bm, sfe), :344-364 (en_convs[0..1])
 // Frames are independent here, so (b,t) is flattened: grid ceil(B*T/8), 288 threads, 8 frames per CTA
@@ -368,7 +449,14 @@ constexpr int FR_SLOT = FR_FEAT + FR_ERB + FR_SFE;
 static_assert(FR_A0 <= FR_FEAT + FR_ERB, "a0 must fit in the dead feat|erb region");
 constexpr int FR_FFT_FLOATS = 1540;         // FftTables: tw256 (512) + tw512 (516) + win (512)
 static_assert(sizeof(FftTables) == FR_FFT_FLOATS * 4, "FftTables layout");
-__host__ __device__ constexpr int fr_smem_floats(bool from_wav) { return FR_W_FLOATS + FR_NF * FR_SLOT + (from_wav ? FR_FFT_FLOATS : 0); }
+// tensor-core en1 (TCE): the slot regions are regrouped as [feat x NF | erb x NF | sfe x NF] so that the dead feat | erb area holds the
+// fp16 activation planes of all slots contiguously; plane stride = 282 rows: the two parity planes then sit 64 bytes (mod 128) apart
+// and the en0 epilogue's 16-byte stores of neighbouring (odd / even) bins do not collide
+constexpr int TCE_PLANE = 282 * 16;          // bytes per activation plane in k_front: [(hl * 2 + parity) * 2 + ci chunk]
+static_assert(7 * TCE_PLANE + (3 * 128 + 2) * 16 <= FR_NF * (FR_FEAT + FR_ERB) * 4, "over-read of the last tile stays inside the dead region");
+__host__ __device__ constexpr int fr_smem_floats(bool from_wav, bool tce = false) {
+    return FR_W_FLOATS + (tce ? TCW_EN1_WORDS : 0) + FR_NF * FR_SLOT + (from_wav ? FR_FFT_FLOATS : 0);
+}
 
 // Model variant of the per-frame front / back kernels.  VAR 0: GTCRN-Micro (SFE-Lite, dense en1 / de3).  VAR 1: original-GTCRN-style
 // (BASELINE configs[3]): unfold SFE -- en0 contracts 9 channels x 5 taps (gtcrn_micro.py:346 `# 3 * 3,  # SFE`) -- and en1 / de3 with
@@ -446,18 +534,29 @@ __device__ __forceinline__ void front_en1(const PB& prm, const float* slots, int
 // FROM_WAV = true : the STFT is fused in: frames are cut from `wav` [B][L] (reflect padding, sqrt-Hann), transformed in
 //                   shared memory (the FFT ping-pong buffers overlay the slot's own feat / sfe regions) and the spectrum is
 //                   written once to `spec_out` [B][T][257][2] for the mask stage; it is never read back here.
-template <bool FROM_WAV, int VAR>
+template <bool FROM_WAV, int VAR, bool TCE = false>
 __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float* __restrict__ spec, int64_t sb, int64_t sf, int64_t st, int64_t sc,
                                                          const float* __restrict__ wav, int64_t wav_stride, int L, float* __restrict__ spec_out,
                                                          int T, int64_t nframes, const float* __restrict__ blobp,
                                                          const __grid_constant__ ParamBlock<FrontL<VAR>::SIZE> prm,
-                                                         float* __restrict__ en0, float* __restrict__ en1) {
+                                                         float* __restrict__ en0, float* __restrict__ en1, const uint32_t* __restrict__ tcw = nullptr) {
+    static_assert(!TCE || (VAR == 0 && FR_NF == 8), "tensor-core en1: GTCRN-Micro, 8 frame slots");
     using LY = FrontL<VAR>;
     extern __shared__ float4 smem4[];
+    __shared__ __align__(8) uint64_t tc_bars[3];
+    __shared__ uint32_t tmem_base_s;
     float* W = reinterpret_cast<float*>(smem4);
-    float* slots = W + FR_W_FLOATS;            // per slot: [feat | erb | sfe]; a0 overlays feat|erb
+    float* Btc = W + FR_W_FLOATS;              // TCE: en1 weight matrices (k_prep_ends_tc layout)
+    float* slots = Btc + (TCE ? TCW_EN1_WORDS : 0);   // per slot: [feat | erb | sfe]; a0 overlays feat|erb (TCE: regrouped, see featp)
     const int tid = threadIdx.x;
     const int64_t fi0 = (int64_t)blockIdx.x * FR_NF;              // first flattened frame (b * T + t) of this CTA
+    auto featp = [&](int s_) { return TCE ? slots + s_ * FR_FEAT : slots + s_ * FR_SLOT; };
+    auto erbp = [&](int s_) { return TCE ? slots + FR_NF * FR_FEAT + s_ * FR_ERB : slots + s_ * FR_SLOT + FR_FEAT; };
+    auto sfep = [&](int s_) { return TCE ? slots + FR_NF * (FR_FEAT + FR_ERB) + s_ * FR_SFE : slots + s_ * FR_SLOT + FR_FEAT + FR_ERB; };
+    if (TCE) {
+        if (tid < 32) { tc::tmem_alloc(&tmem_base_s, 128); tc::fence_before(); }     // 3 tiles x 32 accumulator columns
+        if (tid == 32) { for (int i = 0; i < 3; ++i) tc::mbar_init(&tc_bars[i], 1); tc::fence_async_smem(); }
+    }
 
     if (FROM_WAV) {
         // ---- a (fused STFT): 4 frames per round, 64 threads per 256-point FFT.  A = slot's sfe region, B = slot's feat region.
@@ -487,14 +586,15 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
         load_fft_tables_async(tb, blobp, tid, FR_THREADS);         // needed by the FFT right after the barrier
         cp_async_commit();
         copy_f4_async(W, blobp + LY::OFF, FR_W_FLOATS, tid, FR_THREADS);   // ERB / SFE tables: needed after the FFT phase
+        if (TCE) copy_f4_async(Btc, reinterpret_cast<const float*>(tcw), TCW_EN1_WORDS, tid, FR_THREADS);
         cp_async_commit();
         cp_async_wait_group<1>();
         __syncthreads();
         if (warp < FR_NF) {                                        // (only __syncwarp inside)
             const int slot = warp;
             const int64_t fi = fi_w;
-            float2* A = reinterpret_cast<float2*>(slots + slot * FR_SLOT + FR_FEAT + FR_ERB);
-            float2* Bf = reinterpret_cast<float2*>(slots + slot * FR_SLOT);
+            float2* A = reinterpret_cast<float2*>(sfep(slot));
+            float2* Bf = reinterpret_cast<float2*>(featp(slot));
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int n = lane + 32 * q;
@@ -502,7 +602,7 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
             }
             __syncwarp();
             fft256_warp(A, Bf, tb.tw256, lane);
-            float4* fs = reinterpret_cast<float4*>(slots + slot * FR_SLOT);   // feat region (B is dead now)
+            float4* fs = reinterpret_cast<float4*>(featp(slot));              // feat region (B is dead now)
             float2* o = valid ? reinterpret_cast<float2*>(spec_out + fi * kSpecFrame) : nullptr;
             for (int k = lane; k <= 256; k += 32) {
                 const float2 zk = A[k & 255];
@@ -519,7 +619,7 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
         cp_async_wait_group<0>();                                  // ERB / SFE tables
         __syncthreads();
         for (int i = tid; i < FR_NF * 4; i += FR_THREADS) {       // sfe pad columns (its region held FFT buffer A until now)
-            float4* sfe4 = reinterpret_cast<float4*>(slots + (i >> 2) * FR_SLOT + FR_FEAT + FR_ERB);
+            float4* sfe4 = reinterpret_cast<float4*>(sfep(i >> 2));
             const int c = i & 3;                                  // padded bins 0, 1, 131, 132 -> (parity, entry)
             sfe4[c == 0 ? 0 : c == 1 ? 67 : c == 2 ? 67 + 65 : 66] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -542,8 +642,9 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
             }
         }
         copy_f4_async(W, blobp + LY::OFF, FR_W_FLOATS, tid, FR_THREADS);
+        if (TCE) copy_f4_async(Btc, reinterpret_cast<const float*>(tcw), TCW_EN1_WORDS, tid, FR_THREADS);
         for (int i = tid; i < FR_NF * 4; i += FR_THREADS) {
-            float4* sfe4 = reinterpret_cast<float4*>(slots + (i >> 2) * FR_SLOT + FR_FEAT + FR_ERB);
+            float4* sfe4 = reinterpret_cast<float4*>(sfep(i >> 2));
             const int c = i & 3;                                  // padded bins 0, 1, 131, 132 -> (parity, entry)
             sfe4[c == 0 ? 0 : c == 1 ? 67 : c == 2 ? 67 + 65 : 66] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -552,7 +653,7 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
             const int idx = tid + i * FR_THREADS;
             if (idx < FR_NF * kBins) {
                 const int slot = idx / kBins, k = idx - slot * kBins;
-                reinterpret_cast<float4*>(slots + slot * FR_SLOT)[k] = make_float4(sqrtf(re[i] * re[i] + im[i] * im[i] + 1e-12f), re[i], im[i], 0.f);
+                reinterpret_cast<float4*>(featp(slot))[k] = make_float4(sqrtf(re[i] * re[i] + im[i] * im[i] + 1e-12f), re[i], im[i], 0.f);
             }
         }
         cp_async_wait_all();
@@ -564,8 +665,8 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
         const int bnd = tid & 63, sp2 = tid >> 6;
         const int s = reinterpret_cast<const int*>(W + blob::FRONT_ERB_START)[bnd], n = reinterpret_cast<const int*>(W + blob::FRONT_ERB_CNT)[bnd];
         const float* ew = W + blob::FRONT_ERB_W + bnd * blob::kErbMaxTap;
-        const float4* f0 = reinterpret_cast<const float4*>(slots + (2 * sp2) * FR_SLOT) + 65 + s;
-        const float4* f1 = reinterpret_cast<const float4*>(slots + (2 * sp2 + 1) * FR_SLOT) + 65 + s;
+        const float4* f0 = reinterpret_cast<const float4*>(featp(2 * sp2)) + 65 + s;
+        const float4* f1 = reinterpret_cast<const float4*>(featp(2 * sp2 + 1)) + 65 + s;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
         for (int i = 0; i < n; ++i) {
             const float w = ew[i];
@@ -573,8 +674,8 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
             a0.x = fmaf(w, x0.x, a0.x); a0.y = fmaf(w, x0.y, a0.y); a0.z = fmaf(w, x0.z, a0.z);
             a1.x = fmaf(w, x1.x, a1.x); a1.y = fmaf(w, x1.y, a1.y); a1.z = fmaf(w, x1.z, a1.z);
         }
-        reinterpret_cast<float4*>(slots + (2 * sp2) * FR_SLOT + FR_FEAT)[bnd] = a0;
-        reinterpret_cast<float4*>(slots + (2 * sp2 + 1) * FR_SLOT + FR_FEAT)[bnd] = a1;
+        reinterpret_cast<float4*>(erbp(2 * sp2))[bnd] = a0;
+        reinterpret_cast<float4*>(erbp(2 * sp2 + 1))[bnd] = a1;
     }
     __syncthreads();
     // ---- c: SFE-Lite (depthwise 3-tap along the 129 compressed bins, zero padded, no bias)
@@ -582,8 +683,8 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
         const float* sw = W + blob::FRONT_SFE_W;                   // [c][k]
         for (int idx = tid; idx < FR_NF * kErb; idx += FR_THREADS) {
             const int slot = idx / kErb, f = idx - slot * kErb;
-            const float4* lo = reinterpret_cast<const float4*>(slots + slot * FR_SLOT);            // compressed bins 0..64 = spectrum bins
-            const float4* hi = reinterpret_cast<const float4*>(slots + slot * FR_SLOT + FR_FEAT);  // compressed bins 65..128 = ERB bands
+            const float4* lo = reinterpret_cast<const float4*>(featp(slot));   // compressed bins 0..64 = spectrum bins
+            const float4* hi = reinterpret_cast<const float4*>(erbp(slot));    // compressed bins 65..128 = ERB bands
             float4 t[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -596,22 +697,33 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
             v.z = sw[6] * t[0].z + sw[7] * t[1].z + sw[8] * t[2].z;
             v.w = 0.f;
             const int c = f + 2;
-            reinterpret_cast<float4*>(slots + slot * FR_SLOT + FR_FEAT + FR_ERB)[(c & 1) * 67 + (c >> 1)] = v;
+            reinterpret_cast<float4*>(sfep(slot))[(c & 1) * 67 + (c >> 1)] = v;
         }
     }
     __syncthreads();
     // ---- d: en0  (thread = 2 slots x 16 co at one f').  Output a0 overlays the dead feat|erb region; its pad bins are zeroed here.
-    if (tid >= FR_HALF && tid < FR_HALF + FR_NF * 16) {
+    if (TCE) {
+        // pad rows of the fp16 planes: entries 0 and 34 of both parities and entry 33 of the odd one (padded bins 0, 1, 67, 68 and
+        // the unused 69), for 8 slots x 8 planes: 320 16-byte rows, zeroed by the 60 threads that have no en0 position
+        if (tid >= (FR_NF / 2) * kF1) {
+            uint4* pl = reinterpret_cast<uint4*>(slots);
+            for (int i = tid - (FR_NF / 2) * kF1; i < FR_NF * 8 * 5; i += FR_THREADS - (FR_NF / 2) * kF1) {
+                const int slot = i / 40, r = i - slot * 40, plane = r / 5, c = r - plane * 5;       // plane = (hl * 2 + parity) * 2 + chunk
+                const int par = (plane >> 1) & 1, e = c == 0 ? 0 : c == 1 ? 34 : c == 2 ? 33 : -1;
+                if (e >= 0 && (par == 1 || c < 2)) pl[plane * (TCE_PLANE / 16) + slot * 35 + e] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+    } else if (tid >= FR_HALF && tid < FR_HALF + FR_NF * 16) {
         const int i = tid - FR_HALF, slot = i >> 4, q = (i >> 2) & 3, c = i & 3;   // padded bins 0, 1, 67, 68
-        reinterpret_cast<float4*>(slots + slot * FR_SLOT)[q * 70 + (c == 0 ? 0 : c == 1 ? 35 : c == 2 ? 35 + 33 : 34)] = make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<float4*>(featp(slot))[q * 70 + (c == 0 ? 0 : c == 1 ? 35 : c == 2 ? 35 + 33 : 34)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (tid < (FR_NF / 2) * kF1) {
         const int sp2 = tid / kF1, f = tid - sp2 * kF1, s0 = 2 * sp2, s1 = s0 + 1;
         float acc0[16], acc1[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = prm.w[LY::EN0_B + c];
-        const float4* i0p = reinterpret_cast<const float4*>(slots + s0 * FR_SLOT + FR_FEAT + FR_ERB) + f;
-        const float4* i1p = reinterpret_cast<const float4*>(slots + s1 * FR_SLOT + FR_FEAT + FR_ERB) + f;
+        const float4* i0p = reinterpret_cast<const float4*>(sfep(s0)) + f;
+        const float4* i1p = reinterpret_cast<const float4*>(sfep(s1)) + f;
         if constexpr (VAR == 0) {
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
@@ -663,13 +775,25 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
         const float a = prm.w[LY::SLOPE + 0];
 #pragma unroll
         for (int c = 0; c < 16; c += 2) { prelu_pair(acc0[c], acc0[c + 1], a); prelu_pair(acc1[c], acc1[c + 1], a); }
-        float4* o0 = reinterpret_cast<float4*>(slots + s0 * FR_SLOT);
-        float4* o1 = reinterpret_cast<float4*>(slots + s1 * FR_SLOT);
         const int cp = f + 2, po = (cp & 1) * 35 + (cp >> 1);
+        if (TCE) {
+            // A operand of the en1 MMAs: fp16 hi' / lo rows of the parity plane of this bin (row = slot * 35 + entry)
+            uint4* pl = reinterpret_cast<uint4*>(slots) + (cp & 1) * 2 * (TCE_PLANE / 16) + (cp >> 1);
+            uint4 hi[2], lo[2];
+            split_f16_row(acc0, hi, lo);
+            pl[s0 * 35] = hi[0]; pl[(TCE_PLANE / 16) + s0 * 35] = hi[1];
+            pl[4 * (TCE_PLANE / 16) + s0 * 35] = lo[0]; pl[5 * (TCE_PLANE / 16) + s0 * 35] = lo[1];
+            split_f16_row(acc1, hi, lo);
+            pl[s1 * 35] = hi[0]; pl[(TCE_PLANE / 16) + s1 * 35] = hi[1];
+            pl[4 * (TCE_PLANE / 16) + s1 * 35] = lo[0]; pl[5 * (TCE_PLANE / 16) + s1 * 35] = lo[1];
+        } else {
+            float4* o0 = reinterpret_cast<float4*>(featp(s0));
+            float4* o1 = reinterpret_cast<float4*>(featp(s1));
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            o0[q * 70 + po] = make_float4(acc0[4 * q], acc0[4 * q + 1], acc0[4 * q + 2], acc0[4 * q + 3]);
-            o1[q * 70 + po] = make_float4(acc1[4 * q], acc1[4 * q + 1], acc1[4 * q + 2], acc1[4 * q + 3]);
+            for (int q = 0; q < 4; ++q) {
+                o0[q * 70 + po] = make_float4(acc0[4 * q], acc0[4 * q + 1], acc0[4 * q + 2], acc0[4 * q + 3]);
+                o1[q * 70 + po] = make_float4(acc1[4 * q], acc1[4 * q + 1], acc1[4 * q + 2], acc1[4 * q + 3]);
+            }
         }
         if (fi0 + s0 < nframes) {
             float4* g = reinterpret_cast<float4*>(en0 + ((fi0 + s0) * kF1 + f) * 16);
@@ -682,6 +806,59 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
             for (int q = 0; q < 4; ++q) g[q] = make_float4(acc1[4 * q], acc1[4 * q + 1], acc1[4 * q + 2], acc1[4 * q + 3]);
         }
     }
+    if constexpr (TCE) {
+        // ---- e (tensor cores): en1 = 5 taps x (hi' [W_hi | W_lo], lo W_hi) per 128-row tile; tap k reads parity plane k & 1 shifted
+        //      by k >> 1 rows.  Accumulator of tile i: TMEM columns 32 i .. 32 i + 31 (hi' W_hi + lo W_hi | hi' W_lo).
+        tc::fence_async_smem();                                    // the planes (generic-proxy stores) and the cp.async'ed weights
+        __syncthreads();
+        tc::fence_after();
+        const uint32_t tm = tmem_base_s;
+        if (tid == 0) {
+            constexpr uint32_t id32 = tc::make_idesc_f16(128, 32), id16 = tc::make_idesc_f16(128, 16);
+            const uint32_t a_base = tc::smem_u32(slots), b_base = tc::smem_u32(Btc);
+#pragma unroll 1
+            for (int tile = 0; tile < 3; ++tile) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const uint32_t a_hi = a_base + (uint32_t)((k & 1) * 2 * TCE_PLANE + (128 * tile + (k >> 1)) * 16);
+                    const uint64_t da_hi = tc::make_desc(a_hi, TCE_PLANE, 128), da_lo = tc::make_desc(a_hi + 4 * TCE_PLANE, TCE_PLANE, 128);
+                    const uint64_t db_st = tc::make_desc(b_base + k * 1536, 512, 128), db_lo = tc::make_desc(b_base + k * 1536 + 1024, 256, 128);
+                    tc::mma_f16_ss(tm + 32 * tile, da_hi, db_st, id32, k > 0);
+                    tc::mma_f16_ss(tm + 32 * tile, da_lo, db_lo, id16, 1);
+                }
+                tc::commit(&tc_bars[tile]);
+            }
+        }
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp < 9) {
+            // accumulator rows back: warps 0-3 tile 0, 4-7 tile 1, warp 8 the 24 live rows of tile 2 (a warp reads TMEM lanes 32 (w % 4) ..)
+            const int tile = warp < 8 ? warp >> 2 : 2, lg = warp & 3;
+            tc::mbar_wait(&tc_bars[tile], 0);
+            tc::fence_after();
+            float d0[16], d1[16];
+            const uint32_t ta = tm + ((uint32_t)(lg * 32) << 16) + 32 * tile;
+            tc::tmem_ld16_nowait(ta, d0);
+            tc::tmem_ld16_nowait(ta + 16, d1);
+            tc::tmem_wait_ld(d0);
+            tc::tmem_wait_ld(d1);
+            const int r = 128 * tile + 32 * lg + lane, slot = r / 35, e = r - slot * 35;
+            const float winv = Btc[TCW_EN1_WORDS - 4], a = prm.w[LY::SLOPE + 1];
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) {
+                add_pair(d0[c], d0[c + 1], d1[c], d1[c + 1]);
+                d0[c] = fmaf(d0[c], winv, prm.w[LY::EN1_B + c]); d0[c + 1] = fmaf(d0[c + 1], winv, prm.w[LY::EN1_B + c + 1]);
+                prelu_pair(d0[c], d0[c + 1], a);
+            }
+            if (r < TCE_ROWS && e < kF2 && fi0 + slot < nframes) {
+                float4* g = reinterpret_cast<float4*>(en1 + ((fi0 + slot) * kF2 + e) * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) g[q] = make_float4(d0[4 * q], d0[4 * q + 1], d0[4 * q + 2], d0[4 * q + 3]);
+            }
+        }
+        tc::fence_before();
+        __syncthreads();
+        if (tid < 32) tc::tmem_dealloc(tm, 128);
+    } else {
     __syncthreads();
     // ---- e: en1: output-channel half 0 on warps 0-4, half 1 on warps 5-9 (132 of 160 lanes each)
     {
@@ -690,6 +867,7 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
             if (half == 0) front_en1<0, VAR>(prm, slots, r, fi0, nframes, en1);
             else front_en1<1, VAR>(prm, slots, r, fi0, nframes, en1);
         }
+    }
     }
 }
 

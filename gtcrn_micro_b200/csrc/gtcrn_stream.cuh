@@ -527,6 +527,8 @@ struct HostParams {
     gk::ParamBlock<blob::FRONT_SIZE> front;
     gk::ParamBlock<blob::BACK_SIZE> back;
     bool tc_stream = false;                       // decoder blocks of a hop on the tensor cores (k_gtconv_dec_tc<4, true>)
+    bool tc_ends = false;                         // en1 / de3 on the tensor cores (k_front / k_back <.., true>), weights in tcw
+    const uint32_t* tcw = nullptr;
     int sm_count = 148;
     void load(const float* blob_host) {
         memcpy(front.w, blob_host + blob::FRONT_OFF, sizeof(front.w));
@@ -547,7 +549,11 @@ inline int model_step(const float* blobp, const HostParams& hp, void* state, con
     const unsigned gfr = (unsigned)((N + FR_NF - 1) / FR_NF), gbk = (unsigned)((N + BK_NF - 1) / BK_NF);
     // T = 1: strides {b: 514, f: 2, t: 0, c: 1}.  k_front / k_back do not know about `skip`; on the skipped call
     // (first wav hop) they run on a zero spectrum and their outputs are simply never consumed.
-    k_front<false, 0><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, kSpecFrame, 2, 0, 1, nullptr, 0, 0, nullptr, 1, N, blobp, hp.front, ws.en0, ws.act[0]);
+    if (hp.tc_ends)
+        k_front<false, 0, true><<<gfr, FR_THREADS, fr_smem_floats(false, true) * sizeof(float), st>>>(spec, kSpecFrame, 2, 0, 1, nullptr, 0, 0, nullptr, 1, N, blobp, hp.front,
+                                                                                                      ws.en0, ws.act[0], hp.tcw);
+    else
+        k_front<false, 0><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, kSpecFrame, 2, 0, 1, nullptr, 0, 0, nullptr, 1, N, blobp, hp.front, ws.en0, ws.act[0]);
     ++launches;
     const unsigned gsg = (unsigned)((N + SG_NS - 1) / SG_NS);
     for (int i = 0; i < 3; ++i) {

@@ -471,6 +471,72 @@ class StreamGTCRNMicro(_B200Module):
         return out.permute(1, 0, 2).reshape(state.n, 512)
 
 
+class StreamPool:
+    """N concurrent real-time streams served from HOST buffers (the frame-by-frame loop of gtcrn_micro_stream.py:618-636 for many
+    callers at once).  The streams are split into groups with a device state each; per hop the H2D copy of group g + 1, the kernels
+    of group g and the D2H copy of group g - 1 overlap on three CUDA streams, so only the first copy in and the last copy out are
+    exposed (one serial H2D -> step -> D2H chain spends 45 % of a 160,000-stream hop in the copies).  Streams are independent, so
+    the result is bit-identical to one `step_wav` over all of them."""
+
+    GROUP_STREAMS = 8192
+
+    def __init__(self, smodel: "StreamGTCRNMicro", n_streams: int, device=None, groups: Optional[int] = None):
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.smodel, self.n, self.device = smodel, int(n_streams), dev
+        g = groups if groups is not None else max(1, min(8, self.n // self.GROUP_STREAMS))
+        g = max(1, min(g, self.n))
+        self.sizes = [self.n // g + (1 if i < self.n % g else 0) for i in range(g)]
+        self.offsets = [sum(self.sizes[:i]) for i in range(g)]
+        self.states = [smodel.new_state(k, dev) for k in self.sizes]
+        self.din = [torch.empty(k, 256, device=dev) for k in self.sizes]
+        self.dout = [torch.empty(k, 256, device=dev) for k in self.sizes]
+        with torch.cuda.device(dev):
+            self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self.ev_in = [torch.cuda.Event() for _ in range(g)]
+            self.ev_step = [torch.cuda.Event() for _ in range(g)]
+            self.ev_out = [torch.cuda.Event() for _ in range(g)]
+        self._hops = 0
+
+    @staticmethod
+    def _check_host(t: torch.Tensor, n: int, name: str) -> None:
+        if t.device.type != "cpu" or t.dtype != torch.float32 or tuple(t.shape) != (n, 256) or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous float32 CPU tensor [{n},256] (pinned for overlap)")
+
+    @torch.no_grad()
+    def step_wav_host(self, hop_in: torch.Tensor, hop_out: torch.Tensor) -> torch.Tensor:
+        """One 16 ms hop for all streams: hop_in [N,256] new samples (host) -> hop_out [N,256] enhanced samples (host), delayed by
+        two hops like `step_wav`.  Asynchronous: the caller's current CUDA stream completes when hop_out has landed."""
+        self._check_host(hop_in, self.n, "hop_in")
+        self._check_host(hop_out, self.n, "hop_out")
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream()
+            self.s_in.wait_stream(cur)                         # whatever the caller queued before this hop (e.g. a reset)
+            for g, (o, k) in enumerate(zip(self.offsets, self.sizes)):
+                with torch.cuda.stream(self.s_in):
+                    if self._hops:
+                        self.s_in.wait_event(self.ev_step[g])  # the previous hop's kernels have consumed din[g]
+                    self.din[g].copy_(hop_in[o:o + k], non_blocking=True)
+                    self.ev_in[g].record()
+                cur.wait_event(self.ev_in[g])
+                if self._hops:
+                    cur.wait_event(self.ev_out[g])             # dout[g] of the previous hop is on the host
+                self.smodel.step_wav(self.din[g], self.states[g], self.dout[g])
+                self.ev_step[g].record(cur)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(self.ev_step[g])
+                    hop_out[o:o + k].copy_(self.dout[g], non_blocking=True)
+                    self.ev_out[g].record()
+            cur.wait_event(self.ev_out[-1])
+            for e in self.ev_out[:-1]:
+                cur.wait_event(e)
+        self._hops += 1
+        return hop_out
+
+    def reset(self) -> None:
+        for st in self.states:
+            self.smodel.reset(st)
+
+
 def convert_to_stream(stream_model: nn.Module, model: nn.Module) -> None:
     """Copy offline weights into the streaming twin (same contract as convert.py:7-56, including the
     ConvTranspose2d weight re-layout and `ValueError("Key error!")` for unknown keys)."""

@@ -233,3 +233,25 @@ def test_stream_parity_at_scale_16384(oracle, weights_dns3, b200_lib):
     e = rel_err(torch.stack(sub_out, dim=2), ref)
     print(f"16384 streams x {T} hops: subset rel err vs oracle stream loop {e:.2e}")
     assert e <= REL_TOL
+
+
+@pytest.mark.parametrize("groups", [1, 3])
+def test_stream_pool_host_buffers_equal_single_state(oracle, weights_dns3, b200_lib, groups):
+    # StreamPool.step_wav_host: pinned host buffers in / out, streams split into groups whose copies overlap the other groups'
+    # kernels.  Streams are independent, so every hop must equal one step_wav over all streams bit for bit (graphs kick in on the
+    # second hop of every group: rotating keys).
+    m, s = models(weights_dns3)
+    N, HOPS = 37, 12
+    pool = G.StreamPool(s, N, DEV, groups=groups)
+    assert sum(pool.sizes) == N and len(pool.sizes) == groups
+    st = s.new_state(N, DEV)
+    g = torch.Generator().manual_seed(5)
+    hin, hout = torch.empty(N, 256).pin_memory(), torch.empty(N, 256).pin_memory()
+    for k in range(HOPS):
+        hin.copy_(0.1 * torch.randn(N, 256, generator=g))
+        pool.step_wav_host(hin, hout)
+        want = s.step_wav(hin.to(DEV), st)
+        torch.cuda.synchronize()
+        assert torch.equal(hout, want.cpu()), k
+    with pytest.raises(ValueError):
+        pool.step_wav_host(hin[:5], hout)

@@ -12,7 +12,7 @@ def col(name):
     return H.index(name) if name in H else None
 si, wi, xi, ii = col("# Samples"), col("L1 Wavefronts Shared"), col("L1 Wavefronts Shared Excessive"), col("Instructions Executed")
 def geti(r, i):
-    return int(r[i]) if i is not None and r[i].strip() else 0
+    return int(r[i]) if i is not None and r[i].strip().isdigit() else 0
 stall_cols = [(n[6:], i) for i, n in enumerate(H) if n.startswith("stall_") and "Not Issued" not in n]
 lines = [r for r in rows[hi + 1:] if r and r[0].strip().isdigit()]
 tot = sum(geti(r, si) for r in lines); twf = sum(geti(r, wi) for r in lines)
