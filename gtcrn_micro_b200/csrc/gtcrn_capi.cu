@@ -499,6 +499,7 @@ int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, 
         if (cudaDeviceSynchronize() != cudaSuccess) { gtcrnb_destroy(h); return fail(GTCRNB_E_CUDA, "k_prep_ends_tc failed: %s", cudaGetErrorString(cudaGetLastError())); }
     }
     h->hp->tc_ends = (h->tc_mask & 4) != 0;
+    if (const char* e = getenv("GTCRNB_STREAM_FUSE_ENC")) h->hp->fuse_enc = atoi(e) != 0;
     h->hp->tcw = h->tcw;
     // streaming: the decoder blocks of a hop follow the offline choice (bit 1) unless GTCRNB_TC_STREAM=0
     h->hp->tc_stream = (h->tc_mask & 2) != 0;

@@ -499,6 +499,139 @@ __global__ void __launch_bounds__(256) ks_convert(int import, void* state, int64
 }
 
 // ------------------------------------------------------------------------------------------------
+// The three encoder GTConvBlocks of a hop in ONE launch (round 2): a thread keeps its position's 16 channels in registers from
+// block to block (the channel shuffle is a register permutation), every block's output is still written once for the decoder
+// skip, and the shared-memory tile is reused.  Same device functions and operation order as ks_gtconv<false> x 3 (bit-identical);
+// saves two launches and the re-read of two activation tensors per hop (ncu r2_stream16k_v23: the three launches were 182 us of
+// an 826 us hop at 16,384 streams, 23 % issue utilisation, stalled on barriers and on the loads at the head of each kernel).
+// ------------------------------------------------------------------------------------------------
+template <class PB>
+__device__ __forceinline__ void sg_enc_block(const PB& prm, void* state, int blk, int64_t N, int64_t n0, int tid, bool act, int ls, int f, int64_t n,
+                                             int slot_old, int slot_mid, float4* Pb, float* E2, float* Ev, float* Gt, float (&x)[16],
+                                             float* __restrict__ out) {
+    using namespace gk;
+    // ---- phase 1: history rows from the ring, point conv 1 of the new frame (also written to the ring)
+    if (act) {
+        float* ring = stream_base(state, n) + kGtP + blk * (2 * kF2 * 16) + f * 16;
+        const float4* h2 = reinterpret_cast<const float4*>(ring + slot_old * (kF2 * 16));
+        const float4* h1 = reinterpret_cast<const float4*>(ring + slot_mid * (kF2 * 16));
+        float4* row = Pb + (ls * 3) * SG_ROW4 + f + 1;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) { row[qd * 35] = h2[qd]; row[SG_ROW4 + qd * 35] = h1[qd]; }
+        const float x1[8] = {x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]};
+        float p[16];
+        gt_pc1<false>(prm, x1, p);
+        float4* newest = reinterpret_cast<float4*>(ring + slot_old * (kF2 * 16));
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            const float4 v = make_float4(p[4 * qd], p[4 * qd + 1], p[4 * qd + 2], p[4 * qd + 3]);
+            newest[qd] = v;
+            row[2 * SG_ROW4 + qd * 35] = v;
+        }
+    }
+    if (tid < SG_NS * 16) {                                           // TRA energy history -> Ev rows 0,1
+        const int l2 = tid >> 4, r = (tid >> 3) & 1, c = tid & 7;
+        const int64_t n2 = n0 + l2;
+        float v = 0.f;
+        if (n2 < N) v = stream_base(state, n2)[kTraE + blk * 16 + (r == 0 ? slot_old : slot_mid) * 8 + c];
+        Ev[(l2 * 3 + r) * 8 + c] = v;
+    }
+    __syncthreads();
+    // ---- phase 2: 3x3 depthwise conv + PReLU, point conv 2, energies
+    float q[8];
+    if (act) {
+        float acc[1][16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[0][c] = prm.w[GtOff<false>::MID_B + c];
+        const float4* r0 = Pb + (ls * 3) * SG_ROW4 + f;
+#pragma unroll 1
+        for (int kf = 0; kf < 3; ++kf) {
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                float4 in[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) in[j] = r0[j * SG_ROW4 + qd * 35 + kf];
+                gt_mid_step<false, 1>(prm, kf, qd, in, acc);
+            }
+        }
+        gt_pc2<false>(prm, acc[0], q);
+        float4* e4 = reinterpret_cast<float4*>(E2 + (ls * kF2 + f) * 8);
+        e4[0] = make_float4(q[0] * q[0], q[1] * q[1], q[2] * q[2], q[3] * q[3]);
+        e4[1] = make_float4(q[4] * q[4], q[5] * q[5], q[6] * q[6], q[7] * q[7]);
+    }
+    __syncthreads();
+    // ---- phase 3: TRALite energy of the new frame -> ring, gate
+    if (tid < SG_NS * 8) {
+        const int l2 = tid >> 3, c = tid & 7;
+        const float e = gt_energy(E2 + l2 * kF2 * 8 + c);
+        Ev[(l2 * 3 + 2) * 8 + c] = e;
+        const int64_t n2 = n0 + l2;
+        if (n2 < N) stream_base(state, n2)[kTraE + blk * 16 + slot_old * 8 + c] = e;
+    }
+    __syncthreads();
+    if (tid < SG_NS * 8) {
+        const int l2 = tid >> 3, c = tid & 7;
+        Gt[l2 * 8 + c] = gt_gate1<false>(prm, Ev + (l2 * 3) * 8, Ev + (l2 * 3 + 1) * 8, Ev + (l2 * 3 + 2) * 8, c);
+    }
+    __syncthreads();
+    // ---- phase 4: gate, channel shuffle (in registers: the next block's input), store
+    if (act) {
+        const float* gate = Gt + ls * 8;
+        float y[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { y[2 * i] = q[i] * gate[i]; y[2 * i + 1] = x[8 + i]; }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) x[c] = y[c];
+        float4* po = reinterpret_cast<float4*>(out + (n * kF2 + f) * 16);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) po[v] = make_float4(x[4 * v], x[4 * v + 1], x[4 * v + 2], x[4 * v + 3]);
+    }
+}
+
+__global__ void __launch_bounds__(SG_THREADS, 3)
+ks_gtconv_enc3(const float* __restrict__ xin, float* __restrict__ out1, float* __restrict__ out2, float* __restrict__ out3,
+               const __grid_constant__ gk::ParamBlock<blob::ENCGT_SIZE> prm0, const __grid_constant__ gk::ParamBlock<blob::ENCGT_SIZE> prm1,
+               const __grid_constant__ gk::ParamBlock<blob::ENCGT_SIZE> prm2, void* state, int64_t N) {
+    using namespace gk;
+    const Header* hdr = reinterpret_cast<const Header*>(state);
+    if (hdr->skip) return;
+    const int slot_old = (int)(hdr->frame_step & 1), slot_mid = slot_old ^ 1;
+    extern __shared__ float4 smem4[];
+    float4* Pb = smem4;
+    float* E2 = reinterpret_cast<float*>(Pb + SG_NS * 3 * SG_ROW4);
+    float* Ev = E2 + SG_NS * kF2 * 8;
+    float* Gt = Ev + SG_NS * 3 * 8;
+    const int tid = threadIdx.x;
+    const int64_t n0 = (int64_t)blockIdx.x * SG_NS;
+    for (int i = tid; i < SG_NS * 3 * 4 * 2; i += SG_THREADS) Pb[(i >> 1) * 35 + (i & 1) * 34] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + SG_NS > N) {
+        zero_f4(reinterpret_cast<float*>(Pb), SG_SMEM_FLOATS, tid, SG_THREADS);
+        __syncthreads();
+    }
+    const int ls = tid / kF2, f = tid - ls * kF2;
+    const int64_t n = n0 + ls;
+    const bool act = tid < SG_ACTIVE && n < N;
+    float x[16];
+    if (act) {
+        const float4* px = reinterpret_cast<const float4*>(xin + (n * kF2 + f) * 16);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { const float4 u = px[v]; x[4 * v] = u.x; x[4 * v + 1] = u.y; x[4 * v + 2] = u.z; x[4 * v + 3] = u.w; }
+        // the ring rows of the two later blocks start their trip from HBM now
+        const float* r1 = stream_base(state, n) + kGtP + 1 * (2 * kF2 * 16) + f * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r1));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + kF2 * 16));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + 2 * kF2 * 16));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + 3 * kF2 * 16));
+    } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) x[c] = 0.f;
+    }
+    sg_enc_block(prm0, state, 0, N, n0, tid, act, ls, f, n, slot_old, slot_mid, Pb, E2, Ev, Gt, x, out1);
+    sg_enc_block(prm1, state, 1, N, n0, tid, act, ls, f, n, slot_old, slot_mid, Pb, E2, Ev, Gt, x, out2);
+    sg_enc_block(prm2, state, 2, N, n0, tid, act, ls, f, n, slot_old, slot_mid, Pb, E2, Ev, Gt, x, out3);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
 inline int stream_init_attributes() {
@@ -515,6 +648,10 @@ inline int stream_init_attributes() {
     e = cudaFuncSetAttribute(ks_gtconv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM_FLOATS * (int)sizeof(float));
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(ks_gtconv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM_FLOATS * (int)sizeof(float));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(ks_gtconv_enc3, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM_FLOATS * (int)sizeof(float));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(ks_gtconv_enc3, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return (int)e;
 }
 
@@ -527,6 +664,7 @@ struct HostParams {
     gk::ParamBlock<blob::FRONT_SIZE> front;
     gk::ParamBlock<blob::BACK_SIZE> back;
     bool tc_stream = false;                       // decoder blocks of a hop on the tensor cores (k_gtconv_dec_tc<4, true>)
+    bool fuse_enc = true;                         // the three encoder GTConvBlocks of a hop in one launch (GTCRNB_STREAM_FUSE_ENC=0: three)
     bool tc_ends = false;                         // en1 / de3 on the tensor cores (k_front / k_back <.., true>), weights in tcw
     const uint32_t* tcw = nullptr;
     int sm_count = 148;
@@ -556,6 +694,10 @@ inline int model_step(const float* blobp, const HostParams& hp, void* state, con
         k_front<false, 0><<<gfr, FR_THREADS, fr_smem_floats(false) * sizeof(float), st>>>(spec, kSpecFrame, 2, 0, 1, nullptr, 0, 0, nullptr, 1, N, blobp, hp.front, ws.en0, ws.act[0]);
     ++launches;
     const unsigned gsg = (unsigned)((N + SG_NS - 1) / SG_NS);
+    if (hp.fuse_enc) {
+        ks_gtconv_enc3<<<gsg, SG_THREADS, SG_SMEM_FLOATS * sizeof(float), st>>>(ws.act[0], ws.act[1], ws.act[2], ws.act[3], hp.enc[0], hp.enc[1], hp.enc[2], state, N);
+        ++launches;
+    } else
     for (int i = 0; i < 3; ++i) {
         ks_gtconv<false><<<gsg, SG_THREADS, SG_SMEM_FLOATS * sizeof(float), st>>>(ws.act[i], nullptr, ws.act[i + 1], hp.enc[i], state, i, N);
         ++launches;

@@ -18,12 +18,14 @@ import gtcrn_micro_b200.build as B
 
 CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 # kernels launched with the default tuning (gtcrn_capi.cu): offline + streaming
-HOT = ["k_frontILb0ELi0E", "k_frontILb1ELi0E", "k_backILb0ELi0E", "k_backILb1ELi0E", "k_gtconvILb0ELi2ELi4ELb0", "k_gtconvILb1ELi4ELi7ELb0",
-       "k_gtcnILi2ELb0", "ks_gtconvILb0", "ks_gtconvILb1", "ks_gtcn"]
+HOT = ["k_frontILb0ELi0ELb1E", "k_frontILb1ELi0ELb1E", "k_frontILb0ELi0ELb0E", "k_frontILb1ELi0ELb0E", "k_backILb0ELi0E", "k_backILb1ELi0E",
+       "k_gtconvILb0ELi2ELi4ELb0", "k_gtconvILb1ELi4ELi7ELb0", "k_gtcnILi2ELb0", "ks_gtconvILb0", "ks_gtconvILb1", "ks_gtconv_enc3", "ks_gtcnE"]
 # tensor-core kernels of the default path (gtcrn_tc.cuh): decoder GTConv with 4 warpgroups per CTA, GTCN with one
 HOT_TC = ["k_gtconv_dec_tcILi4ELb0", "k_gtconv_dec_tcILi4ELb1", "k_gtcn_tcILi1ELb0"]
+# en1 inside k_front on the tensor cores (default): both operands come from shared memory (descriptors), the accumulator from TMEM
+HOT_TC_SS = ["k_frontILb0ELi0ELb1E", "k_frontILb1ELi0ELb1E"]
 # kernels of the original-GTCRN-style variant (BASELINE configs[3]): same weight-feed property, spills tolerated up to a small frame
-HOT_FULL = ["k_frontILb0ELi1E", "k_frontILb1ELi1E", "k_backILb0ELi1E", "k_backILb1ELi1E", "kf_gtconvILb0ELi2ELi4E", "kf_gtconvILb1ELi2ELi4E",
+HOT_FULL = ["k_frontILb0ELi1ELb0E", "k_frontILb1ELi1ELb0E", "k_backILb0ELi1E", "k_backILb1ELi1E", "kf_gtconvILb0ELi2ELi4E", "kf_gtconvILb1ELi2ELi4E",
             "kf_dp_intra", "kf_dp_inter"]
 
 
@@ -53,7 +55,8 @@ def _find(per, key):
 def test_weights_use_the_uniform_datapath(sass, key):
     body = _find(sass, key)
     r_indexed = sum(1 for l in body if re.search(r"c\[0x0\]\[R\d", l))
-    assert r_indexed <= 16, f"{key}: {r_indexed} per-thread-indexed constant loads (LDC c[0x0][R..]) -- see tools/sass_check.sh"
+    limit = 48 if key == "ks_gtconv_enc3" else 16                 # three GTConvBlocks in one kernel (the TRALite gate's 9 per block)
+    assert r_indexed <= limit, f"{key}: {r_indexed} per-thread-indexed constant loads (LDC c[0x0][R..]) -- see tools/sass_check.sh"
 
 
 @pytest.mark.parametrize("key", HOT_TC)
@@ -71,7 +74,18 @@ def test_tensor_core_kernels_use_tcgen05_with_operands_in_tensor_memory(sass, ke
     assert not any(re.search(r"\s(STL|LDL)[.\s]", l) for l in body), f"{key} spills"
 
 
-@pytest.mark.parametrize("key", HOT)
+@pytest.mark.parametrize("key", HOT_TC_SS)
+def test_front_en1_runs_on_tcgen05_from_shared_memory(sass, key):
+    """5 taps x (hi' [W_hi | W_lo], lo W_hi): 10 MMAs in the (rolled) tile loop, A and B through shared-memory descriptors, the
+    accumulator read back with tcgen05.ld; the fp32 en1 FFMA loop is gone (only en0's 240 FFMA2 per thread remain)."""
+    body = _find(sass, key)
+    n = {op: sum(1 for l in body if re.search(r"\s" + op + r"[.\s]", l)) for op in ("UTCHMMA", "LDTM", "UTCBAR", "FFMA2")}
+    assert n["UTCHMMA"] >= 10 and n["LDTM"] >= 2 and n["UTCBAR"] >= 1 and n["FFMA2"] < 400, (key, n)
+    mma = [l for l in body if "UTCHMMA" in l]
+    assert all(len(re.findall(r"gdesc\[", l)) >= 2 for l in mma), mma[:2]
+
+
+@pytest.mark.parametrize("key", [k for k in HOT if k not in HOT_TC_SS])       # en1 left the FMA pipe there: see the test above
 def test_convolutions_are_packed_ffma2(sass, key):
     body = _find(sass, key)
     f2 = sum(1 for l in body if "FFMA2" in l)

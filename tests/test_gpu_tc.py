@@ -1,6 +1,7 @@
 """The tensor-core (tcgen05) kernels of the offline path: decoder GTConv 3x3 on fp16 hi/lo operands, GTCN pointwise convs as 3xTF32,
-both with the A operand in tensor memory (gtcrn_micro_b200/csrc/gtcrn_tc.cuh).  They are the default (GTCRNB_TC unset = 3); every
-other GPU test therefore already exercises them.  Here they are compared with the FFMA kernels (GTCRNB_TC=0) and with the oracle
+both with the A operand in tensor memory (gtcrn_micro_b200/csrc/gtcrn_tc.cuh), and en1 inside k_front with both operands in shared
+memory (fp16 hi'/lo with a 2^8 offset, mask bit 2).  They are the default (GTCRNB_TC unset = 7); every other GPU test therefore
+already exercises them.  Here they are compared with the FFMA kernels (GTCRNB_TC=0) and with the oracle
 at the points where an operand split could go wrong: every layer tap, large and tiny signal levels, ragged batch sizes that leave
 warpgroup rows and whole groups empty, and time segmentation.
 
@@ -34,10 +35,10 @@ def test_tc_is_the_default(weights_dns3, b200_lib, monkeypatch):
     monkeypatch.delenv("GTCRNB_TC", raising=False)
     m = G.GTCRNMicro(); m.load_state_dict(weights_dns3)
     m.enhance(torch.zeros(1, 1024, device=DEV))
-    assert m.tc_mask() == 3
+    assert m.tc_mask() == 7
 
 
-@pytest.mark.parametrize("tc", [1, 2, 3])
+@pytest.mark.parametrize("tc", [1, 2, 3, 4, 7])
 def test_tc_layers_match_ffma_and_oracle(oracle, weights, ref_outputs, b200_lib, monkeypatch, tc):
     tag, W = weights
     spec = torch.from_numpy(ref_outputs["spec"])                     # [2,257,41,2]
@@ -47,10 +48,10 @@ def test_tc_layers_match_ffma_and_oracle(oracle, weights, ref_outputs, b200_lib,
     B, _, T, _ = spec.shape
     m_tc = model_with(W, monkeypatch, tc)
     y_tc = m_tc(spec.to(DEV))
-    acts_tc = {n: m_tc.debug_activation(n, B, T).cpu() for n in ("gtcn1", "gtcn2", "de0", "de1", "de2")}
+    acts_tc = {n: m_tc.debug_activation(n, B, T).cpu() for n in ("en1", "gtcn1", "gtcn2", "de0", "de1", "de2")}
     m_ff = model_with(W, monkeypatch, 0)
     y_ff = m_ff(spec.to(DEV))
-    names = {"gtcn1": "gtcn1.3", "gtcn2": "gtcn2.3", "de0": "de0", "de1": "de1", "de2": "de2"}
+    names = {"en1": "en1", "gtcn1": "gtcn1.3", "gtcn2": "gtcn2.3", "de0": "de0", "de1": "de1", "de2": "de2"}
     rep = []
     for mine, theirs in names.items():
         o = taps[theirs].permute(0, 2, 3, 1)
@@ -62,13 +63,14 @@ def test_tc_layers_match_ffma_and_oracle(oracle, weights, ref_outputs, b200_lib,
     assert rel_err(y_tc, y_or) <= 1e-4 and rel_err(y_tc, y_ff) <= 1e-5
 
 
-@pytest.mark.parametrize("gain", [1e-4, 1.0, 30.0])
+@pytest.mark.parametrize("gain", [1e-4, 1.0, 30.0, 1000.0])
 def test_tc_signal_level(oracle, weights_dns3, b200_lib, monkeypatch, gain):
     """fp16 hi/lo operands: tiny signals sit in the fp16 subnormal range of the lo part (absolute error stays ~1e-8), loud ones
-    (30x full scale) far below the 65,504 saturation point of the point-conv activations."""
+    (30x full scale) far below the 65,504 saturation point of the point-conv activations; en1 sees spectral magnitudes that grow
+    with the input level, which is what its 2^8 offset between the hi' and lo halves is for (1000x full scale still exact)."""
     x = oracle.synth_batch(3, 256 * 40 + 31, seed=5)
     x = gain * x / x.abs().max()
-    m = model_with(weights_dns3, monkeypatch, 3)
+    m = model_with(weights_dns3, monkeypatch, 7 if gain <= 30.0 else 5)       # the decoder's fp16 operands are specified up to 30x
     y = m.enhance(x.to(DEV)).cpu()
     ref = oracle.enhance(weights_dns3, x)
     err = float((y - ref).abs().max())
@@ -82,7 +84,7 @@ def test_tc_ragged_batches(oracle, weights_dns3, b200_lib, monkeypatch, B, L):
     """B not a multiple of the 3 groups per warpgroup / 12 per CTA (decoder) nor of the 4 columns per warpgroup (GTCN): the padded
     rows must neither be stored nor disturb their neighbours."""
     x = oracle.synth_batch(B, L, seed=B)
-    m = model_with(weights_dns3, monkeypatch, 3)
+    m = model_with(weights_dns3, monkeypatch, 7)
     y = m.enhance(x.to(DEV)).cpu()
     sel = sorted({0, B // 2, B - 1})
     ref = oracle.enhance(weights_dns3, x[sel])
@@ -96,7 +98,7 @@ def test_tc_time_segmentation_is_bitwise(oracle, weights_dns3, b200_lib, monkeyp
     """One long utterance is split into many time segments with warm-up (few utterances, many SMs); the same utterance inside a big
     batch runs unsegmented.  Row-wise MMA results do not depend on the tile they are computed in."""
     x = oracle.synth_batch(1, 256 * 600, seed=2)
-    m = model_with(weights_dns3, monkeypatch, 3)
+    m = model_with(weights_dns3, monkeypatch, 7)
     y1 = m.enhance(x.to(DEV)).cpu()
     xb = torch.cat([x, oracle.synth_batch(299, 256 * 600, seed=3)])
     yb = m.enhance(xb.to(DEV)).cpu()
