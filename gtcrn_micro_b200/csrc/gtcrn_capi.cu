@@ -66,6 +66,7 @@ struct gtcrnb_handle {
     int tc_dec_nwg = 4;                           // warpgroups per CTA of k_gtconv_dec_tc (GTCRNB_TC_DEC_NWG: 1, 2, 4 or 5; 96 TMEM columns each)
     bool tc_stack = false;                        // [W_hi | W_lo] stacked along N: 4 MMAs per conv and 32 accumulator columns instead of 6 and 16
     int gt_enc = 0, gt_dec = 0;                   // index into kGtVariants for the encoder / decoder GTConv kernels
+    int seg_waves = 1;                            // CTAs per resident slot of the walking kernels (GTCRNB_SEG_WAVES), see pick_flat
     // activation workspace for one chunk of utterances
     int64_t cap_frames = 0;
     float* en0 = nullptr;
@@ -163,8 +164,8 @@ constexpr int kNumGtVariants = (int)(sizeof(kGtVariants) / sizeof(kGtVariants[0]
 
 template <bool DEC>
 cudaError_t launch_gtconv(const GtVariant& v, dim3 grid, cudaStream_t st, const float* x, const float* skip, float* out,
-                          const gk::ParamBlock<gk::gt_chunk<DEC>()>& prm, int T, int seg) {
-    void* args[] = {(void*)&x, (void*)&skip, (void*)&out, (void*)&prm, (void*)&T, (void*)&seg};
+                          const gk::ParamBlock<gk::gt_chunk<DEC>()>& prm, int T, int seg, int B) {
+    void* args[] = {(void*)&x, (void*)&skip, (void*)&out, (void*)&prm, (void*)&T, (void*)&seg, (void*)&B};
     return cudaLaunchKernel(DEC ? v.dec : v.enc, grid, dim3((unsigned)v.threads), args, (size_t)(DEC ? v.smem_dec : v.smem_enc), st);
 }
 
@@ -231,6 +232,16 @@ int pick_seg_len(int64_t ctas_per_seg_row, int T, int gran, int warm, int slots)
     return best_len;
 }
 
+// Balanced segmentation of a walking kernel: `units` x T frames flattened, one contiguous range of `len` frames per CTA, `waves`
+// CTAs per resident slot (1 = every CTA does exactly 1 / slots of the work).  A range is never shorter than 4 warm-ups.
+struct FlatSeg { int len; unsigned ctas; };
+FlatSeg pick_flat(int64_t units, int T, int warm, int64_t slots, int waves) {
+    const int64_t total = units * (int64_t)T, want = std::max<int64_t>(1, slots * std::max(1, waves));
+    int64_t len = std::max<int64_t>((total + want - 1) / want, std::min<int64_t>(total, 4 * warm));
+    len = std::min<int64_t>(len, (int64_t)1 << 30);
+    return {(int)len, (unsigned)((total + len - 1) / len)};
+}
+
 // Phases of the model, so that the host pipeline can run the per-frame ends (front: STFT .. en1, back: de3 .. iSTFT) on small
 // copy chunks -- utterances [u0, u0 + nu) of the workspace -- and the walking kernels in between on whole utterance groups.
 enum { PH_FRONT = 1, PH_BODY = 2, PH_BACK = 4, PH_ALL = 7 };
@@ -295,11 +306,11 @@ void launch_body_micro(gtcrnb_handle* h, int64_t B, int64_t T, cudaStream_t st) 
     const int64_t nframes = B * T;
     {
         const GtVariant& v = kGtVariants[h->gt_enc];
-        const int seg = pick_seg_len(B, Ti, v.ps, GT_WARMUP, h->sm_count * h->occ_gt_enc);
-        const dim3 g((unsigned)((Ti + seg - 1) / seg), (unsigned)B);
+        const FlatSeg fs = pick_flat(B, Ti, GT_WARMUP, (int64_t)h->sm_count * h->occ_gt_enc, h->seg_waves);
+        const dim3 g(fs.ctas);
         for (int i = 0; i < 3; ++i) {
             ProfScope ps(h, KC_ENC_GT, nframes, st);
-            launch_gtconv<false>(v, g, st, h->act[i], nullptr, h->act[i + 1], h->hp->enc[i], Ti, seg);
+            launch_gtconv<false>(v, g, st, h->act[i], nullptr, h->act[i + 1], h->hp->enc[i], Ti, fs.len, (int)B);
             h->launches++;
         }
     }
@@ -346,12 +357,12 @@ void launch_body_micro(gtcrnb_handle* h, int64_t B, int64_t T, cudaStream_t st) 
         }
     } else {
         const GtVariant& v = kGtVariants[h->gt_dec];
-        const int seg = pick_seg_len(B, Ti, v.ps, GT_WARMUP, h->sm_count * h->occ_gt_dec);
-        const dim3 g((unsigned)((Ti + seg - 1) / seg), (unsigned)B);
+        const FlatSeg fs = pick_flat(B, Ti, GT_WARMUP, (int64_t)h->sm_count * h->occ_gt_dec, h->seg_waves);
+        const dim3 g(fs.ctas);
         for (int i = 0; i < 3; ++i) {
             // de_i consumes (previous + en_outs[4 - i]) : skips en4, en3, en2 = act[3], act[2], act[1]
             ProfScope ps(h, KC_DEC_GT, nframes, st);
-            launch_gtconv<true>(v, g, st, h->act[5 + i], h->act[3 - i], h->act[6 + i], h->hp->dec[i], Ti, seg);
+            launch_gtconv<true>(v, g, st, h->act[5 + i], h->act[3 - i], h->act[6 + i], h->hp->dec[i], Ti, fs.len, (int)B);
             h->launches++;
         }
     }
@@ -493,6 +504,7 @@ int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, 
     if (const char* e = getenv("GTCRNB_TCN_SMEMW")) h->tcn_smem_w = atoi(e) != 0;
     if (const char* e = getenv("GTCRNB_STREAM_GRAPH")) h->stream_graphs = atoi(e) != 0;
     if (const char* e = getenv("GTCRNB_TC")) h->tc_mask = atoi(e);
+    if (const char* e = getenv("GTCRNB_SEG_WAVES")) h->seg_waves = std::max(1, std::min(64, atoi(e)));
     if (h->tc_mask & 4) {
         if (cudaMalloc(&h->tcw, sizeof(uint32_t) * gk::TCW_WORDS) != cudaSuccess) { cudaGetLastError(); gtcrnb_destroy(h); return fail(GTCRNB_E_NOMEM, "cudaMalloc(tcw) failed"); }
         gk::k_prep_ends_tc<<<1, 256>>>(h->blob, h->tcw);

@@ -583,6 +583,7 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
 #pragma unroll
             for (int q = 0; q < 8; ++q) xr0[q] = xr1[q] = 0.f;
         }
+        // (an L2 prefetch of the samples of the CTA one residency wave ahead, as k_back does for its operands, made this kernel 2 % slower)
         load_fft_tables_async(tb, blobp, tid, FR_THREADS);         // needed by the FFT right after the barrier
         cp_async_commit();
         copy_f4_async(W, blobp + LY::OFF, FR_W_FLOATS, tid, FR_THREADS);   // ERB / SFE tables: needed after the FFT phase
@@ -1004,7 +1005,7 @@ __device__ __forceinline__ float gt_energy(const float* e2_slot_c) {
 template <bool DEC, int PS, int G, bool SMEM_W>
 __global__ void __launch_bounds__(gt_threads(G), gt_min_blocks(PS, G))
 k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* __restrict__ out,
-         const __grid_constant__ ParamBlock<gt_chunk<DEC>()> prm_c, int T, int seg_len) {
+         const __grid_constant__ ParamBlock<gt_chunk<DEC>()> prm_c, int T, int seg_len, int B) {
     constexpr int NT = G * PS, R = NT + 2, GT_THREADS = gt_threads(G), GT_ACTIVE = G * kF2;
     static_assert(NT * 8 <= GT_THREADS, "phase 3 needs one thread per (slot, channel)");
     extern __shared__ float4 smem4[];
@@ -1012,11 +1013,12 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
     float* E2 = reinterpret_cast<float*>(Pb + R * GT_ROW4);           // [NT][33][8] q^2 of the current tile
     float* Ev = E2 + NT * kF2 * 8;                                    // ring: R rows x 8 TRA energies
 
-    const int tid = threadIdx.x, b = blockIdx.y;
-    const int s0 = blockIdx.x * seg_len, s1 = min(T, s0 + seg_len);
-    if (s0 >= s1) return;
-    const int tw0 = max(0, s0 - GT_WARMUP);
-    zero_f4(reinterpret_cast<float*>(Pb), gt_smem_floats(PS, G), tid, GT_THREADS);
+    const int tid = threadIdx.x;
+    // Balanced segmentation (round 2): the (utterance, frame) space is flattened and CTA c walks frames [c seg_len, (c + 1) seg_len)
+    // of it -- every CTA gets the same amount of work whatever B is (with one grid row per utterance and equal segments the last
+    // wave was up to 30 % empty).  A range that crosses an utterance boundary restarts with zero history at t = 0 of the next
+    // utterance; a range that starts inside an utterance warms up on the 4 preceding frames as before (bit-identical).
+    const int64_t fl_end = min((int64_t)(blockIdx.x + 1) * seg_len, (int64_t)B * T);
     // weight source: kernel parameter (constant bank) or a shared-memory copy read with broadcast LDS.128
     float* Gt = Ev + R * 8;                                           // [NT][8] TRALite gates of the current tile
     float* wsm = Gt + NT * 8;
@@ -1024,10 +1026,18 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
         for (int i = tid; i < gt_chunk<DEC>(); i += GT_THREADS) wsm[i] = prm_c.w[i];
     const SmemWeights prm_s{static_cast<const float*>(__builtin_assume_aligned(wsm, 16))};
     const auto& prm = pick_weights<SMEM_W>(prm_s, prm_c);
-    __syncthreads();
-
     const bool act = tid < GT_ACTIVE;
     const int g = tid / kF2, f = tid - g * kF2;
+
+    for (int64_t fl = (int64_t)blockIdx.x * seg_len; fl < fl_end;) {
+    const int b = (int)(fl / T);
+    const int s0 = (int)(fl - (int64_t)b * T), s1 = (int)min((int64_t)T, s0 + (fl_end - fl));
+    fl += s1 - s0;
+    const int tw0 = max(0, s0 - GT_WARMUP);
+    __syncthreads();                                                  // the previous piece's last readers of the tile buffers are done
+    zero_f4(reinterpret_cast<float*>(Pb), gt_smem_floats(PS, G), tid, GT_THREADS);
+    __syncthreads();
+
     const int64_t ubase = (int64_t)b * T * kF2 * 16;
     int rb = 2;                                                       // ring row of slot 0 (rows 0,1: zero history)
 
@@ -1195,6 +1205,7 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
         rb -= (rb >= R) ? R : 0;
         // no barrier needed here: the next phase 1 only writes ring rows whose readers finished before the
         // barrier after phase 2, and every later writer of E2 / Ev / Gt is separated from this tile's readers by >= 2 barriers
+    }
     }
 }
 
@@ -1396,6 +1407,7 @@ k_gtcn(const float* __restrict__ xin, float* __restrict__ out, const __grid_cons
 // ================================================================================================
 constexpr int BK_NF = 8;
 constexpr int BK_THREADS = 288;
+constexpr int kAheadCtas = 3 * 148;              // resident CTAs of the per-frame kernels on a B200 (3 per SM): look-ahead distance of their L2 prefetches
 constexpr int BK_X4 = 4 * 35;                    // float4 per slot: [q][f + 1]
 constexpr int BK_Y4 = 4 * 67;                    // float4 per slot: [q][g + 1]
 constexpr int BK_M = 130 * 2;                    // floats per slot: [h][2] -- overlays X (dead after de3)
@@ -1537,6 +1549,20 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
             for (int qd = 0; qd < 4; ++qd) { u[s][qd] = pa[qd]; v[s][qd] = pb[qd]; }
         }
     }
+#ifndef GTCRNB_NO_AHEAD_PREFETCH
+    {
+        // CTAs start in blockIdx order as slots free up, so CTA blockIdx + kAheadCtas begins roughly when this one ends: pull its
+        // first operands (de2, en1 rows: what every thread of that CTA will wait for at its first barrier) from HBM into L2 now
+        const int64_t fa = fi0 + (int64_t)kAheadCtas * BK_NF;
+        if (fa < nframes && tid * 128 < BK_NF * kF2 * 64) {
+            const int64_t left = min((int64_t)BK_NF, nframes - fa) * kF2 * 64;
+            if (tid * 128 < left) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(de2 + fa * kF2 * 16) + tid * 128));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(en1 + fa * kF2 * 16) + tid * 128));
+            }
+        }
+    }
+#endif
     {
         const int nf = (int)min((int64_t)BK_NF, nframes - fi0);                      // frames of this CTA (contiguous rows)
         static_assert(BK_THREADS * 128 >= BK_NF * kF1 * 64 && BK_THREADS * 128 >= BK_NF * kSpecFrame * 4, "one 128-byte line per thread covers the rows");
