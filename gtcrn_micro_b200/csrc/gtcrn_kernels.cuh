@@ -583,7 +583,6 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
 #pragma unroll
             for (int q = 0; q < 8; ++q) xr0[q] = xr1[q] = 0.f;
         }
-        // (an L2 prefetch of the samples of the CTA one residency wave ahead, as k_back does for its operands, made this kernel 2 % slower)
         load_fft_tables_async(tb, blobp, tid, FR_THREADS);         // needed by the FFT right after the barrier
         cp_async_commit();
         copy_f4_async(W, blobp + LY::OFF, FR_W_FLOATS, tid, FR_THREADS);   // ERB / SFE tables: needed after the FFT phase
@@ -617,6 +616,22 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
                 fs[k] = make_float4(sqrtf(re * re + im * im + 1e-12f), re, im, 0.f);
             }
         }
+#ifndef GTCRNB_NO_AHEAD_PREFETCH
+        else {
+            // the two warps without a frame to transform pull the samples of the CTA that will take over this slot (kAheadCtas CTAs
+            // ahead, see k_back) from HBM into L2: 8 frames = 9 hops = 9 KB = 72 lines.  [Issued by all threads at kernel start
+            // this made the kernel 2 % slower; here it is free.]
+            const int64_t fa = fi0 + (int64_t)(3 * 148) * FR_NF;
+            const int i = tid - FR_NF * 32;
+            if (fa < nframes && nframes < (int64_t)1 << 31) {
+                const int ba = (int)fa / T, ta = (int)fa - ba * T;
+                for (int line = i; line < 74; line += FR_THREADS - FR_NF * 32) {
+                    const int64_t s_first = (int64_t)kHop * ta - kHop + (int64_t)line * 32;
+                    if (s_first >= 0 && s_first < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(wav + (int64_t)ba * wav_stride + s_first));
+                }
+            }
+        }
+#endif
         cp_async_wait_group<0>();                                  // ERB / SFE tables
         __syncthreads();
         for (int i = tid; i < FR_NF * 4; i += FR_THREADS) {       // sfe pad columns (its region held FFT buffer A until now)
