@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "../../include/gtcrn_b200.h"
@@ -666,7 +667,7 @@ HostSchedule host_schedule(int64_t B, int64_t L) {
     auto envi = [](const char* name, int dflt, int lo, int hi) { const char* e = getenv(name); return e ? std::max(lo, std::min(hi, atoi(e))) : dflt; };
     auto units = [&](int64_t u) { return std::max<int64_t>(1, (u * 160000) / L); };        // knobs are in 10-second-utterance equivalents
     HostSchedule s;
-    s.copy = units(envi("GTCRNB_HOST_COPY", 24, 1, 4096));
+    s.copy = units(envi("GTCRNB_HOST_COPY", 48, 1, 4096));
     const int64_t gmax = std::min<int64_t>({B, units(envi("GTCRNB_HOST_CHUNK", 384, 1, 65535)), std::max<int64_t>(1, kMaxChunkFrames / (1 + L / gk::kHop))});
     const int64_t g1 = std::min(gmax, units(envi("GTCRNB_HOST_G1", 48, 1, 65535))), gl = std::min(gmax, units(envi("GTCRNB_HOST_GLAST", 24, 1, 65535)));
     const double up = envi("GTCRNB_HOST_GROWTH", 200, 101, 1000) / 100.0, down = envi("GTCRNB_HOST_DECAY", 160, 101, 1000) / 100.0;
@@ -771,6 +772,7 @@ int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, 
     };
     int64_t b0 = 0;
     const int64_t is[4] = {T * gk::kSpecFrame, 2, gk::kSpecFrame, 1};
+    const auto t_enq0 = std::chrono::steady_clock::now();
     // (measured: no gain from a second walking-kernel stream -- every walking kernel is sized to fill the SMs in one wave; kept as a knob)
     const bool two_body = getenv("GTCRNB_HOST_BODY2") ? atoi(getenv("GTCRNB_HOST_BODY2")) != 0 : false;
     for (size_t g = 0; g < sch.groups.size(); b0 += sch.groups[g], ++g) {
@@ -824,11 +826,11 @@ int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, 
         // ---- backs, copies out
         CU(cudaStreamWaitEvent(h->s_back, h->ev_body[slot], 0));
         if (reuse) CU(cudaStreamWaitEvent(h->s_back, h->ev_d2h[slot], 0));  // output staging of group g - kStage drained
+        if (split) CU(cudaMemsetAsync(out_f, 0, sizeof(float) * ng * Lout, h->s_back));           // the fused iSTFT overlap-adds onto zeros
         for (int64_t u0 = 0; u0 < ng; u0 += cc) {
             const int64_t nu = std::min(cc, ng - u0);
             tbegin((int)g, nu, 3, h->s_back);
             if (split) {
-                CU(cudaMemsetAsync(out_f + u0 * Lout, 0, sizeof(float) * nu * Lout, h->s_back));   // the fused iSTFT overlap-adds onto zeros
                 const int rc = run_model(h, nullptr, is, ng, T, nullptr, is, h->s_back, nullptr, 0, (int)L, out_f, Lout, PH_BACK, u0, nu);
                 if (rc) return rc;
             }
@@ -848,6 +850,7 @@ int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, 
         CU(cudaEventRecord(h->ev_backs[slot], h->s_back));
         CU(cudaEventRecord(h->ev_d2h[slot], h->s_d2h));
     }
+    const double enq_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enq0).count();
     CU(cudaStreamSynchronize(h->s_d2h));
     CU(cudaStreamSynchronize(h->s_back));
     CU(cudaStreamSynchronize(h->s_body));
@@ -856,7 +859,7 @@ int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, 
     CU(cudaStreamSynchronize(h->s_h2d));
     if (trace) {
         static const char* const kKind[5] = {"h2d", "front", "body", "back", "d2h"};
-        fprintf(stderr, "groups:");
+        fprintf(stderr, "host enqueue of the whole schedule: %.3f ms\ngroups:", enq_ms);
         for (int64_t g : sch.groups) fprintf(stderr, " %lld", (long long)g);
         fprintf(stderr, "  copy chunk %lld\ngroup  utts  engine   start     end   (ms from the first H2D)\n", (long long)sch.copy);
         for (const auto& r : rows) {
