@@ -352,9 +352,38 @@ void launch_body_micro(gtcrnb_handle* h, int64_t B, int64_t T, cudaStream_t st) 
             const float* xi = h->act[5 + i]; const float* sk = h->act[3 - i]; float* xo = h->act[6 + i];
             int seg_i = seg, Bi = (int)B, Tl = Ti;
             void* nostate = nullptr; int blk0 = 0; long long n0 = 0;
+#ifdef GTCRNB_DEC_TRACE
+            static long long* trc_dev = nullptr;
+            if (!trc_dev) { cudaMalloc(&trc_dev, 8 * 32 * 12 * sizeof(long long)); }
+            cudaMemsetAsync(trc_dev, 0, 8 * 32 * 12 * sizeof(long long), st);
+            nostate = trc_dev;
+#endif
             void* args[] = {(void*)&xi, (void*)&sk, (void*)&xo, (void*)&h->hp->dec[i], (void*)&Tl, (void*)&seg_i, (void*)&Bi, (void*)&nostate, (void*)&blk0, (void*)&n0};
             cudaLaunchKernel(tc_dec_fn(nwg), g, dim3(128 * nwg), args, gtt_smem_floats(nwg) * sizeof(float), st);
             h->launches++;
+#ifdef GTCRNB_DEC_TRACE
+            if (i == 2 && getenv("GTCRNB_DEC_TRACE_PRINT")) {
+                std::vector<long long> hbuf(8 * 32 * 12);
+                cudaStreamSynchronize(st);
+                cudaMemcpy(hbuf.data(), trc_dev, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+                static const char* const names[12] = {"top", "loads", "pc1+split", "wait_st", "bar1", "issue", "gate", "mma_wait", "fetch+xchg", "bar2", "store", "epilogue"};
+                for (int row = 0; row < 8; ++row) {
+                    double acc[12] = {}; int n = 0;
+                    for (int k = 0; k + 1 < 32; ++k) {
+                        const long long* a = &hbuf[(row * 32 + k) * 12]; const long long* b = &hbuf[(row * 32 + k + 1) * 12];
+                        if (!a[0] || !b[0]) continue;
+                        for (int j = 0; j < 11; ++j) acc[j + 1] += (double)(a[j + 1] - a[j]);
+                        acc[0] += (double)(b[0] - a[11]);
+                        ++n;
+                    }
+                    if (!n) continue;
+                    double tot = 0; for (double v : acc) tot += v;
+                    fprintf(stderr, "wg %d thread %s: step %.0f cycles:", row / 2, row & 1 ? "row40" : "issuer", tot / n);
+                    for (int j = 0; j < 12; ++j) fprintf(stderr, " %s %.0f", j == 0 ? "loop" : names[j], acc[j] / n);
+                    fprintf(stderr, "\n");
+                }
+            }
+#endif
         }
     } else {
         const GtVariant& v = kGtVariants[h->gt_dec];
@@ -476,6 +505,18 @@ int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, 
         // without this the driver picks the smallest carveout that fits ONE CTA and occupancy collapses (ncu: occ_smem = 1)
         if (e == cudaSuccess) e = cudaFuncSetAttribute(a.fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { gtcrnb_destroy(h); return fail(GTCRNB_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); }
+    }
+    if (const char* e = getenv("GTCRNB_TC_DEC_CARVEOUT")) {        // percent of the maximum shared-memory carve-out for the decoder TC kernel (rest = L1)
+        const int pct = std::max(0, std::min(100, atoi(e)));
+        for (int nwg : {1, 2, 4, 5}) cudaFuncSetAttribute(tc_dec_fn(nwg), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
+    if (const char* e = getenv("GTCRNB_GT_ENC_CARVEOUT")) {
+        const int pct = std::max(0, std::min(100, atoi(e)));
+        for (const GtVariant& v : kGtVariants) cudaFuncSetAttribute(v.enc, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
+    if (const char* e = getenv("GTCRNB_TC_GTCN_CARVEOUT")) {
+        const int pct = std::max(0, std::min(100, atoi(e)));
+        for (int nwg : {1, 2, 4}) cudaFuncSetAttribute(tc_gtcn_fn(nwg, false), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
     int e2 = gs::stream_init_attributes();
     if (e2 != 0) { gtcrnb_destroy(h); return fail(GTCRNB_E_CUDA, "stream kernel attribute setup failed: %s", cudaGetErrorString((cudaError_t)e2)); }

@@ -359,6 +359,11 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
         tc::tmem_wait_st();
     }
     const uint64_t bdesc0 = tc::make_desc(tc::smem_u32(Bw), 768, 128);       // LBO = one k-chunk plane (48 rows x 16 B), SBO = 8 rows
+    // Who does what between the two barriers of a step (clock64 trace, tools/gpu_dec_trace.sh): issuing 9 MMAs + commit keeps one
+    // thread busy for ~1,000 cycles, the TRALite gate of the previous frame is a ~1,000-cycle dependent chain on 24 threads, and the
+    // MMAs complete ~50 cycles after the last one is issued.  Originally thread 0 did both one after the other (it is row (0, 0), one
+    // of the gate threads: 6,700 cycles per step).  Now thread 0 issues and the gate runs on lanes 0..23 of WARP 3, whose rows 99..127
+    // are idle: the two overlap, and warps 0-2 go straight to the completion wait.
     const bool issuer = tig == 0;
     const int bar_id = 1 + wg;
     uint64_t* bar = &bars[wg];
@@ -367,8 +372,9 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
     const bool active = tig < GTT_ROWS;
     const int rr = active ? tig : GTT_ROWS - 1;                          // idle lanes shadow the last row (no stores, no smem writes)
     const int g = rr / kF2, f = rr - g * kF2;
-    const bool is_gate_thread = active && f < 8;
-    const unsigned gmask = 0xFFu << ((g * kF2) & 31);                    // lanes of (g, c = 0..7): 33 g + c = g + c (mod 32)
+    const bool is_gate_thread = tig >= 96 && tig < 96 + 8 * GTT_G;       // warp 3, lanes 0..23: gate thread (gg, gc)
+    const int gg = is_gate_thread ? (tig - 96) >> 3 : 0, gc = tig & 7;
+    const unsigned gmask = 0xFFu << (8 * gg);
     constexpr int FS4 = kF2 * 4;                                         // float4 per frame
 
     // fp16 hi/lo split of a 16-channel row into ring slot `slot` of the A operand (8 columns of hi pairs, 8 of lo pairs)
@@ -455,8 +461,8 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
     float ea = 0.f, eb = 0.f;
     auto gate_phase = [&]() {
         if (is_gate_thread) {
-            const int c = f;
-            const float* e2c = E2 + g * kF2 * 8 + c;
+            const int c = gc;
+            const float* e2c = E2 + gg * kF2 * 8 + c;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
             for (int ff = 0; ff < 32; ff += 4) {
@@ -470,10 +476,10 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
             y = fmaf(Gw[16 + c], en, y);
             ea = eb; eb = en;
             float v = Gw[96 + c];
-            const int lane0 = (g * kF2) & 31;
+            const int lane0 = 8 * gg;
 #pragma unroll
             for (int ci = 0; ci < 8; ++ci) v = fmaf(Gw[32 + ci * 8 + c], __shfl_sync(gmask, y, lane0 + ci), v);
-            Gt[g * 8 + c] = 1.0f / (1.0f + expf(-v));
+            Gt[gg * 8 + c] = 1.0f / (1.0f + expf(-v));
         }
     };
     // gate, channel shuffle [q0 g0, x2_0, q1 g1, x2_1, ...], store
@@ -512,9 +518,10 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
                 float4 a[4], c[4], u2[4], u1[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) { a[v] = px[v]; c[v] = ps[v]; u2[v] = h2[v]; u1[v] = h1[v]; }
-                if (is_gate_thread) {
-                    ea = sb[gs::kTraE + blk * 16 + slot_old * 8 + f];
-                    eb = sb[gs::kTraE + blk * 16 + slot_mid * 8 + f];
+                if (is_gate_thread) {                                         // energy history of stream (tile, gg), channel gc
+                    const float* sg = gs::stream_base(state, min(tile * GTT_G + gg, N - 1));
+                    ea = sg[gs::kTraE + blk * 16 + slot_old * 8 + gc];
+                    eb = sg[gs::kTraE + blk * 16 + slot_mid * 8 + gc];
                 }
 #pragma unroll
                 for (int v = 0; v < 4; ++v) cx[v] = make_float4(a[v].x + c[v].x, a[v].y + c[v].y, a[v].z + c[v].z, a[v].w + c[v].w);
@@ -553,7 +560,7 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
             epilogue(m, q);
             tc::bar_sync(bar_id, 128);
             gate_phase();
-            if (is_gate_thread && valid) sb[gs::kTraE + blk * 16 + slot_old * 8 + f] = eb;
+            if (is_gate_thread && tile * GTT_G + gg < N) gs::stream_base(state, tile * GTT_G + gg)[gs::kTraE + blk * 16 + slot_old * 8 + gc] = eb;
             tc::bar_sync(bar_id, 128);
             if (valid) store_row(reinterpret_cast<float4*>(out + (n * kF2 + f) * 16), q, cx[2], cx[3]);
         }
@@ -575,19 +582,36 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
             float4 x2pa = make_float4(0.f, 0.f, 0.f, 0.f), x2pb = x2pa;
 #pragma unroll
             for (int c = 0; c < 8; ++c) qp[c] = 0.f;
-            for (int t = tw0; t < s1; ++t) {
-                float4 cx[4];                                             // x + skip of this frame (the next one is on its way to L2)
-                {
-                    float4 a[4], c[4];
+#ifdef GTCRNB_DEC_TRACE
+            long long* trc = reinterpret_cast<long long*>(state);
+            const bool tracer = trc && blockIdx.x == 0 && blockIdx.y == 0 && (tig == 0 || tig == 40) ;
+            const int trow = (tid >> 7) * 2 + (tig == 40);
+#define TRC(i) do { if (tracer && t >= tw0 + 16 && t < tw0 + 48) { long long c_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_)); trc[((trow * 32 + (t - tw0 - 16)) * 12) + (i)] = c_; } } while (0)
+#else
+#define TRC(i) do { } while (0)
+#endif
+            // The point-conv half (channels 0..7) of x and skip of the NEXT frame is requested right after the stores of step t, so that
+            // its L2 latency (~1,200 cycles on the trace) hides behind the epilogue instead of opening the next step; the pass-through
+            // half is requested at the top of its own step and only consumed at its end.  The frame after next is on its way to L2.
+            float4 a[2], c[2];
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) { a[v] = px[(int64_t)t * FS4 + v]; c[v] = ps[(int64_t)t * FS4 + v]; }
-                    if (t + 1 < s1) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(px + (int64_t)(t + 1) * FS4));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + (int64_t)(t + 1) * FS4));
+            for (int v = 0; v < 2; ++v) { a[v] = px[(int64_t)tw0 * FS4 + v]; c[v] = ps[(int64_t)tw0 * FS4 + v]; }
+            if (tw0 + 1 < s1) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(px + (int64_t)(tw0 + 1) * FS4));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + (int64_t)(tw0 + 1) * FS4));
+            }
+            for (int t = tw0; t < s1; ++t) {
+                TRC(0);
+                float4 cx[4];                                             // x + skip of this frame
+                {
+                    if (t + 2 < s1) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(px + (int64_t)(t + 2) * FS4));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + (int64_t)(t + 2) * FS4));
                     }
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) cx[v] = make_float4(a[v].x + c[v].x, a[v].y + c[v].y, a[v].z + c[v].z, a[v].w + c[v].w);
+                    for (int v = 0; v < 2; ++v) cx[v] = make_float4(a[v].x + c[v].x, a[v].y + c[v].y, a[v].z + c[v].z, a[v].w + c[v].w);
                 }
+                TRC(1);
                 // ---- point conv 1 on the first channel half, fp16 hi/lo split, into ring slot r of the A operand
                 {
                     const float x1[8] = {cx[0].x, cx[0].y, cx[0].z, cx[0].w, cx[1].x, cx[1].y, cx[1].z, cx[1].w};
@@ -595,19 +619,37 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
                     gt_pc1<true>(prm, x1, p);
                     store_slot(r, p);
                 }
+                TRC(2);
                 tc::tmem_wait_st();
                 tc::fence_before();
+                TRC(3);
                 tc::bar_sync(bar_id, 128);                                // A(t) complete; also: E2(t-1) visible to the gate threads
+                TRC(4);
                 if (issuer) issue_mmas(r);
+                TRC(5);
                 if (t > tw0) gate_phase();                                // frame t-1, while the tensor core works on frame t
+                TRC(6);
                 tc::mbar_wait(bar, parity);
                 parity ^= 1;
                 tc::fence_after();
+                TRC(7);
                 float m[16];
                 fetch_and_exchange(m);
+                TRC(8);
                 tc::bar_sync(bar_id, 128);                                // exchange buffer and the gate of frame t-1 are visible
+                TRC(9);
                 if (t > tw0 && store_ok && t - 1 >= s0) store_row(po + (int64_t)(t - 1) * FS4, qp, x2pa, x2pb);
+                TRC(10);
+                // pass-through half of THIS frame: only needed once the epilogue is done
+                const float4 a2 = px[(int64_t)t * FS4 + 2], a3 = px[(int64_t)t * FS4 + 3], c2 = ps[(int64_t)t * FS4 + 2], c3 = ps[(int64_t)t * FS4 + 3];
+                if (t + 1 < s1) {
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) { a[v] = px[(int64_t)(t + 1) * FS4 + v]; c[v] = ps[(int64_t)(t + 1) * FS4 + v]; }
+                }
                 epilogue(m, qp);
+                cx[2] = make_float4(a2.x + c2.x, a2.y + c2.y, a2.z + c2.z, a2.w + c2.w);
+                cx[3] = make_float4(a3.x + c3.x, a3.y + c3.y, a3.z + c3.z, a3.w + c3.w);
+                TRC(11);
                 x2pa = cx[2]; x2pb = cx[3];
                 r = r == 2 ? 0 : r + 1;
             }
