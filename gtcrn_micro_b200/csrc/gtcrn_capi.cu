@@ -684,6 +684,22 @@ int gtcrnb_enhance(gtcrnb_handle* h, const float* wav_dev, int64_t B, int64_t L,
         rc = gtcrnb_istft(h, h->spec_out, nb, T, out_dev + b0 * out_stride, out_stride, stream);
         if (rc) return rc;
     }
+#ifdef GTCRNB_FB_TRACE
+    if (getenv("GTCRNB_FB_TRACE_PRINT")) {
+        cudaStreamSynchronize((cudaStream_t)stream);
+        long long t[2][3][16];
+        cudaMemcpyFromSymbol(t, gk::g_fb_trace, sizeof(t));
+        static const char* const fn[15] = {"start", "loads issued", "bar(tables)", "FFT+feat", "bar", "pads", "bar", "ERB", "bar", "SFE", "bar", "en0", "bar", "en1 mma+epilogue", "bar"};
+        static const char* const bn[11] = {"start", "phase a (loads, x planes)", "bar", "de3", "bar", "de4", "bar", "mask", "iFFT prep", "iFFT", "OLA"};
+        for (int k = 0; k < 2; ++k)
+            for (int w = 0; w < 3; ++w) {
+                fprintf(stderr, "%s warp %d:", k ? "k_back" : "k_front", 4 * w);
+                const int n = k ? 11 : 15;
+                for (int i = 1; i < n; ++i) fprintf(stderr, " %s %lld |", k ? bn[i] : fn[i], t[k][w][i] && t[k][w][i - 1] ? t[k][w][i] - t[k][w][i - 1] : -1);
+                fprintf(stderr, " total %lld\n", t[k][w][n - 1] - t[k][w][0]);
+            }
+    }
+#endif
     note_user_work(h, (cudaStream_t)stream);
     return GTCRNB_OK;
 }

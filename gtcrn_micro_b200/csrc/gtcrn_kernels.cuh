@@ -360,6 +360,14 @@ __global__ void __launch_bounds__(256) k_istft(const float* __restrict__ spec, i
 // The weight matrices are identical for every CTA: k_prep_ends_tc builds them once per handle in the exact shared-memory layout
 // (no-swizzle K-major, [k chunk][n][8 halves]) and the kernels copy them with cp.async.
 // ================================================================================================
+#ifdef GTCRNB_FB_TRACE
+// phase timeline of ONE CTA of k_front / k_back in steady state (clock64 stamps of the first lane of warps 0, 4 and 8): tools/gpu_fb_trace.sh
+__device__ long long g_fb_trace[2][3][16];
+#define FBT(kern, i) do { if (blockIdx.x == 20000 && (threadIdx.x == 0 || threadIdx.x == 128 || threadIdx.x == 256)) { long long c_; \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_)); g_fb_trace[kern][threadIdx.x >> 7][i] = c_; } } while (0)
+#else
+#define FBT(kern, i) do { } while (0)
+#endif
 constexpr int TCW_EN1_WORDS = 5 * 384 + 4;      // 5 taps x ([2][32][8] + [2][16][8] halves) + {1 / s, 0, 0, 0}
 constexpr int TCW_DE3_WORDS = 3 * 768 + 4;      // 3 taps x 3 x [2][32][8] halves + {1 / s, 0, 0, 0}
 constexpr int TCW_WORDS = TCW_EN1_WORDS + TCW_DE3_WORDS;
@@ -550,6 +558,7 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
     float* slots = Btc + (TCE ? TCW_EN1_WORDS : 0);   // per slot: [feat | erb | sfe]; a0 overlays feat|erb (TCE: regrouped, see featp)
     const int tid = threadIdx.x;
     const int64_t fi0 = (int64_t)blockIdx.x * FR_NF;              // first flattened frame (b * T + t) of this CTA
+    FBT(0, 0);
     auto featp = [&](int s_) { return TCE ? slots + s_ * FR_FEAT : slots + s_ * FR_SLOT; };
     auto erbp = [&](int s_) { return TCE ? slots + FR_NF * FR_FEAT + s_ * FR_ERB : slots + s_ * FR_SLOT + FR_FEAT; };
     auto sfep = [&](int s_) { return TCE ? slots + FR_NF * (FR_FEAT + FR_ERB) + s_ * FR_SFE : slots + s_ * FR_SLOT + FR_FEAT + FR_ERB; };
@@ -589,7 +598,9 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
         if (TCE) copy_f4_async(Btc, reinterpret_cast<const float*>(tcw), TCW_EN1_WORDS, tid, FR_THREADS);
         cp_async_commit();
         cp_async_wait_group<1>();
+    FBT(0, 1);
         __syncthreads();
+    FBT(0, 2);
         if (warp < FR_NF) {                                        // (only __syncwarp inside)
             const int slot = warp;
             const int64_t fi = fi_w;
@@ -633,7 +644,9 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
         }
 #endif
         cp_async_wait_group<0>();                                  // ERB / SFE tables
+    FBT(0, 3);
         __syncthreads();
+    FBT(0, 4);
         for (int i = tid; i < FR_NF * 4; i += FR_THREADS) {       // sfe pad columns (its region held FFT buffer A until now)
             float4* sfe4 = reinterpret_cast<float4*>(sfep(i >> 2));
             const int c = i & 3;                                  // padded bins 0, 1, 131, 132 -> (parity, entry)
@@ -674,7 +687,9 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
         }
         cp_async_wait_all();
     }
+    FBT(0, 5);
     __syncthreads();
+    FBT(0, 6);
     // ---- b: ERB compress (sparse triangular bank, <= 12 contiguous taps per band): thread = (band, slot pair); each tap weight
     //      is loaded once and applied to the (mag, re, im) float4 of two slots.  The 65 low bins are used in place (no copy).
     if (tid < 64 * (FR_NF / 2)) {
@@ -693,7 +708,9 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
         reinterpret_cast<float4*>(erbp(2 * sp2))[bnd] = a0;
         reinterpret_cast<float4*>(erbp(2 * sp2 + 1))[bnd] = a1;
     }
+    FBT(0, 7);
     __syncthreads();
+    FBT(0, 8);
     // ---- c: SFE-Lite (depthwise 3-tap along the 129 compressed bins, zero padded, no bias)
     {
         const float* sw = W + blob::FRONT_SFE_W;                   // [c][k]
@@ -716,7 +733,9 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
             reinterpret_cast<float4*>(sfep(slot))[(c & 1) * 67 + (c >> 1)] = v;
         }
     }
+    FBT(0, 9);
     __syncthreads();
+    FBT(0, 10);
     // ---- d: en0  (thread = 2 slots x 16 co at one f').  Output a0 overlays the dead feat|erb region; its pad bins are zeroed here.
     if (TCE) {
         // pad rows of the fp16 planes: entries 0 and 34 of both parities and entry 33 of the odd one (padded bins 0, 1, 67, 68 and
@@ -826,7 +845,9 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
         // ---- e (tensor cores): en1 = 5 taps x (hi' [W_hi | W_lo], lo W_hi) per 128-row tile; tap k reads parity plane k & 1 shifted
         //      by k >> 1 rows.  Accumulator of tile i: TMEM columns 32 i .. 32 i + 31 (hi' W_hi + lo W_hi | hi' W_lo).
         tc::fence_async_smem();                                    // the planes (generic-proxy stores) and the cp.async'ed weights
+    FBT(0, 11);
         __syncthreads();
+    FBT(0, 12);
         tc::fence_after();
         const uint32_t tm = tmem_base_s;
         if (tid == 0) {
@@ -872,7 +893,9 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
             }
         }
         tc::fence_before();
+    FBT(0, 13);
         __syncthreads();
+    FBT(0, 14);
         if (tid < 32) tc::tmem_dealloc(tm, 128);
     } else {
     __syncthreads();
@@ -1548,29 +1571,40 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
     constexpr int M_STRIDE = BK_X4 * 4;
     const int tid = threadIdx.x;
     const int64_t fi0 = (int64_t)blockIdx.x * BK_NF;
+    FBT(1, 0);
 
-    // ---- a: x = de2 + en1 into X.  The loads are issued first, the table copies run while they are in flight, and the
-    //      operands this CTA needs much later (en0 skip rows for de3, the spectrum for the mask) are pulled towards L2 now
-    //      (ncu r1_v13: 12 % of the kernel's samples were long_scoreboard on exactly those three consumers).
-    const bool loader = tid < (BK_NF / 2) * kF2;
-    const int sp2_a = tid / kF2, f_a = tid - sp2_a * kF2;
-    float4 u[2][4], v[2][4];
-    if (loader) {
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const int slot = 2 * sp2_a + s;
-            const bool ok = fi0 + slot < nframes;
-            const int64_t off = ((fi0 + (ok ? slot : 0)) * kF2 + f_a) * 16;
-            const float4* pa = reinterpret_cast<const float4*>(de2 + off);
-            const float4* pb = reinterpret_cast<const float4*>(en1 + off);
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) { u[s][qd] = pa[qd]; v[s][qd] = pb[qd]; }
+    // ---- a: x = de2 + en1 into X.  The two input tiles of a CTA are contiguous 16.9 KB blocks and the tables are the same for
+    //      every CTA: ONE thread moves all of it with 1-D bulk copies (TMA, cp.async.bulk -> SASS UBLKCP) into shared memory -- the
+    //      tiles into the Y3 region, which is dead until de3 writes it -- and everybody waits on the copies' mbarrier.  [Per-thread
+    //      LDG.128 + cp.async of the same bytes: 2,700 requests per CTA through the LSU; the clock64 trace (tools/gpu_fb_trace.sh)
+    //      showed this phase taking 9,800 of a CTA's 34,000 cycles.]  The operands this CTA needs much later (en0 skip rows for de3,
+    //      the spectrum for the mask) are pulled towards L2 now, and so are the tiles of the CTA one residency wave ahead.
+    __shared__ __align__(8) uint64_t ld_bar;
+    const int nf_a = (int)min((int64_t)BK_NF, nframes - fi0);                        // frames of this CTA (contiguous rows)
+    if (tid == 0) {
+        tc::mbar_init(&ld_bar, 1);
+        tc::fence_barrier_init();
+        const uint32_t tile_bytes = (uint32_t)nf_a * kF2 * 64, fft_bytes = TO_WAV ? 2048u + 2064u + 2048u + 1024u : 0u;
+        tc::mbar_expect_tx(&ld_bar, 2 * tile_bytes + BK_W_FLOATS * 4 + fft_bytes);
+        tc::bulk_g2s(Y3, de2 + fi0 * kF2 * 16, tile_bytes, &ld_bar);
+        tc::bulk_g2s(reinterpret_cast<char*>(Y3) + BK_NF * kF2 * 64, en1 + fi0 * kF2 * 16, tile_bytes, &ld_bar);
+        tc::bulk_g2s(Wsm, blobp + LY::OFF + BK_W_OFF, BK_W_FLOATS * 4, &ld_bar);     // de4 / inverse-ERB tables
+        if (TO_WAV) {                                                                // iSTFT tables: FftTables order + 1 / envelope
+            FftTables& tb0 = *reinterpret_cast<FftTables*>(Wsm + bk_smem_floats(false));
+            const float* fb = blobp + blob::FFT_OFF;
+            tc::bulk_g2s(tb0.tw256, fb + blob::FFT_TW256, 2048, &ld_bar);
+            tc::bulk_g2s(tb0.tw512, fb + blob::FFT_TW512, 2064, &ld_bar);
+            tc::bulk_g2s(tb0.win, fb + blob::FFT_WIN, 2048, &ld_bar);
+            tc::bulk_g2s(reinterpret_cast<float*>(&tb0) + FR_FFT_FLOATS, fb + blob::FFT_INV_ENV, 1024, &ld_bar);
         }
     }
+    static_assert(BK_NF * BK_Y4 * 16 >= 2 * BK_NF * kF2 * 64 && sizeof(FftTables) == 2048 + 2064 + 2048, "staging fits the Y3 region; table sizes");
+    const bool loader = tid < (BK_NF / 2) * kF2;
+    const int sp2_a = tid / kF2, f_a = tid - sp2_a * kF2;
 #ifndef GTCRNB_NO_AHEAD_PREFETCH
     {
         // CTAs start in blockIdx order as slots free up, so CTA blockIdx + kAheadCtas begins roughly when this one ends: pull its
-        // first operands (de2, en1 rows: what every thread of that CTA will wait for at its first barrier) from HBM into L2 now
+        // tiles from HBM into L2 now
         const int64_t fa = fi0 + (int64_t)kAheadCtas * BK_NF;
         if (fa < nframes && tid * 128 < BK_NF * kF2 * 64) {
             const int64_t left = min((int64_t)BK_NF, nframes - fa) * kF2 * 64;
@@ -1583,44 +1617,49 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
     }
 #endif
     {
-        const int nf = (int)min((int64_t)BK_NF, nframes - fi0);                      // frames of this CTA (contiguous rows)
         static_assert(BK_THREADS * 128 >= BK_NF * kF1 * 64 && BK_THREADS * 128 >= BK_NF * kSpecFrame * 4, "one 128-byte line per thread covers the rows");
-        if (tid * 128 < nf * kF1 * 64)
+        if (tid * 128 < nf_a * kF1 * 64)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(en0 + fi0 * kF1 * 16) + tid * 128));
-        if (TO_WAV && tid * 128 < nf * kSpecFrame * 4)                               // fused mode: spec is the contiguous [frame][257][2] buffer
+        if (TO_WAV && tid * 128 < nf_a * kSpecFrame * 4)                             // fused mode: spec is the contiguous [frame][257][2] buffer
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(spec + fi0 * kSpecFrame) + tid * 128));
     }
-    // tables (de4 / inverse-ERB weights, iSTFT tables) are not needed before de4: asynchronous copies that land during de3
-    copy_f4_async(Wsm, blobp + LY::OFF + BK_W_OFF, BK_W_FLOATS, tid, BK_THREADS);
-    if (TO_WAV) {
-        FftTables& tb0 = *reinterpret_cast<FftTables*>(Wsm + bk_smem_floats(false));
-        load_fft_tables_async(tb0, blobp, tid, BK_THREADS);
-        copy_f4_async(reinterpret_cast<float*>(&tb0) + FR_FFT_FLOATS, blobp + blob::FFT_OFF + blob::FFT_INV_ENV, 256, tid, BK_THREADS);
+    for (int i = tid; i < BK_NF * 8; i += BK_THREADS) {            // zero pad columns 0 and 34 of X (those of Y3 follow once the staging is consumed)
+        const int slot = i >> 3, q = (i >> 1) & 3, side = i & 1;
+        X[slot * BK_X4 + q * 35 + (side ? 34 : 0)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    __syncthreads();                                               // the mbarrier is initialised for everybody
+    tc::mbar_wait(&ld_bar, 0);
     if (loader) {
+        const float4* sa = reinterpret_cast<const float4*>(Y3);
+        const float4* sb_ = sa + BK_NF * kF2 * 4;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const int slot = 2 * sp2_a + s;
+            const int o = (slot * kF2 + f_a) * 4;
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd)
-                X[slot * BK_X4 + qd * 35 + f_a + 1] = make_float4(u[s][qd].x + v[s][qd].x, u[s][qd].y + v[s][qd].y, u[s][qd].z + v[s][qd].z, u[s][qd].w + v[s][qd].w);
+            for (int qd = 0; qd < 4; ++qd) {
+                const float4 u = sa[o + qd], v = sb_[o + qd];
+                X[slot * BK_X4 + qd * 35 + f_a + 1] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+            }
         }
     }
-    for (int i = tid; i < BK_NF * 8; i += BK_THREADS) {            // zero pad columns of X (0, 34) and Y3 (0, 66)
+    FBT(1, 1);
+    __syncthreads();
+    FBT(1, 2);
+    // ---- b: de3: even output bins on warps 0-4 (132 of 160 lanes), odd bins on warps 5-8 (128 lanes)
+    for (int i = tid; i < BK_NF * 8; i += BK_THREADS) {            // pad columns 0 and 66 of Y3 (the staged tiles are consumed)
         const int slot = i >> 3, q = (i >> 1) & 3, side = i & 1;
-        X[slot * BK_X4 + q * 35 + (side ? 34 : 0)] = make_float4(0.f, 0.f, 0.f, 0.f);
         Y3[slot * BK_Y4 + q * 67 + (side ? 66 : 0)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncthreads();
-    // ---- b: de3: even output bins on warps 0-4 (132 of 160 lanes), odd bins on warps 5-8 (128 lanes)
     if (tid < 160) {
         if (tid < (BK_NF / 2) * 33) back_de3<0, VAR>(prm, X, Y3, tid / 33, tid % 33, fi0, nframes, en0);
     } else {
         const int r = tid - 160;
         back_de3<1, VAR>(prm, X, Y3, r >> 5, r & 31, fi0, nframes, en0);
     }
-    cp_async_wait_all();                                           // this thread's share of the table copies has landed
+    FBT(1, 3);
     __syncthreads();
+    FBT(1, 4);
     // ---- c: de4 (16 -> 2) + tanh -> mask on the 129 compressed bins: even bins (65) on warps 0-4, odd bins (64) on warps 5-8
     static_assert(BK_NF == 8, "de4 mapping assumes two groups of four slots");
     if (tid < 160) {
@@ -1629,7 +1668,9 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
         const int r = tid - 160;
         back_de4<1, VAR>(prm, Y3, M, M_STRIDE, r >> 6, r & 63);
     }
+    FBT(1, 5);
     __syncthreads();
+    FBT(1, 6);
     // ---- d: ERB expand + complex ratio mask (+ e: fused iSTFT).  mask(i) on the 257 spectrum bins from the 129 compressed ones.
     const int* ib0 = reinterpret_cast<const int*>(W + LY::IERB_B0);
     const float* iw = W + LY::IERB_W;
@@ -1697,6 +1738,7 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
                 }
             }
             __syncwarp();
+            FBT(1, 7);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int k = lane + 32 * q;                        // 0..255
@@ -1709,7 +1751,9 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
                 A[k] = valid ? make_float2(0.5f * (xk.x + xc.x) - 0.5f * bq, -(0.5f * (xk.y + xc.y) + 0.5f * a)) : make_float2(0.f, 0.f);
             }
             __syncwarp();
+            FBT(1, 8);
             fft256_warp(A, Bf, tb.tw256, lane);
+            FBT(1, 9);
             if (valid) {
                 float* o = wav_out + b * wav_stride + (int64_t)(t - 1) * kHop;      // frame t covers output samples 256 (t-1) .. 256 (t+1)
 #pragma unroll
@@ -1727,6 +1771,7 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
             }
         }
     }
+    FBT(1, 10);
 }
 
 // ================================================================================================

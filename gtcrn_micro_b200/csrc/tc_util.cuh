@@ -71,6 +71,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
                  "@!p bra WAIT_%=;\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// 1-D bulk copy global -> shared through the TMA unit (SASS UBLKCP): one instruction moves `bytes` (multiple of 16, both addresses
+// 16-byte aligned) and signals `bar` with the byte count; the issuing thread announces the total with mbar_expect_tx first
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
