@@ -562,6 +562,24 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
     auto featp = [&](int s_) { return TCE ? slots + s_ * FR_FEAT : slots + s_ * FR_SLOT; };
     auto erbp = [&](int s_) { return TCE ? slots + FR_NF * FR_FEAT + s_ * FR_ERB : slots + s_ * FR_SLOT + FR_FEAT; };
     auto sfep = [&](int s_) { return TCE ? slots + FR_NF * (FR_FEAT + FR_ERB) + s_ * FR_SFE : slots + s_ * FR_SLOT + FR_FEAT + FR_ERB; };
+    // tables (FFT twiddles / window, ERB / SFE tables, en1 weight matrices): identical for every CTA, moved by ONE thread with 1-D TMA
+    // bulk copies (was 1,100 cp.async requests per CTA; the clock64 trace showed 5,700 of a CTA's 34,000 cycles waiting for them)
+    __shared__ __align__(8) uint64_t tb_bar;
+    if (tid == 64) {
+        tc::mbar_init(&tb_bar, 1);
+        tc::fence_barrier_init();
+        tc::mbar_expect_tx(&tb_bar, FR_W_FLOATS * 4 + (TCE ? TCW_EN1_WORDS * 4 : 0) + (FROM_WAV ? FR_FFT_FLOATS * 4 : 0));
+        if (FROM_WAV) {
+            FftTables& tb0 = *reinterpret_cast<FftTables*>(slots + FR_NF * FR_SLOT);
+            const float* fb = blobp + LY::FFT;
+            tc::bulk_g2s(tb0.tw256, fb + blob::FFT_TW256, 2048, &tb_bar);
+            tc::bulk_g2s(tb0.tw512, fb + blob::FFT_TW512, 2064, &tb_bar);
+            tc::bulk_g2s(tb0.win, fb + blob::FFT_WIN, 2048, &tb_bar);
+        }
+        tc::bulk_g2s(W, blobp + LY::OFF, FR_W_FLOATS * 4, &tb_bar);
+        if (TCE) tc::bulk_g2s(Btc, tcw, TCW_EN1_WORDS * 4, &tb_bar);
+    }
+    static_assert(FR_W_FLOATS % 4 == 0 && TCW_EN1_WORDS % 4 == 0 && FR_FFT_FLOATS * 4 == 2048 + 2064 + 2048, "bulk copy sizes are multiples of 16 bytes");
     if (TCE) {
         if (tid < 32) { tc::tmem_alloc(&tmem_base_s, 128); tc::fence_before(); }     // 3 tiles x 32 accumulator columns
         if (tid == 32) { for (int i = 0; i < 3; ++i) tc::mbar_init(&tc_bars[i], 1); tc::fence_async_smem(); }
@@ -592,14 +610,9 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
 #pragma unroll
             for (int q = 0; q < 8; ++q) xr0[q] = xr1[q] = 0.f;
         }
-        load_fft_tables_async(tb, blobp, tid, FR_THREADS);         // needed by the FFT right after the barrier
-        cp_async_commit();
-        copy_f4_async(W, blobp + LY::OFF, FR_W_FLOATS, tid, FR_THREADS);   // ERB / SFE tables: needed after the FFT phase
-        if (TCE) copy_f4_async(Btc, reinterpret_cast<const float*>(tcw), TCW_EN1_WORDS, tid, FR_THREADS);
-        cp_async_commit();
-        cp_async_wait_group<1>();
     FBT(0, 1);
-        __syncthreads();
+        __syncthreads();                                           // the tables' mbarrier is initialised for everybody
+        tc::mbar_wait(&tb_bar, 0);
     FBT(0, 2);
         if (warp < FR_NF) {                                        // (only __syncwarp inside)
             const int slot = warp;
@@ -643,7 +656,6 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
             }
         }
 #endif
-        cp_async_wait_group<0>();                                  // ERB / SFE tables
     FBT(0, 3);
         __syncthreads();
     FBT(0, 4);
@@ -670,8 +682,6 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
                 else { re[i] = p[0]; im[i] = p[sc]; }
             }
         }
-        copy_f4_async(W, blobp + LY::OFF, FR_W_FLOATS, tid, FR_THREADS);
-        if (TCE) copy_f4_async(Btc, reinterpret_cast<const float*>(tcw), TCW_EN1_WORDS, tid, FR_THREADS);
         for (int i = tid; i < FR_NF * 4; i += FR_THREADS) {
             float4* sfe4 = reinterpret_cast<float4*>(sfep(i >> 2));
             const int c = i & 3;                                  // padded bins 0, 1, 131, 132 -> (parity, entry)
@@ -685,10 +695,10 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
                 reinterpret_cast<float4*>(featp(slot))[k] = make_float4(sqrtf(re[i] * re[i] + im[i] * im[i] + 1e-12f), re[i], im[i], 0.f);
             }
         }
-        cp_async_wait_all();
     }
     FBT(0, 5);
     __syncthreads();
+    if (!FROM_WAV) tc::mbar_wait(&tb_bar, 0);                      // ERB / SFE tables (and the en1 matrices) have landed
     FBT(0, 6);
     // ---- b: ERB compress (sparse triangular bank, <= 12 contiguous taps per band): thread = (band, slot pair); each tap weight
     //      is loaded once and applied to the (mag, re, im) float4 of two slots.  The 65 low bins are used in place (no copy).
