@@ -60,7 +60,7 @@ struct gtcrnb_handle {
     int tcn_p = 2;                                // frame slots per lane of the GTCN kernel (2..4)
     // tensor-core (tcgen05, 3xTF32) kernels: bit 0 GTCN pointwise convs, bit 1 decoder GTConv 3x3 (GTCRNB_TC, default both);
     // 0 selects the FFMA kernels, whose results are bit-identical to the streaming path
-    int tc_mask = 7;                              // bit 2: en1 (k_front) and de3 (k_back) as tcgen05 MMAs (round 2)
+    int tc_mask = 15;                             // bit 2: en1 (k_front), bit 3: de3 (k_back) as tcgen05 MMAs (round 2)
     uint32_t* tcw = nullptr;                      // their fp16 hi / lo weight matrices (k_prep_ends_tc)
     int tc_gtcn_nwg = 1;                          // warpgroups per CTA of k_gtcn_tc (GTCRNB_TC_GTCN_NWG: 1, 2 or 4)
     int occ_tcn_tc = 1;
@@ -287,8 +287,22 @@ void launch_back(gtcrnb_handle* h, const HP& hp, const float* spec, const int64_
     const float* de2 = h->act[8] + f0 * kF2 * 16;
     const float* en1 = h->act[0] + f0 * kF2 * 16;
     const float* en0 = h->en0 + f0 * kF1 * 16;
+    const int64_t ss[4] = {T * kSpecFrame, 2, kSpecFrame, 1};
+    if constexpr (VAR == 0) {
+        if (h->tc_mask & 8) {
+            if (fused)
+                k_back<true, 0, true><<<gbk, BK_THREADS, bk_smem_floats(true, true) * sizeof(float), st>>>(de2, en1, en0, h->spec_in + f0 * kSpecFrame, ss[0], ss[1], ss[2], ss[3],
+                                                                                                           nullptr, 0, 0, 0, 0, wav_out + u0 * wav_out_stride, wav_out_stride,
+                                                                                                           (int)T, nframes, h->blob, hp.back, h->tcw);
+            else
+                k_back<false, 0, true><<<gbk, BK_THREADS, bk_smem_floats(false, true) * sizeof(float), st>>>(de2, en1, en0, spec + u0 * is[0], is[0], is[1], is[2], is[3],
+                                                                                                             out + u0 * os[0], os[0], os[1], os[2], os[3], nullptr, 0,
+                                                                                                             (int)T, nframes, h->blob, hp.back, h->tcw);
+            h->launches++;
+            return;
+        }
+    }
     if (fused) {
-        const int64_t ss[4] = {T * kSpecFrame, 2, kSpecFrame, 1};
         k_back<true, VAR><<<gbk, BK_THREADS, bk_smem_floats(true) * sizeof(float), st>>>(de2, en1, en0, h->spec_in + f0 * kSpecFrame, ss[0], ss[1], ss[2], ss[3],
                                                                                           nullptr, 0, 0, 0, 0, wav_out + u0 * wav_out_stride, wav_out_stride,
                                                                                           (int)T, nframes, h->blob, hp.back);
@@ -387,12 +401,12 @@ void launch_body_micro(gtcrnb_handle* h, int64_t B, int64_t T, cudaStream_t st) 
         }
     } else {
         const GtVariant& v = kGtVariants[h->gt_dec];
-        const FlatSeg fs = pick_flat(B, Ti, GT_WARMUP, (int64_t)h->sm_count * h->occ_gt_dec, h->seg_waves);
-        const dim3 g(fs.ctas);
+        const int seg = pick_seg_len(B, Ti, v.ps, GT_WARMUP, h->sm_count * h->occ_gt_dec);
+        const dim3 g((unsigned)((Ti + seg - 1) / seg), (unsigned)B);
         for (int i = 0; i < 3; ++i) {
             // de_i consumes (previous + en_outs[4 - i]) : skips en4, en3, en2 = act[3], act[2], act[1]
             ProfScope ps(h, KC_DEC_GT, nframes, st);
-            launch_gtconv<true>(v, g, st, h->act[5 + i], h->act[3 - i], h->act[6 + i], h->hp->dec[i], Ti, fs.len, (int)B);
+            launch_gtconv<true>(v, g, st, h->act[5 + i], h->act[3 - i], h->act[6 + i], h->hp->dec[i], Ti, seg, (int)B);
             h->launches++;
         }
     }
@@ -489,6 +503,7 @@ int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, 
         {(const void*)k_front<false, 0, true>, fr_smem_floats(false, true)}, {(const void*)k_front<true, 0, true>, fr_smem_floats(true, true)},
         {(const void*)k_gtcn<2, false>, wc_smem_floats(2)}, {(const void*)k_gtcn<2, true>, wc_smem_floats(2, true)},
         {(const void*)k_back<false, 0>, bk_smem_floats(false)}, {(const void*)k_back<true, 0>, bk_smem_floats(true)},
+        {(const void*)k_back<false, 0, true>, bk_smem_floats(false, true)}, {(const void*)k_back<true, 0, true>, bk_smem_floats(true, true)},
         {(const void*)k_stft, 0},
         {(const void*)k_istft, 0},
         {tc_gtcn_fn(1, false), tct_smem_floats(1)}, {tc_gtcn_fn(2, false), tct_smem_floats(2)}, {tc_gtcn_fn(4, false), tct_smem_floats(4)},
@@ -547,12 +562,13 @@ int gtcrnb_create_variant(const float* blob_host, size_t n_floats, int variant, 
     if (const char* e = getenv("GTCRNB_STREAM_GRAPH")) h->stream_graphs = atoi(e) != 0;
     if (const char* e = getenv("GTCRNB_TC")) h->tc_mask = atoi(e);
     if (const char* e = getenv("GTCRNB_SEG_WAVES")) h->seg_waves = std::max(1, std::min(64, atoi(e)));
-    if (h->tc_mask & 4) {
+    if (h->tc_mask & 12) {
         if (cudaMalloc(&h->tcw, sizeof(uint32_t) * gk::TCW_WORDS) != cudaSuccess) { cudaGetLastError(); gtcrnb_destroy(h); return fail(GTCRNB_E_NOMEM, "cudaMalloc(tcw) failed"); }
         gk::k_prep_ends_tc<<<1, 256>>>(h->blob, h->tcw);
         if (cudaDeviceSynchronize() != cudaSuccess) { gtcrnb_destroy(h); return fail(GTCRNB_E_CUDA, "k_prep_ends_tc failed: %s", cudaGetErrorString(cudaGetLastError())); }
     }
     h->hp->tc_ends = (h->tc_mask & 4) != 0;
+    h->hp->tc_back = (h->tc_mask & 8) != 0;
     if (const char* e = getenv("GTCRNB_STREAM_FUSE_ENC")) h->hp->fuse_enc = atoi(e) != 0;
     h->hp->tcw = h->tcw;
     // streaming: the decoder blocks of a hop follow the offline choice (bit 1) unless GTCRNB_TC_STREAM=0
@@ -698,6 +714,14 @@ int gtcrnb_enhance(gtcrnb_handle* h, const float* wav_dev, int64_t B, int64_t L,
                 for (int i = 1; i < n; ++i) fprintf(stderr, " %s %lld |", k ? bn[i] : fn[i], t[k][w][i] && t[k][w][i - 1] ? t[k][w][i] - t[k][w][i - 1] : -1);
                 fprintf(stderr, " total %lld\n", t[k][w][n - 1] - t[k][w][0]);
             }
+        long long g[4][16];
+        cudaMemcpyFromSymbol(g, gk::g_tcn_trace, sizeof(g));
+        static const char* const gn[8] = {"", "conv1: split, st, bar, MMAs, wait", "ld + bias + PReLU", "Y store", "depthwise taps", "conv3: split, st, bar, MMAs, wait", "history", "ld + residual + PReLU"};
+        for (int w = 0; w < 4; ++w) {
+            fprintf(stderr, "k_gtcn_tc warp %d (one TCN of a 32-frame tile):", w);
+            for (int i = 1; i < 8; ++i) fprintf(stderr, " %s %lld |", gn[i], g[w][i] - g[w][i - 1]);
+            fprintf(stderr, " total %lld\n", g[w][7] - g[w][0]);
+        }
     }
 #endif
     note_user_work(h, (cudaStream_t)stream);

@@ -1066,7 +1066,10 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
     // of it -- every CTA gets the same amount of work whatever B is (with one grid row per utterance and equal segments the last
     // wave was up to 30 % empty).  A range that crosses an utterance boundary restarts with zero history at t = 0 of the next
     // utterance; a range that starts inside an utterance warms up on the 4 preceding frames as before (bit-identical).
-    const int64_t fl_end = min((int64_t)(blockIdx.x + 1) * seg_len, (int64_t)B * T);
+    // (The FFMA decoder instantiation keeps one grid row per utterance and one segment per CTA: with the extra loop level ptxas fell
+    //  back to per-thread-indexed constant loads and spills for its 2,304-weight contraction -- tests/test_build_static.py.)
+    const int64_t fl_begin = DEC ? (int64_t)blockIdx.y * T + (int64_t)blockIdx.x * seg_len : (int64_t)blockIdx.x * seg_len;
+    const int64_t fl_end = DEC ? min(fl_begin + seg_len, (int64_t)(blockIdx.y + 1) * T) : min(fl_begin + seg_len, (int64_t)B * T);
     // weight source: kernel parameter (constant bank) or a shared-memory copy read with broadcast LDS.128
     float* Gt = Ev + R * 8;                                           // [NT][8] TRALite gates of the current tile
     float* wsm = Gt + NT * 8;
@@ -1077,9 +1080,11 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
     const bool act = tid < GT_ACTIVE;
     const int g = tid / kF2, f = tid - g * kF2;
 
-    for (int64_t fl = (int64_t)blockIdx.x * seg_len; fl < fl_end;) {
-    const int b = (int)(fl / T);
-    const int s0 = (int)(fl - (int64_t)b * T), s1 = (int)min((int64_t)T, s0 + (fl_end - fl));
+    int64_t fl = fl_begin;
+    if (DEC && fl >= fl_end) return;
+    do {
+    const int b = DEC ? (int)blockIdx.y : (int)(fl / T);
+    const int s0 = DEC ? (int)(blockIdx.x * seg_len) : (int)(fl - (int64_t)b * T), s1 = (int)min((int64_t)T, s0 + (fl_end - fl));
     fl += s1 - s0;
     const int tw0 = max(0, s0 - GT_WARMUP);
     __syncthreads();                                                  // the previous piece's last readers of the tile buffers are done
@@ -1254,7 +1259,7 @@ k_gtconv(const float* __restrict__ xin, const float* __restrict__ skip, float* _
         // no barrier needed here: the next phase 1 only writes ring rows whose readers finished before the
         // barrier after phase 2, and every later writer of E2 / Ev / Gt is separated from this tile's readers by >= 2 barriers
     }
-    }
+    } while (!DEC && fl < fl_end);
 }
 
 // ================================================================================================
@@ -1467,7 +1472,11 @@ constexpr int BK_FFT_FLOATS = FR_FFT_FLOATS + 256;        // FftTables + 1/envel
 constexpr int BK_W_FLOATS = blob::BACK_SIZE - blob::BACK_DE4_W;   // only de4 / inverse-ERB tables go to shared memory (non-uniform indices);
                                                                   // the de3 weights are a kernel parameter
 static_assert(BK_W_FLOATS == blobf::BACK_SIZE - blobf::BACK_DE4_W, "both variants copy the same number of table floats");
-__host__ __device__ constexpr int bk_smem_floats(bool to_wav) { return BK_W_FLOATS + BK_NF * (BK_X4 * 4 + BK_Y4 * 4) + (to_wav ? BK_FFT_FLOATS : 0); }
+__host__ __device__ constexpr int bk_smem_floats(bool to_wav, bool tcb = false) {
+    return BK_W_FLOATS + (tcb ? TCW_DE3_WORDS : 0) + BK_NF * (BK_X4 * 4 + BK_Y4 * 4) + (to_wav ? BK_FFT_FLOATS : 0);
+}
+constexpr int TCB_PLANE = TCE_ROWS * 16;        // bytes per activation plane in k_back: [hl * 2 + ci chunk][row = slot * 35 + bin + 1][8 halves]
+static_assert(4 * TCB_PLANE == BK_NF * BK_X4 * 16, "the four fp16 planes occupy exactly the fp32 X region");
 
 // de3 for output bins of one parity (compile-time, so tap set and weight indices are warp-uniform): thread = 2 slots x 16 co.
 // transposed conv in gather form: even g = 2m uses taps k = 0,2,4 on input bins m+1, m, m-1; odd g = 2m+1 taps k = 1,3 on m+1, m.
@@ -1561,20 +1570,24 @@ __device__ __forceinline__ void back_de4(const PB& prm, const float4* Y3, float*
         *reinterpret_cast<float2*>(M + (4 * sg + s) * m_stride + 2 * h) = make_float2(tanhf(a0[s]), tanhf(a1[s]));
 }
 
-template <bool TO_WAV, int VAR>
+template <bool TO_WAV, int VAR, bool TCB = false>
 __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict__ de2, const float* __restrict__ en1,
                                                         const float* __restrict__ en0, const float* __restrict__ spec,
                                                         int64_t sb, int64_t sf, int64_t st, int64_t sc,
                                                         float* __restrict__ outp, int64_t ob, int64_t of, int64_t ot, int64_t oc,
                                                         float* __restrict__ wav_out, int64_t wav_stride,
                                                         int T, int64_t nframes, const float* __restrict__ blobp,
-                                                        const __grid_constant__ ParamBlock<BackL<VAR>::SIZE> prm) {
+                                                        const __grid_constant__ ParamBlock<BackL<VAR>::SIZE> prm, const uint32_t* __restrict__ tcw = nullptr) {
+    static_assert(!TCB || VAR == 0, "tensor-core de3: GTCRN-Micro");
     using LY = BackL<VAR>;
     constexpr int BK_W_OFF = LY::DE4_W;
     extern __shared__ float4 smem4[];
+    __shared__ __align__(8) uint64_t tc_bars[3];
+    __shared__ uint32_t tmem_base_s;
     float* Wsm = reinterpret_cast<float*>(smem4);
     float* W = Wsm - BK_W_OFF;                       // so that W[LY::xxx] addresses the copied sub-range
-    float4* X = reinterpret_cast<float4*>(Wsm + BK_W_FLOATS);
+    float* Btc = Wsm + BK_W_FLOATS;                  // TCB: de3 weight matrices (k_prep_ends_tc layout)
+    float4* X = reinterpret_cast<float4*>(Btc + (TCB ? TCW_DE3_WORDS : 0));
     float4* const X4all = X;
     float4* Y3 = X + BK_NF * BK_X4;
     float* M = reinterpret_cast<float*>(X);          // stride BK_X4 * 4 floats per slot
@@ -1595,12 +1608,13 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
         tc::mbar_init(&ld_bar, 1);
         tc::fence_barrier_init();
         const uint32_t tile_bytes = (uint32_t)nf_a * kF2 * 64, fft_bytes = TO_WAV ? 2048u + 2064u + 2048u + 1024u : 0u;
-        tc::mbar_expect_tx(&ld_bar, 2 * tile_bytes + BK_W_FLOATS * 4 + fft_bytes);
+        tc::mbar_expect_tx(&ld_bar, 2 * tile_bytes + BK_W_FLOATS * 4 + fft_bytes + (TCB ? TCW_DE3_WORDS * 4 : 0));
+        if (TCB) tc::bulk_g2s(Btc, tcw + TCW_EN1_WORDS, TCW_DE3_WORDS * 4, &ld_bar);
         tc::bulk_g2s(Y3, de2 + fi0 * kF2 * 16, tile_bytes, &ld_bar);
         tc::bulk_g2s(reinterpret_cast<char*>(Y3) + BK_NF * kF2 * 64, en1 + fi0 * kF2 * 16, tile_bytes, &ld_bar);
         tc::bulk_g2s(Wsm, blobp + LY::OFF + BK_W_OFF, BK_W_FLOATS * 4, &ld_bar);     // de4 / inverse-ERB tables
         if (TO_WAV) {                                                                // iSTFT tables: FftTables order + 1 / envelope
-            FftTables& tb0 = *reinterpret_cast<FftTables*>(Wsm + bk_smem_floats(false));
+            FftTables& tb0 = *reinterpret_cast<FftTables*>(Wsm + bk_smem_floats(false, TCB));
             const float* fb = blobp + blob::FFT_OFF;
             tc::bulk_g2s(tb0.tw256, fb + blob::FFT_TW256, 2048, &ld_bar);
             tc::bulk_g2s(tb0.tw512, fb + blob::FFT_TW512, 2064, &ld_bar);
@@ -1609,6 +1623,10 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
         }
     }
     static_assert(BK_NF * BK_Y4 * 16 >= 2 * BK_NF * kF2 * 64 && sizeof(FftTables) == 2048 + 2064 + 2048, "staging fits the Y3 region; table sizes");
+    if (TCB) {
+        if (tid >= 32 && tid < 64) { tc::tmem_alloc(&tmem_base_s, 128); tc::fence_before(); }     // 3 tiles x 32 accumulator columns (even | odd bins)
+        if (tid == 64) { for (int i = 0; i < 3; ++i) tc::mbar_init(&tc_bars[i], 1); tc::fence_async_smem(); }
+    }
     const bool loader = tid < (BK_NF / 2) * kF2;
     const int sp2_a = tid / kF2, f_a = tid - sp2_a * kF2;
 #ifndef GTCRNB_NO_AHEAD_PREFETCH
@@ -1635,7 +1653,8 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
     }
     for (int i = tid; i < BK_NF * 8; i += BK_THREADS) {            // zero pad columns 0 and 34 of X (those of Y3 follow once the staging is consumed)
         const int slot = i >> 3, q = (i >> 1) & 3, side = i & 1;
-        X[slot * BK_X4 + q * 35 + (side ? 34 : 0)] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (TCB) reinterpret_cast<uint4*>(X)[q * TCE_ROWS + slot * 35 + (side ? 34 : 0)] = make_uint4(0u, 0u, 0u, 0u);   // q = plane (hl * 2 + chunk)
+        else X[slot * BK_X4 + q * 35 + (side ? 34 : 0)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();                                               // the mbarrier is initialised for everybody
     tc::mbar_wait(&ld_bar, 0);
@@ -1646,13 +1665,28 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
         for (int s = 0; s < 2; ++s) {
             const int slot = 2 * sp2_a + s;
             const int o = (slot * kF2 + f_a) * 4;
+            if (TCB) {
+                // A operand of the de3 MMAs: x = de2 + en1 as fp16 hi' / lo rows (row = slot * 35 + bin + 1) of four planes
+                float xs[16];
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    const float4 u = sa[o + qd], v = sb_[o + qd];
+                    xs[4 * qd] = u.x + v.x; xs[4 * qd + 1] = u.y + v.y; xs[4 * qd + 2] = u.z + v.z; xs[4 * qd + 3] = u.w + v.w;
+                }
+                uint4 hi[2], lo[2];
+                split_f16_row(xs, hi, lo);
+                uint4* pl = reinterpret_cast<uint4*>(X) + slot * 35 + f_a + 1;
+                pl[0] = hi[0]; pl[TCE_ROWS] = hi[1]; pl[2 * TCE_ROWS] = lo[0]; pl[3 * TCE_ROWS] = lo[1];
+            } else {
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) {
                 const float4 u = sa[o + qd], v = sb_[o + qd];
                 X[slot * BK_X4 + qd * 35 + f_a + 1] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
             }
+            }
         }
     }
+    if (TCB) tc::fence_async_smem();                               // the planes are read by the tensor core (async proxy)
     FBT(1, 1);
     __syncthreads();
     FBT(1, 2);
@@ -1661,14 +1695,68 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
         const int slot = i >> 3, q = (i >> 1) & 3, side = i & 1;
         Y3[slot * BK_Y4 + q * 67 + (side ? 66 : 0)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if constexpr (TCB) {
+        // transposed conv in gather form on the tensor cores: tap pair j reads the planes shifted by 2 - j rows; N = 32 accumulator
+        // columns = [even bins g = 2m | odd bins g = 2m + 1] x 16 channels; three MMAs per tap pair: hi' W_hi, hi' W_lo, lo W_hi
+        tc::fence_after();
+        const uint32_t tm = tmem_base_s;
+        if (tid == 0) {
+            constexpr uint32_t id32 = tc::make_idesc_f16(128, 32);
+            const uint32_t a_base = tc::smem_u32(X), b_base = tc::smem_u32(Btc);
+#pragma unroll 1
+            for (int tile = 0; tile < 3; ++tile) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const uint32_t a_hi = a_base + (uint32_t)((128 * tile + 2 - j) * 16);
+                    const uint64_t da_hi = tc::make_desc(a_hi, TCB_PLANE, 128), da_lo = tc::make_desc(a_hi + 2 * TCB_PLANE, TCB_PLANE, 128);
+                    const uint32_t bj = b_base + j * 3072;
+                    tc::mma_f16_ss(tm + 32 * tile, da_hi, tc::make_desc(bj, 512, 128), id32, j > 0);
+                    tc::mma_f16_ss(tm + 32 * tile, da_hi, tc::make_desc(bj + 1024, 512, 128), id32, 1);
+                    tc::mma_f16_ss(tm + 32 * tile, da_lo, tc::make_desc(bj + 2048, 512, 128), id32, 1);
+                }
+                tc::commit(&tc_bars[tile]);
+            }
+        }
+        const int warp = tid >> 5, lane = tid & 31;
+        {
+            const int tile = warp < 8 ? warp >> 2 : 2, lg = warp & 3;
+            tc::mbar_wait(&tc_bars[tile], 0);
+            tc::fence_after();
+            const int r = 128 * tile + 32 * lg + lane, slot = r / 35, m = r - slot * 35;
+            const bool ok = r < TCE_ROWS && m < kF2 && fi0 + slot < nframes;
+            const uint32_t ta = tm + ((uint32_t)(lg * 32) << 16) + 32 * tile;
+            const float winv = Btc[TCW_DE3_WORDS - 4], a = prm.w[LY::SLOPE + 0];
+#pragma unroll
+            for (int odd = 0; odd < 2; ++odd) {
+                float d[16];
+                tc::tmem_ld16_nowait(ta + 16 * odd, d);
+                tc::tmem_wait_ld(d);
+                const int g = 2 * m + odd;
+                if (ok && g < kF1) {
+                    const float4* pe = reinterpret_cast<const float4*>(en0 + ((fi0 + slot) * kF1 + g) * 16);
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        const float4 e = pe[qd];
+                        float v[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[i] = prelu(fmaf(d[4 * qd + i], winv, prm.w[LY::DE3_B + 4 * qd + i]), a);
+                        Y3[slot * BK_Y4 + qd * 67 + g + 1] = make_float4(v[0] + e.x, v[1] + e.y, v[2] + e.z, v[3] + e.w);
+                    }
+                }
+            }
+        }
+        tc::fence_before();
+    } else {
     if (tid < 160) {
         if (tid < (BK_NF / 2) * 33) back_de3<0, VAR>(prm, X, Y3, tid / 33, tid % 33, fi0, nframes, en0);
     } else {
         const int r = tid - 160;
         back_de3<1, VAR>(prm, X, Y3, r >> 5, r & 31, fi0, nframes, en0);
     }
+    }
     FBT(1, 3);
     __syncthreads();
+    if (TCB && tid >= 32 && tid < 64) tc::tmem_dealloc(tmem_base_s, 128);     // every accumulator row has been read
     FBT(1, 4);
     // ---- c: de4 (16 -> 2) + tanh -> mask on the 129 compressed bins: even bins (65) on warps 0-4, odd bins (64) on warps 5-8
     static_assert(BK_NF == 8, "de4 mapping assumes two groups of four slots");
@@ -1715,7 +1803,7 @@ __global__ void __launch_bounds__(BK_THREADS, 3) k_back(const float* __restrict_
         // lives in the slot's X region -- but that region still holds the mask M until this warp has consumed it, so B is only
         // touched after the __syncwarp that follows the masking loop.
         static_assert(BK_Y4 * 4 >= 544 + 512 && BK_X4 * 4 >= 512, "fused iSTFT buffers must fit in the dead slot regions");
-        FftTables& tb = *reinterpret_cast<FftTables*>(Wsm + bk_smem_floats(false));
+        FftTables& tb = *reinterpret_cast<FftTables*>(Wsm + bk_smem_floats(false, TCB));
         const float* inv_env = reinterpret_cast<const float*>(&tb) + FR_FFT_FLOATS;
         const int warp = tid >> 5, lane = tid & 31;
         if (warp < BK_NF) {

@@ -665,7 +665,8 @@ struct HostParams {
     gk::ParamBlock<blob::BACK_SIZE> back;
     bool tc_stream = false;                       // decoder blocks of a hop on the tensor cores (k_gtconv_dec_tc<4, true>)
     bool fuse_enc = true;                         // the three encoder GTConvBlocks of a hop in one launch (GTCRNB_STREAM_FUSE_ENC=0: three)
-    bool tc_ends = false;                         // en1 / de3 on the tensor cores (k_front / k_back <.., true>), weights in tcw
+    bool tc_ends = false;                         // en1 on the tensor cores (k_front<.., true>), weights in tcw
+    bool tc_back = false;                         // de3 on the tensor cores (k_back<.., true>)
     const uint32_t* tcw = nullptr;
     int sm_count = 148;
     void load(const float* blob_host) {
@@ -709,6 +710,10 @@ inline int model_step(const float* blobp, const HostParams& hp, void* state, con
         else ks_gtconv<true><<<gsg, SG_THREADS, SG_SMEM_FLOATS * sizeof(float), st>>>(ws.act[5 + i], ws.act[3 - i], ws.act[6 + i], hp.dec[i], state, 3 + i, N);
         ++launches;
     }
+    if (hp.tc_back)
+        k_back<false, 0, true><<<gbk, BK_THREADS, bk_smem_floats(false, true) * sizeof(float), st>>>(ws.act[8], ws.act[0], ws.en0, spec, kSpecFrame, 2, 0, 1,
+                                                                                                     out, kSpecFrame, 2, 0, 1, nullptr, 0, 1, N, blobp, hp.back, hp.tcw);
+    else
     k_back<false, 0><<<gbk, BK_THREADS, bk_smem_floats(false) * sizeof(float), st>>>(ws.act[8], ws.act[0], ws.en0, spec, kSpecFrame, 2, 0, 1,
                                                                                   out, kSpecFrame, 2, 0, 1, nullptr, 0, 1, N, blobp, hp.back);
     ++launches;

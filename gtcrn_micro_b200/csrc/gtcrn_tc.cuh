@@ -103,6 +103,13 @@ __device__ __forceinline__ void tct_fetch8(uint32_t tm, uint32_t lane_base, int 
     }
 }
 
+#ifdef GTCRNB_FB_TRACE
+__device__ long long g_tcn_trace[4][16];
+#define TCT(i) do { if (blockIdx.x == 3000 && blockIdx.y == 0 && lane == 0 && k == 2 && t0 == tw0 + 96) { long long c_; \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_)); g_tcn_trace[warp & 3][i] = c_; } } while (0)
+#else
+#define TCT(i) do { } while (0)
+#endif
 template <int NWG, bool STACK>
 __global__ void __launch_bounds__(128 * NWG, tct_min_blocks(NWG))
 k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_constant__ ParamBlock<4 * blob::TCN_SIZE> prm,
@@ -169,7 +176,9 @@ k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_c
             for (int k = 0; k < 4; ++k) {
                 const int d = 1 << k, coff = (2 << k) - 2, wo = k * blob::TCN_SIZE;
                 float y[16];
+                TCT(0);
                 tct_conv16_issue<STACK>(x, tm, lane_base, bdesc0 + (uint64_t)(2 * k) * 128, bar, parity, 1 + wg, issuer);
+                TCT(1);
                 {
                     const float a1 = prm.w[wo + blob::TCN_SLOPE + 0];
 #pragma unroll
@@ -184,9 +193,11 @@ k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_c
                         }
                     }
                 }
+                TCT(2);
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) Y[qd * 32 + lane] = make_float4(y[4 * qd], y[4 * qd + 1], y[4 * qd + 2], y[4 * qd + 3]);
                 __syncwarp();
+                TCT(3);
                 {
                     // depthwise dilated taps, one channel quad at a time (8 instead of 32 tap registers live)
                     const float a2 = prm.w[wo + blob::TCN_SLOPE + 1];
@@ -206,17 +217,20 @@ k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_c
                         }
                     }
                 }
+                TCT(4);
                 tct_conv16_issue<STACK>(y, tm, lane_base, bdesc0 + (uint64_t)(2 * k + 1) * 128, bar, parity, 1 + wg, issuer);
+                TCT(5);
                 // history <- the last 2d conv1 rows of this tile.  The warpgroup barrier inside the call above separates these writes
                 // from every lane's tap reads, the one of the next conv1 separates the Y reads from the next Y writes.
-                if (lane < 8 * d) {
-                    const int qd = lane / (2 * d), j = lane - qd * 2 * d;
+                if (lane < 8 * d) {                                         // (shifts and masks: 2d = 2 << k)
+                    const int qd = lane >> (k + 1), j = lane & (2 * d - 1);
                     H[qd * 30 + coff + j] = Y[qd * 32 + 32 - 2 * d + j];
                 }
-                if (lane + 32 < 8 * d) {                                    // d = 8: 64 float4 to move
-                    const int i = lane + 32, qd = i / (2 * d), j = i - qd * 2 * d;
-                    H[qd * 30 + coff + j] = Y[qd * 32 + 32 - 2 * d + j];
+                if (k == 3) {                                               // d = 8: 64 float4 to move
+                    const int i = lane + 32, qd = i >> 4, j = i & 15;
+                    H[qd * 30 + coff + j] = Y[qd * 32 + 16 + j];
                 }
+                TCT(6);
                 {
                     const float a3 = prm.w[wo + blob::TCN_SLOPE + 2];
 #pragma unroll
@@ -231,6 +245,7 @@ k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_c
                         }
                     }
                 }
+                TCT(7);
             }
             if (col_ok && t >= s0 && t < s1) {
                 float4* po = reinterpret_cast<float4*>(ocol + (int64_t)t * (kF2 * 16));

@@ -18,14 +18,15 @@ import gtcrn_micro_b200.build as B
 
 CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 # kernels launched with the default tuning (gtcrn_capi.cu): offline + streaming
-HOT = ["k_frontILb0ELi0ELb1E", "k_frontILb1ELi0ELb1E", "k_frontILb0ELi0ELb0E", "k_frontILb1ELi0ELb0E", "k_backILb0ELi0E", "k_backILb1ELi0E",
+HOT = ["k_frontILb0ELi0ELb1E", "k_frontILb1ELi0ELb1E", "k_frontILb0ELi0ELb0E", "k_frontILb1ELi0ELb0E",
+       "k_backILb0ELi0ELb1E", "k_backILb1ELi0ELb1E", "k_backILb0ELi0ELb0E", "k_backILb1ELi0ELb0E",
        "k_gtconvILb0ELi2ELi4ELb0", "k_gtconvILb1ELi4ELi7ELb0", "k_gtcnILi2ELb0", "ks_gtconvILb0", "ks_gtconvILb1", "ks_gtconv_enc3", "ks_gtcnE"]
 # tensor-core kernels of the default path (gtcrn_tc.cuh): decoder GTConv with 4 warpgroups per CTA, GTCN with one
 HOT_TC = ["k_gtconv_dec_tcILi4ELb0", "k_gtconv_dec_tcILi4ELb1", "k_gtcn_tcILi1ELb0"]
 # en1 inside k_front on the tensor cores (default): both operands come from shared memory (descriptors), the accumulator from TMEM
-HOT_TC_SS = ["k_frontILb0ELi0ELb1E", "k_frontILb1ELi0ELb1E"]
+HOT_TC_SS = ["k_frontILb0ELi0ELb1E", "k_frontILb1ELi0ELb1E", "k_backILb0ELi0ELb1E", "k_backILb1ELi0ELb1E"]
 # kernels of the original-GTCRN-style variant (BASELINE configs[3]): same weight-feed property, spills tolerated up to a small frame
-HOT_FULL = ["k_frontILb0ELi1ELb0E", "k_frontILb1ELi1ELb0E", "k_backILb0ELi1E", "k_backILb1ELi1E", "kf_gtconvILb0ELi2ELi4E", "kf_gtconvILb1ELi2ELi4E",
+HOT_FULL = ["k_frontILb0ELi1ELb0E", "k_frontILb1ELi1ELb0E", "k_backILb0ELi1ELb0E", "k_backILb1ELi1ELb0E", "kf_gtconvILb0ELi2ELi4E", "kf_gtconvILb1ELi2ELi4E",
             "kf_dp_intra", "kf_dp_inter"]
 
 
@@ -75,12 +76,13 @@ def test_tensor_core_kernels_use_tcgen05_with_operands_in_tensor_memory(sass, ke
 
 
 @pytest.mark.parametrize("key", HOT_TC_SS)
-def test_front_en1_runs_on_tcgen05_from_shared_memory(sass, key):
-    """5 taps x (hi' [W_hi | W_lo], lo W_hi): 10 MMAs in the (rolled) tile loop, A and B through shared-memory descriptors, the
-    accumulator read back with tcgen05.ld; the fp32 en1 FFMA loop is gone (only en0's 240 FFMA2 per thread remain)."""
+def test_ends_run_en1_and_de3_on_tcgen05_from_shared_memory(sass, key):
+    """k_front: 5 taps x (hi' [W_hi | W_lo], lo W_hi) = 10 MMAs in the (rolled) tile loop; k_back: 3 tap pairs x 3 = 9.  A and B through
+    shared-memory descriptors, the accumulator read back with tcgen05.ld; the fp32 en1 / de3 FFMA loops are gone (en0's 240 and
+    de4's FFMA2 remain); tables and tiles arrive by TMA bulk copies (UBLKCP)."""
     body = _find(sass, key)
-    n = {op: sum(1 for l in body if re.search(r"\s" + op + r"[.\s]", l)) for op in ("UTCHMMA", "LDTM", "UTCBAR", "FFMA2")}
-    assert n["UTCHMMA"] >= 10 and n["LDTM"] >= 2 and n["UTCBAR"] >= 1 and n["FFMA2"] < 400, (key, n)
+    n = {op: sum(1 for l in body if re.search(r"\s" + op + r"[.\s]", l)) for op in ("UTCHMMA", "LDTM", "UTCBAR", "FFMA2", "UBLKCP")}
+    assert n["UTCHMMA"] >= 9 and n["LDTM"] >= 2 and n["UTCBAR"] >= 1 and n["FFMA2"] < 400 and n["UBLKCP"] >= 2, (key, n)
     mma = [l for l in body if "UTCHMMA" in l]
     assert all(len(re.findall(r"gdesc\[", l)) >= 2 for l in mma), mma[:2]
 

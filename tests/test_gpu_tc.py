@@ -35,10 +35,10 @@ def test_tc_is_the_default(weights_dns3, b200_lib, monkeypatch):
     monkeypatch.delenv("GTCRNB_TC", raising=False)
     m = G.GTCRNMicro(); m.load_state_dict(weights_dns3)
     m.enhance(torch.zeros(1, 1024, device=DEV))
-    assert m.tc_mask() == 7
+    assert m.tc_mask() == 15
 
 
-@pytest.mark.parametrize("tc", [1, 2, 3, 4, 7])
+@pytest.mark.parametrize("tc", [1, 2, 3, 4, 8, 15])
 def test_tc_layers_match_ffma_and_oracle(oracle, weights, ref_outputs, b200_lib, monkeypatch, tc):
     tag, W = weights
     spec = torch.from_numpy(ref_outputs["spec"])                     # [2,257,41,2]
@@ -70,7 +70,7 @@ def test_tc_signal_level(oracle, weights_dns3, b200_lib, monkeypatch, gain):
     with the input level, which is what its 2^8 offset between the hi' and lo halves is for (1000x full scale still exact)."""
     x = oracle.synth_batch(3, 256 * 40 + 31, seed=5)
     x = gain * x / x.abs().max()
-    m = model_with(weights_dns3, monkeypatch, 7 if gain <= 30.0 else 5)       # the decoder's fp16 operands are specified up to 30x
+    m = model_with(weights_dns3, monkeypatch, 15 if gain <= 30.0 else 13)      # the decoder's fp16 operands are specified up to 30x
     y = m.enhance(x.to(DEV)).cpu()
     ref = oracle.enhance(weights_dns3, x)
     err = float((y - ref).abs().max())
@@ -84,7 +84,7 @@ def test_tc_ragged_batches(oracle, weights_dns3, b200_lib, monkeypatch, B, L):
     """B not a multiple of the 3 groups per warpgroup / 12 per CTA (decoder) nor of the 4 columns per warpgroup (GTCN): the padded
     rows must neither be stored nor disturb their neighbours."""
     x = oracle.synth_batch(B, L, seed=B)
-    m = model_with(weights_dns3, monkeypatch, 7)
+    m = model_with(weights_dns3, monkeypatch, 15)
     y = m.enhance(x.to(DEV)).cpu()
     sel = sorted({0, B // 2, B - 1})
     ref = oracle.enhance(weights_dns3, x[sel])
@@ -98,7 +98,7 @@ def test_tc_time_segmentation_is_bitwise(oracle, weights_dns3, b200_lib, monkeyp
     """One long utterance is split into many time segments with warm-up (few utterances, many SMs); the same utterance inside a big
     batch runs unsegmented.  Row-wise MMA results do not depend on the tile they are computed in."""
     x = oracle.synth_batch(1, 256 * 600, seed=2)
-    m = model_with(weights_dns3, monkeypatch, 7)
+    m = model_with(weights_dns3, monkeypatch, 15)
     y1 = m.enhance(x.to(DEV)).cpu()
     xb = torch.cat([x, oracle.synth_batch(299, 256 * 600, seed=3)])
     yb = m.enhance(xb.to(DEV)).cpu()
