@@ -71,8 +71,8 @@ MICRO_CLASS_INFO = {
 MICRO_TC_INFO = {
     "dec_gtconv": {"kernel": "k_gtconv_dec_tc (decoder GTConvBlock, 3x3 conv as tcgen05 kind::f16 MMAs on fp16 hi/lo operands in tensor memory)", "bound": "hbm",
                    "why": "the 2,304-MAC 3x3 contraction runs on the tensor cores (9 MMAs per 99-position tile); the rest is bounded by HBM traffic "
-                          "(6,336 B per frame) and latency: ncu r2 L1TEX data pipe 68 %, DRAM 34 %, tensor pipe < 10 %",
-                   "dram_bytes": 6396, "dram_note": "ncu r2 (profiles/ncu_r2_dec_tc_summary.txt): 2.78 GB read + 1.32 GB written per launch of 641,024 frames = 1.01 x algorithmic"},
+                          "(6,336 B per frame) and the dependent chain of a step: ncu r2 v25 DRAM 35 %, issue 40 %, tensor pipe < 10 %; clock64 trace 5,900 cycles per step (DESIGN 4.1a)",
+                   "dram_bytes": 6396, "dram_note": "ncu r2 (profiles/ncu_r2_v25_summary.txt): 2.78 GB read + 1.32 GB written per launch of 641,024 frames = 1.01 x algorithmic"},
     "gtcn": {"kernel": "k_gtcn_tc (4 dilated TCNs, pointwise convs as tcgen05 kind::tf32 3xTF32 MMAs, A operand in tensor memory)", "bound": "hbm",
              "why": "the 512 of 560 MACs per position-TCN that are pointwise contractions run on the tensor cores; the kernel is instruction-issue "
                     "bound (ncu r2: issue 63 %), nearest hardware roof HBM", "dram_bytes": 4155,
@@ -680,7 +680,8 @@ def run_b200(args):
             "share_of_step": round(dk["ms"] / step_kernel_ms, 4) if step_kernel_ms else None,
             "dominant_class_by_time": dom,
             "tensor_core_layers": {"mask": tc_mask, "gtcn_pointwise": bool(tc_mask & 1), "decoder_3x3": bool(tc_mask & 2),
-                                   "operands": "fp16 hi/lo (decoder), 3xTF32 (GTCN): fp32-class accuracy, A operand in tensor memory"},
+                                   "front_en1": bool(tc_mask & 4), "back_de3": bool(tc_mask & 8),
+                                   "operands": "fp16 hi/lo (decoder, en1, de3), 3xTF32 (GTCN): fp32-class accuracy; A operand in tensor memory (decoder, GTCN) or shared memory (en1, de3)"},
             "whole_path": whole,
             "per_class_ms": {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]},
             "per_class": {k: {"ms": round(v["ms"] / args.steps, 3),
