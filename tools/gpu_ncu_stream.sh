@@ -2,7 +2,7 @@
 # ncu --set full on the kernels of ONE streaming hop at N concurrent streams.  Usage: tools/gpu_ncu_stream.sh tag [N] [wav|spec]
 cd "$(dirname "$0")/.."
 TAG=$1; N=${2:-16384}; KIND=${3:-spec}
-mkdir -p gpurun_out
+mkdir -p gpurun_out /tmp/ncu
 cat > gpurun_out/stream_hops.py <<'PY'
 import sys, torch
 sys.path.insert(0, '.')
@@ -26,5 +26,5 @@ PY
 # hop = 10 launches (spec) / 12 (wav): skip 6 warm hops, capture one whole hop
 PER=10; [ "$KIND" = wav ] && PER=12
 GTCRNB_STREAM_GRAPH=0 timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:k_front|ks_|k_back|k_gtconv_dec_tc" -s $((6 * PER)) -c $PER -f \
-    -o gpurun_out/prof_$TAG python gpurun_out/stream_hops.py $N $KIND 8 > gpurun_out/ncu_$TAG.log 2>&1
+    -o /tmp/ncu/prof_$TAG python gpurun_out/stream_hops.py $N $KIND 8 > gpurun_out/ncu_$TAG.log 2>&1
 echo "ncu rc=$?"; tail -2 gpurun_out/ncu_$TAG.log
