@@ -11,7 +11,7 @@ for cfg in sys.argv[1:]:
     for k in [k for k in os.environ if k.startswith("GTCRNB_HOST_")]: del os.environ[k]
     for kv in cfg.split():
         k, v = kv.split("="); os.environ["GTCRNB_HOST_" + k] = v
-    m = G.GTCRNMicro()                      # stream priorities are fixed when the pipeline is first used
+    m = G.GTCRN() if os.environ.get('VARIANT') == 'full' else G.GTCRNMicro()    # stream priorities are fixed when the pipeline is first used
     for _ in range(2): m.enhance_host(x, y)
     best = 1e9
     for rep in range(3):
