@@ -744,13 +744,15 @@ namespace {
 //   s_back  : back(c) per copy chunk                        s_d2h   : D2H of copy chunk c as soon as back(c) is done
 // The first H2D and the last D2H cannot overlap with anything, so groups ramp up from g1 and down to glast utterances.
 struct HostSchedule { int64_t copy; std::vector<int64_t> groups; int64_t gmax; };
-HostSchedule host_schedule(int64_t B, int64_t L) {
+HostSchedule host_schedule(int64_t B, int64_t L, int variant) {
     auto envi = [](const char* name, int dflt, int lo, int hi) { const char* e = getenv(name); return e ? std::max(lo, std::min(hi, atoi(e))) : dflt; };
     auto units = [&](int64_t u) { return std::max<int64_t>(1, (u * 160000) / L); };        // knobs are in 10-second-utterance equivalents
     HostSchedule s;
     s.copy = units(envi("GTCRNB_HOST_COPY", 48, 1, 4096));
     const int64_t gmax = std::min<int64_t>({B, units(envi("GTCRNB_HOST_CHUNK", 384, 1, 65535)), std::max<int64_t>(1, kMaxChunkFrames / (1 + L / gk::kHop))});
-    const int64_t g1 = std::min(gmax, units(envi("GTCRNB_HOST_G1", 48, 1, 65535))), gl = std::min(gmax, units(envi("GTCRNB_HOST_GLAST", 24, 1, 65535)));
+    // variant 1's GTConv / DPGRNN kernels are persistent over time (one CTA or warp per utterance): small groups leave SMs empty
+    const int64_t g1 = std::min(gmax, units(envi("GTCRNB_HOST_G1", variant == 1 ? 96 : 48, 1, 65535)));
+    const int64_t gl = std::min(gmax, units(envi("GTCRNB_HOST_GLAST", variant == 1 ? 96 : 24, 1, 65535)));
     const double up = envi("GTCRNB_HOST_GROWTH", 200, 101, 1000) / 100.0, down = envi("GTCRNB_HOST_DECAY", 160, 101, 1000) / 100.0;
     std::vector<int64_t> head, tail;
     int64_t used = 0;
@@ -790,7 +792,7 @@ int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, 
         for (int i = 0; i < kStage; ++i)
             for (cudaEvent_t* e : {&h->ev_fronts[i], &h->ev_body[i], &h->ev_backs[i], &h->ev_d2h[i]}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
-    const HostSchedule sch = host_schedule(B, L);
+    const HostSchedule sch = host_schedule(B, L, h->variant);
     const size_t need_in = (size_t)sch.gmax * L, need_out = (size_t)sch.gmax * Lout;
     if (need_in > h->stage_in_floats || need_out > h->stage_out_floats) {
         for (int i = 0; i < kStage; ++i) {
@@ -854,8 +856,10 @@ int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, 
     int64_t b0 = 0;
     const int64_t is[4] = {T * gk::kSpecFrame, 2, gk::kSpecFrame, 1};
     const auto t_enq0 = std::chrono::steady_clock::now();
-    // (measured: no gain from a second walking-kernel stream -- every walking kernel is sized to fill the SMs in one wave; kept as a knob)
-    const bool two_body = getenv("GTCRNB_HOST_BODY2") ? atoi(getenv("GTCRNB_HOST_BODY2")) != 0 : false;
+    // second walking-kernel stream (by group parity).  GTCRN-Micro: no gain, every walking kernel is sized to fill the SMs in one wave
+    // (21.8 vs 22.3 ms); variant 1: its persistent one-CTA-per-utterance kernels leave most SMs idle on a 100-utterance group, two groups
+    // side by side give 252 k against 140 k audio-s/s
+    const bool two_body = getenv("GTCRNB_HOST_BODY2") ? atoi(getenv("GTCRNB_HOST_BODY2")) != 0 : h->variant == 1;
     for (size_t g = 0; g < sch.groups.size(); b0 += sch.groups[g], ++g) {
         const int slot = (int)(g % kStage);
         const int64_t ng = sch.groups[g];
