@@ -15,6 +15,8 @@ for k in range(6):
     o = sm.step_wav(x[:1, 256 * k:256 * (k + 1)].repeat(5, 1).contiguous(), st)
 pm = m.pair_metrics(x[:, :y.shape[1]].contiguous(), y)
 yh = m.enhance_host(x.cpu().pin_memory())
+pool = G.StreamPool(sm, 7, 'cuda:0', groups=2); hin = x[:7, :256].cpu().pin_memory(); hout = torch.empty(7, 256).pin_memory()
+for k in range(3): pool.step_wav_host(hin, hout)
 torch.cuda.synchronize(); print('ok', y.shape, float((y - z).abs().max()), bool(torch.equal(yh, y.cpu())), pm.shape, 'tc mask', m.tc_mask())
 PY
 for tool in memcheck racecheck; do
