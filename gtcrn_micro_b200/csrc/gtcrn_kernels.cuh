@@ -723,7 +723,9 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
     FBT(0, 8);
     // ---- c: SFE-Lite (depthwise 3-tap along the 129 compressed bins, zero padded, no bias)
     {
-        const float* sw = W + blob::FRONT_SFE_W;                   // [c][k]
+        float sw[9];                                               // [c][k]: in registers (the stores below would otherwise force a re-load per item)
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sw[i] = W[blob::FRONT_SFE_W + i];
         for (int idx = tid; idx < FR_NF * kErb; idx += FR_THREADS) {
             const int slot = idx / kErb, f = idx - slot * kErb;
             const float4* lo = reinterpret_cast<const float4*>(featp(slot));   // compressed bins 0..64 = spectrum bins
