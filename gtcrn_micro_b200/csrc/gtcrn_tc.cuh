@@ -594,7 +594,6 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
             // MMAs of frame t run, and frame t-1 is stored after the barrier that publishes the gate -- two warpgroup barriers per frame.
             int r = tw0 % 3;                                              // ring slot of the current frame
             float qp[8];                                                  // previous frame: point-conv-2 output and pass-through half
-            float4 x2pa = make_float4(0.f, 0.f, 0.f, 0.f), x2pb = x2pa;
 #pragma unroll
             for (int c = 0; c < 8; ++c) qp[c] = 0.f;
 #ifdef GTCRNB_DEC_TRACE
@@ -607,7 +606,8 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
 #endif
             // The point-conv half (channels 0..7) of x and skip of the NEXT frame is requested right after the stores of step t, so that
             // its L2 latency (~1,200 cycles on the trace) hides behind the epilogue instead of opening the next step; the pass-through
-            // half is requested at the top of its own step and only consumed at its end.  The frame after next is on its way to L2.
+            // half of a frame is only needed for its store one step later and is requested during that step's MMA wait.  The frame after next is on
+            // its way to L2.
             float4 a[2], c[2];
 #pragma unroll
             for (int v = 0; v < 2; ++v) { a[v] = px[(int64_t)tw0 * FS4 + v]; c[v] = ps[(int64_t)tw0 * FS4 + v]; }
@@ -617,7 +617,7 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
             }
             for (int t = tw0; t < s1; ++t) {
                 TRC(0);
-                float4 cx[4];                                             // x + skip of this frame
+                float4 cx[2];                                             // x + skip of this frame, point-conv half
                 {
                     if (t + 2 < s1) {
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(px + (int64_t)(t + 2) * FS4));
@@ -642,6 +642,10 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
                 TRC(4);
                 if (issuer) issue_mmas(r);
                 TRC(5);
+                // pass-through half (channels 8..15) of frame t-1, stored below: requested here, where few registers are live and the
+                // MMAs / the gate give its L2 latency ~1,000 cycles (it shares its 128-byte line with the half loaded a step ago)
+                const int tp = t > tw0 ? t - 1 : t;
+                const float4 a2 = px[(int64_t)tp * FS4 + 2], a3 = px[(int64_t)tp * FS4 + 3], c2 = ps[(int64_t)tp * FS4 + 2], c3 = ps[(int64_t)tp * FS4 + 3];
                 if (t > tw0) gate_phase();                                // frame t-1, while the tensor core works on frame t
                 TRC(6);
                 tc::mbar_wait(bar, parity);
@@ -653,26 +657,26 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
                 TRC(8);
                 tc::bar_sync(bar_id, 128);                                // exchange buffer and the gate of frame t-1 are visible
                 TRC(9);
-                if (t > tw0 && store_ok && t - 1 >= s0) store_row(po + (int64_t)(t - 1) * FS4, qp, x2pa, x2pb);
+                if (t > tw0 && store_ok && t - 1 >= s0)
+                    store_row(po + (int64_t)(t - 1) * FS4, qp, make_float4(a2.x + c2.x, a2.y + c2.y, a2.z + c2.z, a2.w + c2.w),
+                              make_float4(a3.x + c3.x, a3.y + c3.y, a3.z + c3.z, a3.w + c3.w));
                 TRC(10);
-                // pass-through half of THIS frame: only needed once the epilogue is done
-                const float4 a2 = px[(int64_t)t * FS4 + 2], a3 = px[(int64_t)t * FS4 + 3], c2 = ps[(int64_t)t * FS4 + 2], c3 = ps[(int64_t)t * FS4 + 3];
                 if (t + 1 < s1) {
 #pragma unroll
                     for (int v = 0; v < 2; ++v) { a[v] = px[(int64_t)(t + 1) * FS4 + v]; c[v] = ps[(int64_t)(t + 1) * FS4 + v]; }
                 }
                 epilogue(m, qp);
-                cx[2] = make_float4(a2.x + c2.x, a2.y + c2.y, a2.z + c2.z, a2.w + c2.w);
-                cx[3] = make_float4(a3.x + c3.x, a3.y + c3.y, a3.z + c3.z, a3.w + c3.w);
                 TRC(11);
-                x2pa = cx[2]; x2pb = cx[3];
                 r = r == 2 ? 0 : r + 1;
             }
             // ---- drain: gate and store of the last frame
+            const float4 a2 = px[(int64_t)(s1 - 1) * FS4 + 2], a3 = px[(int64_t)(s1 - 1) * FS4 + 3], c2 = ps[(int64_t)(s1 - 1) * FS4 + 2], c3 = ps[(int64_t)(s1 - 1) * FS4 + 3];
             tc::bar_sync(bar_id, 128);
             gate_phase();
             tc::bar_sync(bar_id, 128);
-            if (store_ok) store_row(po + (int64_t)(s1 - 1) * FS4, qp, x2pa, x2pb);
+            if (store_ok)
+                store_row(po + (int64_t)(s1 - 1) * FS4, qp, make_float4(a2.x + c2.x, a2.y + c2.y, a2.z + c2.z, a2.w + c2.w),
+                          make_float4(a3.x + c3.x, a3.y + c3.y, a3.z + c3.z, a3.w + c3.w));
         }
     }
     tc::fence_before();
