@@ -430,8 +430,10 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
             float d0[16], d2[16];
             tc::tmem_ld16_nowait(tm + lane_base, d0);
             tc::tmem_ld16_nowait(tm + lane_base + 32, d2);
+            tc::tmem_ld16_nowait(tm + lane_base + 16, m);                 // all three blocks in one tensor-memory round trip
             tc::tmem_wait_ld(d0);
             tc::tmem_wait_ld(d2);
+            tc::tmem_wait_ld(m);
             if (active) {
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
@@ -440,8 +442,6 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
                 }
             }
         }
-        tc::tmem_ld16_nowait(tm + lane_base + 16, m);                 // the centre block stays with this thread
-        tc::tmem_wait_ld(m);
         tc::fence_before();                                           // orders the tcgen05.ld above before the next step's MMAs
     };
     // second half: neighbours' blocks, weight scale + bias, PReLU, point conv 2, q^2 for the TRALite energy
