@@ -596,15 +596,22 @@ __global__ void __launch_bounds__(FR_THREADS, FR_MIN_BLOCKS) k_front(const float
         const bool valid = warp < FR_NF && fi_w < nframes;
         float xr0[8], xr1[8];
         if (valid) {
-            const int64_t b = fi_w / T;
+            const int64_t b = nframes < ((int64_t)1 << 31) ? (int64_t)((uint32_t)fi_w / (uint32_t)T) : fi_w / T;   // (a 64-bit division is ~100 instructions)
             const int t = (int)(fi_w - b * T);
             const float* x = wav + b * wav_stride;
             const int base = kHop * t - kHop;
+            if (base >= 0 && base + kNfft <= L && ((reinterpret_cast<uintptr_t>(x + base) & 7) == 0)) {
+                // interior frame: no reflection, sample pairs are aligned 8-byte loads (8 instead of 16 requests per lane)
+                const float2* x2 = reinterpret_cast<const float2*>(x + base);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { const float2 v = x2[lane + 32 * q]; xr0[q] = v.x; xr1[q] = v.y; }
+            } else {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int n = lane + 32 * q;
                 xr0[q] = x[reflect_idx(base + 2 * n, L)];
                 xr1[q] = x[reflect_idx(base + 2 * n + 1, L)];
+            }
             }
         } else {
 #pragma unroll
