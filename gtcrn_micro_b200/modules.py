@@ -191,7 +191,7 @@ class _B200Module(nn.Module):
         return int(_lib.load().gtcrnb_launch_count(self._handle)) if self._handle.value is not None else 0
 
     def tc_mask(self) -> int:
-        """Layers running on the tensor cores: bit 0 GTCN pointwise convs, bit 1 decoder GTConv 3x3 (GTCRNB_TC, default 3)."""
+        """Layers running on the tensor cores: bit 0 GTCN pointwise convs, bit 1 decoder GTConv 3x3, bit 2 en1, bit 3 de3 (GTCRNB_TC, default 15)."""
         return int(_lib.load().gtcrnb_tc_mask(self._handle)) if self._handle.value is not None else 0
 
     @staticmethod

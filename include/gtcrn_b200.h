@@ -140,8 +140,8 @@ int gtcrnb_profile_read(gtcrnb_handle* h, int reset, double* ms_out, int64_t* la
 int gtcrnb_profile_num_classes(void);
 const char* gtcrnb_profile_class_name(int i);
 /* Which layers of a GTCRNB_VARIANT_MICRO handle run on the tensor cores (tcgen05, fp32-class accuracy through hi/lo operand splits):
- * bit 0 the GTCN pointwise convolutions, bit 1 the decoder GTConv 3x3 convolution.  Default 3; the environment variable GTCRNB_TC
- * (read at gtcrnb_create) overrides it, 0 = FFMA kernels only, whose offline results are bit-identical to the streaming path. */
+ * bit 0 the GTCN pointwise convolutions, bit 1 the decoder GTConv 3x3 convolution, bit 2 en1 inside the front kernel, bit 3 de3 inside
+ * the back kernel.  Default 15; the environment variable GTCRNB_TC (read at gtcrnb_create) overrides it, 0 = FFMA kernels only, whose offline results are bit-identical to the streaming path. */
 int gtcrnb_tc_mask(const gtcrnb_handle* h);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t gtcrnb_launch_count(const gtcrnb_handle* h);
