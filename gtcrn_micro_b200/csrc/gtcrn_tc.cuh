@@ -47,7 +47,7 @@ __host__ __device__ constexpr int tct_min_blocks(int nwg) { return nwg == 1 ? 6 
 // one pointwise 16 -> 16 convolution of the warpgroup's 128 rows, first half: v (registers) -> A in TMEM, MMAs, completion wait.
 // STACK: 4 MMAs, the accumulator holds hi*w_hi + lo*w_hi in columns 0..15 and hi*w_lo in 16..31 (dependent chain of 4);
 // otherwise 6 MMAs accumulate all three terms into columns 0..15 (chain of 6, half the tcgen05.ld traffic).
-template <bool STACK>
+template <bool STACK, bool WAIT = true>
 __device__ __forceinline__ void tct_conv16_issue(const float (&v)[16], uint32_t tm, uint32_t lane_base, uint64_t bdesc, uint64_t* bar,
                                                   uint32_t& parity, int bar_id, bool issuer) {
 #pragma unroll
@@ -83,6 +83,14 @@ __device__ __forceinline__ void tct_conv16_issue(const float (&v)[16], uint32_t 
         }
         tc::commit(bar);
     }
+    if (WAIT) {
+        tc::mbar_wait(bar, parity);
+        parity ^= 1;
+        tc::fence_after();
+    }
+}
+// completion wait of a convolution started with WAIT = false (whatever does not need its result goes in between)
+__device__ __forceinline__ void tct_conv16_wait(uint64_t* bar, uint32_t& parity) {
     tc::mbar_wait(bar, parity);
     parity ^= 1;
     tc::fence_after();
@@ -218,10 +226,11 @@ k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_c
                     }
                 }
                 TCT(4);
-                tct_conv16_issue<STACK>(y, tm, lane_base, bdesc0 + (uint64_t)(2 * k + 1) * 128, bar, parity, 1 + wg, issuer);
+                tct_conv16_issue<STACK, false>(y, tm, lane_base, bdesc0 + (uint64_t)(2 * k + 1) * 128, bar, parity, 1 + wg, issuer);
                 TCT(5);
-                // history <- the last 2d conv1 rows of this tile.  The warpgroup barrier inside the call above separates these writes
-                // from every lane's tap reads, the one of the next conv1 separates the Y reads from the next Y writes.
+                // history <- the last 2d conv1 rows of this tile, WHILE the MMAs of the second convolution run (the clock64 trace showed
+                // this copy at ~550 of a TCN's 4,450 cycles after the completion wait).  The warpgroup barrier inside the call above
+                // separates these writes from every lane's tap reads, the one of the next conv1 separates the Y reads from the next Y writes.
                 if (lane < 8 * d) {                                         // (shifts and masks: 2d = 2 << k)
                     const int qd = lane >> (k + 1), j = lane & (2 * d - 1);
                     H[qd * 30 + coff + j] = Y[qd * 32 + 32 - 2 * d + j];
@@ -230,6 +239,7 @@ k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_c
                     const int i = lane + 32, qd = i >> 4, j = i & 15;
                     H[qd * 30 + coff + j] = Y[qd * 32 + 16 + j];
                 }
+                tct_conv16_wait(bar, parity);
                 TCT(6);
                 {
                     const float a3 = prm.w[wo + blob::TCN_SLOPE + 2];
