@@ -842,6 +842,8 @@ int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, 
         h->user_pending = false;
     }
     struct PipelineFlag { gtcrnb_handle* h; PipelineFlag(gtcrnb_handle* h_) : h(h_) { h->in_pipeline = true; } ~PipelineFlag() { h->in_pipeline = false; select_workspace(h, 0); } } pflag(h);
+    // a failed launch must not leave work of this call running on the internal streams behind the caller's back
+    auto drain = [&](int rc_) { for (cudaStream_t st_ : {h->s_h2d, h->s_front, h->s_body, h->s_body2, h->s_back, h->s_d2h}) if (st_) cudaStreamSynchronize(st_); cudaGetLastError(); return rc_; };
     // GTCRNB_HOST_TRACE=1: per-chunk engine timeline on stderr (diagnostic; adds timing events, not for benchmarking)
     const bool trace = getenv("GTCRNB_HOST_TRACE") != nullptr;
     struct TraceRow { int group; int64_t utts; int kind; cudaEvent_t e0, e1; };    // kind 0 h2d, 1 front, 2 body, 3 back, 4 d2h
@@ -889,7 +891,7 @@ int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, 
             }
             if (split) {
                 const int rc = run_model(h, nullptr, is, ng, T, nullptr, is, h->s_front, in_f, L, (int)L, nullptr, 0, PH_FRONT, u0, nu);
-                if (rc) return rc;
+                if (rc) return drain(rc);
             }
             tend(h->s_front);
         }
@@ -900,11 +902,11 @@ int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, 
         tbegin((int)g, ng, 2, sb);
         if (split) {
             const int rc = run_model(h, nullptr, is, ng, T, nullptr, is, sb, nullptr, 0, 0, nullptr, 0, PH_BODY);
-            if (rc) return rc;
+            if (rc) return drain(rc);
         } else {
             if (reuse) CU(cudaStreamWaitEvent(sb, h->ev_d2h[slot], 0));
             const int rc = gtcrnb_enhance(h, in_f, ng, L, L, out_f, Lout, sb);
-            if (rc) return rc;
+            if (rc) return drain(rc);
         }
         tend(sb);
         CU(cudaEventRecord(h->ev_body[slot], sb));
@@ -917,7 +919,7 @@ int host_pipeline(gtcrnb_handle* h, const void* wav_host, int64_t B, int64_t L, 
             tbegin((int)g, nu, 3, h->s_back);
             if (split) {
                 const int rc = run_model(h, nullptr, is, ng, T, nullptr, is, h->s_back, nullptr, 0, (int)L, out_f, Lout, PH_BACK, u0, nu);
-                if (rc) return rc;
+                if (rc) return drain(rc);
             }
             if (pcm) {
                 gk::k_f32_to_pcm16<<<h->sm_count * 8, 256, 0, h->s_back>>>(out_f + u0 * Lout, h->pcm_out[slot] + u0 * Lout, nu * Lout);

@@ -644,6 +644,8 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
                     gt_pc1<true>(prm, x1, p);
                     store_slot(r, p);
                 }
+                const int tp = t > tw0 ? t - 1 : t;
+                const float4 a2 = px[(int64_t)tp * FS4 + 2], a3 = px[(int64_t)tp * FS4 + 3], c2 = ps[(int64_t)tp * FS4 + 2], c3 = ps[(int64_t)tp * FS4 + 3];
                 TRC(2);
                 tc::tmem_wait_st();
                 tc::fence_before();
@@ -654,8 +656,6 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
                 TRC(5);
                 // pass-through half (channels 8..15) of frame t-1, stored below: requested here, where few registers are live and the
                 // MMAs / the gate give its L2 latency ~1,000 cycles (it shares its 128-byte line with the half loaded a step ago)
-                const int tp = t > tw0 ? t - 1 : t;
-                const float4 a2 = px[(int64_t)tp * FS4 + 2], a3 = px[(int64_t)tp * FS4 + 3], c2 = ps[(int64_t)tp * FS4 + 2], c3 = ps[(int64_t)tp * FS4 + 3];
                 if (t > tw0) gate_phase();                                // frame t-1, while the tensor core works on frame t
                 TRC(6);
                 tc::mbar_wait(bar, parity);
