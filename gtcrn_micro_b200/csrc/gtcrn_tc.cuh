@@ -628,6 +628,8 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
             for (int t = tw0; t < s1; ++t) {
                 TRC(0);
                 float4 cx[2];                                             // x + skip of this frame, point-conv half
+                const int tp = t > tw0 ? t - 1 : t;
+                const float4 a2 = px[(int64_t)tp * FS4 + 2], a3 = px[(int64_t)tp * FS4 + 3], c2 = ps[(int64_t)tp * FS4 + 2], c3 = ps[(int64_t)tp * FS4 + 3];
                 {
                     if (t + 2 < s1) {
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(px + (int64_t)(t + 2) * FS4));
@@ -644,8 +646,6 @@ k_gtconv_dec_tc(const float* __restrict__ xin, const float* __restrict__ skip, f
                     gt_pc1<true>(prm, x1, p);
                     store_slot(r, p);
                 }
-                const int tp = t > tw0 ? t - 1 : t;
-                const float4 a2 = px[(int64_t)tp * FS4 + 2], a3 = px[(int64_t)tp * FS4 + 3], c2 = ps[(int64_t)tp * FS4 + 2], c3 = ps[(int64_t)tp * FS4 + 3];
                 TRC(2);
                 tc::tmem_wait_st();
                 tc::fence_before();
