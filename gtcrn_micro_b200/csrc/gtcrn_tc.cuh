@@ -17,6 +17,7 @@
 // MMA adds lo*w_hi: 2 MMAs per K = 8 step instead of 3; the two column blocks are added in registers after tcgen05.ld.
 #pragma once
 #include <algorithm>
+#include <type_traits>
 #include "gtcrn_kernels.cuh"
 #include "gtcrn_stream.cuh"
 #include <cuda_fp16.h>
@@ -165,23 +166,26 @@ k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_c
         const float* xcol = xin + (b * T * kF2 + f) * 16;
         float* ocol = out + (b * T * kF2 + f) * 16;
 
-        for (int t0 = tw0; t0 < s1; t0 += 32) {
-            const int t = t0 + lane;
-            float x[16];
+        float4 xn[4];                                                 // rows of the next tile (loaded one tile ahead)
+        {
+            const int t = tw0 + lane;
             if (t < s1) {
                 const float4* px = reinterpret_cast<const float4*>(xcol + (int64_t)t * (kF2 * 16));
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const float4 u = px[v];
-                    x[4 * v] = u.x; x[4 * v + 1] = u.y; x[4 * v + 2] = u.z; x[4 * v + 3] = u.w;
-                }
+                for (int v = 0; v < 4; ++v) xn[v] = px[v];
                 if (t + 32 < s1) asm volatile("prefetch.global.L2 [%0];" ::"l"(xcol + (int64_t)(t + 32) * (kF2 * 16)));
             } else {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) x[c] = 0.f;
+                for (int v = 0; v < 4; ++v) xn[v] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-#pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
+        }
+        for (int t0 = tw0; t0 < s1; t0 += 32) {
+            const int t = t0 + lane;
+            float x[16];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) { x[4 * v] = xn[v].x; x[4 * v + 1] = xn[v].y; x[4 * v + 2] = xn[v].z; x[4 * v + 3] = xn[v].w; }
+            auto tcn = [&](const int k, auto last_c) {
+
                 const int d = 1 << k, coff = (2 << k) - 2, wo = k * blob::TCN_SIZE;
                 float y[16];
                 TCT(0);
@@ -239,6 +243,20 @@ k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_c
                     const int i = lane + 32, qd = i >> 4, j = i & 15;
                     H[qd * 30 + coff + j] = Y[qd * 32 + 16 + j];
                 }
+                if constexpr (decltype(last_c)::value) {
+                    // next tile's rows, requested in the shadow of the LAST convolution of this tile (an L2 hit costs > 2,000 cycles under
+                    // this load; at the top of the next tile nothing covered it).  Only this peeled copy of the TCN body carries them.
+                    const int tn = t + 32;
+                    if (tn < s1) {
+                        const float4* pn = reinterpret_cast<const float4*>(xcol + (int64_t)tn * (kF2 * 16));
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) xn[v] = pn[v];
+                        if (tn + 32 < s1) asm volatile("prefetch.global.L2 [%0];" ::"l"(xcol + (int64_t)(tn + 32) * (kF2 * 16)));
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) xn[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
                 tct_conv16_wait(bar, parity);
                 TCT(6);
                 {
@@ -256,7 +274,10 @@ k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_c
                     }
                 }
                 TCT(7);
-            }
+                        };
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) tcn(k, std::false_type{});
+            tcn(3, std::true_type{});                                   // peeled: carries the next tile's loads
             if (col_ok && t >= s0 && t < s1) {
                 float4* po = reinterpret_cast<float4*>(ocol + (int64_t)t * (kF2 * 16));
 #pragma unroll
