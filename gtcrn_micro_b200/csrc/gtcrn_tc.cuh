@@ -229,6 +229,20 @@ k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_c
                         }
                     }
                 }
+                if constexpr (decltype(last_c)::value) {
+                    // next tile's rows, requested before the LAST convolution of this tile (an L2 hit costs > 2,000 cycles under
+                    // this load; at the top of the next tile nothing covered it).  Only this peeled copy of the TCN body carries them.
+                    const int tn = t + 32;
+                    if (tn < s1) {
+                        const float4* pn = reinterpret_cast<const float4*>(xcol + (int64_t)tn * (kF2 * 16));
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) xn[v] = pn[v];
+                        if (tn + 32 < s1) asm volatile("prefetch.global.L2 [%0];" ::"l"(xcol + (int64_t)(tn + 32) * (kF2 * 16)));
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) xn[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
                 TCT(4);
                 tct_conv16_issue<STACK, false>(y, tm, lane_base, bdesc0 + (uint64_t)(2 * k + 1) * 128, bar, parity, 1 + wg, issuer);
                 TCT(5);
@@ -242,20 +256,6 @@ k_gtcn_tc(const float* __restrict__ xin, float* __restrict__ out, const __grid_c
                 if (k == 3) {                                               // d = 8: 64 float4 to move
                     const int i = lane + 32, qd = i >> 4, j = i & 15;
                     H[qd * 30 + coff + j] = Y[qd * 32 + 16 + j];
-                }
-                if constexpr (decltype(last_c)::value) {
-                    // next tile's rows, requested in the shadow of the LAST convolution of this tile (an L2 hit costs > 2,000 cycles under
-                    // this load; at the top of the next tile nothing covered it).  Only this peeled copy of the TCN body carries them.
-                    const int tn = t + 32;
-                    if (tn < s1) {
-                        const float4* pn = reinterpret_cast<const float4*>(xcol + (int64_t)tn * (kF2 * 16));
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) xn[v] = pn[v];
-                        if (tn + 32 < s1) asm volatile("prefetch.global.L2 [%0];" ::"l"(xcol + (int64_t)(tn + 32) * (kF2 * 16)));
-                    } else {
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) xn[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
                 }
                 tct_conv16_wait(bar, parity);
                 TCT(6);
