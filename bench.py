@@ -72,12 +72,12 @@ MICRO_TC_INFO = {
     "dec_gtconv": {"kernel": "k_gtconv_dec_tc (decoder GTConvBlock, 3x3 conv as tcgen05 kind::f16 MMAs on fp16 hi/lo operands in tensor memory)", "bound": "hbm",
                    "why": "the 2,304-MAC 3x3 contraction runs on the tensor cores (9 MMAs per 99-position tile); the rest is bounded by HBM traffic "
                           "(6,336 B per frame) and the dependent chain of a step: ncu r2 v27 DRAM 40 %, issue 41 %, tensor pipe < 10 %; clock64 trace of a step in DESIGN 4.1a",
-                   "dram_bytes": 6396, "dram_note": "ncu r2 (profiles/ncu_r2_v29_summary.txt): 2.78 GB read + 1.32 GB written per launch of 641,024 frames = 1.01 x algorithmic"},
+                   "dram_bytes": 6396, "dram_note": "ncu r2 (profiles/ncu_r2_v30_summary.txt): 2.78 GB read + 1.32 GB written per launch of 641,024 frames = 1.01 x algorithmic"},
     "gtcn": {"kernel": "k_gtcn_tc (4 dilated TCNs, pointwise convs as tcgen05 kind::tf32 3xTF32 MMAs, A operand in tensor memory)", "bound": "hbm",
              "why": "the 512 of 560 MACs per position-TCN that are pointwise contractions run on the tensor cores; the kernel is bound by "
                     "the dependent chain of a TCN (clock64 trace: 4,450 cycles per 32-frame tile and TCN with 6 CTAs per SM; ncu r2 v27 issue 55 %; "
                     "cutting 7 % of its instructions changed nothing), nearest hardware roof HBM", "dram_bytes": 4155,
-             "dram_note": "ncu r2 (profiles/ncu_r2_v29_summary.txt): 1.35 GB read + 1.31 GB written per launch"},
+             "dram_note": "ncu r2 (profiles/ncu_r2_v30_summary.txt): 1.35 GB read + 1.31 GB written per launch"},
 }
 WEIGHTS = os.path.join(ROOT, "tests", "golden", "weights_dns3.npz")
 # BASELINE configs[3], `--variant full`: the original-GTCRN-style architecture (parity unpinned, oracle/gtcrn_full_oracle.py).
